@@ -1,0 +1,167 @@
+/*
+ * phylo_b200.h -- C ABI of libphylo_b200.so: Felsenstein-pruning log-likelihood and its
+ * analytic gradient on one B200 (sm_100a), behind the reference's operator surface.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   phylo_b200_create[_tipdata]  the compile-time constants baked into eigen.hpp by
+ *                                eigen/eigen.j2:19-38 (child_parent, postorder, tip partials, pi, Q)
+ *                                == the Stan data block peel/tipdata/weights/C of
+ *                                phylostan/generate_script.py:1186-1197 filled by
+ *                                phylostan/phylostan.py:183,204,255-272
+ *   phylo_b200_eval              value_grad vbsky_loglik(const vector<double>&)  eigen/eigen.j2:56-168
+ *                                and the model-block loops of generate_script.py:961-1055 with the
+ *                                P-matrix functions of generate_script.py:755-892
+ *   phylo_b200_eval (want_grad=0) double pruning_loglik(Matrix<double,-1,1>, ostream*) eigen/eigen.j2:171-177
+ *   phylo_b200_eval (want_grad=1) var pruning_loglik(Matrix<var,-1,1>, ostream*)  eigen/prune_stan.hpp:9-17
+ *                                (value + the gradient vector handed to precomputed_gradients)
+ *   phylo_b200_eval_batch        no reference counterpart (Stan evaluates draws serially,
+ *                                phylostan/phylostan.py:311-313); used for batches of ELBO draws
+ *   struct of outputs            struct value_grad { double log_P; VectorXd grad; }  eigen/value_grad.hpp:5-8
+ *
+ * Conventions are the reference's: node ids 1-based, tips 1..S, internals S+1..2S-1 in post-order,
+ * root 2S-1 (phylostan/utils.py:59-72); blens[k-1] is the branch above node k
+ * (generate_script.py:660-679); states A,C,G,T (utils.py:180).  The gradient returned is the TRUE
+ * d logL / d blens (eigen/eigen.j2:165 returns blens[k] times that).
+ *
+ * All functions return 0 on success, a negative PHYLO_B200_E* code otherwise;
+ * phylo_b200_last_error() describes the last failure on the calling thread.  There is no CPU
+ * fallback: without a usable sm_100 device phylo_b200_create fails.
+ */
+#ifndef PHYLO_B200_H
+#define PHYLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHYLO_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PHYLO_B200_API __attribute__((visibility("default")))
+#else
+#define PHYLO_B200_API
+#endif
+
+/* substitution models (generate_script.py:755, :783, :839) */
+#define PHYLO_B200_JC69 0 /* no parameters, freqs fixed to 1/4                      */
+#define PHYLO_B200_HKY  1 /* subst = {kappa}                                       */
+#define PHYLO_B200_GTR  2 /* subst = {AC, AG, AT, CG, CT, GT} (generate_script.py:855-858) */
+
+/* flags */
+#define PHYLO_B200_ROOTED   1 /* clock tree, bcount = 2S-2; otherwise unrooted, bcount = 2S-3
+                                 and node 2S-2 carries no branch (generate_script.py:1034)   */
+#define PHYLO_B200_NO_NORMQ 2 /* do not normalise Q to one substitution per unit time
+                                 (eigen/eigen.py:47-50 bakes such a Q)                       */
+
+/* error codes */
+#define PHYLO_B200_EINVAL   -1 /* bad argument (sizes, peel order, NULL)         */
+#define PHYLO_B200_ECUDA    -2 /* CUDA runtime / launch failure                  */
+#define PHYLO_B200_ENODEV   -3 /* no sm_100 device                               */
+#define PHYLO_B200_EDOMAIN  -4 /* non-finite or out-of-domain parameter / result */
+#define PHYLO_B200_ENOMEM   -5
+
+typedef struct phylo_b200_ctx *phylo_b200_handle;
+
+/*
+ * peel     int32 [S-1][3]  (child1, child2, parent), post-order, 1-based
+ * tipmask  uint8 [S][L]    bit s set <=> tipdata[tip][pattern][s] != 0
+ * weights  double [L]      pattern weights (NULL = all 1)
+ * C        number of rate categories (>= 1)
+ * device   CUDA device ordinal
+ */
+PHYLO_B200_API int phylo_b200_create(phylo_b200_handle *out, int S, int L, int C, int model, int flags,
+                      const int32_t *peel, const uint8_t *tipmask, const double *weights,
+                      int device);
+
+/* Same, with the reference's own Stan-data layout: tipdata double [S][L][4] in {0,1}
+ * ("real tipdata[S,L,4]", generate_script.py:1188). */
+PHYLO_B200_API int phylo_b200_create_tipdata(phylo_b200_handle *out, int S, int L, int C, int model, int flags,
+                              const int32_t *peel, const double *tipdata, const double *weights,
+                              int device);
+
+PHYLO_B200_API void phylo_b200_destroy(phylo_b200_handle h);
+
+/* sizes of the per-evaluation arrays */
+PHYLO_B200_API int phylo_b200_bcount(phylo_b200_handle h);  /* 2S-2 rooted, 2S-3 unrooted */
+PHYLO_B200_API int phylo_b200_nsubst(phylo_b200_handle h);  /* 0 / 1 / 6                   */
+PHYLO_B200_API int phylo_b200_ncat(phylo_b200_handle h);
+/* length of one packed output row: 1 + bcount + nsubst + 4 + C + C
+ * = [logL | d/dblens | d/dsubst | d/dfreqs | d/drs | d/dps] */
+PHYLO_B200_API int phylo_b200_nout(phylo_b200_handle h);
+
+/*
+ * One evaluation with HOST arrays (blocking).  Inputs: blens[bcount], subst[nsubst] (may be NULL
+ * when nsubst == 0), freqs[4] (ignored for JC69; may be NULL), rs[C], ps[C] (NULL: rs = 1, ps = 1/C).
+ * Outputs: logp[1]; with want_grad != 0 any non-NULL g_* array is filled:
+ * g_blens[bcount], g_subst[nsubst], g_freqs[4], g_rs[C], g_ps[C].  d/dsubst and d/dfreqs are the
+ * unconstrained partial derivatives of the formulas at generate_script.py:799-812 / 855-868;
+ * d/dfreqs includes the root term of generate_script.py:1007.
+ */
+PHYLO_B200_API int phylo_b200_eval(phylo_b200_handle h, const double *blens, const double *subst,
+                    const double *freqs, const double *rs, const double *ps, int want_grad,
+                    double *logp, double *g_blens, double *g_subst, double *g_freqs,
+                    double *g_rs, double *g_ps);
+
+/* B independent parameter draws, row-major leading dimension B on every array. */
+PHYLO_B200_API int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double *blens, const double *subst,
+                          const double *freqs, const double *rs, const double *ps, int want_grad,
+                          double *logp, double *g_blens, double *g_subst, double *g_freqs,
+                          double *g_rs, double *g_ps);
+
+/*
+ * Split form of eval_batch for callers that keep parameters resident on the device between
+ * evaluations (benchmarks, batched drivers, multi-GPU ranks):
+ *   upload   host parameters -> device (one H2D copy); also derives the eigen system per draw
+ *   run      P-matrix kernel + sweep kernel(s) + contraction on the handle's stream, no host sync;
+ *            results stay in the device output buffer [B][nout]
+ *   device_out   device pointer of that buffer (e.g. for an NCCL all-reduce across pattern shards)
+ *   download synchronises the stream and copies [B][nout] to the host
+ */
+PHYLO_B200_API int phylo_b200_upload(phylo_b200_handle h, int B, const double *blens, const double *subst,
+                      const double *freqs, const double *rs, const double *ps);
+PHYLO_B200_API int phylo_b200_run(phylo_b200_handle h, int B, int want_grad);
+PHYLO_B200_API int phylo_b200_device_out(phylo_b200_handle h, void **dptr, int *ld);
+PHYLO_B200_API int phylo_b200_download(phylo_b200_handle h, int B, double *out /* [B][nout] */);
+
+/* Use a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the handle's own. */
+PHYLO_B200_API int phylo_b200_set_stream(phylo_b200_handle h, void *stream);
+PHYLO_B200_API int phylo_b200_sync(phylo_b200_handle h);
+
+/* Tuning: patterns per thread (1, 2 or 4) and pattern blocks (warps per category) per CTA;
+ * 0 = automatic.  Takes effect on the next run. */
+PHYLO_B200_API int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int pattern_blocks);
+
+/* Device time of the kernels of the last run (CUDA events on the handle's stream):
+ * ms[0] P-matrix kernel, ms[1] sweep kernel, ms[2] contraction kernel, ms[3] whole run.
+ * Enable before the run; disabled by default (events force a sync when read). */
+PHYLO_B200_API int phylo_b200_set_timing(phylo_b200_handle h, int enabled);
+PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
+
+/* Introspection: what = 0 stack depth D, 1 patterns per thread, 2 threads per CTA, 3 grid size,
+ * 4 dynamic shared memory bytes, 5 padded pattern count, 6 kernels launched by the last run,
+ * 7 scratch bytes allocated on the device, 8 / 9 post- / pre-order stack depth, 10 pattern tiles. */
+PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
+
+/*
+ * Host-only hooks (no GPU needed), used by the CPU test-suite:
+ *   plan    the depth-first traversal plan derived from `peel` (replaces the run-time std::map
+ *           bookkeeping of eigen/eigen.j2:82-108): post gets S-1 rows of 8 int32
+ *           (a, b, slot_a, slot_b, slot_out, node, 0, 0), pre gets S-1 rows of 12 int32
+ *           (node, a, b, slot_node, slot_a, slot_b, row_node, row_a, row_b, 0, 0, 0),
+ *           depth[2] = {post-order, pre-order} shared-memory stack depth.
+ *   derive  the per-draw model algebra of generate_script.py:799-825 / 855-881:
+ *           out = [pi 4 | lambda 4 | m1 16 | m2 16 | Q 16 | X_theta ntheta*16]; returns ntheta.
+ */
+PHYLO_B200_API int phylo_b200_plan(int S, const int32_t *peel, int32_t *post, int32_t *pre, int32_t *depth);
+PHYLO_B200_API int phylo_b200_derive(int model, int flags, const double *subst, const double *freqs, double *out);
+
+PHYLO_B200_API const char *phylo_b200_last_error(void);
+PHYLO_B200_API int phylo_b200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLO_B200_H */

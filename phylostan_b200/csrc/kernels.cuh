@@ -1,0 +1,79 @@
+// kernels.cuh -- device side of libphylo_b200: hand-written CUDA for sm_100a.
+//
+// Three kernels per evaluation (batch of B parameter draws):
+//   pmat_kernel      P(t_b r_c) = m1 diag(exp(lambda t_b r_c)) m2 for every (draw, category, node)
+//                    (phylostan/generate_script.py:824-829, 880-885; JC69 closed form :765-766)
+//   sweep_kernel     per (draw, pattern tile): depth-first post-order partials
+//                    (eigen/eigen.j2:122-141, generate_script.py:998-1005), root likelihood with
+//                    per-(pattern,category) rescaling (generate_script.py:1006-1010), then the
+//                    depth-first pre-order sweep (eigen/eigen.j2:144-157) accumulating the 4x4
+//                    branch statistics G_b,c = sum_l (w_l/L_l) A_b p_b^T that carry every gradient
+//   contract_kernel  G -> d/dblens (eigen/eigen.j2:163-166 without its times[i] factor),
+//                    d/drs, d/d(rates|kappa), d/dfreqs
+//
+// Memory plan: the live partials of a tile sit in a shared-memory stack [slot][k][half][thread]
+// of double2 (bank-conflict free, one thread = one (pattern, category)); the only HBM traffic is
+// one coalesced double2 write per internal-node partial in the post-order (to the CTA's scratch
+// rows) and one read of it in the pre-order, plus 1-byte tip codes.  q never leaves the SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "plan.hpp"
+
+namespace phylo {
+
+// offsets (in doubles) inside one draw's parameter block
+struct ParamLayout {
+    int nn, C, ntheta, nsubst;
+    int off_t;    // [nn]  branch length above node k (0 where the node carries no branch)
+    int off_rs;   // [C]
+    int off_ps;   // [C]
+    int off_pi;   // [4]
+    int off_lam;  // [4]
+    int off_m1;   // [16]
+    int off_m2;   // [16]
+    int off_Q;    // [16]
+    int off_X;    // [ntheta][16]
+    int stride;
+};
+
+struct SweepArgs {
+    const uint8_t* tips;     // [S][Lpad] 4-bit state masks
+    const double* weights;   // [Lpad]
+    const double* P;         // [B][C][nn][16]
+    const double* params;    // [B][stride]
+    const PostStep* post;    // [S-1]
+    const PreStep* pre;      // [S-1]
+    double2* scratch;        // [grid][S-1][K][2][NT]
+    int8_t* dscr;            // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
+    double* G;               // [B][nn][C][16]
+    double* out;             // [B][nout]
+    ParamLayout lay;
+    long long scratch_stride, dscr_stride;
+    int S, nsteps, Lpad, ntiles, nitems, C, nn, nout, D;
+    int off_out_freqs, off_out_ps;
+};
+
+struct ContractArgs {
+    const double* P;
+    const double* params;
+    const double* G;
+    double* out;
+    ParamLayout lay;
+    int bcount, C, nn, nout, nsubst;
+    int off_out_subst, off_out_freqs, off_out_rs;
+};
+
+void launch_pmat(const double* params, ParamLayout lay, int bcount, int jc_closed, double* P, int B,
+                 cudaStream_t stream);
+// K in {1,2,4}; returns cudaError
+cudaError_t launch_sweep(const SweepArgs& a, int K, bool grad, int grid, int nthreads, size_t smem,
+                         cudaStream_t stream);
+cudaError_t sweep_occupancy(int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
+void launch_contract(const ContractArgs& a, int B, cudaStream_t stream);
+
+size_t sweep_smem_bytes(int D, int K, int nthreads);
+int sweep_max_threads(int K);  // largest CTA the K-variant is compiled for
+
+}  // namespace phylo

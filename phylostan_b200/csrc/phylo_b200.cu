@@ -1,0 +1,536 @@
+// phylo_b200.cu -- host side of libphylo_b200.so: context, parameter packing, launches, C ABI.
+// See include/phylo_b200.h for the contract and the reference interfaces each entry replaces.
+#include "phylo_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+#include "subst.hpp"
+
+using namespace phylo;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(PHYLO_B200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+constexpr int kPadPatterns = 512;  // pattern axis padded so every tile shape divides it
+constexpr int kMaxCategories = 16;
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct phylo_b200_ctx {
+    int S = 0, L = 0, C = 0, model = 0, flags = 0, device = 0;
+    int nn = 0, bcount = 0, nsubst = 0, nout = 0, Lpad = 0;
+    bool rooted = false, normalize = true, jc_closed = false;
+    int off_subst = 0, off_freqs = 0, off_rs = 0, off_ps = 0;
+    Plan plan;
+    ParamLayout lay{};
+    int num_sms = 0;
+    size_t smem_optin = 0;
+
+    // static device data
+    DevBuf<uint8_t> d_tips;
+    DevBuf<double> d_weights;
+    DevBuf<PostStep> d_post;
+    DevBuf<PreStep> d_pre;
+    // per-batch device data
+    DevBuf<double> d_params, d_P, d_G, d_out;
+    DevBuf<double2> d_scratch;
+    DevBuf<int8_t> d_dscr;
+    PinnedBuf<double> h_params, h_out;
+
+    // tiling (user request, 0 = auto) and the resolved launch shape of the last run
+    int req_K = 0, req_PB = 0;
+    int K = 1, PB = 1, NT = 0, grid = 0, ntiles = 0;
+    size_t smem = 0;
+    int last_launches = 0;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    bool timing = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false, ev_has_contract = false;
+
+    ~phylo_b200_ctx() {
+        cudaSetDevice(device);
+        d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
+        d_params.release(); d_P.release(); d_G.release(); d_out.release();
+        d_scratch.release(); d_dscr.release();
+        h_params.release(); h_out.release();
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
+namespace {
+
+// Resolve (K, PB) -> launch shape.  Auto policy: small problems spread thin (K=1, one pattern
+// block per CTA) to reach every SM; large ones amortise the per-node work (step decode,
+// P-matrix loads, the 4x4 statistics reduction) over K=2 patterns per thread.
+int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
+    const int C = h->C, D = h->plan.depth();
+    int K = h->req_K, PB = h->req_PB;
+    if (K == 0) {
+        const long long work = (long long)B * ((h->L + 31) / 32);  // warps of patterns per category
+        K = work >= 8LL * h->num_sms ? 2 : 1;
+    }
+    if (K != 1 && K != 2 && K != 4) return fail(PHYLO_B200_EINVAL, "patterns_per_thread must be 1, 2 or 4");
+    if (PB == 0) PB = 1;
+    if (PB != 1 && PB != 2 && PB != 4) return fail(PHYLO_B200_EINVAL, "pattern_blocks must be 1, 2 or 4");
+    while (PB > 1 && 32 * C * PB > sweep_max_threads(K)) PB >>= 1;
+    while (K > 1 && 32 * C * PB > sweep_max_threads(K)) K >>= 1;
+    int NT = 32 * C * PB;
+    if (NT > sweep_max_threads(K)) return fail(PHYLO_B200_EINVAL, "too many rate categories for one CTA");
+    size_t smem = sweep_smem_bytes(D, K, NT);
+    while (smem > h->smem_optin && K > 1) { K >>= 1; smem = sweep_smem_bytes(D, K, NT); }
+    while (smem > h->smem_optin && PB > 1) { PB >>= 1; NT = 32 * C * PB; smem = sweep_smem_bytes(D, K, NT); }
+    if (smem > h->smem_optin)
+        return fail(PHYLO_B200_EINVAL, "tree too deep for the shared-memory stack (depth " + std::to_string(D) + ")");
+    const int tpat = PB * 32 * K;
+    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem;
+    h->ntiles = (h->L + tpat - 1) / tpat;
+    int occ = 0;
+    CU_TRY(sweep_occupancy(K, grad, NT, smem, &occ));
+    if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
+    const long long items = (long long)B * h->ntiles;
+    h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
+    return 0;
+}
+
+int ensure_batch(phylo_b200_ctx* h, int B) {
+    CU_TRY(h->d_params.ensure((size_t)B * h->lay.stride));
+    CU_TRY(h->d_P.ensure((size_t)B * h->C * h->nn * 16));
+    CU_TRY(h->d_G.ensure((size_t)B * h->nn * h->C * 16));
+    CU_TRY(h->d_out.ensure((size_t)B * h->nout));
+    CU_TRY(h->h_params.ensure((size_t)B * h->lay.stride));
+    CU_TRY(h->h_out.ensure((size_t)B * h->nout));
+    return 0;
+}
+
+int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
+                  const uint8_t* tipmask, const double* tipdata, const double* weights, int device) {
+    if (!out) return fail(PHYLO_B200_EINVAL, "out handle is NULL");
+    *out = nullptr;
+    if (S < 2 || L < 1 || C < 1) return fail(PHYLO_B200_EINVAL, "need S >= 2, L >= 1, C >= 1");
+    if (C > kMaxCategories) return fail(PHYLO_B200_EINVAL, "at most 16 rate categories");
+    if (model < PHYLO_B200_JC69 || model > PHYLO_B200_GTR) return fail(PHYLO_B200_EINVAL, "unknown model");
+    if (!peel || (!tipmask && !tipdata)) return fail(PHYLO_B200_EINVAL, "peel / tip data is NULL");
+    const bool rooted = flags & PHYLO_B200_ROOTED;
+    if (!rooted && S < 3) return fail(PHYLO_B200_EINVAL, "an unrooted tree needs S >= 3");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return fail(PHYLO_B200_ENODEV, "no CUDA device " + std::to_string(device) +
+                                           " (libphylo_b200 has no CPU fallback)");
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(PHYLO_B200_ENODEV, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                           ", this library is built for sm_100a only");
+    CU_TRY(cudaSetDevice(device));
+
+    phylo_b200_ctx* h = new (std::nothrow) phylo_b200_ctx();
+    if (!h) return fail(PHYLO_B200_ENOMEM, "out of host memory");
+    h->S = S; h->L = L; h->C = C; h->model = model; h->flags = flags; h->device = device;
+    h->rooted = rooted;
+    h->normalize = !(flags & PHYLO_B200_NO_NORMQ);
+    h->jc_closed = model == PHYLO_B200_JC69 && h->normalize;
+    h->nn = 2 * S - 1;
+    h->bcount = rooted ? 2 * S - 2 : 2 * S - 3;
+    h->nsubst = n_subst(model);
+    h->off_subst = 1 + h->bcount;
+    h->off_freqs = h->off_subst + h->nsubst;
+    h->off_rs = h->off_freqs + 4;
+    h->off_ps = h->off_rs + C;
+    h->nout = h->off_ps + C;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+
+    std::string err;
+    if (!build_plan(S, peel, h->plan, err)) { delete h; return fail(PHYLO_B200_EINVAL, err); }
+    if (!rooted && peel[3 * (S - 2) + 1] != 2 * S - 2) {
+        delete h;
+        return fail(PHYLO_B200_EINVAL, "unrooted: the last peel row must list node 2S-2 second "
+                                       "(phylostan/phylostan.py:264-267)");
+    }
+
+    ParamLayout& lay = h->lay;
+    lay.nn = h->nn; lay.C = C; lay.nsubst = h->nsubst;
+    lay.ntheta = model == PHYLO_B200_JC69 ? 0 : h->nsubst + 4;
+    int o = 0;
+    lay.off_t = o; o += h->nn;
+    lay.off_rs = o; o += C;
+    lay.off_ps = o; o += C;
+    lay.off_pi = o; o += 4;
+    lay.off_lam = o; o += 4;
+    lay.off_m1 = o; o += 16;
+    lay.off_m2 = o; o += 16;
+    lay.off_Q = o; o += 16;
+    lay.off_X = o; o += 16 * lay.ntheta;
+    lay.stride = (o + 1) & ~1;
+
+    // static data: tip codes [S][Lpad] (padding = all-ambiguous, weight 0), weights, step lists
+    h->Lpad = ((L + kPadPatterns - 1) / kPadPatterns) * kPadPatterns;
+    std::vector<uint8_t> tips((size_t)S * h->Lpad, 0xF);
+    for (int s = 0; s < S; ++s)
+        for (int l = 0; l < L; ++l) {
+            uint8_t m;
+            if (tipmask) {
+                m = tipmask[(size_t)s * L + l] & 0xF;
+            } else {
+                const double* t = tipdata + ((size_t)s * L + l) * 4;
+                m = (uint8_t)((t[0] != 0.0) | ((t[1] != 0.0) << 1) | ((t[2] != 0.0) << 2) | ((t[3] != 0.0) << 3));
+            }
+            tips[(size_t)s * h->Lpad + l] = m;
+        }
+    std::vector<double> w((size_t)h->Lpad, 0.0);
+    for (int l = 0; l < L; ++l) {
+        w[l] = weights ? weights[l] : 1.0;
+        if (!std::isfinite(w[l])) { delete h; return fail(PHYLO_B200_EDOMAIN, "non-finite pattern weight"); }
+    }
+    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
+        cudaError_t e = buf.ensure(vec.size());
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+    if ((e = up(h->d_tips, tips)) != cudaSuccess || (e = up(h->d_weights, w)) != cudaSuccess ||
+        (e = up(h->d_post, h->plan.post)) != cudaSuccess || (e = up(h->d_pre, h->plan.pre)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete h;
+        return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    }
+    h->stream = h->own_stream;
+    for (auto& ev : h->ev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
+            delete h;
+            return fail(PHYLO_B200_ECUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+        }
+    *out = h;
+    return 0;
+}
+
+// Pack one draw into the parameter block (host).  Returns false on out-of-domain input.
+bool pack_draw(const phylo_b200_ctx* h, const double* blens, const double* subst, const double* freqs,
+               const double* rs, const double* ps, double* dst, std::string& why) {
+    const ParamLayout& lay = h->lay;
+    std::memset(dst, 0, sizeof(double) * lay.stride);
+    for (int b = 0; b < h->bcount; ++b) {
+        if (!(blens[b] >= 0.0) || !std::isfinite(blens[b])) { why = "branch length " + std::to_string(b) + " is negative or not finite"; return false; }
+        dst[lay.off_t + b] = blens[b];
+    }
+    for (int c = 0; c < h->C; ++c) {
+        const double r = rs ? rs[c] : 1.0, p = ps ? ps[c] : 1.0 / h->C;
+        if (!(r >= 0.0) || !std::isfinite(r) || !(p >= 0.0) || !std::isfinite(p)) { why = "site rate / proportion is negative or not finite"; return false; }
+        dst[lay.off_rs + c] = r;
+        dst[lay.off_ps + c] = p;
+    }
+    Derived dv;
+    if (!derive(h->model, h->normalize, subst, freqs, dv)) { why = "substitution parameters out of domain"; return false; }
+    std::memcpy(dst + lay.off_pi, dv.pi, sizeof dv.pi);
+    std::memcpy(dst + lay.off_lam, dv.lam, sizeof dv.lam);
+    std::memcpy(dst + lay.off_m1, dv.m1, sizeof dv.m1);
+    std::memcpy(dst + lay.off_m2, dv.m2, sizeof dv.m2);
+    std::memcpy(dst + lay.off_Q, dv.Q, sizeof dv.Q);
+    for (int k = 0; k < lay.ntheta; ++k) std::memcpy(dst + lay.off_X + 16 * k, dv.X[k], sizeof dv.X[k]);
+    return true;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+int phylo_b200_abi_version(void) { return PHYLO_B200_ABI_VERSION; }
+
+const char* phylo_b200_last_error(void) { return g_err.c_str(); }
+
+int phylo_b200_create(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
+                      const uint8_t* tipmask, const double* weights, int device) {
+    return create_common(out, S, L, C, model, flags, peel, tipmask, nullptr, weights, device);
+}
+
+int phylo_b200_create_tipdata(phylo_b200_handle* out, int S, int L, int C, int model, int flags,
+                              const int32_t* peel, const double* tipdata, const double* weights, int device) {
+    return create_common(out, S, L, C, model, flags, peel, nullptr, tipdata, weights, device);
+}
+
+void phylo_b200_destroy(phylo_b200_handle h) { delete h; }
+
+int phylo_b200_bcount(phylo_b200_handle h) { return h ? h->bcount : PHYLO_B200_EINVAL; }
+int phylo_b200_nsubst(phylo_b200_handle h) { return h ? h->nsubst : PHYLO_B200_EINVAL; }
+int phylo_b200_ncat(phylo_b200_handle h) { return h ? h->C : PHYLO_B200_EINVAL; }
+int phylo_b200_nout(phylo_b200_handle h) { return h ? h->nout : PHYLO_B200_EINVAL; }
+
+int phylo_b200_set_stream(phylo_b200_handle h, void* stream) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return 0;
+}
+
+int phylo_b200_sync(phylo_b200_handle h) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int pattern_blocks) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    if (patterns_per_thread != 0 && patterns_per_thread != 1 && patterns_per_thread != 2 && patterns_per_thread != 4)
+        return fail(PHYLO_B200_EINVAL, "patterns_per_thread must be 0, 1, 2 or 4");
+    if (pattern_blocks != 0 && pattern_blocks != 1 && pattern_blocks != 2 && pattern_blocks != 4)
+        return fail(PHYLO_B200_EINVAL, "pattern_blocks must be 0, 1, 2 or 4");
+    h->req_K = patterns_per_thread;
+    h->req_PB = pattern_blocks;
+    return 0;
+}
+
+int phylo_b200_set_timing(phylo_b200_handle h, int enabled) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    h->timing = enabled != 0;
+    h->ev_valid = false;
+    return 0;
+}
+
+int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]) {
+    if (!h || !ms) return fail(PHYLO_B200_EINVAL, "NULL argument");
+    if (!h->ev_valid) return fail(PHYLO_B200_EINVAL, "no timed run recorded (call set_timing(1) then run)");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaEventSynchronize(h->ev[4]));
+    float t = 0;
+    CU_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[1])); ms[0] = t;
+    CU_TRY(cudaEventElapsedTime(&t, h->ev[1], h->ev[2])); ms[1] = t;
+    ms[2] = 0;
+    if (h->ev_has_contract) { CU_TRY(cudaEventElapsedTime(&t, h->ev[2], h->ev[3])); ms[2] = t; }
+    CU_TRY(cudaEventElapsedTime(&t, h->ev[0], h->ev[4])); ms[3] = t;
+    return 0;
+}
+
+long long phylo_b200_info(phylo_b200_handle h, int what) {
+    if (!h) return PHYLO_B200_EINVAL;
+    switch (what) {
+        case 0: return h->plan.depth();
+        case 1: return h->K;
+        case 2: return h->NT;
+        case 3: return h->grid;
+        case 4: return (long long)h->smem;
+        case 5: return h->Lpad;
+        case 6: return h->last_launches;
+        case 7: return (long long)(h->d_scratch.n * sizeof(double2) + h->d_dscr.n);
+        case 8: return h->plan.depth_post;
+        case 9: return h->plan.depth_pre;
+        case 10: return h->ntiles;
+    }
+    return PHYLO_B200_EINVAL;
+}
+
+int phylo_b200_upload(phylo_b200_handle h, int B, const double* blens, const double* subst, const double* freqs,
+                      const double* rs, const double* ps) {
+    if (!h || B < 1 || !blens) return fail(PHYLO_B200_EINVAL, "upload: bad arguments");
+    if (h->nsubst > 0 && !subst) return fail(PHYLO_B200_EINVAL, "upload: subst is NULL");
+    if (h->model != PHYLO_B200_JC69 && !freqs) return fail(PHYLO_B200_EINVAL, "upload: freqs is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    if (int rc = ensure_batch(h, B)) return rc;
+    // the pinned staging buffer may still feed a copy in flight
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    std::string why;
+    for (int d = 0; d < B; ++d) {
+        if (!pack_draw(h, blens + (size_t)d * h->bcount, subst ? subst + (size_t)d * h->nsubst : nullptr,
+                       freqs ? freqs + (size_t)d * 4 : nullptr, rs ? rs + (size_t)d * h->C : nullptr,
+                       ps ? ps + (size_t)d * h->C : nullptr, h->h_params.p + (size_t)d * h->lay.stride, why))
+            return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": " + why);
+    }
+    CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, sizeof(double) * B * h->lay.stride, cudaMemcpyHostToDevice,
+                           h->stream));
+    return 0;
+}
+
+int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
+    if (!h || B < 1) return fail(PHYLO_B200_EINVAL, "run: bad arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    if ((size_t)B * h->lay.stride > h->d_params.n) return fail(PHYLO_B200_EINVAL, "run: upload B draws first");
+    const bool grad = want_grad != 0;
+    if (int rc = resolve_tiling(h, B, grad)) return rc;
+    if (grad) {
+        const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
+        CU_TRY(h->d_scratch.ensure(rows * 2));
+        CU_TRY(h->d_dscr.ensure(rows));
+    }
+    cudaStream_t st = h->stream;
+    CU_TRY(cudaMemsetAsync(h->d_out.p, 0, sizeof(double) * B * h->nout, st));
+    if (grad) CU_TRY(cudaMemsetAsync(h->d_G.p, 0, sizeof(double) * B * h->nn * h->C * 16, st));
+    if (h->timing) CU_TRY(cudaEventRecord(h->ev[0], st));
+    launch_pmat(h->d_params.p, h->lay, h->bcount, h->jc_closed, h->d_P.p, B, st);
+    CU_TRY(cudaGetLastError());
+    if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
+
+    SweepArgs a{};
+    a.tips = h->d_tips.p; a.weights = h->d_weights.p; a.P = h->d_P.p; a.params = h->d_params.p;
+    a.post = h->d_post.p; a.pre = h->d_pre.p;
+    a.scratch = h->d_scratch.p; a.dscr = h->d_dscr.p; a.G = h->d_G.p; a.out = h->d_out.p;
+    a.lay = h->lay;
+    a.scratch_stride = (long long)(h->S - 1) * h->K * 2 * h->NT;
+    a.dscr_stride = (long long)(h->S - 1) * h->K * h->NT;
+    a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
+    a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->plan.depth();
+    a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
+    CU_TRY(launch_sweep(a, h->K, grad, h->grid, h->NT, h->smem, st));
+    if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
+    h->last_launches = 2;
+    if (grad) {
+        ContractArgs ca{};
+        ca.P = h->d_P.p; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
+        ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
+        ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
+        launch_contract(ca, B, st);
+        CU_TRY(cudaGetLastError());
+        if (h->timing) CU_TRY(cudaEventRecord(h->ev[3], st));
+        h->last_launches = 3;
+    }
+    if (h->timing) {
+        CU_TRY(cudaEventRecord(h->ev[4], st));
+        h->ev_valid = true;
+        h->ev_has_contract = grad;
+    }
+    return 0;
+}
+
+int phylo_b200_device_out(phylo_b200_handle h, void** dptr, int* ld) {
+    if (!h || !dptr) return fail(PHYLO_B200_EINVAL, "NULL argument");
+    *dptr = h->d_out.p;
+    if (ld) *ld = h->nout;
+    return h->d_out.p ? 0 : fail(PHYLO_B200_EINVAL, "no output buffer yet (upload first)");
+}
+
+int phylo_b200_download(phylo_b200_handle h, int B, double* out) {
+    if (!h || B < 1 || !out) return fail(PHYLO_B200_EINVAL, "download: bad arguments");
+    if ((size_t)B * h->nout > h->d_out.n) return fail(PHYLO_B200_EINVAL, "download: nothing was run for B draws");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * B * h->nout, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    std::memcpy(out, h->h_out.p, sizeof(double) * B * h->nout);
+    return 0;
+}
+
+int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double* blens, const double* subst,
+                          const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
+                          double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+    if (!h || !logp) return fail(PHYLO_B200_EINVAL, "eval: NULL handle or logp");
+    if (int rc = phylo_b200_upload(h, B, blens, subst, freqs, rs, ps)) return rc;
+    if (int rc = phylo_b200_run(h, B, want_grad)) return rc;
+    CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * B * h->nout, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    bool finite = true;
+    for (int d = 0; d < B; ++d) {
+        const double* o = h->h_out.p + (size_t)d * h->nout;
+        logp[d] = o[0];
+        finite = finite && std::isfinite(o[0]);
+        if (!want_grad) continue;
+        if (g_blens) std::memcpy(g_blens + (size_t)d * h->bcount, o + 1, sizeof(double) * h->bcount);
+        if (g_subst && h->nsubst) std::memcpy(g_subst + (size_t)d * h->nsubst, o + h->off_subst, sizeof(double) * h->nsubst);
+        if (g_freqs) std::memcpy(g_freqs + (size_t)d * 4, o + h->off_freqs, sizeof(double) * 4);
+        if (g_rs) std::memcpy(g_rs + (size_t)d * h->C, o + h->off_rs, sizeof(double) * h->C);
+        if (g_ps) std::memcpy(g_ps + (size_t)d * h->C, o + h->off_ps, sizeof(double) * h->C);
+    }
+    if (!finite) return fail(PHYLO_B200_EDOMAIN, "log-likelihood is not finite (impossible pattern or underflow)");
+    return 0;
+}
+
+int phylo_b200_eval(phylo_b200_handle h, const double* blens, const double* subst, const double* freqs,
+                    const double* rs, const double* ps, int want_grad, double* logp, double* g_blens,
+                    double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+    return phylo_b200_eval_batch(h, 1, blens, subst, freqs, rs, ps, want_grad, logp, g_blens, g_subst, g_freqs,
+                                 g_rs, g_ps);
+}
+
+// Host-only planning hook (no GPU): exercised by the CPU test-suite.
+// post/pre receive S-1 rows of 8 / 12 int32 (the PostStep / PreStep fields); depth[2] = {post, pre}.
+int phylo_b200_plan(int S, const int32_t* peel, int32_t* post, int32_t* pre, int32_t* depth) {
+    Plan plan;
+    std::string err;
+    if (!build_plan(S, peel, plan, err)) return fail(PHYLO_B200_EINVAL, err);
+    if (post) std::memcpy(post, plan.post.data(), plan.post.size() * sizeof(PostStep));
+    if (pre) std::memcpy(pre, plan.pre.data(), plan.pre.size() * sizeof(PreStep));
+    if (depth) { depth[0] = plan.depth_post; depth[1] = plan.depth_pre; }
+    return 0;
+}
+
+// Host-only model algebra hook (no GPU): Q, lambda, m1, m2 and X_theta of one draw.
+// out = [pi 4 | lam 4 | m1 16 | m2 16 | Q 16 | X ntheta*16]; returns ntheta or < 0.
+int phylo_b200_derive(int model, int flags, const double* subst, const double* freqs, double* out) {
+    Derived dv;
+    if (!derive(model, !(flags & PHYLO_B200_NO_NORMQ), subst, freqs, dv))
+        return fail(PHYLO_B200_EDOMAIN, "substitution parameters out of domain");
+    if (out) {
+        std::memcpy(out, dv.pi, sizeof dv.pi);
+        std::memcpy(out + 4, dv.lam, sizeof dv.lam);
+        std::memcpy(out + 8, dv.m1, sizeof dv.m1);
+        std::memcpy(out + 24, dv.m2, sizeof dv.m2);
+        std::memcpy(out + 40, dv.Q, sizeof dv.Q);
+        for (int k = 0; k < dv.ntheta; ++k) std::memcpy(out + 56 + 16 * k, dv.X[k], sizeof dv.X[k]);
+    }
+    return dv.ntheta;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""Synthetic trees, alignments and parameter draws of the shapes BASELINE.json names
+(SURVEY.md section 8d): random Kingman-coalescent topology, GTR + Weibull(4) simulated columns,
+1 % ambiguous tip cells, weights 1 + Poisson(1).  Bench / test harness support, numpy only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Tuple
+
+import numpy as np
+
+from .encode import weibull_rates
+
+SEED_DATA = 20261018
+SEED_DRAWS = 20261019
+RATES0 = np.array([0.10, 0.30, 0.10, 0.10, 0.30, 0.10])
+FREQS0 = np.array([0.30, 0.20, 0.20, 0.30])
+WSHAPE0 = 0.5
+
+
+def coalescent_peel(S: int, rng: np.random.Generator) -> np.ndarray:
+    """Random rooted binary tree (uniform pair merges), returned as the reference's ``peel``:
+    tips 1..S, internals S+1..2S-1 numbered in depth-first post-order, root 2S-1
+    (phylostan/utils.py:59-81)."""
+    left = {}
+    right = {}
+    active = list(range(S))
+    nxt = S
+    for _ in range(S - 1):
+        i, j = rng.choice(len(active), size=2, replace=False)
+        a, b = active[i], active[j]
+        left[nxt], right[nxt] = a, b
+        active = [x for k, x in enumerate(active) if k != i and k != j] + [nxt]
+        nxt += 1
+    root = nxt - 1
+    # renumber internals in DFS post-order (iterative)
+    new_id = {}
+    rows = []
+    counter = S
+    stack = [(root, 0)]
+    while stack:
+        node, stage = stack.pop()
+        if node < S:
+            new_id[node] = node
+            continue
+        if stage == 0:
+            stack.append((node, 1))
+            stack.append((right[node], 0))
+            stack.append((left[node], 0))
+        else:
+            new_id[node] = counter
+            counter += 1
+            rows.append((new_id[left[node]] + 1, new_id[right[node]] + 1, new_id[node] + 1))
+    return np.asarray(rows, dtype=np.int32)
+
+
+def gtr_q(rates: np.ndarray, freqs: np.ndarray) -> np.ndarray:
+    R = np.zeros((4, 4))
+    R[np.triu_indices(4, 1)] = rates
+    R = R + R.T
+    Q = R * freqs[None, :]
+    np.fill_diagonal(Q, -Q.sum(1))
+    return Q / -(np.diag(Q) * freqs).sum()
+
+
+def _pmat(Q: np.ndarray, freqs: np.ndarray, tau: float) -> np.ndarray:
+    sq = np.sqrt(freqs)
+    A = sq[:, None] * Q / sq[None, :]
+    lam, U = np.linalg.eigh((A + A.T) / 2)
+    return ((U / sq[:, None]) * np.exp(lam * tau)[None, :]) @ (U.T * sq[None, :])
+
+
+def simulate_alignment(peel: np.ndarray, blens: np.ndarray, L: int, C: int, rng: np.random.Generator,
+                       rates=RATES0, freqs=FREQS0, wshape=WSHAPE0, ambiguous: float = 0.01,
+                       structured: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """One independent column per pattern.  Returns (tipmask uint8 [S, L], weights [L])."""
+    S = peel.shape[0] + 1
+    if structured:
+        Q = gtr_q(np.asarray(rates), np.asarray(freqs))
+        rs = weibull_rates(wshape, C)
+        cat = rng.integers(0, C, size=L)
+        state = np.zeros((2 * S - 1, L), dtype=np.int8)
+        state[2 * S - 2] = rng.choice(4, size=L, p=freqs)
+        u = np.empty(L)
+        for row in peel[::-1]:  # parents before children
+            for child in (row[0] - 1, row[1] - 1):
+                par = state[row[2] - 1]
+                rng.random(out=u)
+                new = np.zeros(L, dtype=np.int8)
+                for c in range(C):
+                    P = _pmat(Q, np.asarray(freqs), blens[child] * rs[c])
+                    cum = np.cumsum(P, axis=1)
+                    sel = cat == c
+                    new[sel] = (u[sel, None] > cum[par[sel]]).sum(1).clip(0, 3)
+                state[child] = new
+        tips = state[:S]
+    else:  # cheap generator for very large shapes: iid states biased towards a per-column majority
+        major = rng.integers(0, 4, size=L, dtype=np.int8)
+        tips = np.where(rng.random((S, L)) < 0.8, major[None, :], rng.integers(0, 4, size=(S, L), dtype=np.int8))
+    tipmask = (1 << tips.astype(np.uint8)).astype(np.uint8)
+    tipmask[rng.random((S, L)) < ambiguous] = 0xF
+    weights = 1.0 + rng.poisson(1.0, size=L)
+    return tipmask, weights.astype(np.float64)
+
+
+@dataclass
+class SynthProblem:
+    S: int
+    L: int
+    C: int
+    peel: np.ndarray
+    tipmask: np.ndarray
+    weights: np.ndarray
+    blens: np.ndarray   # [2S-2] base branch lengths (rooted convention)
+
+
+def make_problem(S: int, L: int, C: int = 4, seed: int = SEED_DATA, structured: bool = True) -> SynthProblem:
+    rng = np.random.default_rng(seed)
+    peel = coalescent_peel(S, rng)
+    blens = np.clip(rng.exponential(0.02, size=2 * S - 2), 1e-4, 0.5)
+    tipmask, weights = simulate_alignment(peel, blens, L, C, rng, structured=structured)
+    return SynthProblem(S, L, C, peel, tipmask, weights, blens)
+
+
+def make_draws(prob: SynthProblem, B: int, seed: int = SEED_DRAWS):
+    """B parameter draws around the simulation truth: blens * LogNormal(0, 0.1), Dirichlet(200 x)
+    rates and frequencies, wshape * LogNormal(0, 0.1).  Returns (blens, rates, freqs, rs, ps)."""
+    rng = np.random.default_rng(seed)
+    bl = prob.blens[None, :] * rng.lognormal(0.0, 0.1, size=(B, prob.blens.size))
+    rates = rng.dirichlet(200.0 * RATES0 / RATES0.sum(), size=B)
+    freqs = rng.dirichlet(200.0 * FREQS0, size=B)
+    wshape = WSHAPE0 * rng.lognormal(0.0, 0.1, size=B)
+    rs = np.stack([weibull_rates(w, prob.C) for w in wshape])
+    ps = np.full((B, prob.C), 1.0 / prob.C)
+    return bl, rates, freqs, rs, ps

@@ -1,0 +1,296 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libphylo_b200.so) against the CPU oracle,
+the reference's golden vectors, and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are the north star's: |dlogL|/|logL| <= 1e-10, every gradient component within
+1e-8 * max(1, |g|) in fp64.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from phylostan_b200 import encode as E
+from phylostan_b200 import likelihood as lk
+from phylostan_b200 import synth
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOGP = 1e-10
+TOL_GRAD = 1e-8
+MODEL_NAME = {O.JC69: "JC69", O.HKY: "HKY", O.GTR: "GTR"}
+PEEL3 = np.array([[1, 2, 4], [4, 3, 5]], dtype=np.int32)
+
+
+def assert_parity(got: lk.ValueGrad, want: O.Result, jc=False):
+    assert abs(got.log_P - want.logp) <= RTOL_LOGP * abs(want.logp), (got.log_P, want.logp)
+    pairs = [("blens", got.grad_blens, want.grad_blens), ("rs", got.grad_rs, want.grad_rs),
+             ("ps", got.grad_ps, want.grad_ps)]
+    if not jc:
+        pairs += [("subst", got.grad_subst, want.grad_subst), ("freqs", got.grad_freqs, want.grad_freqs)]
+    for name, g, w in pairs:
+        err = np.abs(g - w) / np.maximum(1.0, np.abs(w))
+        assert err.max(initial=0.0) <= TOL_GRAD, (name, err.max(), g[:4], w[:4])
+
+
+def random_params(model, S, rooted, C, rng, scale=0.05):
+    bl = rng.exponential(scale, size=2 * S - 2 if rooted else 2 * S - 3) + 1e-4
+    subst = None if model == O.JC69 else (np.array([rng.lognormal(1.0, 0.5)]) if model == O.HKY
+                                          else rng.dirichlet(np.ones(6) * 3))
+    fr = None if model == O.JC69 else rng.dirichlet(np.ones(4) * 5)
+    rs = E.weibull_rates(rng.uniform(0.3, 1.5), C) if C > 1 else np.ones(1)
+    ps = rng.dirichlet(np.ones(C) * 4)
+    return bl, subst, fr, rs, ps
+
+
+def make(peel, tipmask, weights, model, C, rooted=True, normalize=True):
+    return lk.TreeLikelihood(peel, tipmask, weights, model=MODEL_NAME[model], categories=C, rooted=rooted,
+                             normalize=normalize)
+
+
+# --------------------------------------------------------------------------- reference golden vectors
+
+def test_gpu_closed_form_3taxon():
+    """eigen/test_ll_3tax.py closed form (golden/ll_3tax.json), incl. eigen/eigen.cpp:5's blens = 1."""
+    cases = json.load(open(os.path.join(GOLDEN, "ll_3tax.json")))["cases"]
+    for case in cases:
+        tips = np.array([[0xF if t < 0 else (1 << t)] for t in case["tips"]], dtype=np.uint8)
+        b14, b24, b45, b35 = case["branches_b14_b24_b45_b35"]
+        mu = case["mu"]
+        blens = np.array([b14, b24, b35, b45]) * mu
+        with make(PEEL3, tips, None, O.JC69, 1, normalize=False) as lik:
+            vg = lik.value_grad(blens)
+            assert abs(vg.log_P - case["loglik"]) <= 1e-12 * abs(case["loglik"])
+            g = np.array(case["grad"])[[0, 1, 3, 2]] / mu
+            np.testing.assert_allclose(vg.grad_blens, g, rtol=1e-9, atol=1e-12)
+            assert lik.loglik(blens) == pytest.approx(case["loglik"], rel=1e-12)
+
+
+def test_gpu_eigen_operator_surface_and_quirk():
+    """pruning_loglik(blens) as eigen/example.stan:134 calls it; gradient equals eigen.j2's after its
+    times[i] factor (eigen/eigen.j2:165) is applied."""
+    tips = np.array([[1], [2], [8]], dtype=np.uint8)
+    with make(PEEL3, tips, None, O.JC69, 1, normalize=False) as lik:
+        lk.set_default(lik)
+        assert lk.pruning_loglik(np.ones(4)) == pytest.approx(-4.379876625344838, rel=1e-12)
+        t = np.array([0.1, 0.1, 0.3, 0.2])
+        vg = lk.pruning_loglik_value_grad(t)
+        ref = O.loglik_grad(PEEL3, tips, None, O.JC69, t, normalize=False, rescale=False, quirk_times=True)
+        np.testing.assert_allclose(t * vg.grad_blens, ref.grad_blens, rtol=1e-9)
+        assert vg.log_P == pytest.approx(ref.logp, rel=1e-12)
+        lk.set_default(None)
+
+
+# --------------------------------------------------------------------------- real data sets
+
+@pytest.mark.parametrize("name,model,rooted", [("fluA", O.HKY, True), ("DS1", O.GTR, False), ("HCV", O.GTR, True),
+                                                ("fluA", O.GTR, True), ("DS1", O.JC69, False), ("HCV", O.HKY, True)])
+def test_gpu_matches_oracle_on_reference_datasets(datasets, name, model, rooted):
+    d = datasets[name]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(hash((name, model)) % 2**32)
+    with make(d["peel"], d["tipmask"], d["weights"], model, 4, rooted) as lik:
+        for rep in range(3):
+            bl, subst, fr, rs, ps = random_params(model, S, rooted, 4, rng)
+            want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps, rooted=rooted)
+            noresc = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps,
+                                   rooted=rooted, rescale=False, want_grad=False)
+            got = lik.value_grad(bl, subst, fr, rs, ps)
+            assert_parity(got, want, jc=model == O.JC69)
+            assert abs(got.log_P - noresc.logp) <= RTOL_LOGP * abs(noresc.logp)     # reference arithmetic
+            assert lik.loglik(bl, subst, fr, rs, ps) == pytest.approx(want.logp, rel=RTOL_LOGP)
+
+
+def test_gpu_survey_anchors(datasets):
+    """SURVEY App. B.4 index-free anchors."""
+    d = datasets["fluA"]
+    bl = d["tree_blens"][:136] * 0.00499
+    with make(d["peel"], d["tipmask"], d["weights"], O.HKY, 4) as lik:
+        v = lik.loglik(bl, [5.58], [0.25] * 4, E.weibull_rates(0.488, 4), np.full(4, 0.25))
+        assert v == pytest.approx(-4223.976131712243, rel=1e-11)
+    d = datasets["DS1"]
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4, rooted=False) as lik:
+        v = lik.loglik(np.full(51, 0.05), [.1, .3, .1, .1, .3, .1], [.3, .2, .2, .3], E.weibull_rates(0.5, 4),
+                       np.full(4, 0.25))
+        assert v == pytest.approx(-7301.964517864685, rel=1e-11)
+
+
+# --------------------------------------------------------------------------- tilings, batches, edge cases
+
+def test_gpu_tilings_and_batch_agree(datasets):
+    d = datasets["DS1"]
+    rng = np.random.default_rng(7)
+    B = 5
+    draws = [random_params(O.GTR, 27, False, 4, rng) for _ in range(B)]
+    stack = [np.stack([dr[i] for dr in draws]) for i in range(5)]
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4, rooted=False) as lik:
+        base = None
+        for K, PB in ((1, 1), (2, 1), (4, 1), (1, 2), (2, 2), (1, 4)):
+            lik.set_tiling(K, PB)
+            vg = lik.value_grad(*stack)
+            info = lik.info()
+            assert info["kernel_launches"] == 3
+            flat = np.concatenate([vg.log_P[:, None], vg.grad_blens, vg.grad_subst, vg.grad_freqs, vg.grad_rs,
+                                   vg.grad_ps], axis=1)
+            if base is None:
+                base = flat
+                for i, dr in enumerate(draws):
+                    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, *dr, rooted=False)
+                    one = lik.value_grad(*dr)
+                    assert_parity(one, want)
+                    np.testing.assert_allclose(flat[i], np.concatenate([[one.log_P], one.grad]), rtol=1e-11, atol=1e-9)
+            else:
+                np.testing.assert_allclose(flat, base, rtol=1e-11, atol=1e-9)
+            np.testing.assert_allclose(lik.loglik(*stack), base[:, 0], rtol=1e-12)
+
+
+@pytest.mark.parametrize("S,L,C,model,rooted", [
+    (2, 1, 1, O.JC69, True), (3, 1, 1, O.GTR, False), (3, 33, 2, O.HKY, True), (5, 31, 5, O.GTR, True),
+    (9, 513, 1, O.GTR, False), (17, 100, 8, O.HKY, True), (40, 65, 3, O.JC69, False), (130, 70, 16, O.GTR, True)])
+def test_gpu_ragged_shapes(S, L, C, model, rooted):
+    """Pattern counts off the tile size, single pattern, 1..16 categories, smallest trees."""
+    rng = np.random.default_rng(S * 1000 + L)
+    peel = synth.coalescent_peel(S, rng)
+    if not rooted:
+        peel = E.unrooted_swap(peel)
+    tipmask = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    tipmask[rng.random((S, L)) < 0.1] = 0xF
+    tipmask[rng.random((S, L)) < 0.05] = 0b0101   # partial ambiguity (R = A|G) is supported too
+    weights = 1.0 + rng.poisson(1.0, size=L)
+    weights[rng.random(L) < 0.2] = 0.0
+    bl, subst, fr, rs, ps = random_params(model, S, rooted, C, rng, scale=0.2)
+    want = O.loglik_grad(peel, tipmask, weights, model, bl, subst, fr, rs, ps, rooted=rooted)
+    with make(peel, tipmask, weights, model, C, rooted) as lik:
+        assert_parity(lik.value_grad(bl, subst, fr, rs, ps), want, jc=model == O.JC69)
+
+
+def test_gpu_invariant_category_and_zero_branches():
+    """generate_script.py:250-266: rs[1] = 0 (P = I) for the invariant class; zero-length branches."""
+    rng = np.random.default_rng(21)
+    S, L, C = 12, 200, 5
+    peel = synth.coalescent_peel(S, rng)
+    tipmask = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    tipmask[:, :40] = tipmask[0, :40]   # constant columns, the only ones the invariant class explains
+    weights = np.ones(L)
+    pinv = 0.2
+    rs = np.concatenate([[0.0], E.weibull_rates(0.5, 4) / (1 - pinv)])
+    ps = np.concatenate([[pinv], np.full(4, (1 - pinv) / 4)])
+    bl = rng.exponential(0.1, size=2 * S - 2)
+    bl[[0, 5, 13]] = 0.0
+    subst, fr = rng.dirichlet(np.ones(6)), rng.dirichlet(np.ones(4) * 3)
+    want = O.loglik_grad(peel, tipmask, weights, O.GTR, bl, subst, fr, rs, ps)
+    with make(peel, tipmask, weights, O.GTR, C) as lik:
+        assert_parity(lik.value_grad(bl, subst, fr, rs, ps), want)
+
+
+def test_gpu_tipdata_constructor_matches_mask(datasets):
+    d = datasets["HCV"]
+    rng = np.random.default_rng(5)
+    p = random_params(O.GTR, 63, True, 4, rng)
+    with lk.TreeLikelihood(d["peel"], tipdata=E.mask_to_tipdata(d["tipmask"]), weights=d["weights"], model="GTR",
+                           categories=4) as a, make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4) as b:
+        va, vb = a.value_grad(*p), b.value_grad(*p)
+        assert va.log_P == pytest.approx(vb.log_P, rel=1e-13)
+        np.testing.assert_allclose(va.grad, vb.grad, rtol=1e-10, atol=1e-10)
+
+
+def test_gpu_deep_tree_rescaling():
+    """1200 saturated taxa: site likelihoods ~4^-1200 underflow fp64 (reference arithmetic gives -inf);
+    the per-(pattern,category) power-of-two rescaling must agree with the rescaled oracle."""
+    prob = synth.make_problem(1200, 96, 4, seed=5, structured=False)
+    prob.tipmask[:] = (1 << np.random.default_rng(1).integers(0, 4, size=prob.tipmask.shape)).astype(np.uint8)
+    rs, ps = E.weibull_rates(0.5, 4), np.full(4, 0.25)
+    bl = np.full_like(prob.blens, 2.0)
+    bl[::7] = 1e-3
+    want = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl, synth.RATES0, synth.FREQS0, rs, ps)
+    assert want.logp < -1e5
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        for K in (1, 2, 4):
+            lik.set_tiling(K, 1)
+            assert_parity(lik.value_grad(bl, synth.RATES0, synth.FREQS0, rs, ps), want)
+
+
+def test_gpu_errors():
+    tips = np.array([[1], [2], [8]], dtype=np.uint8)
+    with pytest.raises(lk.PhyloB200Error):
+        make(np.array([[4, 3, 5], [1, 2, 4]], dtype=np.int32), tips, None, O.JC69, 1)   # not post-order
+    with pytest.raises(lk.PhyloB200Error):
+        make(PEEL3, tips, None, O.JC69, 17)                                             # too many categories
+    with make(PEEL3, tips, None, O.GTR, 1) as lik:
+        with pytest.raises(lk.PhyloDomainError):
+            lik.value_grad([0.1, -0.1, 0.1, 0.1], np.ones(6), [0.25] * 4)
+        with pytest.raises(lk.PhyloDomainError):
+            lik.value_grad([0.1, 0.1, 0.1, float("nan")], np.ones(6), [0.25] * 4)
+        with pytest.raises(lk.PhyloDomainError):
+            lik.value_grad([0.1] * 4, np.ones(6), [0.5, 0.5, 0.0, 0.0])
+    # impossible pattern under the invariant-only model: logL = -inf -> domain error, not garbage
+    with make(PEEL3, tips, None, O.JC69, 1) as lik:
+        with pytest.raises(lk.PhyloDomainError):
+            lik.loglik([0.1] * 4, rs=[0.0], ps=[1.0])
+
+
+# --------------------------------------------------------------------------- BASELINE sizes
+
+@pytest.fixture(scope="module")
+def big():
+    """BASELINE config 3 shape: 1000 taxa x 100k patterns, GTR + W4."""
+    return synth.make_problem(1000, 100_000, 4, structured=False)
+
+
+def test_gpu_config3_slice_matches_oracle(big):
+    """Oracle-sized slices of the 1000-taxon problem (the oracle finishes these in seconds)."""
+    bl, rates, freqs, rs, ps = synth.make_draws(big, 2)
+    for lo, hi in ((0, 700), (54_321, 55_000)):
+        tm, w = big.tipmask[:, lo:hi], big.weights[lo:hi]
+        with make(big.peel, tm, w, O.GTR, 4) as lik:
+            for i in range(2):
+                want = O.loglik_grad(big.peel, tm, w, O.GTR, bl[i], rates[i], freqs[i], rs[i], ps[i])
+                assert_parity(lik.value_grad(bl[i], rates[i], freqs[i], rs[i], ps[i]), want)
+
+
+def test_gpu_config3_full_size_properties(big):
+    """Full 1000 x 100k x 4 evaluation: pattern-additivity against two half alignments, the Euler
+    identity sum_b t_b dL/dt_b = sum_c r_c dL/dr_c (both scale every t_b r_c), the category checksum
+    sum_c ps_c dL/dps_c = sum_l w_l, and value-only == value of value+gradient."""
+    B = 2
+    bl, rates, freqs, rs, ps = synth.make_draws(big, B)
+    with make(big.peel, big.tipmask, big.weights, O.GTR, 4) as lik:
+        vg = lik.value_grad(bl, rates, freqs, rs, ps)
+        v = lik.loglik(bl, rates, freqs, rs, ps)
+        info = lik.info()
+    assert info["stack_depth"] <= 11
+    np.testing.assert_allclose(v, vg.log_P, rtol=1e-13)
+    half = big.L // 2
+    parts = []
+    for sl in (slice(0, half), slice(half, big.L)):
+        with make(big.peel, big.tipmask[:, sl], big.weights[sl], O.GTR, 4) as lik:
+            parts.append(lik.value_grad(bl, rates, freqs, rs, ps))
+    np.testing.assert_allclose(parts[0].log_P + parts[1].log_P, vg.log_P, rtol=1e-12)
+    np.testing.assert_allclose(parts[0].grad_blens + parts[1].grad_blens, vg.grad_blens, rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(parts[0].grad_subst + parts[1].grad_subst, vg.grad_subst, rtol=1e-9, atol=1e-6)
+    euler_t = (vg.grad_blens * bl).sum(1)
+    euler_r = (vg.grad_rs * rs).sum(1)
+    np.testing.assert_allclose(euler_t, euler_r, rtol=1e-9)
+    np.testing.assert_allclose((vg.grad_ps * ps).sum(1), big.weights.sum(), rtol=1e-11)
+    assert np.all(np.isfinite(vg.grad))
+
+
+def test_gpu_pulley_principle(datasets):
+    """Reversible models: sliding the root along its edge leaves logL unchanged, and the two root-edge
+    derivatives coincide."""
+    d = datasets["fluA"]
+    rng = np.random.default_rng(9)
+    bl, subst, fr, rs, ps = random_params(O.GTR, 69, True, 4, rng)
+    c1, c2 = d["peel"][-1, 0] - 1, d["peel"][-1, 1] - 1
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4) as lik:
+        a = lik.value_grad(bl, subst, fr, rs, ps)
+        bl2 = bl.copy()
+        tot = bl[c1] + bl[c2]
+        bl2[c1], bl2[c2] = 0.3 * tot, 0.7 * tot
+        b = lik.value_grad(bl2, subst, fr, rs, ps)
+    assert a.log_P == pytest.approx(b.log_P, rel=1e-12)
+    assert a.grad_blens[c1] == pytest.approx(a.grad_blens[c2], rel=1e-8)
+    assert b.grad_blens[c1] == pytest.approx(a.grad_blens[c1], rel=1e-8)

@@ -1,0 +1,228 @@
+"""Host-side logic of the product, CPU only: encoders vs the reference's own encoders (golden
+.npz), the traversal plan, the per-draw model algebra, and that libphylo_b200.so loads and exports
+every symbol include/phylo_b200.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from phylostan_b200 import encode as E
+from phylostan_b200 import likelihood as lk
+from phylostan_b200 import synth
+
+from conftest import ROOT
+
+REF = "/root/reference"
+
+
+# ------------------------------------------------------------------------------- C ABI surface
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "phylo_b200.h")).read()
+    declared = set(re.findall(r"PHYLO_B200_API [\w\s\*]*?\b(phylo_b200_\w+)\(", header))
+    assert len(declared) >= 20
+    L = lk.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.phylo_b200_abi_version() == 1
+
+
+def test_create_fails_loudly_without_a_gpu():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(lk.PhyloB200Error) as ei:
+        lk.TreeLikelihood(np.array([[1, 2, 3]]), np.array([[1], [2]], dtype=np.uint8), model="JC69")
+    assert ei.value.code in (lk.ENODEV, lk.ECUDA)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "phylostan_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower().replace("phylo_oracle", "oracle") or f == "__never__", (dirpath, f)
+
+
+# ------------------------------------------------------------------------------- encoders
+
+@pytest.mark.parametrize("name,tf,af,rooted", [
+    ("fluA", "examples/fluA/fluA.tree", "examples/fluA/fluA.fa", True),
+    ("DS1", "examples/DS1/DS1.trees", "examples/DS1/DS1.nex", False),
+    ("HCV", "examples/HCV/HCV.tree", "examples/HCV/HCV.nexus", True)])
+def test_encoders_match_reference_utils(datasets, name, tf, af, rooted):
+    """phylostan/utils.py:59-104,156-190 run by tests/golden/make_golden_datasets.py vs encode.py."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not mounted (GPU box)")
+    tree = E.read_tree(os.path.join(REF, tf))
+    data = E.encode(tree, E.read_alignment(os.path.join(REF, af)), rooted=rooted)
+    g = datasets[name]
+    np.testing.assert_array_equal(data.peel, g["peel"])
+    np.testing.assert_array_equal(data.map, g["map"])
+    np.testing.assert_array_equal(data.tipmask, g["tipmask"])
+    np.testing.assert_array_equal(data.weights, g["weights"])
+    assert list(g["taxa"]) == data.taxa
+
+
+def test_dataset_shapes_match_survey(datasets):
+    """fluA 69x987 -> 238 patterns, DS1 27x1949 -> 934, HCV 63x411 -> 246."""
+    for name, S, L, sites in (("fluA", 69, 238, 987), ("DS1", 27, 934, 1949), ("HCV", 63, 246, 411)):
+        g = datasets[name]
+        assert g["tipmask"].shape == (S, L) and g["peel"].shape == (S - 1, 3)
+        assert g["weights"].sum() == sites
+        assert g["peel"][-1, 2] == 2 * S - 1
+        assert set(np.unique(g["tipmask"])) <= {1, 2, 4, 8, 15}
+    assert datasets["DS1"]["peel"][-1, 1] == 2 * 27 - 2  # phylostan.py:264-267
+
+
+def test_newick_indexing_convention():
+    """utils.py:59-81 on eigen/example.tree: tips in order of appearance, internals in post-order."""
+    tree = E.parse_newick("((1:0.1,2:0.1):0.2,3:0.3);")
+    E.setup_indexes(tree)
+    np.testing.assert_array_equal(E.get_peeling_order(tree), [[1, 2, 4], [4, 3, 5]])
+    np.testing.assert_array_equal(E.get_preorder(tree), [[5, 0], [4, 5], [1, 4], [2, 4], [3, 5]])
+    np.testing.assert_allclose(E.branch_lengths(tree), [0.1, 0.1, 0.3, 0.2])
+
+
+def test_pattern_compression_and_ambiguity():
+    seqs = {"a": "ACGTAC-N", "b": "ACGTACRT", "c": "AAGTAAYT"}
+    tipmask, w = E.compress_patterns(seqs, ["a", "b", "c"])
+    # columns: AAA CCA GGG TTT AAA CCA -RY NTT -> patterns AAA(2) CCA(2) GGG TTT -RY NTT
+    np.testing.assert_array_equal(w, [2, 2, 1, 1, 1, 1])
+    np.testing.assert_array_equal(tipmask[0], [1, 2, 4, 8, 15, 15])
+    np.testing.assert_array_equal(tipmask[1], [1, 2, 4, 8, 15, 8])   # R is not resolved: utils.py:180-188
+    td = E.mask_to_tipdata(tipmask)
+    np.testing.assert_array_equal(E.tipdata_to_mask(td), tipmask)
+    assert td[0, 4].tolist() == [1, 1, 1, 1]
+
+
+def test_weibull_rates_mean_one():
+    for shape in (0.3, 0.488, 1.0, 3.0):
+        for C in (2, 4, 8):
+            rs = E.weibull_rates(shape, C)
+            assert rs.mean() == pytest.approx(1.0, rel=1e-14) and np.all(np.diff(rs) > 0)
+
+
+# ------------------------------------------------------------------------------- traversal plan
+
+def _check_plan(peel):
+    S = peel.shape[0] + 1
+    p = lk.plan(peel)
+    post, pre = p["post"], p["pre"]
+    children = {int(r[2]) - 1: {int(r[0]) - 1, int(r[1]) - 1} for r in peel}
+    # post-order: every internal node once, children first, slots consistent with a real stack machine
+    done, slot_of, live = set(range(S)), {}, {}
+    for i, (a, b, sa, sb, so, node, _, _) in enumerate(post):
+        assert {a, b} == children[node]
+        for ch, s in ((a, sa), (b, sb)):
+            assert ch in done
+            if ch < S:
+                assert s == -1
+            else:
+                assert live.get(s) == ch, "child partial must still be on the stack"
+                del live[s]
+        assert so not in live
+        live[so] = node
+        assert 0 <= so < p["depth_post"]
+        done.add(node)
+        slot_of[node] = i
+    assert len(done) == 2 * S - 1 and list(live.values()) == [2 * S - 2]
+    # pre-order: parents first, q slots live exactly from producer to consumer
+    qlive = {int(pre[0][3]): 2 * S - 2}
+    seen = set()
+    for node, a, b, sn, sa, sb, rown, rowa, rowb, *_ in pre:
+        assert qlive.pop(sn) == node and {a, b} == children[node]
+        assert rown == slot_of[node]
+        for ch, s, row in ((a, sa, rowa), (b, sb, rowb)):
+            if ch < S:
+                assert s == -1 and row == -1
+            else:
+                assert row == slot_of[ch] and s not in qlive and 0 <= s < p["depth_pre"]
+                qlive[s] = ch
+        seen.add(node)
+    assert not qlive and len(seen) == S - 1
+    return p
+
+
+def test_plan_on_reference_trees(datasets):
+    for name in ("fluA", "DS1", "HCV"):
+        p = _check_plan(datasets[name]["peel"])
+        S = datasets[name]["peel"].shape[0] + 1
+        assert max(p["depth_post"], p["depth_pre"]) <= int(np.log2(S)) + 1
+
+
+def test_plan_depth_bounds():
+    rng = np.random.default_rng(0)
+    for S in (2, 3, 5, 64, 257, 1000):
+        p = _check_plan(synth.coalescent_peel(S, rng))
+        assert max(p["depth_post"], p["depth_pre"]) <= int(np.log2(S)) + 1   # Strahler bound
+    # caterpillar: depth 1; perfectly balanced 64 tips: depth log2(64) = 6
+    S = 50
+    cat = [[1, 2, S + 1]] + [[S + k, k + 2, S + k + 1] for k in range(1, S - 1)]
+    p = _check_plan(np.array(cat, dtype=np.int32))
+    assert p["depth_post"] == 1 and p["depth_pre"] == 1
+    rows, nxt, level = [], 65, list(range(1, 65))
+    while len(level) > 1:
+        new = []
+        for i in range(0, len(level), 2):
+            rows.append([level[i], level[i + 1], nxt]); new.append(nxt); nxt += 1
+        level = new
+    # renumber is unnecessary for the plan: children precede parents
+    p = _check_plan(np.array(rows, dtype=np.int32))
+    assert p["depth_post"] == 6 and p["depth_pre"] == 6
+
+
+def test_plan_rejects_malformed_peel():
+    with pytest.raises(lk.PhyloB200Error):
+        lk.plan(np.array([[4, 3, 5], [1, 2, 4]], dtype=np.int32))      # parent before child
+    with pytest.raises(lk.PhyloB200Error):
+        lk.plan(np.array([[1, 2, 4], [1, 3, 5]], dtype=np.int32))      # node used twice
+    with pytest.raises(lk.PhyloB200Error):
+        lk.plan(np.array([[1, 2, 5], [5, 3, 4]], dtype=np.int32))      # root is not 2S-1
+
+
+# ------------------------------------------------------------------------------- model algebra
+
+def test_derive_reconstructs_q_and_stationarity():
+    rng = np.random.default_rng(2)
+    for model, subst in (("JC69", None), ("HKY", [5.58]), ("GTR", rng.dirichlet(np.ones(6)))):
+        fr = None if model == "JC69" else rng.dirichlet(np.ones(4) * 4)
+        d = lk.derive(model, subst, fr)
+        Q, pi = d["Q"], d["pi"]
+        np.testing.assert_allclose(Q.sum(1), 0, atol=1e-15)
+        assert -(np.diag(Q) * pi).sum() == pytest.approx(1.0, rel=1e-14)          # generate_script.py:868
+        np.testing.assert_allclose(d["m1"] @ np.diag(d["lam"]) @ d["m2"], Q, atol=1e-14)
+        np.testing.assert_allclose(d["m1"] @ d["m2"], np.eye(4), atol=1e-14)
+        np.testing.assert_allclose(pi @ Q, 0, atol=1e-15)
+        assert np.all(np.diff(d["lam"]) >= 0) and abs(d["lam"][-1]) < 1e-14           # eigenvalues_sym order
+    un = lk.derive("JC69", normalize=False)["Q"]                                      # eigen/eigen.py:47-50
+    np.testing.assert_allclose(un, np.full((4, 4), 0.25) - np.eye(4), atol=1e-16)
+
+
+def test_derive_x_theta_matches_finite_differences():
+    """X_theta = m2 dQ/dtheta m1 for every unconstrained parameter (rates, kappa, freqs)."""
+    rng = np.random.default_rng(4)
+    for model, subst in (("HKY", np.array([3.3])), ("GTR", rng.dirichlet(np.ones(6)) * 6)):
+        fr = rng.dirichlet(np.ones(4) * 4)
+        d = lk.derive(model, subst, fr)
+        theta = np.concatenate([subst, fr])
+        for k in range(theta.size):
+            h = 1e-6
+            tp, tm = theta.copy(), theta.copy()
+            tp[k] += h; tm[k] -= h
+            n = subst.size
+            dQ = (lk.derive(model, tp[:n], tp[n:])["Q"] - lk.derive(model, tm[:n], tm[n:])["Q"]) / (2 * h)
+            np.testing.assert_allclose(d["m1"] @ d["X"][k] @ d["m2"], dQ, atol=2e-9)
+
+
+def test_derive_rejects_out_of_domain():
+    with pytest.raises(lk.PhyloDomainError):
+        lk.derive("HKY", [float("nan")], [0.25] * 4)
+    with pytest.raises(lk.PhyloDomainError):
+        lk.derive("GTR", np.ones(6), [0.5, 0.5, 0.0, 0.0])
