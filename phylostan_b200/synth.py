@@ -76,23 +76,23 @@ def simulate_alignment(peel: np.ndarray, blens: np.ndarray, L: int, C: int, rng:
     """One independent column per pattern.  Returns (tipmask uint8 [S, L], weights [L])."""
     S = peel.shape[0] + 1
     if structured:
-        Q = gtr_q(np.asarray(rates), np.asarray(freqs))
+        freqs = np.asarray(freqs)
+        Q = gtr_q(np.asarray(rates), freqs)
+        sq = np.sqrt(freqs)
+        A = sq[:, None] * Q / sq[None, :]
+        lam, U = np.linalg.eigh((A + A.T) / 2)
+        m1, m2 = U / sq[:, None], U.T * sq[None, :]
         rs = weibull_rates(wshape, C)
         cat = rng.integers(0, C, size=L)
         state = np.zeros((2 * S - 1, L), dtype=np.int8)
         state[2 * S - 2] = rng.choice(4, size=L, p=freqs)
-        u = np.empty(L)
         for row in peel[::-1]:  # parents before children
+            par = state[row[2] - 1]
             for child in (row[0] - 1, row[1] - 1):
-                par = state[row[2] - 1]
-                rng.random(out=u)
-                new = np.zeros(L, dtype=np.int8)
-                for c in range(C):
-                    P = _pmat(Q, np.asarray(freqs), blens[child] * rs[c])
-                    cum = np.cumsum(P, axis=1)
-                    sel = cat == c
-                    new[sel] = (u[sel, None] > cum[par[sel]]).sum(1).clip(0, 3)
-                state[child] = new
+                P = np.einsum("ik,ck,kj->cij", m1, np.exp(lam[None, :] * (blens[child] * rs)[:, None]), m2)
+                cum = np.cumsum(P, axis=2)[:, :, :3]                     # [C, 4, 3]
+                u = rng.random(L)
+                state[child] = (u[:, None] > cum[cat, par]).sum(1)
         tips = state[:S]
     else:  # cheap generator for very large shapes: iid states biased towards a per-column majority
         major = rng.integers(0, 4, size=L, dtype=np.int8)
