@@ -5,10 +5,6 @@ namespace phylo {
 
 namespace {
 
-// threads per CTA allowed for K patterns per thread (register budget: 128 / 128 / 255)
-constexpr int max_threads(int K) { return K == 1 ? 512 : (K == 2 ? 256 : 128); }
-constexpr int min_blocks(int K) { return K == 1 ? 1 : 2; }
-
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
@@ -17,11 +13,12 @@ __device__ __forceinline__ double pow2_64k(int k) {  // 2^(64 k), -15 <= k <= 15
     return __hiloint2double((1023 + 64 * k) << 20, 0);
 }
 
-__device__ __forceinline__ void load_mat(const double* __restrict__ M, double (&m)[16]) {
-    const double2* q = reinterpret_cast<const double2*>(M);
+// 4x4 row-major matrix from shared memory (warp-uniform address: broadcast LDS.128)
+__device__ __forceinline__ void lds_mat(const unsigned char* p, double (&m)[16]) {
+    const double2* q = reinterpret_cast<const double2*>(p);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        double2 v = __ldg(q + i);
+        double2 v = q[i];
         m[2 * i] = v.x;
         m[2 * i + 1] = v.y;
     }
@@ -84,62 +81,141 @@ __device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], doub
     if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), a1);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
 // ------------------------------------------------------------------------------------------
-// K1: transition matrices
+// K1: instruction streams (step descriptor + both transition matrices per record)
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) pmat_kernel(const double* __restrict__ params, ParamLayout lay, int bcount,
-                                                   int jc_closed, double* __restrict__ P, int total) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int k = idx % lay.nn, c = (idx / lay.nn) % lay.C, d = idx / (lay.nn * lay.C);
-    const double* prm = params + (size_t)d * lay.stride;
-    double* out = P + (size_t)idx * 16;
-    double m[16];
-    if (k >= bcount) {  // root, or the unrooted second root child: no branch
+__device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const ParamLayout& lay, int node, int c,
+                                        int bcount, int jc_closed, double (&m)[16]) {
+    if (node >= bcount) {  // root, or the unrooted second root child: no branch
 #pragma unroll
         for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 : 0.0;
-    } else {
-        const double tau = prm[lay.off_t + k] * prm[lay.off_rs + c];
-        if (jc_closed) {  // generate_script.py:765-766
-            const double e = exp(-tau / 0.75);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 0.25 + 0.75 * e : 0.25 - 0.25 * e;
-        } else {  // generate_script.py:824-829
-            double ex[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ex[j] = exp(prm[lay.off_lam + j] * tau);
-            const double* m1 = prm + lay.off_m1;
-            const double* m2 = prm + lay.off_m2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) s += (m1[4 * i + q] * ex[q]) * m2[4 * q + j];
-                    m[4 * i + j] = s;
-                }
-        }
+        return;
     }
-    double2* o2 = reinterpret_cast<double2*>(out);
+    const double tau = prm[lay.off_t + node] * prm[lay.off_rs + c];
+    if (jc_closed) {  // generate_script.py:765-766
+        const double e = exp(-tau / 0.75);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o2[i] = make_double2(m[2 * i], m[2 * i + 1]);
+        for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 0.25 + 0.75 * e : 0.25 - 0.25 * e;
+        return;
+    }
+    double ex[4];  // generate_script.py:824-829
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ex[j] = exp(prm[lay.off_lam + j] * tau);
+    const double* m1 = prm + lay.off_m1;
+    const double* m2 = prm + lay.off_m2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s += (m1[4 * i + q] * ex[q]) * m2[4 * q + j];
+            m[4 * i + j] = s;
+        }
+}
+
+__global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
+    const int per = a.lay.C * a.nsteps;
+    const int total = 2 * a.B * per;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int which = idx / (a.B * per);  // 0 post-order stream, 1 pre-order stream
+    const int r = idx - which * a.B * per;
+    const int d = r / per, c = (r / a.nsteps) % a.lay.C, i = r % a.nsteps;
+    const double* prm = a.params + (size_t)d * a.lay.stride;
+    unsigned char* rec = (which ? a.spre : a.spost) + (size_t)r * kRecBytes;
+    int na, nb;
+    int4* rd = reinterpret_cast<int4*>(rec);
+    if (which == 0) {
+        const int4* s = reinterpret_cast<const int4*>(a.post + i);
+        const int4 s0 = __ldg(s), s1 = __ldg(s + 1);
+        na = s0.x; nb = s0.y;
+        rd[0] = s0; rd[1] = s1; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
+    } else {
+        const int4* s = reinterpret_cast<const int4*>(a.pre + i);
+        const int4 s0 = __ldg(s), s1 = __ldg(s + 1), s2 = __ldg(s + 2);
+        na = s0.y; nb = s0.z;
+        rd[0] = s0; rd[1] = s1; rd[2] = s2; rd[3] = make_int4(0, 0, 0, 0);
+    }
+    double m[16];
+    double2* o2 = reinterpret_cast<double2*>(rec + 64);
+    pmatrix(prm, a.lay, na, c, a.bcount, a.jc_closed, m);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o2[q] = make_double2(m[2 * q], m[2 * q + 1]);
+    pmatrix(prm, a.lay, nb, c, a.bcount, a.jc_closed, m);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o2[8 + q] = make_double2(m[2 * q], m[2 * q + 1]);
 }
 
 // ------------------------------------------------------------------------------------------
 // K2/K3: fused depth-first post-order + pre-order sweep
 // ------------------------------------------------------------------------------------------
 
-template <int K, bool GRAD>
-__global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(const SweepArgs a) {
+// Per-warp record ring fed by cp.async: chunk n lives in buffer n % kRecBufs.
+struct Ring {
+    unsigned char* buf;         // this warp's ring in shared memory
+    const unsigned char* src;   // this warp's stream in global memory
+    int nrec;                   // records in the stream
+    int lane;
+
+    __device__ __forceinline__ void issue(int chunk) const {
+        const int first = chunk * kRecChunk;
+        const int bytes = min(kRecChunk, nrec - first) * kRecBytes;  // <= 0 past the end
+        unsigned char* dst = buf + (chunk % kRecBufs) * (kRecChunk * kRecBytes);
+        const unsigned char* s = src + (size_t)first * kRecBytes;
+        for (int off = lane * 16; off < bytes; off += 512) cp_async16(dst + off, s + off);
+        cp_async_commit();  // always commit: keeps the group count uniform
+    }
+    __device__ __forceinline__ void start(const unsigned char* stream, int n) {
+        src = stream;
+        nrec = n;
+        cp_async_wait<0>();
+        __syncwarp();
+        issue(0);
+        issue(1);
+    }
+    // call at the top of step i: afterwards the records of steps i .. i+kRecChunk (at least) are readable
+    __device__ __forceinline__ void advance(int i) const {
+        if ((i % kRecChunk) == 0) {
+            __syncwarp();  // every lane is done with the buffer about to be overwritten
+            issue(i / kRecChunk + 2);
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+    }
+    __device__ __forceinline__ const unsigned char* rec(int i) const {
+        return buf + (((i / kRecChunk) % kRecBufs) * kRecChunk + (i % kRecChunk)) * kRecBytes;
+    }
+};
+
+template <int K, bool GRAD, int NTMAX, int MINB>
+__global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.C;
     const int c = warp % C, pb = warp / C;
-    double2* st = reinterpret_cast<double2*>(smem_raw);                    // [D][K][2][NT]
+    double2* st = reinterpret_cast<double2*>(smem_raw);                       // [D][K][2][NT]
     double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * 2 * NT);  // [K][NT]
-    int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                     // [K][NT]
+    int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                        // [K][NT]
+    Ring ring;
+    ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * kRingBytesPerWarp;
+    ring.lane = lane;
+    ring.src = nullptr;
+    ring.nrec = 0;
     const int tpat = (NT / (32 * C)) * 32 * K;
 
     double2* sc = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
@@ -152,38 +228,47 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
         const double* prm = a.params + (size_t)d * a.lay.stride;
-        const double* Pd = a.P + ((size_t)d * C + c) * a.nn * 16;
         const int pat0 = tile * tpat + pb * 32 * K + lane;  // pattern of sub-index j: pat0 + 32 j
+        const uint8_t* tipp = a.tips + pat0;
+        const size_t stream_off = ((size_t)d * C + c) * a.nsteps * kRecBytes;
 
         // -------------------------------------------------------------- post-order
         int etot[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) etot[j] = 0;
         int so_last = 0;
+        ring.start(a.spost + stream_off, a.nsteps);
         for (int i = 0; i < a.nsteps; ++i) {
-            const int4 s0 = __ldg(reinterpret_cast<const int4*>(a.post + i));
-            const int4 s1 = __ldg(reinterpret_cast<const int4*>(a.post + i) + 1);
-            const int na = s0.x, nb = s0.y, sa = s0.z, sb = s0.w, so = s1.x;
+            ring.advance(i);
+            const unsigned char* rec = ring.rec(i);
+            const int4 s0 = *reinterpret_cast<const int4*>(rec);
+            const int so = *reinterpret_cast<const int*>(rec + 16);
+            const int na = s0.x, nb = s0.y, sa = s0.z, sb = s0.w;
             so_last = so;
+            if (i + 2 < a.nsteps) {  // tip codes of step i+2 -> L2
+                const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(i + 2));
+                if (n0.z < 0) prefetch_l2(tipp + (size_t)n0.x * a.Lpad);
+                if (n0.w < 0) prefetch_l2(tipp + (size_t)n0.y * a.Lpad);
+            }
             double M[16], ma[K][4];
-            load_mat(Pd + (size_t)na * 16, M);
+            lds_mat(rec + 64, M);
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 double p[4];
                 if (sa < 0) {
-                    tip_vec(a.tips[(size_t)na * a.Lpad + pat0 + 32 * j], p);
+                    tip_vec(tipp[(size_t)na * a.Lpad + 32 * j], p);
                 } else {
                     double2 u = ST(sa, j, 0), v = ST(sa, j, 1);
                     p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
                 }
                 matvec(M, p, ma[j]);
             }
-            load_mat(Pd + (size_t)nb * 16, M);
+            lds_mat(rec + 192, M);
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 double p[4], mb[4];
                 if (sb < 0) {
-                    tip_vec(a.tips[(size_t)nb * a.Lpad + pat0 + 32 * j], p);
+                    tip_vec(tipp[(size_t)nb * a.Lpad + 32 * j], p);
                 } else {
                     double2 u = ST(sb, j, 0), v = ST(sb, j, 1);
                     p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
@@ -217,6 +302,7 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
         double pi[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
+        if (GRAD) ring.start(a.spre + stream_off, a.nsteps);  // overlaps the root exchange
         double proot[K][4], rdot[K];
         __syncthreads();  // previous item's readers of ex_* are done
 #pragma unroll
@@ -253,8 +339,9 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
 
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
+            ring.advance(0);
             {
-                const int sroot = __ldg(&a.pre[0].sn);
+                const int sroot = *reinterpret_cast<const int*>(ring.rec(0) + 12);
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     const double f = fac[j] * ps_c;
@@ -264,68 +351,105 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
             for (int i = 0; i < a.nsteps; ++i) {
-                const int4 s0 = __ldg(reinterpret_cast<const int4*>(a.pre + i));
-                const int4 s1 = __ldg(reinterpret_cast<const int4*>(a.pre + i) + 1);
-                const int4 s2 = __ldg(reinterpret_cast<const int4*>(a.pre + i) + 2);
+                if (i) ring.advance(i);
+                const unsigned char* rec = ring.rec(i);
+                const int4 s0 = *reinterpret_cast<const int4*>(rec);
+                const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);
+                const int rowb = *reinterpret_cast<const int*>(rec + 32);
                 const int na = s0.y, nb = s0.z, sn = s0.w;
-                const int sa = s1.x, sb = s1.y, rown = s1.z, rowa = s1.w, rowb = s2.x;
-                double qn[K][4];
+                const int sa = s1.x, sb = s1.y, rown = s1.z, rowa = s1.w;
+                if (i + 2 < a.nsteps) {  // operands of step i+2 -> L2
+                    const unsigned char* nr = ring.rec(i + 2);
+                    const int4 n0 = *reinterpret_cast<const int4*>(nr);
+                    const int4 n1 = *reinterpret_cast<const int4*>(nr + 16);
+                    const int nrowb = *reinterpret_cast<const int*>(nr + 32);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (n1.w < 0) {
+                            if (j == 0) prefetch_l2(tipp + (size_t)n0.y * a.Lpad);
+                        } else {
+                            prefetch_l2(&SC(n1.w, j, 0));
+                            prefetch_l2(&SC(n1.w, j, 1));
+                        }
+                        if (nrowb < 0) {
+                            if (j == 0) prefetch_l2(tipp + (size_t)n0.z * a.Lpad);
+                        } else {
+                            prefetch_l2(&SC(nrowb, j, 0));
+                            prefetch_l2(&SC(nrowb, j, 1));
+                        }
+                    }
+                }
+                double qn[K][4], pa[K][4], pbv[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
+                    if (rowa < 0) {
+                        tip_vec(tipp[(size_t)na * a.Lpad + 32 * j], pa[j]);
+                    } else {
+                        double2 u = SC(rowa, j, 0), v = SC(rowa, j, 1);
+                        pa[j][0] = u.x; pa[j][1] = u.y; pa[j][2] = v.x; pa[j][3] = v.y;
+                    }
+                    if (rowb < 0) {
+                        tip_vec(tipp[(size_t)nb * a.Lpad + 32 * j], pbv[j]);
+                    } else {
+                        double2 u = SC(rowb, j, 0), v = SC(rowb, j, 1);
+                        pbv[j][0] = u.x; pbv[j][1] = u.y; pbv[j][2] = v.x; pbv[j][3] = v.y;
+                    }
                     double2 u = ST(sn, j, 0), v = ST(sn, j, 1);
                     const double f = pow2_64k((int)DL(rown, j));
                     qn[j][0] = u.x * f; qn[j][1] = u.y * f; qn[j][2] = v.x * f; qn[j][3] = v.y * f;
                 }
-                double MA[16], MB[16];
-                load_mat(Pd + (size_t)na * 16, MA);
-                load_mat(Pd + (size_t)nb * 16, MB);
-                double GA[16], GB[16];
-#pragma unroll
-                for (int x = 0; x < 16; ++x) GA[x] = GB[x] = 0.0;
+                double MA[16], MB[16], ma[K][4], mb[K][4];
+                lds_mat(rec + 64, MA);
+                lds_mat(rec + 192, MB);
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    double pa[4], pbv[4], ma[4], mb[4], AA[4], AB[4];
-                    if (rowa < 0) {
-                        tip_vec(a.tips[(size_t)na * a.Lpad + pat0 + 32 * j], pa);
-                    } else {
-                        double2 u = SC(rowa, j, 0), v = SC(rowa, j, 1);
-                        pa[0] = u.x; pa[1] = u.y; pa[2] = v.x; pa[3] = v.y;
-                    }
-                    if (rowb < 0) {
-                        tip_vec(a.tips[(size_t)nb * a.Lpad + pat0 + 32 * j], pbv);
-                    } else {
-                        double2 u = SC(rowb, j, 0), v = SC(rowb, j, 1);
-                        pbv[0] = u.x; pbv[1] = u.y; pbv[2] = v.x; pbv[3] = v.y;
-                    }
-                    matvec(MA, pa, ma);
-                    matvec(MB, pbv, mb);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {  // eq (7) of eigen.j2:148
-                        AA[s] = qn[j][s] * mb[s];
-                        AB[s] = qn[j][s] * ma[s];
-                    }
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) {
-                            GA[4 * x + y] = fma(AA[x], pa[y], GA[4 * x + y]);
-                            GB[4 * x + y] = fma(AB[x], pbv[y], GB[4 * x + y]);
-                        }
-                    if (sa >= 0) {
-                        double q[4];
-                        matTvec(MA, AA, q);  // eigen.j2:151-153
-                        ST(sa, j, 0) = make_double2(q[0], q[1]);
-                        ST(sa, j, 1) = make_double2(q[2], q[3]);
-                    }
-                    if (sb >= 0) {
-                        double q[4];
-                        matTvec(MB, AB, q);
-                        ST(sb, j, 0) = make_double2(q[0], q[1]);
-                        ST(sb, j, 1) = make_double2(q[2], q[3]);
-                    }
+                    matvec(MA, pa[j], ma[j]);
+                    matvec(MB, pbv[j], mb[j]);
                 }
-                warp_reduce16_atomic(GA, Gd + (size_t)na * C * 16, lane);
-                warp_reduce16_atomic(GB, Gd + (size_t)nb * C * 16, lane);
+                {   // child a: A_a = q_n o (P_b p_b)   (eq (7), eigen.j2:148)
+                    double G[16];
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) G[x] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        double A[4];
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) A[s] = qn[j][s] * mb[j][s];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(A[x], pa[j][y], G[4 * x + y]);
+                        if (sa >= 0) {
+                            double q[4];
+                            matTvec(MA, A, q);  // eigen.j2:151-153
+                            ST(sa, j, 0) = make_double2(q[0], q[1]);
+                            ST(sa, j, 1) = make_double2(q[2], q[3]);
+                        }
+                    }
+                    warp_reduce16_atomic(G, Gd + (size_t)na * C * 16, lane);
+                }
+                {   // child b
+                    double G[16];
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) G[x] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        double A[4];
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) A[s] = qn[j][s] * ma[j][s];
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(A[x], pbv[j][y], G[4 * x + y]);
+                        if (sb >= 0) {
+                            double q[4];
+                            matTvec(MB, A, q);
+                            ST(sb, j, 0) = make_double2(q[0], q[1]);
+                            ST(sb, j, 1) = make_double2(q[2], q[3]);
+                        }
+                    }
+                    warp_reduce16_atomic(G, Gd + (size_t)nb * C * 16, lane);
+                }
             }
         }
 
@@ -346,6 +470,7 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
             }
         }
     }
+    cp_async_wait<0>();
 #undef ST
 #undef SC
 #undef DL
@@ -354,6 +479,16 @@ __global__ void __launch_bounds__(max_threads(K), min_blocks(K)) sweep_kernel(co
 // ------------------------------------------------------------------------------------------
 // K4: contraction of the branch statistics
 // ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void ldg_mat(const double* __restrict__ M, double (&m)[16]) {
+    const double2* q = reinterpret_cast<const double2*>(M);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double2 v = __ldg(q + i);
+        m[2 * i] = v.x;
+        m[2 * i + 1] = v.y;
+    }
+}
 
 __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
     const int d = blockIdx.y;
@@ -372,6 +507,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) lam[i] = prm[a.lay.off_lam + i];
     const double t = live ? prm[a.lay.off_t + b] : 0.0;
+    const int pos = live ? a.node_pos[b] : 0;
     double dt = 0.0;
     double th[10];
 #pragma unroll
@@ -381,8 +517,9 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         if (live) {
             const double r = prm[a.lay.off_rs + c];
             double G[16], P[16];
-            load_mat(a.G + (((size_t)d * a.nn + b) * a.C + c) * 16, G);
-            load_mat(a.P + (((size_t)d * a.C + c) * a.nn + b) * 16, P);
+            ldg_mat(a.G + (((size_t)d * a.nn + b) * a.C + c) * 16, G);
+            const unsigned char* rec = a.spost + (((size_t)d * a.C + c) * a.nsteps + (pos >> 1)) * kRecBytes;
+            ldg_mat(reinterpret_cast<const double*>(rec + 64 + 128 * (pos & 1)), P);
             // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -444,33 +581,52 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         }
 }
 
+// ------------------------------------------------------------------------------------------
+// launch plumbing
+// ------------------------------------------------------------------------------------------
+
+// CTA-size / register classes per K: small CTAs (one pattern block of 4 categories) get more
+// registers per thread; the 512-thread class covers many categories or several pattern blocks.
+template <int K> struct Cfg;
+template <> struct Cfg<1> { static constexpr int small_nt = 128, small_minb = 4; };
+template <> struct Cfg<2> { static constexpr int small_nt = 128, small_minb = 3; };
+template <> struct Cfg<4> { static constexpr int small_nt = 128, small_minb = 1; };
+
+template <int K, bool GRAD>
+auto pick_kernel(int nthreads) -> void (*)(const SweepArgs) {
+    if (nthreads <= Cfg<K>::small_nt) return sweep_kernel<K, GRAD, Cfg<K>::small_nt, Cfg<K>::small_minb>;
+    return sweep_kernel<K, GRAD, 512, 1>;
+}
+
 template <int K, bool GRAD>
 cudaError_t launch_sweep_t(const SweepArgs& a, int grid, int nthreads, size_t smem, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = pick_kernel<K, GRAD>(nthreads);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    sweep_kernel<K, GRAD><<<grid, nthreads, smem, stream>>>(a);
+    kern<<<grid, nthreads, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
 template <int K, bool GRAD>
 cudaError_t occupancy_t(int nthreads, size_t smem, int* n) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_kernel<K, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = pick_kernel<K, GRAD>(nthreads);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, sweep_kernel<K, GRAD>, nthreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, nthreads, smem);
 }
 
 }  // namespace
 
-int sweep_max_threads(int K) { return max_threads(K); }
+int sweep_max_threads(int) { return 512; }
 
 size_t sweep_smem_bytes(int D, int K, int nthreads) {
-    return (size_t)D * K * 2 * nthreads * sizeof(double2) + (size_t)K * nthreads * (sizeof(double) + sizeof(int));
+    return (size_t)D * K * 2 * nthreads * sizeof(double2) + (size_t)K * nthreads * (sizeof(double) + sizeof(int)) +
+           (size_t)(nthreads / 32) * kRingBytesPerWarp;
 }
 
-void launch_pmat(const double* params, ParamLayout lay, int bcount, int jc_closed, double* P, int B,
-                 cudaStream_t stream) {
-    const int total = B * lay.C * lay.nn;
-    pmat_kernel<<<(total + 127) / 128, 128, 0, stream>>>(params, lay, bcount, jc_closed, P, total);
+void launch_stream(const StreamArgs& a, cudaStream_t stream) {
+    const int total = 2 * a.B * a.lay.C * a.nsteps;
+    stream_kernel<<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
 cudaError_t launch_sweep(const SweepArgs& a, int K, bool grad, int grid, int nthreads, size_t smem,

@@ -1,8 +1,11 @@
 // kernels.cuh -- device side of libphylo_b200: hand-written CUDA for sm_100a.
 //
 // Three kernels per evaluation (batch of B parameter draws):
-//   pmat_kernel      P(t_b r_c) = m1 diag(exp(lambda t_b r_c)) m2 for every (draw, category, node)
-//                    (phylostan/generate_script.py:824-829, 880-885; JC69 closed form :765-766)
+//   stream_kernel    P(t_b r_c) = m1 diag(exp(lambda t_b r_c)) m2 for both children of every step
+//                    (phylostan/generate_script.py:824-829, 880-885; JC69 closed form :765-766),
+//                    written as per-(draw, category) INSTRUCTION STREAMS in traversal order:
+//                    one 320-byte record [step descriptor | P_a | P_b] per internal node, one stream
+//                    for the post-order and one for the pre-order sweep
 //   sweep_kernel     per (draw, pattern tile): depth-first post-order partials
 //                    (eigen/eigen.j2:122-141, generate_script.py:998-1005), root likelihood with
 //                    per-(pattern,category) rescaling (generate_script.py:1006-1010), then the
@@ -11,10 +14,13 @@
 //   contract_kernel  G -> d/dblens (eigen/eigen.j2:163-166 without its times[i] factor),
 //                    d/drs, d/d(rates|kappa), d/dfreqs
 //
-// Memory plan: the live partials of a tile sit in a shared-memory stack [slot][k][half][thread]
-// of double2 (bank-conflict free, one thread = one (pattern, category)); the only HBM traffic is
-// one coalesced double2 write per internal-node partial in the post-order (to the CTA's scratch
-// rows) and one read of it in the pre-order, plus 1-byte tip codes.  q never leaves the SM.
+// Memory plan: one thread = one (pattern, category) (x K patterns).  The live partials of a tile
+// sit in a shared-memory stack [slot][k][half][thread] of double2 (bank-conflict free).  Every
+// warp streams its category's records into a private shared-memory ring with cp.async, two chunks
+// ahead, so the step -> matrix -> operand chain never waits on global memory; operand lines of
+// step i+2 are prefetched into L2.  HBM traffic is one coalesced double2 write per internal-node
+// partial in the post-order (the CTA's scratch rows) and one read of it in the pre-order, plus
+// 1-byte tip codes; q never leaves the SM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,6 +28,11 @@
 #include "plan.hpp"
 
 namespace phylo {
+
+constexpr int kRecBytes = 320;   // [desc 64 B | P_a 128 B | P_b 128 B]
+constexpr int kRecChunk = 2;     // records per cp.async group
+constexpr int kRecBufs = 3;      // ring depth in chunks
+constexpr int kRingBytesPerWarp = kRecBytes * kRecChunk * kRecBufs;
 
 // offsets (in doubles) inside one draw's parameter block
 struct ParamLayout {
@@ -38,17 +49,26 @@ struct ParamLayout {
     int stride;
 };
 
+struct StreamArgs {
+    const double* params;     // [B][stride]
+    const PostStep* post;     // [S-1]
+    const PreStep* pre;       // [S-1]
+    unsigned char* spost;     // [B][C][S-1][kRecBytes]
+    unsigned char* spre;      // [B][C][S-1][kRecBytes]
+    ParamLayout lay;
+    int nsteps, bcount, jc_closed, B;
+};
+
 struct SweepArgs {
-    const uint8_t* tips;     // [S][Lpad] 4-bit state masks
-    const double* weights;   // [Lpad]
-    const double* P;         // [B][C][nn][16]
-    const double* params;    // [B][stride]
-    const PostStep* post;    // [S-1]
-    const PreStep* pre;      // [S-1]
-    double2* scratch;        // [grid][S-1][K][2][NT]
-    int8_t* dscr;            // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
-    double* G;               // [B][nn][C][16]
-    double* out;             // [B][nout]
+    const uint8_t* tips;      // [S][Lpad] 4-bit state masks
+    const double* weights;    // [Lpad]
+    const double* params;     // [B][stride]
+    const unsigned char* spost;
+    const unsigned char* spre;
+    double2* scratch;         // [grid][S-1][K][2][NT]
+    int8_t* dscr;             // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
+    double* G;                // [B][nn][C][16]
+    double* out;              // [B][nout]
     ParamLayout lay;
     long long scratch_stride, dscr_stride;
     int S, nsteps, Lpad, ntiles, nitems, C, nn, nout, D;
@@ -56,18 +76,18 @@ struct SweepArgs {
 };
 
 struct ContractArgs {
-    const double* P;
+    const unsigned char* spost;
+    const int32_t* node_pos;  // [nn] 2 * post step + child slot of every non-root node
     const double* params;
     const double* G;
     double* out;
     ParamLayout lay;
-    int bcount, C, nn, nout, nsubst;
+    int bcount, C, nn, nout, nsubst, nsteps;
     int off_out_subst, off_out_freqs, off_out_rs;
 };
 
-void launch_pmat(const double* params, ParamLayout lay, int bcount, int jc_closed, double* P, int B,
-                 cudaStream_t stream);
-// K in {1,2,4}; returns cudaError
+void launch_stream(const StreamArgs& a, cudaStream_t stream);
+// K in {1,2,4}; nthreads <= 512
 cudaError_t launch_sweep(const SweepArgs& a, int K, bool grad, int grid, int nthreads, size_t smem,
                          cudaStream_t stream);
 cudaError_t sweep_occupancy(int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);

@@ -94,7 +94,9 @@ struct phylo_b200_ctx {
     DevBuf<PostStep> d_post;
     DevBuf<PreStep> d_pre;
     // per-batch device data
-    DevBuf<double> d_params, d_P, d_G, d_out;
+    DevBuf<double> d_params, d_G, d_out;
+    DevBuf<unsigned char> d_spost, d_spre;  // per-(draw, category) instruction streams
+    DevBuf<int32_t> d_node_pos;
     DevBuf<double2> d_scratch;
     DevBuf<int8_t> d_dscr;
     PinnedBuf<double> h_params, h_out;
@@ -113,7 +115,8 @@ struct phylo_b200_ctx {
     ~phylo_b200_ctx() {
         cudaSetDevice(device);
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
-        d_params.release(); d_P.release(); d_G.release(); d_out.release();
+        d_params.release(); d_G.release(); d_out.release();
+        d_spost.release(); d_spre.release(); d_node_pos.release();
         d_scratch.release(); d_dscr.release();
         h_params.release(); h_out.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -158,7 +161,8 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
 
 int ensure_batch(phylo_b200_ctx* h, int B) {
     CU_TRY(h->d_params.ensure((size_t)B * h->lay.stride));
-    CU_TRY(h->d_P.ensure((size_t)B * h->C * h->nn * 16));
+    CU_TRY(h->d_spost.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));
+    CU_TRY(h->d_spre.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));
     CU_TRY(h->d_G.ensure((size_t)B * h->nn * h->C * 16));
     CU_TRY(h->d_out.ensure((size_t)B * h->nout));
     CU_TRY(h->h_params.ensure((size_t)B * h->lay.stride));
@@ -252,8 +256,14 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
         if (e != cudaSuccess) return e;
         return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
     };
+    std::vector<int32_t> node_pos((size_t)h->nn, 0);  // non-root node -> 2 * post step + child slot
+    for (size_t i = 0; i < h->plan.post.size(); ++i) {
+        node_pos[h->plan.post[i].a] = (int32_t)(2 * i);
+        node_pos[h->plan.post[i].b] = (int32_t)(2 * i + 1);
+    }
     cudaError_t e = cudaSuccess;
     if ((e = up(h->d_tips, tips)) != cudaSuccess || (e = up(h->d_weights, w)) != cudaSuccess ||
+        (e = up(h->d_node_pos, node_pos)) != cudaSuccess ||
         (e = up(h->d_post, h->plan.post)) != cudaSuccess || (e = up(h->d_pre, h->plan.pre)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
@@ -421,13 +431,17 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     CU_TRY(cudaMemsetAsync(h->d_out.p, 0, sizeof(double) * B * h->nout, st));
     if (grad) CU_TRY(cudaMemsetAsync(h->d_G.p, 0, sizeof(double) * B * h->nn * h->C * 16, st));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[0], st));
-    launch_pmat(h->d_params.p, h->lay, h->bcount, h->jc_closed, h->d_P.p, B, st);
+    StreamArgs sa{};
+    sa.params = h->d_params.p; sa.post = h->d_post.p; sa.pre = h->d_pre.p;
+    sa.spost = h->d_spost.p; sa.spre = h->d_spre.p; sa.lay = h->lay;
+    sa.nsteps = h->S - 1; sa.bcount = h->bcount; sa.jc_closed = h->jc_closed; sa.B = B;
+    launch_stream(sa, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
 
     SweepArgs a{};
-    a.tips = h->d_tips.p; a.weights = h->d_weights.p; a.P = h->d_P.p; a.params = h->d_params.p;
-    a.post = h->d_post.p; a.pre = h->d_pre.p;
+    a.tips = h->d_tips.p; a.weights = h->d_weights.p; a.params = h->d_params.p;
+    a.spost = h->d_spost.p; a.spre = h->d_spre.p;
     a.scratch = h->d_scratch.p; a.dscr = h->d_dscr.p; a.G = h->d_G.p; a.out = h->d_out.p;
     a.lay = h->lay;
     a.scratch_stride = (long long)(h->S - 1) * h->K * 2 * h->NT;
@@ -440,7 +454,7 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     h->last_launches = 2;
     if (grad) {
         ContractArgs ca{};
-        ca.P = h->d_P.p; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
+        ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
         ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
         ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
         launch_contract(ca, B, st);
