@@ -202,11 +202,15 @@ struct Ring {
     }
 };
 
-template <int K, bool GRAD, int NTMAX, int MINB>
-__global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
+// NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
+// immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
+template <int K, bool GRAD, int NTC, int MINB>
+__global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int C = a.C;
+    const int NT = NTC ? NTC : (int)blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.C, nsteps = a.nsteps;
+    const size_t Lpad = (size_t)a.Lpad;
     const int c = warp % C, pb = warp / C;
     double2* st = reinterpret_cast<double2*>(smem_raw);                       // [D][K][2][NT]
     double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * 2 * NT);  // [K][NT]
@@ -217,38 +221,61 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
     ring.src = nullptr;
     ring.nrec = 0;
     const int tpat = (NT / (32 * C)) * 32 * K;
+    const int SS = K * 2 * NT;  // double2 per stack slot / scratch row
 
-    double2* sc = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
-    int8_t* dl = a.dscr + (size_t)blockIdx.x * a.dscr_stride;
+    double2* const stt = st + tid;
+    double2* const sct = a.scratch + (size_t)blockIdx.x * a.scratch_stride + tid;
+    int8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
 
-#define ST(slot, j, h) st[(((slot)*K + (j)) * 2 + (h)) * NT + tid]
-#define SC(row, j, h) sc[(((size_t)(row)*K + (j)) * 2 + (h)) * NT + tid]
-#define DL(row, j) dl[((size_t)(row)*K + (j)) * NT + tid]
+#define ST(slot, j, h) stt[(slot)*SS + ((j)*2 + (h)) * NT]
+#define SC(row, j, h) sct[(size_t)(row)*SS + ((j)*2 + (h)) * NT]
+#define DL(row, j) dlt[(size_t)(row) * (K * NT) + (j)*NT]
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
         const double* prm = a.params + (size_t)d * a.lay.stride;
         const int pat0 = tile * tpat + pb * 32 * K + lane;  // pattern of sub-index j: pat0 + 32 j
         const uint8_t* tipp = a.tips + pat0;
-        const size_t stream_off = ((size_t)d * C + c) * a.nsteps * kRecBytes;
+        const size_t stream_off = ((size_t)d * C + c) * nsteps * kRecBytes;
 
         // -------------------------------------------------------------- post-order
         int etot[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) etot[j] = 0;
         int so_last = 0;
-        ring.start(a.spost + stream_off, a.nsteps);
-        for (int i = 0; i < a.nsteps; ++i) {
-            ring.advance(i);
+        ring.start(a.spost + stream_off, nsteps);
+        ring.advance(0);
+        unsigned ca[K], cb[K];  // tip codes of the current step's children (prefetched one step ahead)
+        {
+            const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(0));
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                ca[j] = n0.z < 0 ? tipp[(size_t)n0.x * Lpad + 32 * j] : 0u;
+                cb[j] = n0.w < 0 ? tipp[(size_t)n0.y * Lpad + 32 * j] : 0u;
+            }
+        }
+        for (int i = 0; i < nsteps; ++i) {
+            if (i) ring.advance(i);
             const unsigned char* rec = ring.rec(i);
             const int4 s0 = *reinterpret_cast<const int4*>(rec);
             const int so = *reinterpret_cast<const int*>(rec + 16);
-            const int na = s0.x, nb = s0.y, sa = s0.z, sb = s0.w;
+            const int sa = s0.z, sb = s0.w;
             so_last = so;
-            if (i + 2 < a.nsteps) {  // tip codes of step i+2 -> L2
+            unsigned nca[K], ncb[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) nca[j] = ncb[j] = 0u;
+            if (i + 1 < nsteps) {  // tip codes of step i+1 -> registers
+                const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(i + 1));
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (n0.z < 0) nca[j] = tipp[(size_t)n0.x * Lpad + 32 * j];
+                    if (n0.w < 0) ncb[j] = tipp[(size_t)n0.y * Lpad + 32 * j];
+                }
+            }
+            if (i + 2 < nsteps) {  // tip codes of step i+2 -> L2
                 const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(i + 2));
-                if (n0.z < 0) prefetch_l2(tipp + (size_t)n0.x * a.Lpad);
-                if (n0.w < 0) prefetch_l2(tipp + (size_t)n0.y * a.Lpad);
+                if (n0.z < 0) prefetch_l2(tipp + (size_t)n0.x * Lpad);
+                if (n0.w < 0) prefetch_l2(tipp + (size_t)n0.y * Lpad);
             }
             double M[16], ma[K][4];
             lds_mat(rec + 64, M);
@@ -256,7 +283,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
             for (int j = 0; j < K; ++j) {
                 double p[4];
                 if (sa < 0) {
-                    tip_vec(tipp[(size_t)na * a.Lpad + 32 * j], p);
+                    tip_vec(ca[j], p);
                 } else {
                     double2 u = ST(sa, j, 0), v = ST(sa, j, 1);
                     p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
@@ -268,7 +295,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
             for (int j = 0; j < K; ++j) {
                 double p[4], mb[4];
                 if (sb < 0) {
-                    tip_vec(tipp[(size_t)nb * a.Lpad + 32 * j], p);
+                    tip_vec(cb[j], p);
                 } else {
                     double2 u = ST(sb, j, 0), v = ST(sb, j, 1);
                     p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
@@ -295,6 +322,8 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
                     DL(i, j) = (int8_t)kexp;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; }
         }
 
         // -------------------------------------------------------------- root: site likelihoods
@@ -302,7 +331,7 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
         double pi[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
-        if (GRAD) ring.start(a.spre + stream_off, a.nsteps);  // overlaps the root exchange
+        if (GRAD) ring.start(a.spre + stream_off, nsteps);  // overlaps the root exchange
         double proot[K][4], rdot[K];
         __syncthreads();  // previous item's readers of ex_* are done
 #pragma unroll
@@ -340,62 +369,85 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
             ring.advance(0);
+            unsigned dcur[K];  // rescale exponent of the current step's node (prefetched)
             {
-                const int sroot = *reinterpret_cast<const int*>(ring.rec(0) + 12);
+                const unsigned char* r0 = ring.rec(0);
+                const int4 n0 = *reinterpret_cast<const int4*>(r0);
+                const int4 n1 = *reinterpret_cast<const int4*>(r0 + 16);
+                const int nrowb = *reinterpret_cast<const int*>(r0 + 32);
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     const double f = fac[j] * ps_c;
-                    ST(sroot, j, 0) = make_double2(pi[0] * f, pi[1] * f);
-                    ST(sroot, j, 1) = make_double2(pi[2] * f, pi[3] * f);
+                    ST(n0.w, j, 0) = make_double2(pi[0] * f, pi[1] * f);
+                    ST(n0.w, j, 1) = make_double2(pi[2] * f, pi[3] * f);
+                    ca[j] = n1.w < 0 ? tipp[(size_t)n0.y * Lpad + 32 * j] : 0u;
+                    cb[j] = nrowb < 0 ? tipp[(size_t)n0.z * Lpad + 32 * j] : 0u;
+                    dcur[j] = (unsigned)DL(n1.z, j);
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
-            for (int i = 0; i < a.nsteps; ++i) {
+            for (int i = 0; i < nsteps; ++i) {
                 if (i) ring.advance(i);
                 const unsigned char* rec = ring.rec(i);
                 const int4 s0 = *reinterpret_cast<const int4*>(rec);
                 const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);
                 const int rowb = *reinterpret_cast<const int*>(rec + 32);
                 const int na = s0.y, nb = s0.z, sn = s0.w;
-                const int sa = s1.x, sb = s1.y, rown = s1.z, rowa = s1.w;
-                if (i + 2 < a.nsteps) {  // operands of step i+2 -> L2
-                    const unsigned char* nr = ring.rec(i + 2);
+                const int sa = s1.x, sb = s1.y, rowa = s1.w;
+                double pa[K][4], pbv[K][4];
+#pragma unroll
+                for (int j = 0; j < K; ++j) {  // issue this step's operand loads first
+                    if (rowa >= 0) {
+                        double2 u = SC(rowa, j, 0), v = SC(rowa, j, 1);
+                        pa[j][0] = u.x; pa[j][1] = u.y; pa[j][2] = v.x; pa[j][3] = v.y;
+                    }
+                    if (rowb >= 0) {
+                        double2 u = SC(rowb, j, 0), v = SC(rowb, j, 1);
+                        pbv[j][0] = u.x; pbv[j][1] = u.y; pbv[j][2] = v.x; pbv[j][3] = v.y;
+                    }
+                }
+                unsigned nca[K], ncb[K], ndl[K];
+#pragma unroll
+                for (int j = 0; j < K; ++j) nca[j] = ncb[j] = ndl[j] = 0u;
+                if (i + 1 < nsteps) {  // byte operands of step i+1 -> registers
+                    const unsigned char* nr = ring.rec(i + 1);
                     const int4 n0 = *reinterpret_cast<const int4*>(nr);
                     const int4 n1 = *reinterpret_cast<const int4*>(nr + 16);
                     const int nrowb = *reinterpret_cast<const int*>(nr + 32);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        if (n1.w < 0) {
-                            if (j == 0) prefetch_l2(tipp + (size_t)n0.y * a.Lpad);
-                        } else {
+                        if (n1.w < 0) nca[j] = tipp[(size_t)n0.y * Lpad + 32 * j];
+                        if (nrowb < 0) ncb[j] = tipp[(size_t)n0.z * Lpad + 32 * j];
+                        ndl[j] = (unsigned)DL(n1.z, j);
+                    }
+                }
+                if (i + 2 < nsteps) {  // operand lines of step i+2 -> L2
+                    const unsigned char* nr = ring.rec(i + 2);
+                    const int4 n0 = *reinterpret_cast<const int4*>(nr);
+                    const int4 n1 = *reinterpret_cast<const int4*>(nr + 16);
+                    const int nrowb = *reinterpret_cast<const int*>(nr + 32);
+                    if (n1.w < 0) prefetch_l2(tipp + (size_t)n0.y * Lpad);
+                    if (nrowb < 0) prefetch_l2(tipp + (size_t)n0.z * Lpad);
+                    prefetch_l2(&DL(n1.z, 0));
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (n1.w >= 0) {
                             prefetch_l2(&SC(n1.w, j, 0));
                             prefetch_l2(&SC(n1.w, j, 1));
                         }
-                        if (nrowb < 0) {
-                            if (j == 0) prefetch_l2(tipp + (size_t)n0.z * a.Lpad);
-                        } else {
+                        if (nrowb >= 0) {
                             prefetch_l2(&SC(nrowb, j, 0));
                             prefetch_l2(&SC(nrowb, j, 1));
                         }
                     }
                 }
-                double qn[K][4], pa[K][4], pbv[K][4];
+                double qn[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (rowa < 0) {
-                        tip_vec(tipp[(size_t)na * a.Lpad + 32 * j], pa[j]);
-                    } else {
-                        double2 u = SC(rowa, j, 0), v = SC(rowa, j, 1);
-                        pa[j][0] = u.x; pa[j][1] = u.y; pa[j][2] = v.x; pa[j][3] = v.y;
-                    }
-                    if (rowb < 0) {
-                        tip_vec(tipp[(size_t)nb * a.Lpad + 32 * j], pbv[j]);
-                    } else {
-                        double2 u = SC(rowb, j, 0), v = SC(rowb, j, 1);
-                        pbv[j][0] = u.x; pbv[j][1] = u.y; pbv[j][2] = v.x; pbv[j][3] = v.y;
-                    }
+                    if (rowa < 0) tip_vec(ca[j], pa[j]);
+                    if (rowb < 0) tip_vec(cb[j], pbv[j]);
                     double2 u = ST(sn, j, 0), v = ST(sn, j, 1);
-                    const double f = pow2_64k((int)DL(rown, j));
+                    const double f = pow2_64k((int)dcur[j]);
                     qn[j][0] = u.x * f; qn[j][1] = u.y * f; qn[j][2] = v.x * f; qn[j][3] = v.y * f;
                 }
                 double MA[16], MB[16], ma[K][4], mb[K][4];
@@ -450,6 +502,8 @@ __global__ void __launch_bounds__(NTMAX, MINB) sweep_kernel(const SweepArgs a) {
                     }
                     warp_reduce16_atomic(G, Gd + (size_t)nb * C * 16, lane);
                 }
+#pragma unroll
+                for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; dcur[j] = ndl[j]; }
             }
         }
 
@@ -585,17 +639,17 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
 // launch plumbing
 // ------------------------------------------------------------------------------------------
 
-// CTA-size / register classes per K: small CTAs (one pattern block of 4 categories) get more
-// registers per thread; the 512-thread class covers many categories or several pattern blocks.
+// Specialised for 128-thread CTAs (one pattern block of 4 categories, the common case) with a
+// per-K register budget; any other CTA size takes the generic variant.
 template <int K> struct Cfg;
-template <> struct Cfg<1> { static constexpr int small_nt = 128, small_minb = 4; };
-template <> struct Cfg<2> { static constexpr int small_nt = 128, small_minb = 3; };
-template <> struct Cfg<4> { static constexpr int small_nt = 128, small_minb = 1; };
+template <> struct Cfg<1> { static constexpr int minb = 4; };
+template <> struct Cfg<2> { static constexpr int minb = 3; };
+template <> struct Cfg<4> { static constexpr int minb = 1; };
 
 template <int K, bool GRAD>
 auto pick_kernel(int nthreads) -> void (*)(const SweepArgs) {
-    if (nthreads <= Cfg<K>::small_nt) return sweep_kernel<K, GRAD, Cfg<K>::small_nt, Cfg<K>::small_minb>;
-    return sweep_kernel<K, GRAD, 512, 1>;
+    if (nthreads == 128) return sweep_kernel<K, GRAD, 128, Cfg<K>::minb>;
+    return sweep_kernel<K, GRAD, 0, 1>;
 }
 
 template <int K, bool GRAD>
