@@ -124,7 +124,7 @@ def run_reference(args):
     from oracle import oracle as O
     cores = O.num_threads()
     prob, draws = build_problem()
-    sample_L = 256 * cores
+    sample_L = min(L_PATTERNS, 2048 * cores)
     sl = slice(0, sample_L)
     bl, rates, freqs, rs, ps = draws
 
@@ -162,7 +162,7 @@ def cpu_baseline_sample(prob, draws):
     bl, rates, freqs, rs, ps = draws
     cores = O.num_threads()
     out = {}
-    for label, nt, nL in (("1 thread", 1, 1024), ("all threads", cores, 512 * cores)):
+    for label, nt, nL in (("1 thread", 1, 16384), ("all threads", cores, min(L_PATTERNS, 8192 * cores))):
         sl = slice(0, nL)
         O.loglik_grad(prob.peel, prob.tipmask[:, :64], prob.weights[:64], O.GTR, bl[0], rates[0], freqs[0], rs[0],
                       ps[0], dp_eigen=True, nthreads=nt)  # warm
@@ -196,7 +196,8 @@ def run_ours(args):
     prob, draws = build_problem(world, rank)
     bl, rates, freqs, rs, ps = draws
     lik = lk.TreeLikelihood(prob.peel, prob.tipmask, prob.weights, model="GTR", categories=N_CAT, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)   # a real (non-default) stream shared by the library,
+    torch.cuda.set_stream(stream)              # the timing events and NCCL
     lik.set_stream(stream.cuda_stream)
     if args.k or args.pb:
         lik.set_tiling(args.k, args.pb)

@@ -197,8 +197,9 @@ struct Ring {
             __syncwarp();
         }
     }
+    // chunk n occupies buffer n % kRecBufs, so record i sits in slot i % (kRecChunk * kRecBufs)
     __device__ __forceinline__ const unsigned char* rec(int i) const {
-        return buf + (((i / kRecChunk) % kRecBufs) * kRecChunk + (i % kRecChunk)) * kRecBytes;
+        return buf + (i % (kRecChunk * kRecBufs)) * kRecBytes;
     }
 };
 
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 
     double2* const stt = st + tid;
     double2* const sct = a.scratch + (size_t)blockIdx.x * a.scratch_stride + tid;
-    int8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
+    uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
 
 #define ST(slot, j, h) stt[(slot)*SS + ((j)*2 + (h)) * NT]
 #define SC(row, j, h) sct[(size_t)(row)*SS + ((j)*2 + (h)) * NT]
@@ -304,22 +305,25 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int s = 0; s < 4; ++s) p[s] = ma[j][s] * mb[s];
                 // per-(pattern,category) rescaling by exact powers of 2^64
-                const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
                 int kexp = 0;
-                if (mx < 2.938735877055719e-39 /* 2^-128 */ && mx > 0.0) {
-                    const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;  // floor(log2 mx), -1023 if subnormal
-                    kexp = min((-e) >> 6, 15);
-                    const double f = pow2_64k(kexp);
+                constexpr double kTiny = 2.938735877055719e-39;  // 2^-128
+                if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {  // rare
+                    const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+                    if (mx > 0.0) {
+                        const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;  // floor(log2 mx), -1023 if subnormal
+                        kexp = min((-e) >> 6, 15);
+                        const double f = pow2_64k(kexp);
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) p[s] *= f;
-                    etot[j] += kexp;
+                        for (int s = 0; s < 4; ++s) p[s] *= f;
+                        etot[j] += kexp;
+                    }
                 }
                 ST(so, j, 0) = make_double2(p[0], p[1]);
                 ST(so, j, 1) = make_double2(p[2], p[3]);
                 if (GRAD) {
                     SC(i, j, 0) = make_double2(p[0], p[1]);
                     SC(i, j, 1) = make_double2(p[2], p[3]);
-                    DL(i, j) = (int8_t)kexp;
+                    DL(i, j) = (uint8_t)kexp;
                 }
             }
 #pragma unroll
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     ST(n0.w, j, 1) = make_double2(pi[2] * f, pi[3] * f);
                     ca[j] = n1.w < 0 ? tipp[(size_t)n0.y * Lpad + 32 * j] : 0u;
                     cb[j] = nrowb < 0 ? tipp[(size_t)n0.z * Lpad + 32 * j] : 0u;
-                    dcur[j] = (unsigned)DL(n1.z, j);
+                    dcur[j] = DL(n1.z, j);
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     for (int j = 0; j < K; ++j) {
                         if (n1.w < 0) nca[j] = tipp[(size_t)n0.y * Lpad + 32 * j];
                         if (nrowb < 0) ncb[j] = tipp[(size_t)n0.z * Lpad + 32 * j];
-                        ndl[j] = (unsigned)DL(n1.z, j);
+                        ndl[j] = DL(n1.z, j);
                     }
                 }
                 if (i + 2 < nsteps) {  // operand lines of step i+2 -> L2

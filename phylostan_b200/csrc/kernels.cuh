@@ -66,7 +66,7 @@ struct SweepArgs {
     const unsigned char* spost;
     const unsigned char* spre;
     double2* scratch;         // [grid][S-1][K][2][NT]
-    int8_t* dscr;             // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
+    uint8_t* dscr;            // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
     double* G;                // [B][nn][C][16]
     double* out;              // [B][nout]
     ParamLayout lay;

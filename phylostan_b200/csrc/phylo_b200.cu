@@ -98,7 +98,7 @@ struct phylo_b200_ctx {
     DevBuf<unsigned char> d_spost, d_spre;  // per-(draw, category) instruction streams
     DevBuf<int32_t> d_node_pos;
     DevBuf<double2> d_scratch;
-    DevBuf<int8_t> d_dscr;
+    DevBuf<uint8_t> d_dscr;
     PinnedBuf<double> h_params, h_out;
 
     // tiling (user request, 0 = auto) and the resolved launch shape of the last run
