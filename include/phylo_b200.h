@@ -158,6 +158,16 @@ PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 PHYLO_B200_API int phylo_b200_plan(int S, const int32_t *peel, int32_t *post, int32_t *pre, int32_t *depth);
 PHYLO_B200_API int phylo_b200_derive(int model, int flags, const double *subst, const double *freqs, double *out);
 
+/*
+ * Process-wide default handle.  The reference bakes tree + alignment into the generated eigen.hpp
+ * (eigen/eigen.j2:19-38), so its Stan-facing pruning_loglik(blens) takes no data argument.  Here the
+ * host program (phylostan run) creates the handle once and publishes it; the Stan shim
+ * (phylostan_b200/stan/phylo_b200_stan.hpp), compiled into the model and linked against this
+ * library, fetches it.  set_default does not take ownership.
+ */
+PHYLO_B200_API int phylo_b200_set_default(phylo_b200_handle h);
+PHYLO_B200_API phylo_b200_handle phylo_b200_get_default(void);
+
 PHYLO_B200_API const char *phylo_b200_last_error(void);
 PHYLO_B200_API int phylo_b200_abi_version(void);
 

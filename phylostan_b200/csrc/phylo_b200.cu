@@ -313,6 +313,10 @@ extern "C" {
 
 int phylo_b200_abi_version(void) { return PHYLO_B200_ABI_VERSION; }
 
+static phylo_b200_handle g_default = nullptr;
+int phylo_b200_set_default(phylo_b200_handle h) { g_default = h; return 0; }
+phylo_b200_handle phylo_b200_get_default(void) { return g_default; }
+
 const char* phylo_b200_last_error(void) { return g_err.c_str(); }
 
 int phylo_b200_create(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
@@ -325,7 +329,10 @@ int phylo_b200_create_tipdata(phylo_b200_handle* out, int S, int L, int C, int m
     return create_common(out, S, L, C, model, flags, peel, nullptr, tipdata, weights, device);
 }
 
-void phylo_b200_destroy(phylo_b200_handle h) { delete h; }
+void phylo_b200_destroy(phylo_b200_handle h) {
+    if (h && h == g_default) g_default = nullptr;
+    delete h;
+}
 
 int phylo_b200_bcount(phylo_b200_handle h) { return h ? h->bcount : PHYLO_B200_EINVAL; }
 int phylo_b200_nsubst(phylo_b200_handle h) { return h ? h->nsubst : PHYLO_B200_EINVAL; }

@@ -53,7 +53,9 @@ def lib() -> ctypes.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(phylostan_b200 has no CPU fallback)")
-    L = ctypes.CDLL(LIB_PATH)
+    # RTLD_GLOBAL: a pystan-compiled model that includes phylo_b200_stan.hpp binds its undefined
+    # phylo_b200_* symbols to this copy at load time (pystan has no link-argument hook)
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
     i, vp = ctypes.c_int, ctypes.c_void_p
     ip, bp = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
     L.phylo_b200_create.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, bp, _dp, i]
@@ -75,6 +77,8 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_info.argtypes = [vp, i]
     L.phylo_b200_info.restype = ctypes.c_longlong
     L.phylo_b200_last_error.restype = ctypes.c_char_p
+    L.phylo_b200_set_default.argtypes = [vp]
+    L.phylo_b200_get_default.restype = vp
     L.phylo_b200_plan.argtypes = [i, ip, ip, ip, ip]
     L.phylo_b200_derive.argtypes = [i, i, _dp, _dp, _dp]
     _lib = L
@@ -304,6 +308,7 @@ def set_default(lik: TreeLikelihood) -> None:
     rendering eigen/eigen.j2 into eigen.hpp (eigen/util.py:104-109)."""
     global _default
     _default = lik
+    lib().phylo_b200_set_default(lik._h if lik is not None else None)
 
 
 def pruning_loglik(blens: Sequence[float]) -> float:

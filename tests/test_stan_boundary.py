@@ -1,0 +1,137 @@
+"""The Stan-facing boundary: generator switch (CPU, against the reference generator when mounted and
+against committed golden programs) and the C++ shim (compiled against stub Stan/Eigen headers; run on
+the GPU against the oracle)."""
+import importlib.util
+import json
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from phylostan_b200 import generate as G
+
+from conftest import GOLDEN, ROOT
+
+REF_GEN = "/root/reference/phylostan/generate_script.py"
+sys.path.insert(0, GOLDEN)
+from make_golden_stan import CASES, params  # noqa: E402
+
+
+def _ref():
+    if not os.path.exists(REF_GEN):
+        pytest.skip("reference tree not mounted (GPU box)")
+    spec = importlib.util.spec_from_file_location("ref_generate_script", REF_GEN)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_generator_switch_matches_golden(name):
+    got = G.get_model(CASES[name], _ref())
+    assert got == open(os.path.join(GOLDEN, name + "-external.stan")).read()
+
+
+def test_golden_programs_call_the_external_function_once():
+    for name in CASES:
+        s = open(os.path.join(GOLDEN, name + "-external.stan")).read()
+        assert s.count("phylo_loglik(") == 2                      # declaration + one call (eigen/example.stan:3,134)
+        assert "real phylo_loglik(vector blens, vector subst, vector freqs, vector rs, vector ps);" in s
+        assert "target += phylo_loglik(blens," in s
+        for gone in ("calculate_", "pmats", "partials[", "probs["):
+            assert gone not in s
+        # everything upstream of the likelihood stays in Stan
+        assert "~ exponential" in s or "~ dirichlet" in s
+
+
+def test_generator_switch_all_model_variants():
+    ref = _ref()
+    for kw in (dict(model="HKY"), dict(model="JC69", categories=1), dict(model="JC69", categories=4),
+               dict(clock=None, coalescent=None, heterochronous=False, estimate_rate=False),
+               dict(invariant=True, categories=1), dict(heterogeneity="discrete"), dict(clock="ucln"),
+               dict(coalescent="skygrid", grid=10, cutoff=50.0), dict(coalescent="skyride")):
+        p = params(**kw)
+        s = G.get_model(p, ref)
+        base = ref.get_model(p)
+        assert s.count("phylo_loglik(") == 2 and "pmats" not in s
+        # only the likelihood changed: priors / transforms / Jacobian lines all survive
+        for line in base.split("\n"):
+            t = line.strip()
+            if t.startswith(("heights ~", "rates ~", "freqs ~", "kappa ~", "wshape ~", "target += log(heights")):
+                assert line in s
+    with pytest.raises(ValueError):
+        G.get_model(params(geo=True), ref)
+
+
+def test_stan_model_kwargs_point_at_existing_files():
+    kw = G.stan_model_kwargs()
+    assert kw["allow_undefined"] is True
+    for inc in kw["includes"]:
+        assert any(os.path.exists(os.path.join(d, inc)) for d in kw["include_dirs"])
+    assert any(os.path.exists(os.path.join(d, "phylo_b200.h")) for d in kw["include_dirs"])
+
+
+# ------------------------------------------------------------------------------- C++ shim
+
+def _build_driver(tmp_path):
+    exe = str(tmp_path / "shim_driver")
+    libdir = os.path.join(ROOT, "phylostan_b200", "csrc")
+    cmd = ["g++", "-std=c++14", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "stubs"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "phylostan_b200", "stan"),
+           os.path.join(ROOT, "tests", "stubs", "shim_driver.cpp"), "-o", exe, "-L" + libdir, "-lphylo_b200",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_shim_compiles_as_cxx14_and_fails_loudly_without_handle(tmp_path):
+    """pystan compiles models with --std=c++14 (eigen/eigen.py:86); no published handle -> runtime_error."""
+    exe = _build_driver(tmp_path)
+    r = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True)
+    assert r.returncode == 0 and "no default handle" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,model,rooted,C", [("fluA", 1, True, 4), ("DS1", 2, False, 4), ("HCV", 0, True, 1)])
+def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, model, rooted, C):
+    from oracle import oracle as O
+    from phylostan_b200 import encode as E
+    d = datasets[name]
+    S, L = d["tipmask"].shape
+    rng = np.random.default_rng(17)
+    bcount = 2 * S - 2 if rooted else 2 * S - 3
+    bl = rng.exponential(0.05, bcount) + 1e-4
+    subst = {0: np.zeros(0), 1: np.array([4.4]), 2: rng.dirichlet(np.ones(6))}[model]
+    fr = rng.dirichlet(np.ones(4) * 5) if model else np.full(4, 0.25)
+    rs = E.weibull_rates(0.5, C) if C > 1 else np.ones(1)
+    ps = rng.dirichlet(np.ones(C) * 3) if C > 1 else np.ones(1)
+    path = tmp_path / "problem.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("5i", S, L, C, model, 1 if rooted else 0))
+        f.write(np.ascontiguousarray(d["peel"], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(d["tipmask"], dtype=np.uint8).tobytes())
+        for a in (d["weights"], bl, subst, fr, rs, ps):
+            f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    exe = _build_driver(tmp_path)
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps, rooted=rooted)
+    for key in ("value_double", "value_var"):
+        assert abs(got[key] - want.logp) <= 1e-10 * abs(want.logp)
+    tol = lambda g, w: np.max(np.abs(np.asarray(g) - w) / np.maximum(1, np.abs(w)), initial=0) <= 1e-8
+    assert tol(got["blens"], want.grad_blens) and tol(got["blens_mixed"], want.grad_blens)
+    assert tol(got["rs"], want.grad_rs) and tol(got["ps"], want.grad_ps)
+    nfree = bcount + len(subst) + 4 + 2 * C
+    assert got["n_operands"] == nfree and got["n_operands_mixed"] == bcount   # operands.size() == grads.size()
+    if model:
+        assert tol(got["subst"], want.grad_subst) and tol(got["freqs"], want.grad_freqs)
+    else:
+        # the reference's own operator: pruning_loglik(blens) (eigen/prune_stan.hpp:9-17)
+        assert abs(got["pruning_loglik"] - want.logp) <= 1e-10 * abs(want.logp)
+        assert tol(got["pruning_grad"], want.grad_blens)
+        assert got["domain_error"] is True
