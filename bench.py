@@ -182,7 +182,7 @@ def cpu_baseline_sample(prob, draws):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from phylostan_b200 import likelihood as lk
+    from phylostan_b200 import likelihood as lk, sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,14 +203,9 @@ def run_ours(args):
         lik.set_tiling(args.k, args.pb)
     B = N_DRAWS
 
-    class _Out:  # device result block [B, nout] as a torch tensor (for the NCCL all-reduce)
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 2}
-
     lik.upload(bl, rates, freqs, rs, ps)
     lik.run(B, True)
-    ptr, ld = lik.device_out()
-    out_t = torch.as_tensor(_Out(ptr, (B, ld)), device=f"cuda:{local}")
+    out_t = sharded.device_out_tensor(lik, B)   # device result block [B, nout] for the NCCL all-reduce
 
     def barrier():
         if world > 1:
