@@ -283,7 +283,8 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_evaluation")
+            traffic = traffic * B if traffic else None   # one launch sweeps B draws
         cpu = cpu_baseline_sample(prob, draws) if world == 1 and not args.no_cpu else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -148,10 +148,11 @@ PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 /*
  * Host-only hooks (no GPU needed), used by the CPU test-suite:
  *   plan    the depth-first traversal plan derived from `peel` (replaces the run-time std::map
- *           bookkeeping of eigen/eigen.j2:82-108): post gets S-1 rows of 8 int32
- *           (a, b, slot_a, slot_b, slot_out, node, 0, 0), pre gets S-1 rows of 12 int32
- *           (node, a, b, slot_node, slot_a, slot_b, row_node, row_a, row_b, 0, 0, 0),
- *           depth[2] = {post-order, pre-order} shared-memory stack depth.
+ *           bookkeeping of eigen/eigen.j2:82-108).  The most recent vector stays in registers (TOS);
+ *           operand sources are -1 tip, -2 TOS, >= 0 shared-memory slot.  post gets S-1 rows of 8 int32
+ *           (a, b, src_a, src_b, spill_slot, node, 0, 0), pre gets S-1 rows of 12 int32
+ *           (node, a, b, src_node, dst_b, a_internal, row_node, row_a, row_b, 0, 0, 0),
+ *           depth[2] = {post-order, pre-order} shared-memory stack depth (TOS excluded).
  *   derive  the per-draw model algebra of generate_script.py:799-825 / 855-881:
  *           out = [pi 4 | lambda 4 | m1 16 | m2 16 | Q 16 | X_theta ntheta*16]; returns ntheta.
  */

@@ -1,6 +1,10 @@
 // kernels.cu -- see kernels.cuh.  sm_100a only.
 #include "kernels.cuh"
 
+#ifndef PHYLO_ABLATE
+#define PHYLO_ABLATE 0  // profiling experiments only: 1 = skip the cross-lane G reduction
+#endif
+
 namespace phylo {
 
 namespace {
@@ -53,6 +57,15 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (8+4+2+1+1 = 16 shuffles instead of 80), then one 128-byte RED per warp: even lane 2i adds
 // entry i to dst[i].
 __device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], double* __restrict__ dst, int lane) {
+#if PHYLO_ABLATE >= 1
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t += v[i];
+        if (t == 1.2345e-300) atomicAdd(dst, t);
+        return;
+    }
+#endif
     double a8[8], a4[4], a2[2], a1;
     bool hi = lane & 16;
 #pragma unroll
@@ -81,9 +94,8 @@ __device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], doub
     if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), a1);
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -95,7 +107,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: instruction streams (step descriptor + both transition matrices per record)
+// K1: instruction streams (step record = descriptor + both transition matrices)
 // ------------------------------------------------------------------------------------------
 
 __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const ParamLayout& lay, int node, int c,
@@ -128,6 +140,8 @@ __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const Pa
         }
 }
 
+// Descriptors carry ready-made offsets (tip rows, stack slots, scratch rows, G blocks) so the sweep
+// does no index arithmetic beyond pointer + offset.
 __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     const int per = a.lay.C * a.nsteps;
     const int total = 2 * a.B * per;
@@ -142,14 +156,37 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     int4* rd = reinterpret_cast<int4*>(rec);
     if (which == 0) {
         const int4* s = reinterpret_cast<const int4*>(a.post + i);
-        const int4 s0 = __ldg(s), s1 = __ldg(s + 1);
+        const int4 s0 = __ldg(s);           // a, b, src_a, src_b
+        const int spill = __ldg(reinterpret_cast<const int*>(s + 1));
         na = s0.x; nb = s0.y;
-        rd[0] = s0; rd[1] = s1; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
+        PostRec pr;
+        pr.tip_a = (long long)na * a.Lpad;
+        pr.tip_b = (long long)nb * a.Lpad;
+        pr.off_a = s0.z >= 0 ? s0.z * a.SS : 0;
+        pr.off_b = s0.w >= 0 ? s0.w * a.SS : 0;
+        pr.off_spill = spill >= 0 ? spill * a.SS : -1;
+        pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
+                   (s0.w == kSrcTos ? 8 : 0);
+        const int4* src = reinterpret_cast<const int4*>(&pr);
+        rd[0] = src[0]; rd[1] = src[1]; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
     } else {
         const int4* s = reinterpret_cast<const int4*>(a.pre + i);
-        const int4 s0 = __ldg(s), s1 = __ldg(s + 1), s2 = __ldg(s + 2);
+        const int4 s0 = __ldg(s), s1 = __ldg(s + 1);  // node a b src_n | dst_b a_internal rown rowa
+        const int rowb = __ldg(reinterpret_cast<const int*>(s + 2));
         na = s0.y; nb = s0.z;
-        rd[0] = s0; rd[1] = s1; rd[2] = s2; rd[3] = make_int4(0, 0, 0, 0);
+        PreRec pr;
+        pr.tip_a = (long long)na * a.Lpad;
+        pr.tip_b = (long long)nb * a.Lpad;
+        pr.row_a = s1.w >= 0 ? s1.w * a.SS : -1;
+        pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
+        pr.dl_n = s1.z * a.KNT;
+        pr.off_n = s0.w >= 0 ? s0.w * a.SS : -1;
+        pr.off_b = s1.x >= 0 ? s1.x * a.SS : -1;
+        pr.g_a = na * a.lay.C * 16;
+        pr.g_b = nb * a.lay.C * 16;
+        pr.flags = s1.y ? 1 : 0;
+        const int4* src = reinterpret_cast<const int4*>(&pr);
+        rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
     }
     double m[16];
     double2* o2 = reinterpret_cast<double2*>(rec + 64);
@@ -165,41 +202,56 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
 // K2/K3: fused depth-first post-order + pre-order sweep
 // ------------------------------------------------------------------------------------------
 
-// Per-warp record ring fed by cp.async: chunk n lives in buffer n % kRecBufs.
+// Per-warp record ring fed by cp.async.  Records sit contiguously: record i lives in ring slot
+// i % 6 (3 chunks of 2 records); chunk n+2 is issued when chunk n starts being consumed.
 struct Ring {
-    unsigned char* buf;         // this warp's ring in shared memory
-    const unsigned char* src;   // this warp's stream in global memory
-    int nrec;                   // records in the stream
+    unsigned char* buf;          // this warp's ring (generic pointer into shared memory)
+    unsigned sbuf;               // the same as a 32-bit shared-window address
+    const unsigned char* next;   // next chunk to fetch from the stream
+    int remaining;               // records not yet issued
+    int wchunk;                  // chunk buffer (0..2) the next issue writes
+    int slot;                    // ring slot (0..5) of the current record
     int lane;
 
-    __device__ __forceinline__ void issue(int chunk) const {
-        const int first = chunk * kRecChunk;
-        const int bytes = min(kRecChunk, nrec - first) * kRecBytes;  // <= 0 past the end
-        unsigned char* dst = buf + (chunk % kRecBufs) * (kRecChunk * kRecBytes);
-        const unsigned char* s = src + (size_t)first * kRecBytes;
-        for (int off = lane * 16; off < bytes; off += 512) cp_async16(dst + off, s + off);
+    __device__ __forceinline__ void issue() {
+        const unsigned dst = sbuf + wchunk * (kRecChunk * kRecBytes) + lane * 16;
+        const unsigned char* s = next + lane * 16;
+        if (remaining >= 2) {
+            cp_async16(dst, s);
+            if (lane < 8) cp_async16(dst + 512, s + 512);
+        } else if (remaining == 1 && lane < kRecBytes / 16) {
+            cp_async16(dst, s);
+        }
         cp_async_commit();  // always commit: keeps the group count uniform
+        next += kRecChunk * kRecBytes;
+        remaining -= kRecChunk;
+        wchunk = wchunk == kRecBufs - 1 ? 0 : wchunk + 1;
     }
+    // afterwards records 0, 1 (and 2, 3 once step 0 ran) are in flight; call step(0) before reading
     __device__ __forceinline__ void start(const unsigned char* stream, int n) {
-        src = stream;
-        nrec = n;
         cp_async_wait<0>();
         __syncwarp();
-        issue(0);
-        issue(1);
+        next = stream;
+        remaining = n;
+        wchunk = 0;
+        slot = 0;
+        issue();
+        issue();
     }
-    // call at the top of step i: afterwards the records of steps i .. i+kRecChunk (at least) are readable
-    __device__ __forceinline__ void advance(int i) const {
-        if ((i % kRecChunk) == 0) {
-            __syncwarp();  // every lane is done with the buffer about to be overwritten
-            issue(i / kRecChunk + 2);
+    // top of step i: afterwards the records of steps i, i+1, i+2 are readable
+    __device__ __forceinline__ void step(int i) {
+        if (i) slot = slot == kRecChunk * kRecBufs - 1 ? 0 : slot + 1;
+        if ((i & 1) == 0) {
+            __syncwarp();  // every lane is done with the chunk about to be overwritten
+            issue();
             cp_async_wait<1>();
             __syncwarp();
         }
     }
-    // chunk n occupies buffer n % kRecBufs, so record i sits in slot i % (kRecChunk * kRecBufs)
-    __device__ __forceinline__ const unsigned char* rec(int i) const {
-        return buf + (i % (kRecChunk * kRecBufs)) * kRecBytes;
+    __device__ __forceinline__ const unsigned char* rec(int ahead) const {
+        int s = slot + ahead;
+        if (s >= kRecChunk * kRecBufs) s -= kRecChunk * kRecBufs;
+        return buf + s * kRecBytes;
     }
 };
 
@@ -211,16 +263,18 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     const int NT = NTC ? NTC : (int)blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.C, nsteps = a.nsteps;
-    const size_t Lpad = (size_t)a.Lpad;
     const int c = warp % C, pb = warp / C;
     double2* st = reinterpret_cast<double2*>(smem_raw);                       // [D][K][2][NT]
     double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * 2 * NT);  // [K][NT]
     int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                        // [K][NT]
     Ring ring;
     ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * kRingBytesPerWarp;
+    ring.sbuf = (unsigned)__cvta_generic_to_shared(ring.buf);
     ring.lane = lane;
-    ring.src = nullptr;
-    ring.nrec = 0;
+    ring.next = nullptr;
+    ring.remaining = 0;
+    ring.wchunk = 0;
+    ring.slot = 0;
     const int tpat = (NT / (32 * C)) * 32 * K;
     const int SS = K * 2 * NT;  // double2 per stack slot / scratch row
 
@@ -228,9 +282,9 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     double2* const sct = a.scratch + (size_t)blockIdx.x * a.scratch_stride + tid;
     uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
 
-#define ST(slot, j, h) stt[(slot)*SS + ((j)*2 + (h)) * NT]
-#define SC(row, j, h) sct[(size_t)(row)*SS + ((j)*2 + (h)) * NT]
-#define DL(row, j) dlt[(size_t)(row) * (K * NT) + (j)*NT]
+    // element (j, h) of the stack entry / scratch row at element offset `off`
+#define ST(off, j, h) stt[(off) + ((j)*2 + (h)) * NT]
+#define SC(off, j, h) sct[(off) + ((j)*2 + (h)) * NT]
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
@@ -241,69 +295,96 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 
         // -------------------------------------------------------------- post-order
         int etot[K];
+        double tos[K][4];  // most recent partial (top of stack), kept in registers
 #pragma unroll
-        for (int j = 0; j < K; ++j) etot[j] = 0;
-        int so_last = 0;
+        for (int j = 0; j < K; ++j) {
+            etot[j] = 0;
+            tos[j][0] = tos[j][1] = tos[j][2] = tos[j][3] = 0.0;
+        }
         ring.start(a.spost + stream_off, nsteps);
-        ring.advance(0);
+        ring.step(0);
         unsigned ca[K], cb[K];  // tip codes of the current step's children (prefetched one step ahead)
         {
-            const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(0));
+            const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
+            const int fl = r0->flags;
+            const long long ta = r0->tip_a, tb = r0->tip_b;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                ca[j] = n0.z < 0 ? tipp[(size_t)n0.x * Lpad + 32 * j] : 0u;
-                cb[j] = n0.w < 0 ? tipp[(size_t)n0.y * Lpad + 32 * j] : 0u;
+                ca[j] = (fl & 1) ? tipp[ta + 32 * j] : 0u;
+                cb[j] = (fl & 2) ? tipp[tb + 32 * j] : 0u;
             }
         }
+        double2* srow = sct;  // scratch row of step i
+        uint8_t* drow = dlt;
         for (int i = 0; i < nsteps; ++i) {
-            if (i) ring.advance(i);
-            const unsigned char* rec = ring.rec(i);
-            const int4 s0 = *reinterpret_cast<const int4*>(rec);
-            const int so = *reinterpret_cast<const int*>(rec + 16);
-            const int sa = s0.z, sb = s0.w;
-            so_last = so;
+            if (i) ring.step(i);
+            const unsigned char* rec = ring.rec(0);
+            const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
+            const int fl = s1.w;
             unsigned nca[K], ncb[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) nca[j] = ncb[j] = 0u;
             if (i + 1 < nsteps) {  // tip codes of step i+1 -> registers
-                const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(i + 1));
+                const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(1));
+                const int nf = n->flags;
+                if (nf & 1) {
+                    const uint8_t* p = tipp + n->tip_a;
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    if (n0.z < 0) nca[j] = tipp[(size_t)n0.x * Lpad + 32 * j];
-                    if (n0.w < 0) ncb[j] = tipp[(size_t)n0.y * Lpad + 32 * j];
+                    for (int j = 0; j < K; ++j) nca[j] = p[32 * j];
+                }
+                if (nf & 2) {
+                    const uint8_t* p = tipp + n->tip_b;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) ncb[j] = p[32 * j];
                 }
             }
             if (i + 2 < nsteps) {  // tip codes of step i+2 -> L2
-                const int4 n0 = *reinterpret_cast<const int4*>(ring.rec(i + 2));
-                if (n0.z < 0) prefetch_l2(tipp + (size_t)n0.x * Lpad);
-                if (n0.w < 0) prefetch_l2(tipp + (size_t)n0.y * Lpad);
+                const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(2));
+                const int nf = n->flags;
+                if (nf & 1) prefetch_l2(tipp + n->tip_a);
+                if (nf & 2) prefetch_l2(tipp + n->tip_b);
             }
             double M[16], ma[K][4];
             lds_mat(rec + 64, M);
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 double p[4];
-                if (sa < 0) {
+                if (fl & 1) {
                     tip_vec(ca[j], p);
+                } else if (fl & 4) {
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
                 } else {
-                    double2 u = ST(sa, j, 0), v = ST(sa, j, 1);
+                    double2 u = ST(s1.x, j, 0), v = ST(s1.x, j, 1);
                     p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
                 }
                 matvec(M, p, ma[j]);
             }
             lds_mat(rec + 192, M);
+            double mb[K][4];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                double p[4], mb[4];
-                if (sb < 0) {
+                double p[4];
+                if (fl & 2) {
                     tip_vec(cb[j], p);
-                } else {
-                    double2 u = ST(sb, j, 0), v = ST(sb, j, 1);
-                    p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
-                }
-                matvec(M, p, mb);
+                } else {  // an internal second child is always the previous step's result
 #pragma unroll
-                for (int s = 0; s < 4; ++s) p[s] = ma[j][s] * mb[s];
+                    for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
+                }
+                matvec(M, p, mb[j]);
+            }
+            if (s1.z >= 0) {  // the previous result still waits for its sibling: park it in shared memory
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    ST(s1.z, j, 0) = make_double2(tos[j][0], tos[j][1]);
+                    ST(s1.z, j, 1) = make_double2(tos[j][2], tos[j][3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                double p[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) p[s] = ma[j][s] * mb[j][s];
                 // per-(pattern,category) rescaling by exact powers of 2^64
                 int kexp = 0;
                 constexpr double kTiny = 2.938735877055719e-39;  // 2^-128
@@ -318,14 +399,16 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         etot[j] += kexp;
                     }
                 }
-                ST(so, j, 0) = make_double2(p[0], p[1]);
-                ST(so, j, 1) = make_double2(p[2], p[3]);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) tos[j][s] = p[s];
                 if (GRAD) {
-                    SC(i, j, 0) = make_double2(p[0], p[1]);
-                    SC(i, j, 1) = make_double2(p[2], p[3]);
-                    DL(i, j) = (uint8_t)kexp;
+                    srow[(j * 2) * NT] = make_double2(p[0], p[1]);
+                    srow[(j * 2 + 1) * NT] = make_double2(p[2], p[3]);
+                    drow[j * NT] = (uint8_t)kexp;
                 }
             }
+            srow += SS;
+            drow += K * NT;
 #pragma unroll
             for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; }
         }
@@ -336,19 +419,16 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
         for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
         if (GRAD) ring.start(a.spre + stream_off, nsteps);  // overlaps the root exchange
-        double proot[K][4], rdot[K];
+        double rdot[K];
         __syncthreads();  // previous item's readers of ex_* are done
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            double2 u = ST(so_last, j, 0), v = ST(so_last, j, 1);
-            proot[j][0] = u.x; proot[j][1] = u.y; proot[j][2] = v.x; proot[j][3] = v.y;
-            rdot[j] = pi[0] * u.x + pi[1] * u.y + pi[2] * v.x + pi[3] * v.y;  // generate_script.py:1007
+            rdot[j] = pi[0] * tos[j][0] + pi[1] * tos[j][1] + pi[2] * tos[j][2] + pi[3] * tos[j][3];  // generate_script.py:1007
             ex_l[j * NT + tid] = ps_c * rdot[j];
             ex_e[j * NT + tid] = etot[j];
         }
         __syncthreads();
         double acc_logl = 0.0, acc_dps = 0.0, acc_dpi[4] = {0.0, 0.0, 0.0, 0.0};
-        double fac[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int base = j * NT + pb * C * 32 + lane;
@@ -362,42 +442,40 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             const double w = a.weights[pat0 + 32 * j];
             if (c == 0) acc_logl += w * (log(sum) - (double)emin * 44.361419555836500 /* 64 ln 2 */);
             const int de = etot[j] - emin;
-            fac[j] = de > 15 ? 0.0 : w * pow2_64k(-de) / sum;
+            const double fac = de > 15 ? 0.0 : w * pow2_64k(-de) / sum;
             if (GRAD) {
-                acc_dps += fac[j] * rdot[j];
+                acc_dps += fac * rdot[j];
+                const double f = fac * ps_c;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) acc_dpi[s] += fac[j] * ps_c * proot[j][s];
+                for (int s = 0; s < 4; ++s) {
+                    acc_dpi[s] += f * tos[j][s];
+                    tos[j][s] = pi[s] * f;  // q(root): weight, 1/L and the category share folded in
+                }
             }
         }
 
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
-            ring.advance(0);
+            ring.step(0);
             unsigned dcur[K];  // rescale exponent of the current step's node (prefetched)
             {
-                const unsigned char* r0 = ring.rec(0);
-                const int4 n0 = *reinterpret_cast<const int4*>(r0);
-                const int4 n1 = *reinterpret_cast<const int4*>(r0 + 16);
-                const int nrowb = *reinterpret_cast<const int*>(r0 + 32);
+                const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
+                const long long ta = r0->tip_a, tb = r0->tip_b;
+                const int ra = r0->row_a, rb = r0->row_b, dn = r0->dl_n;
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    const double f = fac[j] * ps_c;
-                    ST(n0.w, j, 0) = make_double2(pi[0] * f, pi[1] * f);
-                    ST(n0.w, j, 1) = make_double2(pi[2] * f, pi[3] * f);
-                    ca[j] = n1.w < 0 ? tipp[(size_t)n0.y * Lpad + 32 * j] : 0u;
-                    cb[j] = nrowb < 0 ? tipp[(size_t)n0.z * Lpad + 32 * j] : 0u;
-                    dcur[j] = DL(n1.z, j);
+                    ca[j] = ra < 0 ? tipp[ta + 32 * j] : 0u;
+                    cb[j] = rb < 0 ? tipp[tb + 32 * j] : 0u;
+                    dcur[j] = dlt[dn + j * NT];
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
             for (int i = 0; i < nsteps; ++i) {
-                if (i) ring.advance(i);
-                const unsigned char* rec = ring.rec(i);
-                const int4 s0 = *reinterpret_cast<const int4*>(rec);
-                const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);
-                const int rowb = *reinterpret_cast<const int*>(rec + 32);
-                const int na = s0.y, nb = s0.z, sn = s0.w;
-                const int sa = s1.x, sb = s1.y, rowa = s1.w;
+                if (i) ring.step(i);
+                const unsigned char* rec = ring.rec(0);
+                const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
+                const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
+                const int rowa = s1.x, rowb = s1.y;
                 double pa[K][4], pbv[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {  // issue this step's operand loads first
@@ -414,97 +492,111 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int j = 0; j < K; ++j) nca[j] = ncb[j] = ndl[j] = 0u;
                 if (i + 1 < nsteps) {  // byte operands of step i+1 -> registers
-                    const unsigned char* nr = ring.rec(i + 1);
-                    const int4 n0 = *reinterpret_cast<const int4*>(nr);
-                    const int4 n1 = *reinterpret_cast<const int4*>(nr + 16);
-                    const int nrowb = *reinterpret_cast<const int*>(nr + 32);
+                    const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(1));
+                    const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
+                    if (n1.x < 0) {
+                        const uint8_t* p = tipp + n->tip_a;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        if (n1.w < 0) nca[j] = tipp[(size_t)n0.y * Lpad + 32 * j];
-                        if (nrowb < 0) ncb[j] = tipp[(size_t)n0.z * Lpad + 32 * j];
-                        ndl[j] = DL(n1.z, j);
+                        for (int j = 0; j < K; ++j) nca[j] = p[32 * j];
                     }
+                    if (n1.y < 0) {
+                        const uint8_t* p = tipp + n->tip_b;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) ncb[j] = p[32 * j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) ndl[j] = dlt[n1.z + j * NT];
                 }
                 if (i + 2 < nsteps) {  // operand lines of step i+2 -> L2
-                    const unsigned char* nr = ring.rec(i + 2);
-                    const int4 n0 = *reinterpret_cast<const int4*>(nr);
-                    const int4 n1 = *reinterpret_cast<const int4*>(nr + 16);
-                    const int nrowb = *reinterpret_cast<const int*>(nr + 32);
-                    if (n1.w < 0) prefetch_l2(tipp + (size_t)n0.y * Lpad);
-                    if (nrowb < 0) prefetch_l2(tipp + (size_t)n0.z * Lpad);
-                    prefetch_l2(&DL(n1.z, 0));
+                    const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
+                    const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
+                    if (n1.x < 0) {
+                        prefetch_l2(tipp + n->tip_a);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        if (n1.w >= 0) {
-                            prefetch_l2(&SC(n1.w, j, 0));
-                            prefetch_l2(&SC(n1.w, j, 1));
-                        }
-                        if (nrowb >= 0) {
-                            prefetch_l2(&SC(nrowb, j, 0));
-                            prefetch_l2(&SC(nrowb, j, 1));
+                        for (int j = 0; j < K; ++j) {
+                            prefetch_l2(&SC(n1.x, j, 0));
+                            prefetch_l2(&SC(n1.x, j, 1));
                         }
                     }
+                    if (n1.y < 0) {
+                        prefetch_l2(tipp + n->tip_b);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            prefetch_l2(&SC(n1.y, j, 0));
+                            prefetch_l2(&SC(n1.y, j, 1));
+                        }
+                    }
+                    prefetch_l2(dlt + n1.z);
                 }
                 double qn[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (rowa < 0) tip_vec(ca[j], pa[j]);
                     if (rowb < 0) tip_vec(cb[j], pbv[j]);
-                    double2 u = ST(sn, j, 0), v = ST(sn, j, 1);
                     const double f = pow2_64k((int)dcur[j]);
-                    qn[j][0] = u.x * f; qn[j][1] = u.y * f; qn[j][2] = v.x * f; qn[j][3] = v.y * f;
-                }
-                double MA[16], MB[16], ma[K][4], mb[K][4];
-                lds_mat(rec + 64, MA);
-                lds_mat(rec + 192, MB);
+                    if (s1.w < 0) {  // q(node) is the previous step's first child: still in registers
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    matvec(MA, pa[j], ma[j]);
-                    matvec(MB, pbv[j], mb[j]);
+                        for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s] * f;
+                    } else {
+                        double2 u = ST(s1.w, j, 0), v = ST(s1.w, j, 1);
+                        qn[j][0] = u.x * f; qn[j][1] = u.y * f; qn[j][2] = v.x * f; qn[j][3] = v.y * f;
+                    }
                 }
-                {   // child a: A_a = q_n o (P_b p_b)   (eq (7), eigen.j2:148)
-                    double G[16];
+                // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
+                double Aa[K][4], Ab[K][4];
+                {
+                    double M[16], m[4];
+                    lds_mat(rec + 64, M);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        matvec(M, pa[j], m);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
+                    }
+                }
+                {   // child b: q(b) waits in shared memory
+                    double M[16], m[4], G[16];
+                    lds_mat(rec + 192, M);
 #pragma unroll
                     for (int x = 0; x < 16; ++x) G[x] = 0.0;
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        double A[4];
+                        matvec(M, pbv[j], m);
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) A[s] = qn[j][s] * mb[j][s];
+                        for (int s = 0; s < 4; ++s) Aa[j][s] = qn[j][s] * m[s];
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(A[x], pa[j][y], G[4 * x + y]);
-                        if (sa >= 0) {
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
+                        if (s2.x >= 0) {
                             double q[4];
-                            matTvec(MA, A, q);  // eigen.j2:151-153
-                            ST(sa, j, 0) = make_double2(q[0], q[1]);
-                            ST(sa, j, 1) = make_double2(q[2], q[3]);
+                            matTvec(M, Ab[j], q);  // eigen.j2:151-153
+                            ST(s2.x, j, 0) = make_double2(q[0], q[1]);
+                            ST(s2.x, j, 1) = make_double2(q[2], q[3]);
                         }
                     }
-                    warp_reduce16_atomic(G, Gd + (size_t)na * C * 16, lane);
+                    warp_reduce16_atomic(G, Gd + s2.z, lane);
                 }
-                {   // child b
+                {   // child a: processed next when internal, so q(a) stays in the TOS registers
                     double G[16];
 #pragma unroll
                     for (int x = 0; x < 16; ++x) G[x] = 0.0;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        double A[4];
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) A[s] = qn[j][s] * ma[j][s];
+                    for (int j = 0; j < K; ++j)
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(A[x], pbv[j][y], G[4 * x + y]);
-                        if (sb >= 0) {
-                            double q[4];
-                            matTvec(MB, A, q);
-                            ST(sb, j, 0) = make_double2(q[0], q[1]);
-                            ST(sb, j, 1) = make_double2(q[2], q[3]);
-                        }
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
+                    if (s2.w & 1) {
+                        double M[16];
+                        asm volatile("" ::: "memory");  // reload P_a instead of keeping 32 registers alive
+                        lds_mat(rec + 64, M);
+#pragma unroll
+                        for (int j = 0; j < K; ++j) matTvec(M, Aa[j], tos[j]);
                     }
-                    warp_reduce16_atomic(G, Gd + (size_t)nb * C * 16, lane);
+                    warp_reduce16_atomic(G, Gd + s2.y, lane);
                 }
 #pragma unroll
                 for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; dcur[j] = ndl[j]; }
@@ -531,7 +623,6 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     cp_async_wait<0>();
 #undef ST
 #undef SC
-#undef DL
 }
 
 // ------------------------------------------------------------------------------------------
@@ -647,7 +738,10 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
 // per-K register budget; any other CTA size takes the generic variant.
 template <int K> struct Cfg;
 template <> struct Cfg<1> { static constexpr int minb = 4; };
-template <> struct Cfg<2> { static constexpr int minb = 3; };
+#ifndef PHYLO_MINB2
+#define PHYLO_MINB2 3
+#endif
+template <> struct Cfg<2> { static constexpr int minb = PHYLO_MINB2; };
 template <> struct Cfg<4> { static constexpr int minb = 1; };
 
 template <int K, bool GRAD>

@@ -49,6 +49,25 @@ struct ParamLayout {
     int stride;
 };
 
+// Record descriptors (first 64 bytes of a record).  Offsets are ready to add to a base pointer:
+// stack / scratch offsets in double2 elements (slot or row times SS = K*2*NT), tip rows in bytes.
+struct alignas(16) PostRec {
+    long long tip_a, tip_b;   // byte offset of the child's tip-code row (node * Lpad)
+    int32_t off_a, off_b;     // shared-memory stack offset of the child's partial (when it sits in a slot)
+    int32_t off_spill;        // stack offset that receives the previous TOS first, or -1
+    int32_t flags;            // 1: a is a tip, 2: b is a tip, 4: a is the TOS, 8: b is the TOS
+};
+struct alignas(16) PreRec {
+    long long tip_a, tip_b;   // byte offset of the child's tip-code row
+    int32_t row_a, row_b;     // scratch offset of the child's partial, or -1 (tip)
+    int32_t dl_n;             // byte offset of this node's rescale exponents
+    int32_t off_n;            // stack offset of q(node), or -1 when it is the TOS
+    int32_t off_b;            // stack offset receiving q(b), or -1 (b is a tip)
+    int32_t g_a, g_b;         // offsets (doubles) of the children's 4x4 statistics blocks
+    int32_t flags;            // 1: a is internal -> q(a) becomes the TOS
+};
+static_assert(sizeof(PostRec) == 32 && sizeof(PreRec) == 48, "record descriptors must fit the 64-byte header");
+
 struct StreamArgs {
     const double* params;     // [B][stride]
     const PostStep* post;     // [S-1]
@@ -57,6 +76,7 @@ struct StreamArgs {
     unsigned char* spre;      // [B][C][S-1][kRecBytes]
     ParamLayout lay;
     int nsteps, bcount, jc_closed, B;
+    int Lpad, SS, KNT;        // tile geometry baked into the descriptors
 };
 
 struct SweepArgs {

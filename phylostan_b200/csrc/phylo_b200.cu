@@ -442,6 +442,7 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     sa.params = h->d_params.p; sa.post = h->d_post.p; sa.pre = h->d_pre.p;
     sa.spost = h->d_spost.p; sa.spre = h->d_spre.p; sa.lay = h->lay;
     sa.nsteps = h->S - 1; sa.bcount = h->bcount; sa.jc_closed = h->jc_closed; sa.B = B;
+    sa.Lpad = h->Lpad; sa.SS = h->K * 2 * h->NT; sa.KNT = h->K * h->NT;
     launch_stream(sa, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));

@@ -3,8 +3,6 @@
 #include "plan.hpp"
 
 #include <algorithm>
-#include <functional>
-#include <queue>
 
 namespace phylo {
 
@@ -59,7 +57,7 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
         }
     }
 
-    // ---- post-order: iterative DFS, larger stack need first -------------------------------
+    // ---- post-order: iterative DFS, larger stack need first; TOS in registers ---------------
     std::vector<int> row_of(nn, -1);
     {
         struct Frame { int node, stage; int first, second; };
@@ -75,7 +73,8 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
             first = a;
             second = b;
         };
-        int sp = 0, maxsp = 0;
+        int sp = 0, maxsp = 0;      // shared-memory entries
+        bool tos_live = false;      // a finished partial sits in the TOS registers
         Frame f0{plan.root, 0, 0, 0};
         order(plan.root, f0.first, f0.second);
         st.push_back(f0);
@@ -95,14 +94,23 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
             ps.a = f.first;
             ps.b = f.second;
             ps.node = f.node;
-            bool ia = ps.a >= S, ib = ps.b >= S;
-            if (ia && ib) {
-                ps.sa = sp - 2; ps.sb = sp - 1; ps.so = sp - 2; sp -= 1;
-            } else if (ia) {
-                ps.sa = sp - 1; ps.sb = -1; ps.so = sp - 1;
-            } else {
-                ps.sa = ps.sb = -1; ps.so = sp; sp += 1;
+            ps.spill = -1;
+            const bool ia = ps.a >= S, ib = ps.b >= S;
+            if (ia && ib) {  // b was computed last (TOS); a waits on top of the shared-memory stack
+                ps.src_a = sp - 1;
+                ps.src_b = kSrcTos;
+                sp -= 1;
+            } else if (ia) {  // the only internal child was computed by the previous step
+                ps.src_a = kSrcTos;
+                ps.src_b = kSrcTip;
+            } else {  // cherry: whatever is in the TOS still waits for its sibling
+                ps.src_a = ps.src_b = kSrcTip;
+                if (tos_live) {
+                    ps.spill = sp;
+                    sp += 1;
+                }
             }
+            tos_live = true;
             maxsp = std::max(maxsp, sp);
             row_of[f.node] = (int)plan.post.size();
             plan.post.push_back(ps);
@@ -111,39 +119,45 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
         plan.depth_post = maxsp;
     }
 
-    // ---- pre-order: DFS from the root, smaller stack need first, lowest free slot ---------
+    // ---- pre-order: DFS from the root, smaller stack need first; q(first child) stays in TOS ----
     {
-        std::priority_queue<int, std::vector<int>, std::greater<int>> free_slots;
-        int next_slot = 0, maxslot = 0;
-        auto alloc = [&]() {
-            if (!free_slots.empty()) { int s = free_slots.top(); free_slots.pop(); return s; }
-            return next_slot++;
-        };
-        std::vector<std::pair<int, int>> st;  // (node, slot)
-        st.push_back({plan.root, alloc()});
-        maxslot = next_slot;
-        while (!st.empty()) {
-            auto [n, sn] = st.back();
-            st.pop_back();
-            int a = left[n], b = right[n];
+        std::vector<int> pending;  // nodes whose q sits in shared memory, slot = position
+        int maxsp = 0;
+        int cur = plan.root, src = kSrcTos;
+        while (true) {
+            int a = left[cur], b = right[cur];
             bool ia = a >= S, ib = b >= S;
-            if (ia && ib && need_pre[b] < need_pre[a]) std::swap(a, b);  // a descends first
-            else if (!ia && ib) { std::swap(a, b); std::swap(ia, ib); }
-            ia = a >= S; ib = b >= S;
+            if (ia && ib) {
+                if (need_pre[b] < need_pre[a]) std::swap(a, b);  // a descends first
+            } else if (ib) {
+                std::swap(a, b);
+                std::swap(ia, ib);
+            }
             PreStep ps{};
-            ps.node = n; ps.a = a; ps.b = b; ps.sn = sn;
-            ps.rown = row_of[n];
+            ps.node = cur; ps.a = a; ps.b = b; ps.src_n = src;
+            ps.a_internal = ia ? 1 : 0;
+            ps.rown = row_of[cur];
             ps.rowa = ia ? row_of[a] : -1;
             ps.rowb = ib ? row_of[b] : -1;
-            free_slots.push(sn);  // q(node) is in registers before the children are written
-            ps.sa = ia ? alloc() : -1;
-            ps.sb = ib ? alloc() : -1;
-            maxslot = std::max(maxslot, next_slot);
-            if (ib) st.push_back({b, ps.sb});
-            if (ia) st.push_back({a, ps.sa});
+            ps.dst_b = -1;
+            if (ib) {
+                ps.dst_b = (int)pending.size();
+                pending.push_back(b);
+                maxsp = std::max(maxsp, (int)pending.size());
+            }
             plan.pre.push_back(ps);
+            if (ia) {
+                cur = a;
+                src = kSrcTos;
+            } else if (!pending.empty()) {
+                cur = pending.back();
+                pending.pop_back();
+                src = (int)pending.size();
+            } else {
+                break;
+            }
         }
-        plan.depth_pre = maxslot;
+        plan.depth_pre = maxsp;
     }
     if ((int)plan.post.size() != S - 1 || (int)plan.pre.size() != S - 1) {
         err = "peel does not describe a single binary tree";

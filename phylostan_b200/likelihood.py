@@ -22,7 +22,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libphylo_b200.so")
+LIB_PATH = os.environ.get("PHYLO_B200_LIB", os.path.join(_HERE, "csrc", "libphylo_b200.so"))
 
 JC69, HKY, GTR = 0, 1, 2
 MODELS = {"JC69": JC69, "HKY": HKY, "GTR": GTR}

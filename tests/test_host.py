@@ -112,41 +112,58 @@ def test_weibull_rates_mean_one():
 # ------------------------------------------------------------------------------- traversal plan
 
 def _check_plan(peel):
+    """Replay the plan on an abstract stack machine: TOS register + shared-memory slots."""
     S = peel.shape[0] + 1
     p = lk.plan(peel)
     post, pre = p["post"], p["pre"]
+    TIP, TOS = -1, -2
     children = {int(r[2]) - 1: {int(r[0]) - 1, int(r[1]) - 1} for r in peel}
-    # post-order: every internal node once, children first, slots consistent with a real stack machine
-    done, slot_of, live = set(range(S)), {}, {}
-    for i, (a, b, sa, sb, so, node, _, _) in enumerate(post):
+    # post-order: every internal node once, children first; operands come from where they really are
+    done, row_of, slots, tos = set(range(S)), {}, {}, None
+    for i, (a, b, sa, sb, spill, node, _, _) in enumerate(post):
+        a, b, sa, sb, spill, node = map(int, (a, b, sa, sb, spill, node))
         assert {a, b} == children[node]
-        for ch, s in ((a, sa), (b, sb)):
+        consumed_tos = False
+        for ch, src in ((a, sa), (b, sb)):
             assert ch in done
             if ch < S:
-                assert s == -1
+                assert src == TIP
+            elif src == TOS:
+                assert tos == ch, "the TOS must hold this child"
+                consumed_tos = True
             else:
-                assert live.get(s) == ch, "child partial must still be on the stack"
-                del live[s]
-        assert so not in live
-        live[so] = node
-        assert 0 <= so < p["depth_post"]
+                assert slots.pop(src) == ch and src == len(slots), "slots are used as a stack"
+        if spill >= 0:
+            assert not consumed_tos and tos is not None and spill == len(slots)
+            slots[spill] = tos
+        else:
+            assert consumed_tos or tos is None, "a live TOS may only be overwritten after a spill"
+        assert len(slots) <= p["depth_post"]
+        tos = node
         done.add(node)
-        slot_of[node] = i
-    assert len(done) == 2 * S - 1 and list(live.values()) == [2 * S - 2]
-    # pre-order: parents first, q slots live exactly from producer to consumer
-    qlive = {int(pre[0][3]): 2 * S - 2}
-    seen = set()
-    for node, a, b, sn, sa, sb, rown, rowa, rowb, *_ in pre:
-        assert qlive.pop(sn) == node and {a, b} == children[node]
-        assert rown == slot_of[node]
-        for ch, s, row in ((a, sa, rowa), (b, sb, rowb)):
-            if ch < S:
-                assert s == -1 and row == -1
-            else:
-                assert row == slot_of[ch] and s not in qlive and 0 <= s < p["depth_pre"]
-                qlive[s] = ch
+        row_of[node] = i
+    assert len(done) == 2 * S - 1 and not slots and tos == 2 * S - 2
+    # pre-order: q(node) is where the plan says; q(a) -> TOS, q(b) -> slot
+    qslots, tosq, seen = {}, 2 * S - 2, set()
+    for node, a, b, sn, db, a_int, rown, rowa, rowb, *_ in pre:
+        node, a, b, sn, db, a_int, rown, rowa, rowb = map(int, (node, a, b, sn, db, a_int, rown, rowa, rowb))
+        assert {a, b} == children[node] and rown == row_of[node]
+        if sn == TOS:
+            assert tosq == node
+        else:
+            assert qslots.pop(sn) == node and sn == len(qslots)
+        assert (rowa == row_of[a]) if a >= S else (rowa == -1)
+        assert (rowb == row_of[b]) if b >= S else (rowb == -1)
+        assert a_int == (1 if a >= S else 0)
+        if b >= S:
+            assert a >= S and db == len(qslots)      # b internal implies a internal (a descends first)
+            qslots[db] = b
+        else:
+            assert db == -1
+        assert len(qslots) <= p["depth_pre"]
+        tosq = a if a >= S else None
         seen.add(node)
-    assert not qlive and len(seen) == S - 1
+    assert not qslots and len(seen) == S - 1
     return p
 
 
@@ -154,19 +171,19 @@ def test_plan_on_reference_trees(datasets):
     for name in ("fluA", "DS1", "HCV"):
         p = _check_plan(datasets[name]["peel"])
         S = datasets[name]["peel"].shape[0] + 1
-        assert max(p["depth_post"], p["depth_pre"]) <= int(np.log2(S)) + 1
+        assert max(p["depth_post"], p["depth_pre"]) <= int(np.log2(S))
 
 
 def test_plan_depth_bounds():
     rng = np.random.default_rng(0)
     for S in (2, 3, 5, 64, 257, 1000):
         p = _check_plan(synth.coalescent_peel(S, rng))
-        assert max(p["depth_post"], p["depth_pre"]) <= int(np.log2(S)) + 1   # Strahler bound
+        assert max(p["depth_post"], p["depth_pre"]) <= max(int(np.log2(S)), 0)   # Strahler bound minus the TOS
     # caterpillar: depth 1; perfectly balanced 64 tips: depth log2(64) = 6
     S = 50
     cat = [[1, 2, S + 1]] + [[S + k, k + 2, S + k + 1] for k in range(1, S - 1)]
     p = _check_plan(np.array(cat, dtype=np.int32))
-    assert p["depth_post"] == 1 and p["depth_pre"] == 1
+    assert p["depth_post"] == 0 and p["depth_pre"] == 0      # a caterpillar never leaves the registers
     rows, nxt, level = [], 65, list(range(1, 65))
     while len(level) > 1:
         new = []
@@ -175,7 +192,7 @@ def test_plan_depth_bounds():
         level = new
     # renumber is unnecessary for the plan: children precede parents
     p = _check_plan(np.array(rows, dtype=np.int32))
-    assert p["depth_post"] == 6 and p["depth_pre"] == 6
+    assert p["depth_post"] == 5 and p["depth_pre"] == 5      # log2(64) live vectors, one of them in registers
 
 
 def test_plan_rejects_malformed_peel():
