@@ -402,9 +402,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int s = 0; s < 4; ++s) tos[j][s] = p[s];
                 if (GRAD) {
-                    srow[(j * 2) * NT] = make_double2(p[0], p[1]);
-                    srow[(j * 2 + 1) * NT] = make_double2(p[2], p[3]);
-                    drow[j * NT] = (uint8_t)kexp;
+                    // written once, read once much later: stream through L2 (evict-first)
+                    __stcs(srow + (j * 2) * NT, make_double2(p[0], p[1]));
+                    __stcs(srow + (j * 2 + 1) * NT, make_double2(p[2], p[3]));
+                    __stcs(drow + j * NT, (uint8_t)kexp);
                 }
             }
             srow += SS;
@@ -480,11 +481,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int j = 0; j < K; ++j) {  // issue this step's operand loads first
                     if (rowa >= 0) {
-                        double2 u = SC(rowa, j, 0), v = SC(rowa, j, 1);
+                        double2 u = __ldcs(&SC(rowa, j, 0)), v = __ldcs(&SC(rowa, j, 1));
                         pa[j][0] = u.x; pa[j][1] = u.y; pa[j][2] = v.x; pa[j][3] = v.y;
                     }
                     if (rowb >= 0) {
-                        double2 u = SC(rowb, j, 0), v = SC(rowb, j, 1);
+                        double2 u = __ldcs(&SC(rowb, j, 0)), v = __ldcs(&SC(rowb, j, 1));
                         pbv[j][0] = u.x; pbv[j][1] = u.y; pbv[j][2] = v.x; pbv[j][3] = v.y;
                     }
                 }

@@ -294,3 +294,20 @@ def test_gpu_pulley_principle(datasets):
     assert a.log_P == pytest.approx(b.log_P, rel=1e-12)
     assert a.grad_blens[c1] == pytest.approx(a.grad_blens[c2], rel=1e-8)
     assert b.grad_blens[c1] == pytest.approx(a.grad_blens[c1], rel=1e-8)
+
+
+def test_gpu_config4_tree_size_slice():
+    """BASELINE config 4's tree size (10 000 taxa) on an oracle-sized pattern slice: deep stack
+    (Strahler number ~9), rescaling on every pattern, 160 KB gradient vector."""
+    prob = synth.make_problem(10_000, 96, 4, seed=7, structured=False)
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 1)
+    want = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[0], rates[0], freqs[0], rs[0], ps[0])
+    plain = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[0], rates[0], freqs[0], rs[0], ps[0],
+                          rescale=False, want_grad=False)
+    assert not np.isfinite(plain.logp)          # the reference arithmetic underflows here (SURVEY section 0 item 5)
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        for K in (1, 2, 4):
+            lik.set_tiling(K, 1)
+            got = lik.value_grad(bl[0], rates[0], freqs[0], rs[0], ps[0])
+            assert_parity(got, want)
+        assert lik.info()["stack_depth"] <= 13
