@@ -2,7 +2,7 @@
 #include "kernels.cuh"
 
 #ifndef PHYLO_ABLATE
-#define PHYLO_ABLATE 0  // profiling experiments only: 1 = skip the cross-lane G reduction
+#define PHYLO_ABLATE 0  // profiling experiments only: 1 = skip the cross-lane G reduction, 2 = skip only its RED
 #endif
 
 namespace phylo {
@@ -57,7 +57,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (8+4+2+1+1 = 16 shuffles instead of 80), then one 128-byte RED per warp: even lane 2i adds
 // entry i to dst[i].
 __device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], double* __restrict__ dst, int lane) {
-#if PHYLO_ABLATE >= 1
+#if PHYLO_ABLATE == 1
     {
         double t = 0.0;
 #pragma unroll
@@ -91,6 +91,10 @@ __device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], doub
         a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
     a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+#if PHYLO_ABLATE == 2
+    if (a1 == 1.2345e-300) atomicAdd(dst, a1);  // experiment: shuffle reduction without the RED
+    return;
+#endif
     if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), a1);
 }
 
@@ -536,13 +540,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 for (int j = 0; j < K; ++j) {
                     if (rowa < 0) tip_vec(ca[j], pa[j]);
                     if (rowb < 0) tip_vec(cb[j], pbv[j]);
-                    const double f = pow2_64k((int)dcur[j]);
                     if (s1.w < 0) {  // q(node) is the previous step's first child: still in registers
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s] * f;
+                        for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s];
                     } else {
                         double2 u = ST(s1.w, j, 0), v = ST(s1.w, j, 1);
-                        qn[j][0] = u.x * f; qn[j][1] = u.y * f; qn[j][2] = v.x * f; qn[j][3] = v.y * f;
+                        qn[j][0] = u.x; qn[j][1] = u.y; qn[j][2] = v.x; qn[j][3] = v.y;
+                    }
+                    if (dcur[j]) {  // rare: this node was rescaled in the post-order
+                        const double f = pow2_64k((int)dcur[j]);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) qn[j][s] *= f;
                     }
                 }
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
