@@ -112,6 +112,24 @@ PHYLO_B200_API int phylo_b200_eval_batch(phylo_b200_handle h, int B, const doubl
                           double *g_rs, double *g_ps);
 
 /*
+ * Node-height front end for clock trees (replaces the generated Stan loop `heights_to_blens`,
+ * phylostan/generate_script.py:660-679, and its reverse sweep on Stan's tape):
+ *     blens[node] = rate_node * (heights[parent] - heights[node])        internal node
+ *     blens[node] = rate_node * (heights[parent] - lowers[node])         tip (lowers = NULL: 0)
+ * map      int32 [2S-1][2] rows (node, parent) in pre-order, 1-based, row 0 = (root, 0)  (utils.py:84-90)
+ * heights  double [S-1], heights[k] belongs to internal node S+1+k
+ * rates    nrates == 1: strict clock `rate`; nrates == 2S-2: per-branch `substrates[node]`
+ * Returns d logL / d heights [S-1] and d logL / d rates [nrates]; the other outputs as phylo_b200_eval.
+ * Rooted handles only.
+ */
+PHYLO_B200_API int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t *map, const double *heights,
+                                           const double *lowers, const double *rates, int nrates,
+                                           const double *subst, const double *freqs, const double *rs,
+                                           const double *ps, int want_grad, double *logp, double *g_heights,
+                                           double *g_rates, double *g_subst, double *g_freqs, double *g_rs,
+                                           double *g_ps);
+
+/*
  * Split form of eval_batch for callers that keep parameters resident on the device between
  * evaluations (benchmarks, batched drivers, multi-GPU ranks):
  *   upload   host parameters -> device (one H2D copy); also derives the eigen system per draw

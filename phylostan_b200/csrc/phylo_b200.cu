@@ -526,6 +526,43 @@ int phylo_b200_eval(phylo_b200_handle h, const double* blens, const double* subs
                                  g_rs, g_ps);
 }
 
+int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t* map, const double* heights, const double* lowers,
+                            const double* rates, int nrates, const double* subst, const double* freqs,
+                            const double* rs, const double* ps, int want_grad, double* logp, double* g_heights,
+                            double* g_rates, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+    if (!h || !map || !heights || !rates || !logp) return fail(PHYLO_B200_EINVAL, "eval_heights: NULL argument");
+    if (!h->rooted) return fail(PHYLO_B200_EINVAL, "eval_heights needs a rooted (clock) handle");
+    const int S = h->S, nn = h->nn;
+    if (nrates != 1 && nrates != h->bcount) return fail(PHYLO_B200_EINVAL, "eval_heights: nrates must be 1 or 2S-2");
+    std::vector<double> blens(h->bcount, 0.0), gb(h->bcount, 0.0);
+    // generate_script.py:660-679: rows 2..nodeCount of the pre-order map
+    for (int j = 1; j < nn; ++j) {
+        const int node = map[2 * j], par = map[2 * j + 1];
+        if (node < 1 || node >= nn || par <= S || par > nn)
+            return fail(PHYLO_B200_EINVAL, "eval_heights: malformed pre-order map row " + std::to_string(j));
+        const double r = nrates == 1 ? rates[0] : rates[node - 1];
+        const double lo = node > S ? heights[node - S - 1] : (lowers ? lowers[node - 1] : 0.0);
+        blens[node - 1] = r * (heights[par - S - 1] - lo);
+    }
+    int rc = phylo_b200_eval(h, blens.data(), subst, freqs, rs, ps, want_grad, logp, gb.data(), g_subst, g_freqs, g_rs,
+                             g_ps);
+    if (rc || !want_grad) return rc;
+    if (g_heights) std::fill(g_heights, g_heights + (S - 1), 0.0);
+    if (g_rates) std::fill(g_rates, g_rates + nrates, 0.0);
+    for (int j = 1; j < nn; ++j) {
+        const int node = map[2 * j], par = map[2 * j + 1];
+        const double r = nrates == 1 ? rates[0] : rates[node - 1];
+        const double lo = node > S ? heights[node - S - 1] : (lowers ? lowers[node - 1] : 0.0);
+        const double g = gb[node - 1];
+        if (g_heights) {
+            g_heights[par - S - 1] += r * g;
+            if (node > S) g_heights[node - S - 1] -= r * g;
+        }
+        if (g_rates) g_rates[nrates == 1 ? 0 : node - 1] += (heights[par - S - 1] - lo) * g;
+    }
+    return 0;
+}
+
 // Host-only planning hook (no GPU): exercised by the CPU test-suite.
 // post/pre receive S-1 rows of 8 / 12 int32 (the PostStep / PreStep fields); depth[2] = {post, pre}.
 int phylo_b200_plan(int S, const int32_t* peel, int32_t* post, int32_t* pre, int32_t* depth) {

@@ -45,19 +45,48 @@ def likelihood_call(params) -> str:
     return "\ttarget += phylo_loglik(blens, {}, freqs, {});\n".format(subst, site)
 
 
-def externalize(script: str, params, generate_script=None) -> str:
-    """Rewrite a program produced by the reference's ``get_model(params)``."""
+DECLARATION_HEIGHTS = ("\treal phylo_loglik_heights(real[] heights, real[] rates, int[,] map, real[] lowers, "
+                       "vector subst, vector freqs, vector rs, vector ps);\n")
+AUTOCORRELATED = ("acln", "acg", "ace", "aoup", "hsmrf", "gmrf")  # generate_script.py:1333
+
+
+def heights_call(params) -> str:
+    """Replaces ``heights_to_blens`` (generate_script.py:660-679) AND the likelihood: node heights and
+    rate(s) go straight to the library, which returns d/dheights and d/drate(s)."""
+    subst = {"GTR": "rates", "HKY": "rep_vector(kappa, 1)", "JC69": "rep_vector(0.0, 0)"}[params.model]
+    site = "rs, ps" if is_mixture(params) else "rep_vector(1.0, 1), rep_vector(1.0, 1)"
+    strict = params.clock == "strict" or not params.estimate_rate       # generate_script.py:1336
+    rate = "rep_array(rate, 1)" if strict else "substrates"
+    lowers = "lowers" if params.heterochronous else "rep_array(0.0, 2*S-1)"
+    return "\ttarget += phylo_loglik_heights(heights, {}, map, {}, {}, freqs, {});\n".format(rate, lowers, subst, site)
+
+
+def externalize(script: str, params, generate_script=None, heights: bool = False) -> str:
+    """Rewrite a program produced by the reference's ``get_model(params)``.
+
+    ``heights=True`` (clock trees with a strict or uncorrelated clock) also moves the
+    heights -> branch-length loop into the library."""
     g = _reference_generator(generate_script)
     mixture, clock = is_mixture(params), params.clock is not None
     like = g.likelihood(mixture, clock)
     if like not in script:
         raise ValueError("the program does not contain the reference's likelihood block")
-    script = script.replace(like, likelihood_call(params))
+    if heights:
+        if not clock or params.clock in AUTOCORRELATED:
+            raise ValueError("heights=True needs a clock tree with a strict or uncorrelated clock")
+        strict = params.clock == "strict" or not params.estimate_rate
+        h2b = g.heights_to_blens(params.heterochronous, strict)
+        if h2b not in script:
+            raise ValueError("the program does not contain the reference's heights_to_blens block")
+        script = script.replace(h2b, "").replace(like, heights_call(params))
+        script = script.replace("\tvector [bcount] blens; // branch lengths\n", "")
+    else:
+        script = script.replace(like, likelihood_call(params))
     # the P-matrix function, its call and the arrays only the recursion used
     fn = {"GTR": g.GTR, "HKY": g.HKY, "JC69": g.JC69}[params.model](params.categories, params.invariant)
     if fn not in script:
         raise ValueError("the program does not contain the reference's P-matrix function")
-    script = script.replace(fn, DECLARATION)
+    script = script.replace(fn, DECLARATION_HEIGHTS if heights else DECLARATION)
     kept = []
     for line in script.split("\n"):
         s = line.strip()
@@ -68,12 +97,12 @@ def externalize(script: str, params, generate_script=None) -> str:
     return "\n".join(kept)
 
 
-def get_model(params, generate_script=None) -> str:
+def get_model(params, generate_script=None, heights: bool = False) -> str:
     """Drop-in for ``phylostan.generate_script.get_model`` (:1168-1484) with the GPU likelihood."""
     if getattr(params, "geo", False):
         raise ValueError("the phylogeography model (--geo) is outside the accelerated path")
     g = _reference_generator(generate_script)
-    return externalize(g.get_model(params), params, g)
+    return externalize(g.get_model(params), params, g, heights)
 
 
 def stan_model_kwargs() -> Dict[str, Any]:

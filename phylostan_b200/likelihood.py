@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
         getattr(L, "phylo_b200_" + name).argtypes = [vp]
     L.phylo_b200_eval.argtypes = [vp, _dp, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_eval_batch.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.phylo_b200_eval_heights.argtypes = [vp, ip, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp,
+                                          _dp, _dp]
     L.phylo_b200_upload.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_run.argtypes = [vp, i, i]
     L.phylo_b200_device_out.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i)]
@@ -216,6 +218,25 @@ class TreeLikelihood:
         _check(lib().phylo_b200_eval_batch(self._h, B, _ptr(blens), _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps), 0,
                                            _ptr(logp), None, None, None, None, None))
         return float(logp[0]) if single else logp
+
+    def value_grad_heights(self, map_, heights, rates, lowers=None, subst=None, freqs=None, rs=None, ps=None):
+        """Clock-tree front end (generate_script.py:660-679): node heights + rate(s) in, gradient with
+        respect to heights and rate(s) out.  ``rates``: scalar (strict clock) or [2S-2] substrates."""
+        m = np.ascontiguousarray(map_, dtype=np.int32)
+        hts = _arr(heights, (self.S - 1,))
+        rt = _arr(np.atleast_1d(rates))
+        lo = None if lowers is None else _arr(lowers, (2 * self.S - 1,))
+        subst = None if self.nsubst == 0 else _arr(subst, (self.nsubst,))
+        freqs = None if freqs is None else _arr(freqs, (4,))
+        rs = None if rs is None else _arr(rs, (self.C,))
+        ps = None if ps is None else _arr(ps, (self.C,))
+        logp = np.zeros(1)
+        gh, gr = np.zeros(self.S - 1), np.zeros(rt.size)
+        gs, gf, grs, gps = np.zeros(max(self.nsubst, 1)), np.zeros(4), np.zeros(self.C), np.zeros(self.C)
+        _check(lib().phylo_b200_eval_heights(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(hts),
+                                             _ptr(lo), _ptr(rt), rt.size, _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps),
+                                             1, _ptr(logp), _ptr(gh), _ptr(gr), _ptr(gs), _ptr(gf), _ptr(grs), _ptr(gps)))
+        return float(logp[0]), gh, gr, ValueGrad(float(logp[0]), None, gs[:self.nsubst], gf, grs, gps)
 
     # ------------------------------------------------------------------ resident / split form
     def upload(self, blens, subst=None, freqs=None, rs=None, ps=None) -> int:

@@ -15,6 +15,8 @@
 // Stan declarations (functions block, no body):
 //   real pruning_loglik(vector blens);                                         // eigen/example.stan:3
 //   real phylo_loglik(vector blens, vector subst, vector freqs, vector rs, vector ps);
+//   real phylo_loglik_heights(real[] heights, real[] rates, int[,] map, real[] lowers,
+//                             vector subst, vector freqs, vector rs, vector ps);         // clock trees
 //
 // Unlike eigen.hpp, the tree and alignment are not baked in at compile time: the host program creates
 // a handle (phylo_b200_create) and publishes it with phylo_b200_set_default before sampling starts.
@@ -114,6 +116,70 @@ inline typename stan::return_type<T_bl, T_su, T_fr, T_rs, T_ps>::type phylo_logl
         p::push_operands(subst, gs.data(), ops, grads);
         if (freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);
         p::push_operands(rs, gr.data(), ops, grads);
+        p::push_operands(ps, gp.data(), ops, grads);
+    }
+    return p::finish<R>::go(logp, ops, grads);
+}
+
+// real phylo_loglik_heights(real[] heights, real[] rates, int[,] map, real[] lowers,
+//                           vector subst, vector freqs, vector rs, vector ps)
+// Clock trees: replaces the generated heights -> blens loop (generate_script.py:660-679) together with
+// the likelihood.  rates = {rate} (strict clock) or substrates[2S-2]; lowers = tip dates (2S-1 entries).
+namespace phylo_b200_stan {
+template <typename T>
+inline void gather(const std::vector<T>& v, std::vector<double>& x) {
+    x.reserve(x.size() + v.size());
+    for (size_t i = 0; i < v.size(); ++i) x.push_back(stan::math::value_of(v[i]));
+}
+inline void push_operands(const std::vector<stan::math::var>& v, const double* g, std::vector<stan::math::var>& ops,
+                          std::vector<double>& grads) {
+    for (size_t i = 0; i < v.size(); ++i) {
+        ops.push_back(v[i]);
+        grads.push_back(g[i]);
+    }
+}
+inline void push_operands(const std::vector<double>&, const double*, std::vector<stan::math::var>&,
+                          std::vector<double>&) {}
+}  // namespace phylo_b200_stan
+
+template <typename T_h, typename T_r, typename T_su, typename T_fr, typename T_rs, typename T_ps>
+inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_loglik_heights(
+    const std::vector<T_h>& heights, const std::vector<T_r>& rates, const std::vector<std::vector<int> >& map,
+    const std::vector<double>& lowers, const Eigen::Matrix<T_su, Eigen::Dynamic, 1>& subst,
+    const Eigen::Matrix<T_fr, Eigen::Dynamic, 1>& freqs, const Eigen::Matrix<T_rs, Eigen::Dynamic, 1>& rs,
+    const Eigen::Matrix<T_ps, Eigen::Dynamic, 1>& ps, std::ostream* /*pstream__*/) {
+    namespace p = phylo_b200_stan;
+    typedef typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type R;
+    phylo_b200_handle h = p::handle();
+    const int bcount = phylo_b200_bcount(h), nsubst = phylo_b200_nsubst(h), C = phylo_b200_ncat(h);
+    const int S = bcount / 2 + 1;
+    if ((int)heights.size() != S - 1 || (int)map.size() != 2 * S - 1 || (int)lowers.size() != 2 * S - 1 ||
+        ((int)rates.size() != 1 && (int)rates.size() != bcount) || subst.rows() != nsubst || rs.rows() != C ||
+        ps.rows() != C || (nsubst > 0 && freqs.rows() != 4))
+        throw std::invalid_argument("phylo_loglik_heights: argument sizes do not match the published tree/alignment");
+    std::vector<int32_t> fmap(2 * map.size());
+    for (size_t i = 0; i < map.size(); ++i) {
+        fmap[2 * i] = map[i][0];
+        fmap[2 * i + 1] = map[i][1];
+    }
+    std::vector<double> xh, xr, xs, xf, xrs, xp;
+    p::gather(heights, xh); p::gather(rates, xr); p::gather(subst, xs); p::gather(freqs, xf); p::gather(rs, xrs);
+    p::gather(ps, xp);
+    const int want_grad = !p::is_double<R>::value;
+    double logp = 0.0;
+    std::vector<double> gh(S - 1), gr(rates.size()), gs(nsubst > 0 ? nsubst : 1), gf(4), grs(C), gp(C);
+    p::check(phylo_b200_eval_heights(h, fmap.data(), xh.data(), lowers.data(), xr.data(), (int)xr.size(),
+                                     nsubst ? xs.data() : 0, xf.size() == 4 ? xf.data() : 0, xrs.data(), xp.data(),
+                                     want_grad, &logp, gh.data(), gr.data(), gs.data(), gf.data(), grs.data(),
+                                     gp.data()));
+    std::vector<stan::math::var> ops;
+    std::vector<double> grads;
+    if (want_grad) {
+        p::push_operands(heights, gh.data(), ops, grads);
+        p::push_operands(rates, gr.data(), ops, grads);
+        p::push_operands(subst, gs.data(), ops, grads);
+        if (freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);
+        p::push_operands(rs, grs.data(), ops, grads);
         p::push_operands(ps, gp.data(), ops, grads);
     }
     return p::finish<R>::go(logp, ops, grads);

@@ -97,6 +97,24 @@ int main(int argc, char** argv) {
             std::printf(", \"domain_error\": true");
         }
     }
+    if ((flags & PHYLO_B200_ROOTED) && argc > 2) {  // clock-tree front end: heights + rate through Stan types
+        FILE* g = std::fopen(argv[2], "rb");
+        std::vector<int32_t> map(2 * (2 * S - 1));
+        std::vector<double> hts(S - 1), lowers(2 * S - 1), rate(1);
+        bool ok2 = g && std::fread(map.data(), 4, map.size(), g) == map.size() && std::fread(hts.data(), 8, S - 1, g) == (size_t)(S - 1) &&
+                   std::fread(lowers.data(), 8, 2 * S - 1, g) == (size_t)(2 * S - 1) && std::fread(rate.data(), 8, 1, g) == 1;
+        if (g) std::fclose(g);
+        if (!ok2) return 7;
+        std::vector<std::vector<int> > m2(2 * S - 1, std::vector<int>(2));
+        for (int i = 0; i < 2 * S - 1; ++i) { m2[i][0] = map[2 * i]; m2[i][1] = map[2 * i + 1]; }
+        std::vector<stan::math::var> vh(hts.begin(), hts.end()), vrate(rate.begin(), rate.end());
+        stan::math::var r4 = model_namespace::phylo_loglik_heights(vh, vrate, m2, lowers, make<VecD>(su), make<VecD>(fr),
+                                                                   make<VecD>(rs), make<VecD>(ps), &std::cout);
+        r4.grad();
+        std::printf(", \"heights_value\": %.17g, \"heights_nops\": %d, \"heights_grad\": [", r4.val(), (int)r4.vi_->ops.size());
+        for (int i = 0; i < S - 1; ++i) std::printf("%s%.17g", i ? ", " : "", vh[i].adj());
+        std::printf("], \"rate_grad\": %.17g", vrate[0].adj());
+    }
     std::printf("}\n");
     phylo_b200_destroy(h);
     return 0;

@@ -311,3 +311,61 @@ def test_gpu_config4_tree_size_slice():
             got = lik.value_grad(bl[0], rates[0], freqs[0], rs[0], ps[0])
             assert_parity(got, want)
         assert lik.info()["stack_depth"] <= 13
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_gpu_heights_front_end(datasets, strict):
+    """heights -> blens (generate_script.py:660-679) and its chain rule, heterochronous fluA."""
+    d = datasets["fluA"]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(31)
+    # consistent heights from the tree file: height(node) = distance to the most recent tip
+    blt = d["tree_blens"]
+    parent = {int(r[0]): int(r[1]) for r in d["map"][1:]}
+    depth = {2 * S - 1: 0.0}
+    for node, par in d["map"][1:]:
+        depth[int(node)] = depth[int(par)] + blt[int(node) - 1]
+    top = max(depth.values())
+    height = {k: top - v for k, v in depth.items()}
+    heights = np.array([height[S + 1 + k] for k in range(S - 1)])
+    lowers = np.zeros(2 * S - 1)
+    for k in range(1, S + 1):
+        lowers[k - 1] = height[k]
+    rates = np.array([0.005]) if strict else rng.lognormal(np.log(0.005), 0.3, 2 * S - 2)
+    subst, fr, rs, ps = rng.dirichlet(np.ones(6)), rng.dirichlet(np.ones(4) * 5), E.weibull_rates(0.5, 4), np.full(4, 0.25)
+
+    def blens_of(hts, rts):
+        bl = np.zeros(2 * S - 2)
+        for node, par in d["map"][1:]:
+            node, par = int(node), int(par)
+            r = rts[0] if rts.size == 1 else rts[node - 1]
+            lo = hts[node - S - 1] if node > S else lowers[node - 1]
+            bl[node - 1] = r * (hts[par - S - 1] - lo)
+        return bl
+
+    bl = blens_of(heights, rates)
+    assert bl.min() >= -1e-12
+    bl = np.maximum(bl, 0.0)
+    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, bl, subst, fr, rs, ps)
+    gh, gr = np.zeros(S - 1), np.zeros(rates.size)
+    for node, par in d["map"][1:]:
+        node, par = int(node), int(par)
+        r = rates[0] if strict else rates[node - 1]
+        g = want.grad_blens[node - 1]
+        gh[par - S - 1] += r * g
+        if node > S:
+            gh[node - S - 1] -= r * g
+        lo = heights[node - S - 1] if node > S else lowers[node - 1]
+        gr[0 if strict else node - 1] += (heights[par - S - 1] - lo) * g
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4) as lik:
+        logp, got_h, got_r, rest = lik.value_grad_heights(d["map"], heights, rates, lowers, subst, fr, rs, ps)
+    assert abs(logp - want.logp) <= RTOL_LOGP * abs(want.logp)
+    for g, w in ((got_h, gh), (got_r, gr), (rest.grad_subst, want.grad_subst), (rest.grad_freqs, want.grad_freqs)):
+        assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
+    # independent check of the chain rule: central difference on one height and on the rate
+    k, eps = 17, 1e-6
+    hp, hm = heights.copy(), heights.copy()
+    hp[k] += eps; hm[k] -= eps
+    f = lambda hts, rts: O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, blens_of(hts, rts), subst, fr, rs, ps,
+                                       want_grad=False).logp
+    assert (f(hp, rates) - f(hm, rates)) / (2 * eps) == pytest.approx(got_h[k], rel=1e-5, abs=1e-4)

@@ -66,6 +66,21 @@ def test_generator_switch_all_model_variants():
         G.get_model(params(geo=True), ref)
 
 
+def test_generator_switch_heights_variant():
+    """heights=True also replaces generate_script.py:660-679 (strict / uncorrelated clocks only)."""
+    ref = _ref()
+    for kw in (dict(model="HKY"), dict(clock="ucln"), dict(heterochronous=False, estimate_rate=False)):
+        p = params(**kw)
+        s = G.get_model(p, ref, heights=True)
+        body = s.split("model{")[1]
+        assert s.count("phylo_loglik_heights(") == 2 and "blens" not in body and "pmats" not in s
+        assert ("lowers" in body) == p.heterochronous or "rep_array(0.0, 2*S-1)" in body
+        assert "target += log(heights" in body           # the Jacobian of the height transform stays in Stan
+    for kw in (dict(clock="acln"), dict(clock=None, coalescent=None, heterochronous=False, estimate_rate=False)):
+        with pytest.raises(ValueError):
+            G.get_model(params(**kw), ref, heights=True)
+
+
 def test_stan_model_kwargs_point_at_existing_files():
     kw = G.stan_model_kwargs()
     assert kw["allow_undefined"] is True
@@ -116,10 +131,40 @@ def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, mo
         f.write(np.ascontiguousarray(d["tipmask"], dtype=np.uint8).tobytes())
         for a in (d["weights"], bl, subst, fr, rs, ps):
             f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    args = [str(path)]
+    if rooted:  # clock-tree front end (phylo_loglik_heights): heights consistent with bl at rate 0.004
+        rate = 0.004
+        height = {2 * S - 1: 0.0}
+        depth = {2 * S - 1: 0.0}
+        for node, par in d["map"][1:]:
+            depth[int(node)] = depth[int(par)] + bl[int(node) - 1] / rate
+        top = max(depth.values())
+        hts = np.array([top - depth[S + 1 + k] for k in range(S - 1)])
+        lowers = np.array([top - depth[k] if k <= S else 0.0 for k in range(1, 2 * S)])
+        hpath = tmp_path / "heights.bin"
+        with open(hpath, "wb") as f:
+            f.write(np.ascontiguousarray(d["map"], dtype=np.int32).tobytes())
+            for a in (hts, lowers, np.array([rate])):
+                f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+        args.append(str(hpath))
     exe = _build_driver(tmp_path)
-    r = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    r = subprocess.run([exe] + args, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = json.loads(r.stdout.strip().splitlines()[-1])
+    if rooted:
+        assert abs(got["heights_value"] - got["value_var"]) <= 1e-9 * abs(got["value_var"])
+        gh = np.zeros(S - 1)
+        grate = 0.0
+        wb = np.asarray(got["blens"])
+        for node, par in d["map"][1:]:
+            node, par = int(node), int(par)
+            gh[par - S - 1] += rate * wb[node - 1]
+            if node > S:
+                gh[node - S - 1] -= rate * wb[node - 1]
+            grate += bl[node - 1] / rate * wb[node - 1]
+        np.testing.assert_allclose(got["heights_grad"], gh, rtol=1e-7, atol=1e-6)
+        assert got["rate_grad"] == pytest.approx(grate, rel=1e-7)
+        assert got["heights_nops"] == (S - 1) + 1
     want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps, rooted=rooted)
     for key in ("value_double", "value_var"):
         assert abs(got[key] - want.logp) <= 1e-10 * abs(want.logp)
