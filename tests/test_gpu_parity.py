@@ -369,3 +369,38 @@ def test_gpu_heights_front_end(datasets, strict):
     f = lambda hts, rts: O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, blens_of(hts, rts), subst, fr, rs, ps,
                                        want_grad=False).logp
     assert (f(hp, rates) - f(hm, rates)) / (2 * eps) == pytest.approx(got_h[k], rel=1e-5, abs=1e-4)
+
+
+def _caterpillar(S):
+    rows = [[1, 2, S + 1]] + [[S + k, k + 2, S + k + 1] for k in range(1, S - 1)]
+    return np.array(rows, dtype=np.int32)
+
+
+def _balanced(S):
+    rows, nxt, level = [], S + 1, list(range(1, S + 1))
+    while len(level) > 1:
+        new = []
+        for i in range(0, len(level), 2):
+            rows.append([level[i], level[i + 1], nxt]); new.append(nxt); nxt += 1
+        level = new
+    return np.array(rows, dtype=np.int32)
+
+
+@pytest.mark.parametrize("shape,S", [("caterpillar", 300), ("balanced", 256), ("balanced", 2), ("caterpillar", 3)])
+def test_gpu_extreme_tree_shapes(shape, S):
+    """Stack depth 0 (ladder: everything stays in the TOS registers) up to log2(S)-1 (perfectly
+    balanced); time-structured trees like fluA are close to ladders, species trees to balanced."""
+    peel = _caterpillar(S) if shape == "caterpillar" else _balanced(S)
+    rng = np.random.default_rng(S)
+    L, C = 77, 4
+    tipmask = (1 << rng.integers(0, 4, size=(S, L))).astype(np.uint8)
+    tipmask[rng.random((S, L)) < 0.05] = 0xF
+    weights = 1.0 + rng.poisson(1.0, size=L)
+    bl, subst, fr, rs, ps = random_params(O.GTR, S, True, C, rng, scale=0.3)
+    want = O.loglik_grad(peel, tipmask, weights, O.GTR, bl, subst, fr, rs, ps)
+    with make(peel, tipmask, weights, O.GTR, C) as lik:
+        depth = lik.info()["stack_depth"]
+        assert depth == (0 if shape == "caterpillar" or S == 2 else int(np.log2(S)) - 1)
+        for K in (1, 2, 4):
+            lik.set_tiling(K, 1)
+            assert_parity(lik.value_grad(bl, subst, fr, rs, ps), want)
