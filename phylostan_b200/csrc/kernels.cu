@@ -148,11 +148,12 @@ __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const Pa
 // does no index arithmetic beyond pointer + offset.
 __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     const int per = a.lay.C * a.nsteps;
-    const int total = 2 * a.B * per;
+    const int total = 4 * a.B * per;  // (sweep, draw, category, step, child)
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const int which = idx / (a.B * per);  // 0 post-order stream, 1 pre-order stream
-    const int r = idx - which * a.B * per;
+    const int child = idx & 1, rr = idx >> 1;
+    const int which = rr / (a.B * per);  // 0 post-order stream, 1 pre-order stream
+    const int r = rr - which * a.B * per;
     const int d = r / per, c = (r / a.nsteps) % a.lay.C, i = r % a.nsteps;
     const double* prm = a.params + (size_t)d * a.lay.stride;
     unsigned char* rec = (which ? a.spre : a.spost) + (size_t)r * kRecBytes;
@@ -161,45 +162,47 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     if (which == 0) {
         const int4* s = reinterpret_cast<const int4*>(a.post + i);
         const int4 s0 = __ldg(s);           // a, b, src_a, src_b
-        const int spill = __ldg(reinterpret_cast<const int*>(s + 1));
         na = s0.x; nb = s0.y;
-        PostRec pr;
-        pr.tip_a = (long long)na * a.Lpad;
-        pr.tip_b = (long long)nb * a.Lpad;
-        pr.off_a = s0.z >= 0 ? s0.z * a.SS : 0;
-        pr.off_b = s0.w >= 0 ? s0.w * a.SS : 0;
-        pr.off_spill = spill >= 0 ? spill * a.SS : -1;
-        pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
-                   (s0.w == kSrcTos ? 8 : 0);
-        const int4* src = reinterpret_cast<const int4*>(&pr);
-        rd[0] = src[0]; rd[1] = src[1]; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
+        if (child == 0) {
+            const int spill = __ldg(reinterpret_cast<const int*>(s + 1));
+            PostRec pr;
+            pr.tip_a = (long long)na * a.Lpad;
+            pr.tip_b = (long long)nb * a.Lpad;
+            pr.off_a = s0.z >= 0 ? s0.z * a.SS : 0;
+            pr.off_b = s0.w >= 0 ? s0.w * a.SS : 0;
+            pr.off_spill = spill >= 0 ? spill * a.SS : -1;
+            pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
+                       (s0.w == kSrcTos ? 8 : 0);
+            const int4* src = reinterpret_cast<const int4*>(&pr);
+            rd[0] = src[0]; rd[1] = src[1]; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
+        }
     } else {
         const int4* s = reinterpret_cast<const int4*>(a.pre + i);
-        const int4 s0 = __ldg(s), s1 = __ldg(s + 1);  // node a b src_n | dst_b a_internal rown rowa
-        const int rowb = __ldg(reinterpret_cast<const int*>(s + 2));
+        const int4 s0 = __ldg(s);  // node a b src_n
         na = s0.y; nb = s0.z;
-        PreRec pr;
-        pr.tip_a = (long long)na * a.Lpad;
-        pr.tip_b = (long long)nb * a.Lpad;
-        pr.row_a = s1.w >= 0 ? s1.w * a.SS : -1;
-        pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
-        pr.dl_n = s1.z * a.KNT;
-        pr.off_n = s0.w >= 0 ? s0.w * a.SS : -1;
-        pr.off_b = s1.x >= 0 ? s1.x * a.SS : -1;
-        pr.g_a = na * a.lay.C * 16;
-        pr.g_b = nb * a.lay.C * 16;
-        pr.flags = s1.y ? 1 : 0;
-        const int4* src = reinterpret_cast<const int4*>(&pr);
-        rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
+        if (child == 0) {
+            const int4 s1 = __ldg(s + 1);  // dst_b a_internal rown rowa
+            const int rowb = __ldg(reinterpret_cast<const int*>(s + 2));
+            PreRec pr;
+            pr.tip_a = (long long)na * a.Lpad;
+            pr.tip_b = (long long)nb * a.Lpad;
+            pr.row_a = s1.w >= 0 ? s1.w * a.SS : -1;
+            pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
+            pr.dl_n = s1.z * a.KNT;
+            pr.off_n = s0.w >= 0 ? s0.w * a.SS : -1;
+            pr.off_b = s1.x >= 0 ? s1.x * a.SS : -1;
+            pr.g_a = na * a.lay.C * 16;
+            pr.g_b = nb * a.lay.C * 16;
+            pr.flags = s1.y ? 1 : 0;
+            const int4* src = reinterpret_cast<const int4*>(&pr);
+            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
+        }
     }
     double m[16];
-    double2* o2 = reinterpret_cast<double2*>(rec + 64);
-    pmatrix(prm, a.lay, na, c, a.bcount, a.jc_closed, m);
+    double2* o2 = reinterpret_cast<double2*>(rec + 64 + 128 * child);
+    pmatrix(prm, a.lay, child ? nb : na, c, a.bcount, a.jc_closed, m);
 #pragma unroll
     for (int q = 0; q < 8; ++q) o2[q] = make_double2(m[2 * q], m[2 * q + 1]);
-    pmatrix(prm, a.lay, nb, c, a.bcount, a.jc_closed, m);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) o2[8 + q] = make_double2(m[2 * q], m[2 * q + 1]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -648,88 +651,95 @@ __device__ __forceinline__ void ldg_mat(const double* __restrict__ M, double (&m
     }
 }
 
+// One thread per (branch, category); sums over categories / branches go through warp shuffles and
+// a few atomics per warp.
 __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
     const int d = blockIdx.y;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = a.C;
+    const int b = t_ / C, c = t_ - b * C;
     const int lane = threadIdx.x & 31;
     const bool live = b < a.bcount;
     const double* prm = a.params + (size_t)d * a.lay.stride;
     double* od = a.out + (size_t)d * a.nout;
-    double Q[16], m1[16], m2[16], lam[4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        Q[i] = prm[a.lay.off_Q + i];
-        m1[i] = prm[a.lay.off_m1 + i];
-        m2[i] = prm[a.lay.off_m2 + i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) lam[i] = prm[a.lay.off_lam + i];
-    const double t = live ? prm[a.lay.off_t + b] : 0.0;
-    const int pos = live ? a.node_pos[b] : 0;
-    double dt = 0.0;
+    double g = 0.0, tb = 0.0, r = 0.0;
     double th[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) th[k] = 0.0;
-    for (int c = 0; c < a.C; ++c) {
-        double g = 0.0;
-        if (live) {
-            const double r = prm[a.lay.off_rs + c];
-            double G[16], P[16];
-            ldg_mat(a.G + (((size_t)d * a.nn + b) * a.C + c) * 16, G);
-            const unsigned char* rec = a.spost + (((size_t)d * a.C + c) * a.nsteps + (pos >> 1)) * kRecBytes;
-            ldg_mat(reinterpret_cast<const double*>(rec + 64 + 128 * (pos & 1)), P);
-            // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
+    if (live) {
+        tb = prm[a.lay.off_t + b];
+        r = prm[a.lay.off_rs + c];
+        const int pos = a.node_pos[b];
+        double G[16], P[16];
+        ldg_mat(a.G + (((size_t)d * a.nn + b) * C + c) * 16, G);
+        const unsigned char* rec = a.spost + (((size_t)d * C + c) * a.nsteps + (pos >> 1)) * kRecBytes;
+        ldg_mat(reinterpret_cast<const double*>(rec + 64 + 128 * (pos & 1)), P);
+        // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
+        const double* Q = prm + a.lay.off_Q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double qp = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) qp = fma(Q[4 * i + k], P[4 * k + j], qp);
+                g = fma(G[4 * i + j], qp, g);
+            }
+        if (a.lay.ntheta > 0) {
+            // H = m1^T G m2^T ; d logL/dtheta += sum_ij H_ij F_ij X_ij
+            const double* m1 = prm + a.lay.off_m1;
+            const double* m2 = prm + a.lay.off_m2;
+            double lam[4], ex[4], T[16], H[16];
+            const double tau = tb * r;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                lam[i] = prm[a.lay.off_lam + i];
+                ex[i] = exp(lam[i] * tau);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    double qp = 0.0;
+                    double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) qp = fma(Q[4 * i + k], P[4 * k + j], qp);
-                    g = fma(G[4 * i + j], qp, g);
+                    for (int k = 0; k < 4; ++k) s = fma(m1[4 * k + i], G[4 * k + j], s);
+                    T[4 * i + j] = s;
                 }
-            dt = fma(r, g, dt);
-            if (a.lay.ntheta > 0) {
-                // H = m1^T G m2^T ; d logL/dtheta += sum_ij H_ij F_ij X_ij
-                const double tau = t * r;
-                double T[16], H[16], ex[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ex[i] = exp(lam[i] * tau);
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < 4; ++j) {
+                    double s = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double s = 0.0;
+                    for (int k = 0; k < 4; ++k) s = fma(T[4 * i + k], m2[4 * j + k], s);
+                    const double x = (lam[i] - lam[j]) * tau;
+                    const double f = tau * ex[j] * (fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x);
+                    H[4 * i + j] = s * f;
+                }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) s = fma(m1[4 * k + i], G[4 * k + j], s);
-                        T[4 * i + j] = s;
-                    }
+            for (int k = 0; k < 10; ++k)
+                if (k < a.lay.ntheta) {
+                    const double* X = prm + a.lay.off_X + 16 * k;
+                    double s = 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) s = fma(T[4 * i + k], m2[4 * j + k], s);
-                        const double x = (lam[i] - lam[j]) * tau;
-                        const double f = tau * ex[j] * (fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x);
-                        H[4 * i + j] = s * f;
-                    }
-#pragma unroll
-                for (int k = 0; k < 10; ++k)
-                    if (k < a.lay.ntheta) {
-                        const double* X = prm + a.lay.off_X + 16 * k;
-                        double s = 0.0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) s = fma(H[i], X[i], s);
-                        th[k] += s;
-                    }
-            }
+                    for (int i = 0; i < 16; ++i) s = fma(H[i], X[i], s);
+                    th[k] = s;
+                }
         }
-        const double gr = warp_sum(t * g);
-        if (lane == 0 && gr != 0.0) atomicAdd(od + a.off_out_rs + c, gr);
     }
-    if (live) od[1 + b] = dt;
+    // d/dblens[b] = sum_c r_c g_bc ; d/drs[c] = sum_b t_b g_bc
+    double dt = r * g, dr = tb * g;
+    if ((C & (C - 1)) == 0 && C <= 32) {  // categories of one branch sit in adjacent lanes
+        for (int o = 1; o < C; o <<= 1) dt += __shfl_xor_sync(0xffffffffu, dt, o);
+        for (int o = C; o < 32; o <<= 1) dr += __shfl_xor_sync(0xffffffffu, dr, o);
+        if (live && c == 0) od[1 + b] = dt;
+        if (lane < C && dr != 0.0) atomicAdd(od + a.off_out_rs + lane, dr);
+    } else {
+        if (live) {
+            atomicAdd(od + 1 + b, dt);
+            atomicAdd(od + a.off_out_rs + c, dr);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 10; ++k)
         if (k < a.lay.ntheta) {
@@ -786,7 +796,7 @@ size_t sweep_smem_bytes(int D, int K, int nthreads) {
 }
 
 void launch_stream(const StreamArgs& a, cudaStream_t stream) {
-    const int total = 2 * a.B * a.lay.C * a.nsteps;
+    const int total = 4 * a.B * a.lay.C * a.nsteps;
     stream_kernel<<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
@@ -816,7 +826,7 @@ cudaError_t sweep_occupancy(int K, bool grad, int nthreads, size_t smem, int* n)
 }
 
 void launch_contract(const ContractArgs& a, int B, cudaStream_t stream) {
-    dim3 grid((a.bcount + 127) / 128, B);
+    dim3 grid((a.bcount * a.C + 127) / 128, B);
     contract_kernel<<<grid, 128, 0, stream>>>(a);
 }
 

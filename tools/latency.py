@@ -39,4 +39,8 @@ for name, model, rooted in (("fluA", "HKY", True), ("DS1", "GTR", False), ("HCV"
     tc = (time.perf_counter() - t0) / 5
     print(f"{name}: S={S} L={L} {model}+W4  GPU value+grad {tg * 1e6:.0f} us, value {tv * 1e6:.0f} us per call; "
           f"CPU oracle 1 thread value+grad {tc * 1e3:.2f} ms  ({tc / tg:.0f}x)  info={lik.info()['grid']}x{lik.info()['threads_per_cta']}")
+    lik.set_timing(True)
+    lik.value_grad(bl, subst, fr, rs, ps)
+    t = lik.get_timing()
+    print("   device:", {k: round(v * 1e3, 1) for k, v in t.items()}, "us")
     lik.close()
