@@ -201,6 +201,12 @@ def run_ours(args):
     lik.set_stream(stream.cuda_stream)
     if args.k or args.pb:
         lik.set_tiling(args.k, args.pb)
+    ref64 = None
+    if args.fp32:  # error of the fp32 mode against the fp64 path on the same draws, then switch
+        lik.upload(bl, rates, freqs, rs, ps)
+        lik.run(N_DRAWS, True)
+        ref64 = lik.download(N_DRAWS)
+        lik.set_precision(32)
     B = N_DRAWS
 
     lik.upload(bl, rates, freqs, rs, ps)
@@ -289,7 +295,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "taxa": S_TAXA, "patterns_per_gpu": L_PATTERNS, "categories": N_CAT,
                        "draws_per_step": B, "parallelism": f"pattern-sharded x{world}, one NCCL all-reduce per step"
                        if world > 1 else "single GPU",
@@ -315,6 +321,13 @@ def run_ours(args):
             "cpu_baseline": cpu, "clocks": clocks,
             "checksum_logL_draw0": float(res[0, 0]),
         }
+        if ref64 is not None and world == 1:
+            g64, g32 = ref64[:, 1:], res[:, 1:]
+            line["fp32_error_vs_fp64"] = {
+                "logL_max_rel": float(np.max(np.abs(res[:, 0] - ref64[:, 0]) / np.abs(ref64[:, 0]))),
+                "grad_max_abs_over_max_abs": float(np.max(np.abs(g32 - g64)) / np.max(np.abs(g64))),
+                "grad_median_rel": float(np.median(np.abs(g32 - g64) / np.maximum(1e-300, np.abs(g64))))}
+            line["roofline"]["note"] += "; fp32 mode moves half the bytes per entry, byte counts above are the fp64 ones"
         print(json.dumps(line), flush=True)
     lik.close()
     if world > 1:
@@ -339,6 +352,8 @@ def main():
     ap.add_argument("--pb", type=int, default=0, help="pattern blocks per CTA (tuning)")
     ap.add_argument("--kernel-times", action="store_true", help="read per-kernel events every step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fp32", action="store_true",
+                    help="optional fp32-with-scaling mode (reported separately; NOT the headline, dtype f32)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -152,6 +152,12 @@ PHYLO_B200_API int phylo_b200_sync(phylo_b200_handle h);
  * 0 = automatic.  Takes effect on the next run. */
 PHYLO_B200_API int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int pattern_blocks);
 
+/* Arithmetic of the sweeps: 64 (default; the parity-tested product path) or 32, the optional
+ * "fp32 with scaling" mode: partials, transition matrices and 4x4 statistics in float with
+ * power-of-two rescaling in units of 2^24, log-likelihood and gradient sums in double.  Its error is
+ * reported separately; it is not covered by the 1e-10 / 1e-8 parity guarantee. */
+PHYLO_B200_API int phylo_b200_set_precision(phylo_b200_handle h, int bits);
+
 /* Device time of the kernels of the last run (CUDA events on the handle's stream):
  * ms[0] P-matrix kernel, ms[1] sweep kernel, ms[2] contraction kernel, ms[3] whole run.
  * Enable before the run; disabled by default (events force a sync when read). */

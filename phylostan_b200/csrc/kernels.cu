@@ -10,11 +10,76 @@ namespace phylo {
 namespace {
 
 // ------------------------------------------------------------------------------------------
+// precision traits: fp64 is the product path; fp32 is the optional "fp32 with scaling" mode
+// ------------------------------------------------------------------------------------------
+
+template <typename T>
+struct Real;
+template <>
+struct Real<double> {
+    typedef double2 vec;                      // storage vector: a 4-state entry is two of these
+    static constexpr int kVec = 2;
+    static constexpr int kRec = kRecBytes;    // [desc 64 | P_a 128 | P_b 128]
+    static constexpr int kMat = 128;
+    static constexpr int kUnit = 64;          // rescale by powers of 2^64 ...
+    static constexpr int kMaxK = 15;          // ... at most 2^960 at once
+    __device__ static __forceinline__ double tiny() { return 2.938735877055719e-39; }  // 2^-128
+    __device__ static __forceinline__ double pow2(int k) {  // 2^(64 k)
+        return __hiloint2double((1023 + 64 * k) << 20, 0);
+    }
+    __device__ static __forceinline__ int exponent(double x) {  // floor(log2 x); -1023 if subnormal
+        return ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+    }
+};
+template <>
+struct Real<float> {
+    typedef float4 vec;
+    static constexpr int kVec = 1;
+    static constexpr int kRec = kRecBytesF32;  // [desc 64 | P_a 64 | P_b 64]
+    static constexpr int kMat = 64;
+    static constexpr int kUnit = 24;
+    static constexpr int kMaxK = 4;
+    __device__ static __forceinline__ float tiny() { return 5.9604644775390625e-08f; }  // 2^-24
+    __device__ static __forceinline__ float pow2(int k) { return __int_as_float((127 + 24 * k) << 23); }
+    __device__ static __forceinline__ int exponent(float x) { return ((__float_as_int(x) >> 23) & 0xff) - 127; }
+};
+
+// 2^(-bits) in double, 0 <= bits <= 1000
+__device__ __forceinline__ double pow2_neg(int bits) { return __hiloint2double((1023 - bits) << 20, 0); }
+
+// ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ double pow2_64k(int k) {  // 2^(64 k), -15 <= k <= 15
-    return __hiloint2double((1023 + 64 * k) << 20, 0);
+// 4-state entry <-> registers; `nt` is the distance (in vectors) between the two halves of an fp64 entry
+__device__ __forceinline__ void ld4(const double2* p, int nt, double (&x)[4]) {
+    const double2 u = p[0], v = p[nt];
+    x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
+}
+__device__ __forceinline__ void ld4(const float4* p, int, float (&x)[4]) {
+    const float4 u = p[0];
+    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+}
+__device__ __forceinline__ void st4(double2* p, int nt, const double (&x)[4]) {
+    p[0] = make_double2(x[0], x[1]);
+    p[nt] = make_double2(x[2], x[3]);
+}
+__device__ __forceinline__ void st4(float4* p, int, const float (&x)[4]) { p[0] = make_float4(x[0], x[1], x[2], x[3]); }
+// streaming (evict-first) variants for the scratch rows: written once, read once much later
+__device__ __forceinline__ void ld4cs(const double2* p, int nt, double (&x)[4]) {
+    const double2 u = __ldcs(p), v = __ldcs(p + nt);
+    x[0] = u.x; x[1] = u.y; x[2] = v.x; x[3] = v.y;
+}
+__device__ __forceinline__ void ld4cs(const float4* p, int, float (&x)[4]) {
+    const float4 u = __ldcs(p);
+    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w;
+}
+__device__ __forceinline__ void st4cs(double2* p, int nt, const double (&x)[4]) {
+    __stcs(p, make_double2(x[0], x[1]));
+    __stcs(p + nt, make_double2(x[2], x[3]));
+}
+__device__ __forceinline__ void st4cs(float4* p, int, const float (&x)[4]) {
+    __stcs(p, make_float4(x[0], x[1], x[2], x[3]));
 }
 
 // 4x4 row-major matrix from shared memory (warp-uniform address: broadcast LDS.128)
@@ -27,24 +92,35 @@ __device__ __forceinline__ void lds_mat(const unsigned char* p, double (&m)[16])
         m[2 * i + 1] = v.y;
     }
 }
+__device__ __forceinline__ void lds_mat(const unsigned char* p, float (&m)[16]) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 v = q[i];
+        m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
+    }
+}
 
 // y = M x  (row-major)
-__device__ __forceinline__ void matvec(const double (&m)[16], const double (&x)[4], double (&y)[4]) {
+template <typename T>
+__device__ __forceinline__ void matvec(const T (&m)[16], const T (&x)[4], T (&y)[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         y[i] = fma(m[4 * i + 3], x[3], fma(m[4 * i + 2], x[2], fma(m[4 * i + 1], x[1], m[4 * i] * x[0])));
 }
 
 // y = M^T x
-__device__ __forceinline__ void matTvec(const double (&m)[16], const double (&x)[4], double (&y)[4]) {
+template <typename T>
+__device__ __forceinline__ void matTvec(const T (&m)[16], const T (&x)[4], T (&y)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
         y[j] = fma(m[12 + j], x[3], fma(m[8 + j], x[2], fma(m[4 + j], x[1], m[j] * x[0])));
 }
 
-__device__ __forceinline__ void tip_vec(unsigned code, double (&p)[4]) {
+template <typename T>
+__device__ __forceinline__ void tip_vec(unsigned code, T (&p)[4]) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) p[s] = ((code >> s) & 1u) ? 1.0 : 0.0;
+    for (int s = 0; s < 4; ++s) p[s] = ((code >> s) & 1u) ? T(1) : T(0);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -56,46 +132,47 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Sum 16 per-lane values over the 32 lanes of a warp with a recursive-halving exchange
 // (8+4+2+1+1 = 16 shuffles instead of 80), then one 128-byte RED per warp: even lane 2i adds
 // entry i to dst[i].
-__device__ __forceinline__ void warp_reduce16_atomic(const double (&v)[16], double* __restrict__ dst, int lane) {
+template <typename T>
+__device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* __restrict__ dst, int lane) {
 #if PHYLO_ABLATE == 1
     {
-        double t = 0.0;
+        T t = 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) t += v[i];
-        if (t == 1.2345e-300) atomicAdd(dst, t);
+        if (t == T(1.2345e-30)) atomicAdd(dst, (double)t);
         return;
     }
 #endif
-    double a8[8], a4[4], a2[2], a1;
+    T a8[8], a4[4], a2[2], a1;
     bool hi = lane & 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        double send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+        T send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
         a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
     hi = lane & 8;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        double send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
+        T send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
         a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
     }
     hi = lane & 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        double send = hi ? a4[i] : a4[i + 2], keep = hi ? a4[i + 2] : a4[i];
+        T send = hi ? a4[i] : a4[i + 2], keep = hi ? a4[i + 2] : a4[i];
         a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
     }
     hi = lane & 2;
     {
-        double send = hi ? a2[0] : a2[1], keep = hi ? a2[1] : a2[0];
+        T send = hi ? a2[0] : a2[1], keep = hi ? a2[1] : a2[0];
         a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
     a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
 #if PHYLO_ABLATE == 2
-    if (a1 == 1.2345e-300) atomicAdd(dst, a1);  // experiment: shuffle reduction without the RED
+    if (a1 == T(1.2345e-30)) atomicAdd(dst, (double)a1);  // experiment: shuffle reduction without the RED
     return;
 #endif
-    if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), a1);
+    if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), (double)a1);
 }
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {
@@ -144,11 +221,24 @@ __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const Pa
         }
 }
 
+__device__ __forceinline__ void store_mat(unsigned char* dst, const double (&m)[16], double) {
+    double2* o2 = reinterpret_cast<double2*>(dst);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o2[q] = make_double2(m[2 * q], m[2 * q + 1]);
+}
+__device__ __forceinline__ void store_mat(unsigned char* dst, const double (&m)[16], float) {
+    float4* o4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        o4[q] = make_float4((float)m[4 * q], (float)m[4 * q + 1], (float)m[4 * q + 2], (float)m[4 * q + 3]);
+}
+
 // Descriptors carry ready-made offsets (tip rows, stack slots, scratch rows, G blocks) so the sweep
-// does no index arithmetic beyond pointer + offset.
+// does no index arithmetic beyond pointer + offset.  One thread per (sweep, draw, category, step, child).
+template <typename T>
 __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     const int per = a.lay.C * a.nsteps;
-    const int total = 4 * a.B * per;  // (sweep, draw, category, step, child)
+    const int total = 4 * a.B * per;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int child = idx & 1, rr = idx >> 1;
@@ -156,7 +246,7 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     const int r = rr - which * a.B * per;
     const int d = r / per, c = (r / a.nsteps) % a.lay.C, i = r % a.nsteps;
     const double* prm = a.params + (size_t)d * a.lay.stride;
-    unsigned char* rec = (which ? a.spre : a.spost) + (size_t)r * kRecBytes;
+    unsigned char* rec = (which ? a.spre : a.spost) + (size_t)r * Real<T>::kRec;
     int na, nb;
     int4* rd = reinterpret_cast<int4*>(rec);
     if (which == 0) {
@@ -199,10 +289,8 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
         }
     }
     double m[16];
-    double2* o2 = reinterpret_cast<double2*>(rec + 64 + 128 * child);
     pmatrix(prm, a.lay, child ? nb : na, c, a.bcount, a.jc_closed, m);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) o2[q] = make_double2(m[2 * q], m[2 * q + 1]);
+    store_mat(rec + 64 + Real<T>::kMat * child, m, T());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -211,6 +299,7 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
 
 // Per-warp record ring fed by cp.async.  Records sit contiguously: record i lives in ring slot
 // i % 6 (3 chunks of 2 records); chunk n+2 is issued when chunk n starts being consumed.
+template <int REC>
 struct Ring {
     unsigned char* buf;          // this warp's ring (generic pointer into shared memory)
     unsigned sbuf;               // the same as a 32-bit shared-window address
@@ -221,16 +310,17 @@ struct Ring {
     int lane;
 
     __device__ __forceinline__ void issue() {
-        const unsigned dst = sbuf + wchunk * (kRecChunk * kRecBytes) + lane * 16;
+        const unsigned dst = sbuf + wchunk * (kRecChunk * REC) + lane * 16;
         const unsigned char* s = next + lane * 16;
+        constexpr int kTail = kRecChunk * REC - 512;  // bytes beyond the first 32 x 16 B (REC = 320) ...
         if (remaining >= 2) {
-            cp_async16(dst, s);
-            if (lane < 8) cp_async16(dst + 512, s + 512);
-        } else if (remaining == 1 && lane < kRecBytes / 16) {
+            if (kTail >= 0 || lane < (kRecChunk * REC) / 16) cp_async16(dst, s);
+            if (kTail > 0 && lane < kTail / 16) cp_async16(dst + 512, s + 512);
+        } else if (remaining == 1 && lane < REC / 16) {
             cp_async16(dst, s);
         }
         cp_async_commit();  // always commit: keeps the group count uniform
-        next += kRecChunk * kRecBytes;
+        next += kRecChunk * REC;
         remaining -= kRecChunk;
         wchunk = wchunk == kRecBufs - 1 ? 0 : wchunk + 1;
     }
@@ -258,24 +348,27 @@ struct Ring {
     __device__ __forceinline__ const unsigned char* rec(int ahead) const {
         int s = slot + ahead;
         if (s >= kRecChunk * kRecBufs) s -= kRecChunk * kRecBufs;
-        return buf + s * kRecBytes;
+        return buf + s * REC;
     }
 };
 
 // NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
 // immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
-template <int K, bool GRAD, int NTC, int MINB>
+template <typename T, int K, bool GRAD, int NTC, int MINB>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
+    typedef Real<T> R;
+    typedef typename R::vec V;
+    constexpr int VP = R::kVec;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NT = NTC ? NTC : (int)blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.C, nsteps = a.nsteps;
     const int c = warp % C, pb = warp / C;
-    double2* st = reinterpret_cast<double2*>(smem_raw);                       // [D][K][2][NT]
-    double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * 2 * NT);  // [K][NT]
-    int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                        // [K][NT]
-    Ring ring;
-    ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * kRingBytesPerWarp;
+    V* st = reinterpret_cast<V*>(smem_raw);                                    // [D][K][VP][NT]
+    double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * VP * NT);  // [K][NT]
+    int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                         // [K][NT]
+    Ring<R::kRec> ring;
+    ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * (R::kRec * kRecChunk * kRecBufs);
     ring.sbuf = (unsigned)__cvta_generic_to_shared(ring.buf);
     ring.lane = lane;
     ring.next = nullptr;
@@ -283,30 +376,30 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     ring.wchunk = 0;
     ring.slot = 0;
     const int tpat = (NT / (32 * C)) * 32 * K;
-    const int SS = K * 2 * NT;  // double2 per stack slot / scratch row
+    const int SS = K * VP * NT;  // vectors per stack slot / scratch row
 
-    double2* const stt = st + tid;
-    double2* const sct = a.scratch + (size_t)blockIdx.x * a.scratch_stride + tid;
+    V* const stt = st + tid;
+    V* const sct = reinterpret_cast<V*>(a.scratch) + (size_t)blockIdx.x * a.scratch_stride + tid;
     uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
 
-    // element (j, h) of the stack entry / scratch row at element offset `off`
-#define ST(off, j, h) stt[(off) + ((j)*2 + (h)) * NT]
-#define SC(off, j, h) sct[(off) + ((j)*2 + (h)) * NT]
+    // entry j of the stack slot / scratch row at vector offset `off`
+#define ST(off, j) (stt + (off) + (j) * (VP * NT))
+#define SC(off, j) (sct + (off) + (j) * (VP * NT))
 
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
         const double* prm = a.params + (size_t)d * a.lay.stride;
         const int pat0 = tile * tpat + pb * 32 * K + lane;  // pattern of sub-index j: pat0 + 32 j
         const uint8_t* tipp = a.tips + pat0;
-        const size_t stream_off = ((size_t)d * C + c) * nsteps * kRecBytes;
+        const size_t stream_off = ((size_t)d * C + c) * nsteps * R::kRec;
 
         // -------------------------------------------------------------- post-order
         int etot[K];
-        double tos[K][4];  // most recent partial (top of stack), kept in registers
+        T tos[K][4];  // most recent partial (top of stack), kept in registers
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             etot[j] = 0;
-            tos[j][0] = tos[j][1] = tos[j][2] = tos[j][3] = 0.0;
+            tos[j][0] = tos[j][1] = tos[j][2] = tos[j][3] = T(0);
         }
         ring.start(a.spost + stream_off, nsteps);
         ring.step(0);
@@ -321,7 +414,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 cb[j] = (fl & 2) ? tipp[tb + 32 * j] : 0u;
             }
         }
-        double2* srow = sct;  // scratch row of step i
+        V* srow = sct;  // scratch row of step i
         uint8_t* drow = dlt;
         for (int i = 0; i < nsteps; ++i) {
             if (i) ring.step(i);
@@ -351,27 +444,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (nf & 1) prefetch_l2(tipp + n->tip_a);
                 if (nf & 2) prefetch_l2(tipp + n->tip_b);
             }
-            double M[16], ma[K][4];
+            T M[16], ma[K][4];
             lds_mat(rec + 64, M);
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                double p[4];
+                T p[4];
                 if (fl & 1) {
                     tip_vec(ca[j], p);
                 } else if (fl & 4) {
 #pragma unroll
                     for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
                 } else {
-                    double2 u = ST(s1.x, j, 0), v = ST(s1.x, j, 1);
-                    p[0] = u.x; p[1] = u.y; p[2] = v.x; p[3] = v.y;
+                    ld4(ST(s1.x, j), NT, p);
                 }
                 matvec(M, p, ma[j]);
             }
-            lds_mat(rec + 192, M);
-            double mb[K][4];
+            lds_mat(rec + 64 + R::kMat, M);
+            T mb[K][4];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                double p[4];
+                T p[4];
                 if (fl & 2) {
                     tip_vec(cb[j], p);
                 } else {  // an internal second child is always the previous step's result
@@ -382,25 +474,21 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             }
             if (s1.z >= 0) {  // the previous result still waits for its sibling: park it in shared memory
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    ST(s1.z, j, 0) = make_double2(tos[j][0], tos[j][1]);
-                    ST(s1.z, j, 1) = make_double2(tos[j][2], tos[j][3]);
-                }
+                for (int j = 0; j < K; ++j) st4(ST(s1.z, j), NT, tos[j]);
             }
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                double p[4];
+                T p[4];
 #pragma unroll
                 for (int s = 0; s < 4; ++s) p[s] = ma[j][s] * mb[j][s];
-                // per-(pattern,category) rescaling by exact powers of 2^64
+                // per-(pattern,category) rescaling by exact powers of two
                 int kexp = 0;
-                constexpr double kTiny = 2.938735877055719e-39;  // 2^-128
+                const T kTiny = R::tiny();
                 if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {  // rare
-                    const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
-                    if (mx > 0.0) {
-                        const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;  // floor(log2 mx), -1023 if subnormal
-                        kexp = min((-e) >> 6, 15);
-                        const double f = pow2_64k(kexp);
+                    const T mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+                    if (mx > T(0)) {
+                        kexp = min((-R::exponent(mx)) / R::kUnit, R::kMaxK);
+                        const T f = R::pow2(kexp);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) p[s] *= f;
                         etot[j] += kexp;
@@ -409,9 +497,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int s = 0; s < 4; ++s) tos[j][s] = p[s];
                 if (GRAD) {
-                    // written once, read once much later: stream through L2 (evict-first)
-                    __stcs(srow + (j * 2) * NT, make_double2(p[0], p[1]));
-                    __stcs(srow + (j * 2 + 1) * NT, make_double2(p[2], p[3]));
+                    st4cs(srow + j * (VP * NT), NT, p);
                     __stcs(drow + j * NT, (uint8_t)kexp);
                 }
             }
@@ -431,12 +517,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         __syncthreads();  // previous item's readers of ex_* are done
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            rdot[j] = pi[0] * tos[j][0] + pi[1] * tos[j][1] + pi[2] * tos[j][2] + pi[3] * tos[j][3];  // generate_script.py:1007
+            rdot[j] = pi[0] * (double)tos[j][0] + pi[1] * (double)tos[j][1] + pi[2] * (double)tos[j][2] +
+                      pi[3] * (double)tos[j][3];  // generate_script.py:1007
             ex_l[j * NT + tid] = ps_c * rdot[j];
             ex_e[j * NT + tid] = etot[j];
         }
         __syncthreads();
         double acc_logl = 0.0, acc_dps = 0.0, acc_dpi[4] = {0.0, 0.0, 0.0, 0.0};
+        constexpr int kMaxDe = 960 / R::kUnit;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const int base = j * NT + pb * C * 32 + lane;
@@ -445,19 +533,19 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             double sum = 0.0;
             for (int cc = 0; cc < C; ++cc) {
                 const int de = ex_e[base + cc * 32] - emin;
-                sum += de > 15 ? 0.0 : ex_l[base + cc * 32] * pow2_64k(-de);
+                sum += de > kMaxDe ? 0.0 : ex_l[base + cc * 32] * pow2_neg(R::kUnit * de);
             }
             const double w = a.weights[pat0 + 32 * j];
-            if (c == 0) acc_logl += w * (log(sum) - (double)emin * 44.361419555836500 /* 64 ln 2 */);
+            if (c == 0) acc_logl += w * (log(sum) - (double)emin * (R::kUnit * 0.6931471805599453));
             const int de = etot[j] - emin;
-            const double fac = de > 15 ? 0.0 : w * pow2_64k(-de) / sum;
+            const double fac = de > kMaxDe ? 0.0 : w * pow2_neg(R::kUnit * de) / sum;
             if (GRAD) {
                 acc_dps += fac * rdot[j];
                 const double f = fac * ps_c;
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    acc_dpi[s] += f * tos[j][s];
-                    tos[j][s] = pi[s] * f;  // q(root): weight, 1/L and the category share folded in
+                    acc_dpi[s] += f * (double)tos[j][s];
+                    tos[j][s] = (T)(pi[s] * f);  // q(root): weight, 1/L and the category share folded in
                 }
             }
         }
@@ -484,17 +572,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
                 const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
                 const int rowa = s1.x, rowb = s1.y;
-                double pa[K][4], pbv[K][4];
+                T pa[K][4], pbv[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {  // issue this step's operand loads first
-                    if (rowa >= 0) {
-                        double2 u = __ldcs(&SC(rowa, j, 0)), v = __ldcs(&SC(rowa, j, 1));
-                        pa[j][0] = u.x; pa[j][1] = u.y; pa[j][2] = v.x; pa[j][3] = v.y;
-                    }
-                    if (rowb >= 0) {
-                        double2 u = __ldcs(&SC(rowb, j, 0)), v = __ldcs(&SC(rowb, j, 1));
-                        pbv[j][0] = u.x; pbv[j][1] = u.y; pbv[j][2] = v.x; pbv[j][3] = v.y;
-                    }
+                    if (rowa >= 0) ld4cs(SC(rowa, j), NT, pa[j]);
+                    if (rowb >= 0) ld4cs(SC(rowb, j), NT, pbv[j]);
                 }
                 unsigned nca[K], ncb[K], ndl[K];
 #pragma unroll
@@ -522,23 +604,21 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         prefetch_l2(tipp + n->tip_a);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            prefetch_l2(&SC(n1.x, j, 0));
-                            prefetch_l2(&SC(n1.x, j, 1));
-                        }
+                        for (int j = 0; j < K; ++j)
+#pragma unroll
+                            for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.x, j) + h * NT);
                     }
                     if (n1.y < 0) {
                         prefetch_l2(tipp + n->tip_b);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            prefetch_l2(&SC(n1.y, j, 0));
-                            prefetch_l2(&SC(n1.y, j, 1));
-                        }
+                        for (int j = 0; j < K; ++j)
+#pragma unroll
+                            for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
                     prefetch_l2(dlt + n1.z);
                 }
-                double qn[K][4];
+                T qn[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (rowa < 0) tip_vec(ca[j], pa[j]);
@@ -547,19 +627,18 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s];
                     } else {
-                        double2 u = ST(s1.w, j, 0), v = ST(s1.w, j, 1);
-                        qn[j][0] = u.x; qn[j][1] = u.y; qn[j][2] = v.x; qn[j][3] = v.y;
+                        ld4(ST(s1.w, j), NT, qn[j]);
                     }
                     if (dcur[j]) {  // rare: this node was rescaled in the post-order
-                        const double f = pow2_64k((int)dcur[j]);
+                        const T f = R::pow2((int)dcur[j]);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] *= f;
                     }
                 }
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
-                double Aa[K][4], Ab[K][4];
+                T Aa[K][4], Ab[K][4];
                 {
-                    double M[16], m[4];
+                    T M[16], m[4];
                     lds_mat(rec + 64, M);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
@@ -569,10 +648,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                 }
                 {   // child b: q(b) waits in shared memory
-                    double M[16], m[4], G[16];
-                    lds_mat(rec + 192, M);
+                    T M[16], m[4], G[16];
+                    lds_mat(rec + 64 + R::kMat, M);
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) G[x] = 0.0;
+                    for (int x = 0; x < 16; ++x) G[x] = T(0);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         matvec(M, pbv[j], m);
@@ -583,18 +662,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
                         if (s2.x >= 0) {
-                            double q[4];
+                            T q[4];
                             matTvec(M, Ab[j], q);  // eigen.j2:151-153
-                            ST(s2.x, j, 0) = make_double2(q[0], q[1]);
-                            ST(s2.x, j, 1) = make_double2(q[2], q[3]);
+                            st4(ST(s2.x, j), NT, q);
                         }
                     }
                     warp_reduce16_atomic(G, Gd + s2.z, lane);
                 }
                 {   // child a: processed next when internal, so q(a) stays in the TOS registers
-                    double G[16];
+                    T G[16];
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) G[x] = 0.0;
+                    for (int x = 0; x < 16; ++x) G[x] = T(0);
 #pragma unroll
                     for (int j = 0; j < K; ++j)
 #pragma unroll
@@ -602,8 +680,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
                     if (s2.w & 1) {
-                        double M[16];
-                        asm volatile("" ::: "memory");  // reload P_a instead of keeping 32 registers alive
+                        T M[16];
+                        asm volatile("" ::: "memory");  // reload P_a instead of keeping it alive in registers
                         lds_mat(rec + 64, M);
 #pragma unroll
                         for (int j = 0; j < K; ++j) matTvec(M, Aa[j], tos[j]);
@@ -650,9 +728,21 @@ __device__ __forceinline__ void ldg_mat(const double* __restrict__ M, double (&m
         m[2 * i + 1] = v.y;
     }
 }
+__device__ __forceinline__ void ldg_pmat(const unsigned char* p, double (&m)[16], double) {
+    ldg_mat(reinterpret_cast<const double*>(p), m);
+}
+__device__ __forceinline__ void ldg_pmat(const unsigned char* p, double (&m)[16], float) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 v = __ldg(q + i);
+        m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w;
+    }
+}
 
 // One thread per (branch, category); sums over categories / branches go through warp shuffles and
 // a few atomics per warp.
+template <typename T>
 __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
     const int d = blockIdx.y;
     const int t_ = blockIdx.x * blockDim.x + threadIdx.x;
@@ -672,8 +762,8 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         const int pos = a.node_pos[b];
         double G[16], P[16];
         ldg_mat(a.G + (((size_t)d * a.nn + b) * C + c) * 16, G);
-        const unsigned char* rec = a.spost + (((size_t)d * C + c) * a.nsteps + (pos >> 1)) * kRecBytes;
-        ldg_mat(reinterpret_cast<const double*>(rec + 64 + 128 * (pos & 1)), P);
+        const unsigned char* rec = a.spost + (((size_t)d * C + c) * a.nsteps + (pos >> 1)) * Real<T>::kRec;
+        ldg_pmat(rec + 64 + Real<T>::kMat * (pos & 1), P, T());
         // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
         const double* Q = prm + a.lay.off_Q;
 #pragma unroll
@@ -689,7 +779,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
             // H = m1^T G m2^T ; d logL/dtheta += sum_ij H_ij F_ij X_ij
             const double* m1 = prm + a.lay.off_m1;
             const double* m2 = prm + a.lay.off_m2;
-            double lam[4], ex[4], T[16], H[16];
+            double lam[4], ex[4], Tm[16], H[16];
             const double tau = tb * r;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -703,7 +793,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) s = fma(m1[4 * k + i], G[4 * k + j], s);
-                    T[4 * i + j] = s;
+                    Tm[4 * i + j] = s;
                 }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -711,7 +801,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                 for (int j = 0; j < 4; ++j) {
                     double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) s = fma(T[4 * i + k], m2[4 * j + k], s);
+                    for (int k = 0; k < 4; ++k) s = fma(Tm[4 * i + k], m2[4 * j + k], s);
                     const double x = (lam[i] - lam[j]) * tau;
                     const double f = tau * ex[j] * (fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x);
                     H[4 * i + j] = s * f;
@@ -755,79 +845,79 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
 
 // Specialised for 128-thread CTAs (one pattern block of 4 categories, the common case) with a
 // per-K register budget; any other CTA size takes the generic variant.
-template <int K> struct Cfg;
-template <> struct Cfg<1> { static constexpr int minb = 4; };
-#ifndef PHYLO_MINB2
-#define PHYLO_MINB2 3
-#endif
-template <> struct Cfg<2> { static constexpr int minb = PHYLO_MINB2; };
-template <> struct Cfg<4> { static constexpr int minb = 1; };
+template <typename T, int K> struct Cfg;
+template <> struct Cfg<double, 1> { static constexpr int minb = 4; };
+template <> struct Cfg<double, 2> { static constexpr int minb = 3; };
+template <> struct Cfg<double, 4> { static constexpr int minb = 1; };
+template <> struct Cfg<float, 1> { static constexpr int minb = 6; };
+template <> struct Cfg<float, 2> { static constexpr int minb = 5; };
+template <> struct Cfg<float, 4> { static constexpr int minb = 3; };
 
-template <int K, bool GRAD>
-auto pick_kernel(int nthreads) -> void (*)(const SweepArgs) {
-    if (nthreads == 128) return sweep_kernel<K, GRAD, 128, Cfg<K>::minb>;
-    return sweep_kernel<K, GRAD, 0, 1>;
+typedef void (*SweepFn)(const SweepArgs);
+
+template <typename T, int K, bool GRAD>
+SweepFn pick_kernel(int nthreads) {
+    if (nthreads == 128) return sweep_kernel<T, K, GRAD, 128, Cfg<T, K>::minb>;
+    return sweep_kernel<T, K, GRAD, 0, 1>;
 }
 
-template <int K, bool GRAD>
-cudaError_t launch_sweep_t(const SweepArgs& a, int grid, int nthreads, size_t smem, cudaStream_t stream) {
-    auto kern = pick_kernel<K, GRAD>(nthreads);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, nthreads, smem, stream>>>(a);
-    return cudaGetLastError();
+template <typename T>
+SweepFn pick_kernel_k(int K, bool grad, int nthreads) {
+    switch (K * 2 + (grad ? 1 : 0)) {
+        case 2: return pick_kernel<T, 1, false>(nthreads);
+        case 3: return pick_kernel<T, 1, true>(nthreads);
+        case 4: return pick_kernel<T, 2, false>(nthreads);
+        case 5: return pick_kernel<T, 2, true>(nthreads);
+        case 8: return pick_kernel<T, 4, false>(nthreads);
+        case 9: return pick_kernel<T, 4, true>(nthreads);
+    }
+    return nullptr;
 }
 
-template <int K, bool GRAD>
-cudaError_t occupancy_t(int nthreads, size_t smem, int* n) {
-    auto kern = pick_kernel<K, GRAD>(nthreads);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, nthreads, smem);
+SweepFn pick(int prec, int K, bool grad, int nthreads) {
+    return prec == 32 ? pick_kernel_k<float>(K, grad, nthreads) : pick_kernel_k<double>(K, grad, nthreads);
 }
 
 }  // namespace
 
 int sweep_max_threads(int) { return 512; }
 
-size_t sweep_smem_bytes(int D, int K, int nthreads) {
-    return (size_t)D * K * 2 * nthreads * sizeof(double2) + (size_t)K * nthreads * (sizeof(double) + sizeof(int)) +
-           (size_t)(nthreads / 32) * kRingBytesPerWarp;
+int record_bytes(int prec) { return prec == 32 ? kRecBytesF32 : kRecBytes; }
+
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec) {
+    const size_t entry = prec == 32 ? 16 : 32;  // bytes per 4-state vector
+    return (size_t)D * K * nthreads * entry + (size_t)K * nthreads * (sizeof(double) + sizeof(int)) +
+           (size_t)(nthreads / 32) * record_bytes(prec) * kRecChunk * kRecBufs;
 }
 
-void launch_stream(const StreamArgs& a, cudaStream_t stream) {
+void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
     const int total = 4 * a.B * a.lay.C * a.nsteps;
-    stream_kernel<<<(total + 127) / 128, 128, 0, stream>>>(a);
+    if (prec == 32) stream_kernel<float><<<(total + 127) / 128, 128, 0, stream>>>(a);
+    else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
-cudaError_t launch_sweep(const SweepArgs& a, int K, bool grad, int grid, int nthreads, size_t smem,
+cudaError_t launch_sweep(const SweepArgs& a, int prec, int K, bool grad, int grid, int nthreads, size_t smem,
                          cudaStream_t stream) {
-    switch (K * 2 + (grad ? 1 : 0)) {
-        case 2: return launch_sweep_t<1, false>(a, grid, nthreads, smem, stream);
-        case 3: return launch_sweep_t<1, true>(a, grid, nthreads, smem, stream);
-        case 4: return launch_sweep_t<2, false>(a, grid, nthreads, smem, stream);
-        case 5: return launch_sweep_t<2, true>(a, grid, nthreads, smem, stream);
-        case 8: return launch_sweep_t<4, false>(a, grid, nthreads, smem, stream);
-        case 9: return launch_sweep_t<4, true>(a, grid, nthreads, smem, stream);
-    }
-    return cudaErrorInvalidValue;
+    SweepFn kern = pick(prec, K, grad, nthreads);
+    if (!kern) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, nthreads, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
-cudaError_t sweep_occupancy(int K, bool grad, int nthreads, size_t smem, int* n) {
-    switch (K * 2 + (grad ? 1 : 0)) {
-        case 2: return occupancy_t<1, false>(nthreads, smem, n);
-        case 3: return occupancy_t<1, true>(nthreads, smem, n);
-        case 4: return occupancy_t<2, false>(nthreads, smem, n);
-        case 5: return occupancy_t<2, true>(nthreads, smem, n);
-        case 8: return occupancy_t<4, false>(nthreads, smem, n);
-        case 9: return occupancy_t<4, true>(nthreads, smem, n);
-    }
-    return cudaErrorInvalidValue;
+cudaError_t sweep_occupancy(int prec, int K, bool grad, int nthreads, size_t smem, int* n) {
+    SweepFn kern = pick(prec, K, grad, nthreads);
+    if (!kern) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, nthreads, smem);
 }
 
-void launch_contract(const ContractArgs& a, int B, cudaStream_t stream) {
+void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream) {
     dim3 grid((a.bcount * a.C + 127) / 128, B);
-    contract_kernel<<<grid, 128, 0, stream>>>(a);
+    if (prec == 32) contract_kernel<float><<<grid, 128, 0, stream>>>(a);
+    else contract_kernel<double><<<grid, 128, 0, stream>>>(a);
 }
 
 }  // namespace phylo

@@ -29,10 +29,10 @@
 
 namespace phylo {
 
-constexpr int kRecBytes = 320;   // [desc 64 B | P_a 128 B | P_b 128 B]
+constexpr int kRecBytes = 320;   // fp64 record: [desc 64 B | P_a 128 B | P_b 128 B]
+constexpr int kRecBytesF32 = 192;  // fp32 mode: [desc 64 B | P_a 64 B | P_b 64 B]
 constexpr int kRecChunk = 2;     // records per cp.async group
 constexpr int kRecBufs = 3;      // ring depth in chunks
-constexpr int kRingBytesPerWarp = kRecBytes * kRecChunk * kRecBufs;
 
 // offsets (in doubles) inside one draw's parameter block
 struct ParamLayout {
@@ -85,12 +85,12 @@ struct SweepArgs {
     const double* params;     // [B][stride]
     const unsigned char* spost;
     const unsigned char* spre;
-    double2* scratch;         // [grid][S-1][K][2][NT]
+    void* scratch;            // [grid][S-1][K][NT] 4-state entries: double2 x 2 (fp64) or float4 (fp32)
     uint8_t* dscr;            // [grid][S-1][K][NT]   rescale exponents (units of 2^64)
     double* G;                // [B][nn][C][16]
     double* out;              // [B][nout]
     ParamLayout lay;
-    long long scratch_stride, dscr_stride;
+    long long scratch_stride, dscr_stride;   // per CTA, in 16-byte vectors / bytes
     int S, nsteps, Lpad, ntiles, nitems, C, nn, nout, D;
     int off_out_freqs, off_out_ps;
 };
@@ -106,14 +106,15 @@ struct ContractArgs {
     int off_out_subst, off_out_freqs, off_out_rs;
 };
 
-void launch_stream(const StreamArgs& a, cudaStream_t stream);
-// K in {1,2,4}; nthreads <= 512
-cudaError_t launch_sweep(const SweepArgs& a, int K, bool grad, int grid, int nthreads, size_t smem,
+// prec: 64 (product path) or 32 (optional fp32-with-scaling mode); K in {1,2,4}; nthreads <= 512
+void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
+cudaError_t launch_sweep(const SweepArgs& a, int prec, int K, bool grad, int grid, int nthreads, size_t smem,
                          cudaStream_t stream);
-cudaError_t sweep_occupancy(int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
-void launch_contract(const ContractArgs& a, int B, cudaStream_t stream);
+cudaError_t sweep_occupancy(int prec, int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
+void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
 
-size_t sweep_smem_bytes(int D, int K, int nthreads);
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec);
+int record_bytes(int prec);
 int sweep_max_threads(int K);  // largest CTA the K-variant is compiled for
 
 }  // namespace phylo

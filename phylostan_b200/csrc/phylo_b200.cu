@@ -102,6 +102,7 @@ struct phylo_b200_ctx {
     PinnedBuf<double> h_params, h_out;
 
     // tiling (user request, 0 = auto) and the resolved launch shape of the last run
+    int prec = 64;  // 64: product path; 32: optional fp32-with-scaling mode
     int req_K = 0, req_PB = 0;
     int K = 1, PB = 1, NT = 0, grid = 0, ntiles = 0;
     size_t smem = 0;
@@ -134,7 +135,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     int K = h->req_K, PB = h->req_PB;
     if (K == 0) {
         const long long work = (long long)B * ((h->L + 31) / 32);  // warps of patterns per category
-        K = work >= 8LL * h->num_sms ? 2 : 1;
+        K = work >= 8LL * h->num_sms ? (h->prec == 32 ? 4 : 2) : 1;  // fp32 entries are half the size
     }
     if (K != 1 && K != 2 && K != 4) return fail(PHYLO_B200_EINVAL, "patterns_per_thread must be 1, 2 or 4");
     if (PB == 0) PB = 1;
@@ -143,16 +144,16 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     while (K > 1 && 32 * C * PB > sweep_max_threads(K)) K >>= 1;
     int NT = 32 * C * PB;
     if (NT > sweep_max_threads(K)) return fail(PHYLO_B200_EINVAL, "too many rate categories for one CTA");
-    size_t smem = sweep_smem_bytes(D, K, NT);
-    while (smem > h->smem_optin && K > 1) { K >>= 1; smem = sweep_smem_bytes(D, K, NT); }
-    while (smem > h->smem_optin && PB > 1) { PB >>= 1; NT = 32 * C * PB; smem = sweep_smem_bytes(D, K, NT); }
+    size_t smem = sweep_smem_bytes(D, K, NT, h->prec);
+    while (smem > h->smem_optin && K > 1) { K >>= 1; smem = sweep_smem_bytes(D, K, NT, h->prec); }
+    while (smem > h->smem_optin && PB > 1) { PB >>= 1; NT = 32 * C * PB; smem = sweep_smem_bytes(D, K, NT, h->prec); }
     if (smem > h->smem_optin)
         return fail(PHYLO_B200_EINVAL, "tree too deep for the shared-memory stack (depth " + std::to_string(D) + ")");
     const int tpat = PB * 32 * K;
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem;
     h->ntiles = (h->L + tpat - 1) / tpat;
     int occ = 0;
-    CU_TRY(sweep_occupancy(K, grad, NT, smem, &occ));
+    CU_TRY(sweep_occupancy(h->prec, K, grad, NT, smem, &occ));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -161,7 +162,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
 
 int ensure_batch(phylo_b200_ctx* h, int B) {
     CU_TRY(h->d_params.ensure((size_t)B * h->lay.stride));
-    CU_TRY(h->d_spost.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));
+    CU_TRY(h->d_spost.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));  // sized for the larger (fp64) record
     CU_TRY(h->d_spre.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));
     CU_TRY(h->d_G.ensure((size_t)B * h->nn * h->C * 16));
     CU_TRY(h->d_out.ensure((size_t)B * h->nout));
@@ -363,6 +364,13 @@ int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int patt
     return 0;
 }
 
+int phylo_b200_set_precision(phylo_b200_handle h, int bits) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    if (bits != 32 && bits != 64) return fail(PHYLO_B200_EINVAL, "precision must be 64 or 32");
+    h->prec = bits;
+    return 0;
+}
+
 int phylo_b200_set_timing(phylo_b200_handle h, int enabled) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     h->timing = enabled != 0;
@@ -431,7 +439,7 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     if (int rc = resolve_tiling(h, B, grad)) return rc;
     if (grad) {
         const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
-        CU_TRY(h->d_scratch.ensure(rows * 2));
+        CU_TRY(h->d_scratch.ensure(rows * 2));  // 16-byte vectors; fp32 uses half of them
         CU_TRY(h->d_dscr.ensure(rows));
     }
     cudaStream_t st = h->stream;
@@ -442,8 +450,9 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     sa.params = h->d_params.p; sa.post = h->d_post.p; sa.pre = h->d_pre.p;
     sa.spost = h->d_spost.p; sa.spre = h->d_spre.p; sa.lay = h->lay;
     sa.nsteps = h->S - 1; sa.bcount = h->bcount; sa.jc_closed = h->jc_closed; sa.B = B;
-    sa.Lpad = h->Lpad; sa.SS = h->K * 2 * h->NT; sa.KNT = h->K * h->NT;
-    launch_stream(sa, st);
+    const int VP = h->prec == 32 ? 1 : 2;  // 16-byte vectors per 4-state entry
+    sa.Lpad = h->Lpad; sa.SS = h->K * VP * h->NT; sa.KNT = h->K * h->NT;
+    launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
 
@@ -452,12 +461,12 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     a.spost = h->d_spost.p; a.spre = h->d_spre.p;
     a.scratch = h->d_scratch.p; a.dscr = h->d_dscr.p; a.G = h->d_G.p; a.out = h->d_out.p;
     a.lay = h->lay;
-    a.scratch_stride = (long long)(h->S - 1) * h->K * 2 * h->NT;
+    a.scratch_stride = (long long)(h->S - 1) * h->K * VP * h->NT;
     a.dscr_stride = (long long)(h->S - 1) * h->K * h->NT;
     a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
     a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->plan.depth();
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
-    CU_TRY(launch_sweep(a, h->K, grad, h->grid, h->NT, h->smem, st));
+    CU_TRY(launch_sweep(a, h->prec, h->K, grad, h->grid, h->NT, h->smem, st));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {
@@ -465,7 +474,7 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
         ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
         ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
         ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
-        launch_contract(ca, B, st);
+        launch_contract(ca, h->prec, B, st);
         CU_TRY(cudaGetLastError());
         if (h->timing) CU_TRY(cudaEventRecord(h->ev[3], st));
         h->last_launches = 3;

@@ -74,6 +74,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_download.argtypes = [vp, i, _dp]
     L.phylo_b200_set_stream.argtypes = [vp, vp]
     L.phylo_b200_set_tiling.argtypes = [vp, i, i]
+    L.phylo_b200_set_precision.argtypes = [vp, i]
     L.phylo_b200_set_timing.argtypes = [vp, i]
     L.phylo_b200_get_timing.argtypes = [vp, _dp]
     L.phylo_b200_info.argtypes = [vp, i]
@@ -266,6 +267,10 @@ class TreeLikelihood:
 
     def set_tiling(self, patterns_per_thread: int = 0, pattern_blocks: int = 0) -> None:
         _check(lib().phylo_b200_set_tiling(self._h, patterns_per_thread, pattern_blocks))
+
+    def set_precision(self, bits: int) -> None:
+        """64 (default, parity-tested) or 32 (optional fp32-with-scaling mode, error reported separately)."""
+        _check(lib().phylo_b200_set_precision(self._h, int(bits)))
 
     def set_timing(self, enabled: bool) -> None:
         _check(lib().phylo_b200_set_timing(self._h, int(enabled)))

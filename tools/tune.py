@@ -19,6 +19,9 @@ prob = synth.make_problem(S, L, 4, structured=False)
 draws = synth.make_draws(prob, B)
 print(f"problem {S}x{L} built in {time.time() - t0:.1f}s", flush=True)
 lik = lk.TreeLikelihood(prob.peel, prob.tipmask, prob.weights, model="GTR", categories=4)
+PREC = int(os.environ.get("PHYLO_PREC", "64"))
+lik.set_precision(PREC)
+print("precision", PREC, flush=True)
 lik.upload(*draws)
 alg = (32.0 * L * 4 * (5 * S - 9) + 2.0 * S * L + 8.0 * L) * B
 ref = None
