@@ -4,8 +4,8 @@
 //   stream_kernel    P(t_b r_c) = m1 diag(exp(lambda t_b r_c)) m2 for both children of every step
 //                    (phylostan/generate_script.py:824-829, 880-885; JC69 closed form :765-766),
 //                    written as per-(draw, category) INSTRUCTION STREAMS in traversal order:
-//                    one 320-byte record [step descriptor | P_a | P_b] per internal node, one stream
-//                    for the post-order and one for the pre-order sweep
+//                    one 320-byte record [step descriptor with ready-made offsets | P_a | P_b] per
+//                    internal node, one stream for the post-order and one for the pre-order sweep
 //   sweep_kernel     per (draw, pattern tile): depth-first post-order partials
 //                    (eigen/eigen.j2:122-141, generate_script.py:998-1005), root likelihood with
 //                    per-(pattern,category) rescaling (generate_script.py:1006-1010), then the
@@ -14,8 +14,9 @@
 //   contract_kernel  G -> d/dblens (eigen/eigen.j2:163-166 without its times[i] factor),
 //                    d/drs, d/d(rates|kappa), d/dfreqs
 //
-// Memory plan: one thread = one (pattern, category) (x K patterns).  The live partials of a tile
-// sit in a shared-memory stack [slot][k][half][thread] of double2 (bank-conflict free).  Every
+// Memory plan: one thread = one (pattern, category) (x K patterns).  The most recent vector of a
+// tile stays in registers, the ones waiting for their sibling in a shared-memory stack
+// [slot][k][half][thread] of double2 (bank-conflict free).  Every
 // warp streams its category's records into a private shared-memory ring with cp.async, two chunks
 // ahead, so the step -> matrix -> operand chain never waits on global memory; operand lines of
 // step i+2 are prefetched into L2.  HBM traffic is one coalesced double2 write per internal-node
