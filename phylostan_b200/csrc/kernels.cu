@@ -19,8 +19,8 @@ template <>
 struct Real<double> {
     typedef double2 vec;                      // storage vector: a 4-state entry is two of these
     static constexpr int kVec = 2;
-    static constexpr int kRec = kRecBytes;    // [desc 64 | P_a 128 | P_b 128]
-    static constexpr int kMat = 128;
+    static constexpr int kRec = kRecBytes;    // [desc 64 | P_a slot 160 | P_b slot 160]
+    static constexpr int kMat = 160;          // 4x4 row-major (128 B) or, for simple tips, 4x5 column-major
     static constexpr int kUnit = 64;          // rescale by powers of 2^64 ...
     static constexpr int kMaxK = 15;          // ... at most 2^960 at once
     __device__ static __forceinline__ double tiny() { return 2.938735877055719e-39; }  // 2^-128
@@ -35,8 +35,8 @@ template <>
 struct Real<float> {
     typedef float4 vec;
     static constexpr int kVec = 1;
-    static constexpr int kRec = kRecBytesF32;  // [desc 64 | P_a 64 | P_b 64]
-    static constexpr int kMat = 64;
+    static constexpr int kRec = kRecBytesF32;  // [desc 64 | P_a slot 80 | P_b slot 80]
+    static constexpr int kMat = 80;
     static constexpr int kUnit = 24;
     static constexpr int kMaxK = 4;
     __device__ static __forceinline__ float tiny() { return 5.9604644775390625e-08f; }  // 2^-24
@@ -117,12 +117,23 @@ __device__ __forceinline__ void matTvec(const T (&m)[16], const T (&x)[4], T (&y
         y[j] = fma(m[12 + j], x[3], fma(m[8 + j], x[2], fma(m[4 + j], x[1], m[j] * x[0])));
 }
 
-template <typename T>
+// tip cell -> 0/1 partial.  IDX = false: `code` is the 4-bit state mask; IDX = true (simple tips):
+// `code` is the column index 0..3, or 4 for an all-ones cell.
+template <bool IDX, typename T>
 __device__ __forceinline__ void tip_vec(unsigned code, T (&p)[4]) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) p[s] = ((code >> s) & 1u) ? T(1) : T(0);
+    for (int s = 0; s < 4; ++s)
+        p[s] = (IDX ? (code == (unsigned)s || code == 4u) : (((code >> s) & 1u) != 0u)) ? T(1) : T(0);
 }
 
+// Simple-tip fast path (TIPS kernels): every tip cell is one-hot or all ones (what the reference's
+// encoder produces, phylostan/utils.py:180-188) and is stored as a column index 0..3 / 4.  The record
+// then holds P column-major with a fifth all-ones column (row sums of a stochastic matrix), so the
+// message of a tip child is one 32-byte load instead of a matrix-vector product.
+template <typename V, typename T>
+__device__ __forceinline__ void tip_msg(const unsigned char* slot, unsigned idx, T (&m)[4]) {
+    ld4(reinterpret_cast<const V*>(slot) + idx * (int)(4 * sizeof(T) / sizeof(V)), 1, m);
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -233,6 +244,26 @@ __device__ __forceinline__ void store_mat(unsigned char* dst, const double (&m)[
         o4[q] = make_float4((float)m[4 * q], (float)m[4 * q + 1], (float)m[4 * q + 2], (float)m[4 * q + 3]);
 }
 
+// column-major 4x5: columns 0..3 of P, then a column of ones
+__device__ __forceinline__ void store_tipmat(unsigned char* dst, const double (&m)[16], double) {
+    double* o = reinterpret_cast<double*>(dst);
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) o[4 * y + x] = m[4 * x + y];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) o[16 + x] = 1.0;
+}
+__device__ __forceinline__ void store_tipmat(unsigned char* dst, const double (&m)[16], float) {
+    float* o = reinterpret_cast<float*>(dst);
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) o[4 * y + x] = (float)m[4 * x + y];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) o[16 + x] = 1.0f;
+}
+
 // Descriptors carry ready-made offsets (tip rows, stack slots, scratch rows, G blocks) so the sweep
 // does no index arithmetic beyond pointer + offset.  One thread per (sweep, draw, category, step, child).
 template <typename T>
@@ -289,8 +320,10 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
         }
     }
     double m[16];
-    pmatrix(prm, a.lay, child ? nb : na, c, a.bcount, a.jc_closed, m);
-    store_mat(rec + 64 + Real<T>::kMat * child, m, T());
+    const int node = child ? nb : na;
+    pmatrix(prm, a.lay, node, c, a.bcount, a.jc_closed, m);
+    if (a.tips_simple && which == 0 && node < a.S) store_tipmat(rec + 64 + Real<T>::kMat * child, m, T());
+    else store_mat(rec + 64 + Real<T>::kMat * child, m, T());
 }
 
 // ------------------------------------------------------------------------------------------
@@ -354,7 +387,7 @@ struct Ring {
 
 // NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
 // immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
-template <typename T, int K, bool GRAD, int NTC, int MINB>
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -444,33 +477,44 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (nf & 1) prefetch_l2(tipp + n->tip_a);
                 if (nf & 2) prefetch_l2(tipp + n->tip_b);
             }
-            T M[16], ma[K][4];
-            lds_mat(rec + 64, M);
+            T ma[K][4], mb[K][4];
+            if (TIPS && (fl & 1)) {  // tip child: its message is a column of P_a
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                T p[4];
-                if (fl & 1) {
-                    tip_vec(ca[j], p);
-                } else if (fl & 4) {
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, ca[j], ma[j]);
+            } else {
+                T M[16];
+                lds_mat(rec + 64, M);
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
-                } else {
-                    ld4(ST(s1.x, j), NT, p);
+                for (int j = 0; j < K; ++j) {
+                    T p[4];
+                    if (!TIPS && (fl & 1)) {
+                        tip_vec<false>(ca[j], p);
+                    } else if (fl & 4) {
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
+                    } else {
+                        ld4(ST(s1.x, j), NT, p);
+                    }
+                    matvec(M, p, ma[j]);
                 }
-                matvec(M, p, ma[j]);
             }
-            lds_mat(rec + 64 + R::kMat, M);
-            T mb[K][4];
+            if (TIPS && (fl & 2)) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                T p[4];
-                if (fl & 2) {
-                    tip_vec(cb[j], p);
-                } else {  // an internal second child is always the previous step's result
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64 + R::kMat, cb[j], mb[j]);
+            } else {
+                T M[16];
+                lds_mat(rec + 64 + R::kMat, M);
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
+                for (int j = 0; j < K; ++j) {
+                    T p[4];
+                    if (!TIPS && (fl & 2)) {
+                        tip_vec<false>(cb[j], p);
+                    } else {  // an internal second child is always the previous step's result
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
+                    }
+                    matvec(M, p, mb[j]);
                 }
-                matvec(M, p, mb[j]);
             }
             if (s1.z >= 0) {  // the previous result still waits for its sibling: park it in shared memory
 #pragma unroll
@@ -621,8 +665,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 T qn[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (rowa < 0) tip_vec(ca[j], pa[j]);
-                    if (rowb < 0) tip_vec(cb[j], pbv[j]);
+                    if (rowa < 0) tip_vec<TIPS>(ca[j], pa[j]);
+                    if (rowb < 0) tip_vec<TIPS>(cb[j], pbv[j]);
                     if (s1.w < 0) {  // q(node) is the previous step's first child: still in registers
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s];
@@ -764,6 +808,16 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         ldg_mat(a.G + (((size_t)d * a.nn + b) * C + c) * 16, G);
         const unsigned char* rec = a.spost + (((size_t)d * C + c) * a.nsteps + (pos >> 1)) * Real<T>::kRec;
         ldg_pmat(rec + 64 + Real<T>::kMat * (pos & 1), P, T());
+        if (a.tips_simple && b < a.S) {  // tip records hold P column-major: transpose back
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i + 1; j < 4; ++j) {
+                    const double t = P[4 * i + j];
+                    P[4 * i + j] = P[4 * j + i];
+                    P[4 * j + i] = t;
+                }
+        }
         // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
         const double* Q = prm + a.lay.off_Q;
 #pragma unroll
@@ -855,27 +909,28 @@ template <> struct Cfg<float, 4> { static constexpr int minb = 3; };
 
 typedef void (*SweepFn)(const SweepArgs);
 
-template <typename T, int K, bool GRAD>
+template <typename T, int K, bool GRAD, bool TIPS>
 SweepFn pick_kernel(int nthreads) {
-    if (nthreads == 128) return sweep_kernel<T, K, GRAD, 128, Cfg<T, K>::minb>;
-    return sweep_kernel<T, K, GRAD, 0, 1>;
+    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb>;
+    return sweep_kernel<T, K, GRAD, TIPS, 0, 1>;
 }
 
-template <typename T>
+template <typename T, bool TIPS>
 SweepFn pick_kernel_k(int K, bool grad, int nthreads) {
     switch (K * 2 + (grad ? 1 : 0)) {
-        case 2: return pick_kernel<T, 1, false>(nthreads);
-        case 3: return pick_kernel<T, 1, true>(nthreads);
-        case 4: return pick_kernel<T, 2, false>(nthreads);
-        case 5: return pick_kernel<T, 2, true>(nthreads);
-        case 8: return pick_kernel<T, 4, false>(nthreads);
-        case 9: return pick_kernel<T, 4, true>(nthreads);
+        case 2: return pick_kernel<T, 1, false, TIPS>(nthreads);
+        case 3: return pick_kernel<T, 1, true, TIPS>(nthreads);
+        case 4: return pick_kernel<T, 2, false, TIPS>(nthreads);
+        case 5: return pick_kernel<T, 2, true, TIPS>(nthreads);
+        case 8: return pick_kernel<T, 4, false, TIPS>(nthreads);
+        case 9: return pick_kernel<T, 4, true, TIPS>(nthreads);
     }
     return nullptr;
 }
 
-SweepFn pick(int prec, int K, bool grad, int nthreads) {
-    return prec == 32 ? pick_kernel_k<float>(K, grad, nthreads) : pick_kernel_k<double>(K, grad, nthreads);
+SweepFn pick(int prec, bool tips, int K, bool grad, int nthreads) {
+    if (prec == 32) return tips ? pick_kernel_k<float, true>(K, grad, nthreads) : pick_kernel_k<float, false>(K, grad, nthreads);
+    return tips ? pick_kernel_k<double, true>(K, grad, nthreads) : pick_kernel_k<double, false>(K, grad, nthreads);
 }
 
 }  // namespace
@@ -896,9 +951,9 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
     else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
-cudaError_t launch_sweep(const SweepArgs& a, int prec, int K, bool grad, int grid, int nthreads, size_t smem,
-                         cudaStream_t stream) {
-    SweepFn kern = pick(prec, K, grad, nthreads);
+cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, int grid, int nthreads,
+                         size_t smem, cudaStream_t stream) {
+    SweepFn kern = pick(prec, tips, K, grad, nthreads);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -906,8 +961,8 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, int K, bool grad, int gri
     return cudaGetLastError();
 }
 
-cudaError_t sweep_occupancy(int prec, int K, bool grad, int nthreads, size_t smem, int* n) {
-    SweepFn kern = pick(prec, K, grad, nthreads);
+cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, int nthreads, size_t smem, int* n) {
+    SweepFn kern = pick(prec, tips, K, grad, nthreads);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -30,8 +30,8 @@
 
 namespace phylo {
 
-constexpr int kRecBytes = 320;   // fp64 record: [desc 64 B | P_a 128 B | P_b 128 B]
-constexpr int kRecBytesF32 = 192;  // fp32 mode: [desc 64 B | P_a 64 B | P_b 64 B]
+constexpr int kRecBytes = 384;   // fp64 record: [desc 64 B | P_a slot 160 B | P_b slot 160 B]
+constexpr int kRecBytesF32 = 224;  // fp32 mode: [desc 64 B | P_a slot 80 B | P_b slot 80 B]
 constexpr int kRecChunk = 2;     // records per cp.async group
 constexpr int kRecBufs = 3;      // ring depth in chunks
 
@@ -78,10 +78,11 @@ struct StreamArgs {
     ParamLayout lay;
     int nsteps, bcount, jc_closed, B;
     int Lpad, SS, KNT;        // tile geometry baked into the descriptors
+    int S, tips_simple;       // tips_simple: tip children get the column-major 4x5 matrix layout
 };
 
 struct SweepArgs {
-    const uint8_t* tips;      // [S][Lpad] 4-bit state masks
+    const uint8_t* tips;      // [S][Lpad] 4-bit state masks, or column indices 0..4 when every tip is simple
     const double* weights;    // [Lpad]
     const double* params;     // [B][stride]
     const unsigned char* spost;
@@ -103,15 +104,15 @@ struct ContractArgs {
     const double* G;
     double* out;
     ParamLayout lay;
-    int bcount, C, nn, nout, nsubst, nsteps;
+    int bcount, C, nn, nout, nsubst, nsteps, S, tips_simple;
     int off_out_subst, off_out_freqs, off_out_rs;
 };
 
 // prec: 64 (product path) or 32 (optional fp32-with-scaling mode); K in {1,2,4}; nthreads <= 512
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
-cudaError_t launch_sweep(const SweepArgs& a, int prec, int K, bool grad, int grid, int nthreads, size_t smem,
-                         cudaStream_t stream);
-cudaError_t sweep_occupancy(int prec, int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
+cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, int grid, int nthreads,
+                         size_t smem, cudaStream_t stream);
+cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
 
 size_t sweep_smem_bytes(int D, int K, int nthreads, int prec);

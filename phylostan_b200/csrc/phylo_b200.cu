@@ -82,6 +82,7 @@ struct phylo_b200_ctx {
     int S = 0, L = 0, C = 0, model = 0, flags = 0, device = 0;
     int nn = 0, bcount = 0, nsubst = 0, nout = 0, Lpad = 0;
     bool rooted = false, normalize = true, jc_closed = false;
+    bool tips_simple = false;  // every tip cell one-hot or all ones -> column-index fast path
     int off_subst = 0, off_freqs = 0, off_rs = 0, off_ps = 0;
     Plan plan;
     ParamLayout lay{};
@@ -127,15 +128,30 @@ struct phylo_b200_ctx {
 
 namespace {
 
-// Resolve (K, PB) -> launch shape.  Auto policy: small problems spread thin (K=1, one pattern
-// block per CTA) to reach every SM; large ones amortise the per-node work (step decode,
-// P-matrix loads, the 4x4 statistics reduction) over K=2 patterns per thread.
+// Resolve (K, PB) -> launch shape.
 int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     const int C = h->C, D = h->plan.depth();
     int K = h->req_K, PB = h->req_PB;
     if (K == 0) {
+        // Small problems spread thin (K = 1).  Large ones take the largest K that still keeps two
+        // CTAs per SM resident: per-step work (record decode, matrix loads, the 4x4 reduction) is
+        // shared by K patterns, but the shared-memory stack grows with K.
         const long long work = (long long)B * ((h->L + 31) / 32);  // warps of patterns per category
-        K = work >= 8LL * h->num_sms ? (h->prec == 32 ? 4 : 2) : 1;  // fp32 entries are half the size
+        K = 1;
+        if (work >= 8LL * h->num_sms && 32 * C * (PB ? PB : 1) <= 128) {
+            for (int k : {4, 2}) {
+                int occ = 0;
+                const size_t sm = sweep_smem_bytes(D, k, 32 * C * (PB ? PB : 1), h->prec);
+                if (sm <= h->smem_optin &&
+                    sweep_occupancy(h->prec, h->tips_simple, k, grad, 32 * C * (PB ? PB : 1), sm, &occ) == cudaSuccess &&
+                    occ >= 2) {
+                    K = k;
+                    break;
+                }
+            }
+        } else if (work >= 8LL * h->num_sms) {
+            K = 2;
+        }
     }
     if (K != 1 && K != 2 && K != 4) return fail(PHYLO_B200_EINVAL, "patterns_per_thread must be 1, 2 or 4");
     if (PB == 0) PB = 1;
@@ -153,7 +169,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem;
     h->ntiles = (h->L + tpat - 1) / tpat;
     int occ = 0;
-    CU_TRY(sweep_occupancy(h->prec, K, grad, NT, smem, &occ));
+    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, NT, smem, &occ));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -247,6 +263,13 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
             }
             tips[(size_t)s * h->Lpad + l] = m;
         }
+    // reference-encoded alignments only hold one-hot or all-ones cells (phylostan/utils.py:180-188):
+    // store the column index 0..3 / 4 instead of the mask and use the tip fast path
+    h->tips_simple = true;
+    for (uint8_t m : tips)
+        if (!(m == 15 || m == 1 || m == 2 || m == 4 || m == 8)) { h->tips_simple = false; break; }
+    if (h->tips_simple)
+        for (uint8_t& m : tips) m = m == 15 ? 4 : (m == 1 ? 0 : (m == 2 ? 1 : (m == 4 ? 2 : 3)));
     std::vector<double> w((size_t)h->Lpad, 0.0);
     for (int l = 0; l < L; ++l) {
         w[l] = weights ? weights[l] : 1.0;
@@ -452,6 +475,7 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     sa.nsteps = h->S - 1; sa.bcount = h->bcount; sa.jc_closed = h->jc_closed; sa.B = B;
     const int VP = h->prec == 32 ? 1 : 2;  // 16-byte vectors per 4-state entry
     sa.Lpad = h->Lpad; sa.SS = h->K * VP * h->NT; sa.KNT = h->K * h->NT;
+    sa.S = h->S; sa.tips_simple = h->tips_simple;
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
@@ -466,12 +490,13 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
     a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->plan.depth();
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
-    CU_TRY(launch_sweep(a, h->prec, h->K, grad, h->grid, h->NT, h->smem, st));
+    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, h->grid, h->NT, h->smem, st));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {
         ContractArgs ca{};
         ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
+        ca.S = h->S; ca.tips_simple = h->tips_simple;
         ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
         ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
         launch_contract(ca, h->prec, B, st);
