@@ -121,9 +121,9 @@ __device__ __forceinline__ void matTvec(const T (&m)[16], const T (&x)[4], T (&y
 // `code` is the column index 0..3, or 4 for an all-ones cell.
 template <bool IDX, typename T>
 __device__ __forceinline__ void tip_vec(unsigned code, T (&p)[4]) {
+    if (IDX) code = (0xF8421u >> (4u * code)) & 0xFu;  // index -> mask: 0..3 -> 1,2,4,8 ; 4 -> 15
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
-        p[s] = (IDX ? (code == (unsigned)s || code == 4u) : (((code >> s) & 1u) != 0u)) ? T(1) : T(0);
+    for (int s = 0; s < 4; ++s) p[s] = ((code >> s) & 1u) ? T(1) : T(0);
 }
 
 // Simple-tip fast path (TIPS kernels): every tip cell is one-hot or all ones (what the reference's
