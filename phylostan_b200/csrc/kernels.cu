@@ -194,6 +194,21 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+// K consecutive bytes (K = 1, 2, 4) of a lane as one packed word: byte j = (w >> 8 j) & 0xff
+template <int K>
+__device__ __forceinline__ unsigned ldg_bytes(const uint8_t* p) {
+    if (K == 4) return __ldg(reinterpret_cast<const unsigned*>(p));
+    if (K == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
+    return __ldg(p);
+}
+template <int K>
+__device__ __forceinline__ void stcs_bytes(uint8_t* p, unsigned w) {
+    if (K == 4) __stcs(reinterpret_cast<unsigned*>(p), w);
+    else if (K == 2) __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)w);
+    else __stcs(p, (uint8_t)w);
+}
+#define BYTE_OF(w, j) (((w) >> (8 * (j))) & 0xffu)
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 
     V* const stt = st + tid;
     V* const sct = reinterpret_cast<V*>(a.scratch) + (size_t)blockIdx.x * a.scratch_stride + tid;
-    uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid;
+    uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid * K;  // K exponents per lane, packed
 
     // entry j of the stack slot / scratch row at vector offset `off`
 #define ST(off, j) (stt + (off) + (j) * (VP * NT))
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
         const double* prm = a.params + (size_t)d * a.lay.stride;
-        const int pat0 = tile * tpat + pb * 32 * K + lane;  // pattern of sub-index j: pat0 + 32 j
+        const int pat0 = tile * tpat + pb * 32 * K + lane * K;  // this lane's K consecutive patterns: pat0 + j
         const uint8_t* tipp = a.tips + pat0;
         const size_t stream_off = ((size_t)d * C + c) * nsteps * R::kRec;
 
@@ -436,15 +451,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         }
         ring.start(a.spost + stream_off, nsteps);
         ring.step(0);
-        unsigned ca[K], cb[K];  // tip codes of the current step's children (prefetched one step ahead)
+        // tip codes of the children of steps i (ca, cb), i+1 (ca1, cb1) and, inside the loop, i+2:
+        // K codes per lane packed in one word, loaded two steps ahead of their use
+        unsigned ca = 0u, cb = 0u, ca1 = 0u, cb1 = 0u;
         {
             const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
-            const int fl = r0->flags;
-            const long long ta = r0->tip_a, tb = r0->tip_b;
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                ca[j] = (fl & 1) ? tipp[ta + 32 * j] : 0u;
-                cb[j] = (fl & 2) ? tipp[tb + 32 * j] : 0u;
+            if (r0->flags & 1) ca = ldg_bytes<K>(tipp + r0->tip_a);
+            if (r0->flags & 2) cb = ldg_bytes<K>(tipp + r0->tip_b);
+            if (nsteps > 1) {
+                const PostRec* r1 = reinterpret_cast<const PostRec*>(ring.rec(1));
+                if (r1->flags & 1) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
+                if (r1->flags & 2) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
             }
         }
         V* srow = sct;  // scratch row of step i
@@ -454,33 +471,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             const unsigned char* rec = ring.rec(0);
             const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
             const int fl = s1.w;
-            unsigned nca[K], ncb[K];
-#pragma unroll
-            for (int j = 0; j < K; ++j) nca[j] = ncb[j] = 0u;
-            if (i + 1 < nsteps) {  // tip codes of step i+1 -> registers
-                const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(1));
-                const int nf = n->flags;
-                if (nf & 1) {
-                    const uint8_t* p = tipp + n->tip_a;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) nca[j] = p[32 * j];
-                }
-                if (nf & 2) {
-                    const uint8_t* p = tipp + n->tip_b;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) ncb[j] = p[32 * j];
-                }
-            }
-            if (i + 2 < nsteps) {  // tip codes of step i+2 -> L2
+            unsigned ca2 = 0u, cb2 = 0u;
+            if (i + 2 < nsteps) {  // tip codes of step i+2 -> registers
                 const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(2));
                 const int nf = n->flags;
-                if (nf & 1) prefetch_l2(tipp + n->tip_a);
-                if (nf & 2) prefetch_l2(tipp + n->tip_b);
+                if (nf & 1) ca2 = ldg_bytes<K>(tipp + n->tip_a);
+                if (nf & 2) cb2 = ldg_bytes<K>(tipp + n->tip_b);
             }
             T ma[K][4], mb[K][4];
             if (TIPS && (fl & 1)) {  // tip child: its message is a column of P_a
 #pragma unroll
-                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, ca[j], ma[j]);
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, BYTE_OF(ca, j), ma[j]);
             } else {
                 T M[16];
                 lds_mat(rec + 64, M);
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 for (int j = 0; j < K; ++j) {
                     T p[4];
                     if (!TIPS && (fl & 1)) {
-                        tip_vec<false>(ca[j], p);
+                        tip_vec<false>(BYTE_OF(ca, j), p);
                     } else if (fl & 4) {
 #pragma unroll
                         for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             }
             if (TIPS && (fl & 2)) {
 #pragma unroll
-                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64 + R::kMat, cb[j], mb[j]);
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), mb[j]);
             } else {
                 T M[16];
                 lds_mat(rec + 64 + R::kMat, M);
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 for (int j = 0; j < K; ++j) {
                     T p[4];
                     if (!TIPS && (fl & 2)) {
-                        tip_vec<false>(cb[j], p);
+                        tip_vec<false>(BYTE_OF(cb, j), p);
                     } else {  // an internal second child is always the previous step's result
 #pragma unroll
                         for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int j = 0; j < K; ++j) st4(ST(s1.z, j), NT, tos[j]);
             }
+            unsigned kpack = 0u;
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 T p[4];
@@ -536,19 +538,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                         for (int s = 0; s < 4; ++s) p[s] *= f;
                         etot[j] += kexp;
+                        kpack |= (unsigned)kexp << (8 * j);
                     }
                 }
 #pragma unroll
                 for (int s = 0; s < 4; ++s) tos[j][s] = p[s];
-                if (GRAD) {
-                    st4cs(srow + j * (VP * NT), NT, p);
-                    __stcs(drow + j * NT, (uint8_t)kexp);
-                }
+                if (GRAD) st4cs(srow + j * (VP * NT), NT, p);
             }
+            if (GRAD) stcs_bytes<K>(drow, kpack);
             srow += SS;
             drow += K * NT;
-#pragma unroll
-            for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; }
+            ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2;
         }
 
         // -------------------------------------------------------------- root: site likelihoods
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 const int de = ex_e[base + cc * 32] - emin;
                 sum += de > kMaxDe ? 0.0 : ex_l[base + cc * 32] * pow2_neg(R::kUnit * de);
             }
-            const double w = a.weights[pat0 + 32 * j];
+            const double w = a.weights[pat0 + j];
             if (c == 0) acc_logl += w * (log(sum) - (double)emin * (R::kUnit * 0.6931471805599453));
             const int de = etot[j] - emin;
             const double fac = de > kMaxDe ? 0.0 : w * pow2_neg(R::kUnit * de) / sum;
@@ -597,16 +597,19 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
             ring.step(0);
-            unsigned dcur[K];  // rescale exponent of the current step's node (prefetched)
+            // packed byte operands of steps i (ca, cb, dcur = rescale exponents of the node) and i+1
+            unsigned dcur, d1 = 0u;
+            ca = cb = ca1 = cb1 = 0u;
             {
                 const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
-                const long long ta = r0->tip_a, tb = r0->tip_b;
-                const int ra = r0->row_a, rb = r0->row_b, dn = r0->dl_n;
-#pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    ca[j] = ra < 0 ? tipp[ta + 32 * j] : 0u;
-                    cb[j] = rb < 0 ? tipp[tb + 32 * j] : 0u;
-                    dcur[j] = dlt[dn + j * NT];
+                if (r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
+                if (r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
+                dcur = ldg_bytes<K>(dlt + r0->dl_n);
+                if (nsteps > 1) {
+                    const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
+                    if (r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
+                    if (r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
+                    d1 = ldg_bytes<K>(dlt + r1->dl_n);
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
@@ -622,30 +625,12 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     if (rowa >= 0) ld4cs(SC(rowa, j), NT, pa[j]);
                     if (rowb >= 0) ld4cs(SC(rowb, j), NT, pbv[j]);
                 }
-                unsigned nca[K], ncb[K], ndl[K];
-#pragma unroll
-                for (int j = 0; j < K; ++j) nca[j] = ncb[j] = ndl[j] = 0u;
-                if (i + 1 < nsteps) {  // byte operands of step i+1 -> registers
-                    const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(1));
-                    const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
-                    if (n1.x < 0) {
-                        const uint8_t* p = tipp + n->tip_a;
-#pragma unroll
-                        for (int j = 0; j < K; ++j) nca[j] = p[32 * j];
-                    }
-                    if (n1.y < 0) {
-                        const uint8_t* p = tipp + n->tip_b;
-#pragma unroll
-                        for (int j = 0; j < K; ++j) ncb[j] = p[32 * j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < K; ++j) ndl[j] = dlt[n1.z + j * NT];
-                }
-                if (i + 2 < nsteps) {  // operand lines of step i+2 -> L2
+                unsigned ca2 = 0u, cb2 = 0u, d2 = 0u;
+                if (i + 2 < nsteps) {  // operands of step i+2: bytes -> registers, scratch lines -> L2
                     const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
                     const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
                     if (n1.x < 0) {
-                        prefetch_l2(tipp + n->tip_a);
+                        ca2 = ldg_bytes<K>(tipp + n->tip_a);
                     } else {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
@@ -653,28 +638,28 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.x, j) + h * NT);
                     }
                     if (n1.y < 0) {
-                        prefetch_l2(tipp + n->tip_b);
+                        cb2 = ldg_bytes<K>(tipp + n->tip_b);
                     } else {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
-                    prefetch_l2(dlt + n1.z);
+                    d2 = ldg_bytes<K>(dlt + n1.z);
                 }
                 T qn[K][4];
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (rowa < 0) tip_vec<TIPS>(ca[j], pa[j]);
-                    if (rowb < 0) tip_vec<TIPS>(cb[j], pbv[j]);
+                    if (rowa < 0) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
+                    if (rowb < 0) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
                     if (s1.w < 0) {  // q(node) is the previous step's first child: still in registers
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s];
                     } else {
                         ld4(ST(s1.w, j), NT, qn[j]);
                     }
-                    if (dcur[j]) {  // rare: this node was rescaled in the post-order
-                        const T f = R::pow2((int)dcur[j]);
+                    if (BYTE_OF(dcur, j)) {  // rare: this node was rescaled in the post-order
+                        const T f = R::pow2((int)BYTE_OF(dcur, j));
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] *= f;
                     }
@@ -732,8 +717,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                     warp_reduce16_atomic(G, Gd + s2.y, lane);
                 }
-#pragma unroll
-                for (int j = 0; j < K; ++j) { ca[j] = nca[j]; cb[j] = ncb[j]; dcur[j] = ndl[j]; }
+                ca = ca1; cb = cb1; dcur = d1; ca1 = ca2; cb1 = cb2; d1 = d2;
             }
         }
 
