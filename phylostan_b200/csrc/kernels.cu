@@ -613,18 +613,23 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
+            // children's partials of the current step; loaded from scratch during the previous step's
+            // tail (after their last use there), so no extra registers and a reduction's worth of cover
+            T pa[K][4], pbv[K][4];
+            {
+                const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(0) + 16);  // row_a, row_b, ...
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                    if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                }
+            }
             for (int i = 0; i < nsteps; ++i) {
                 if (i) ring.step(i);
                 const unsigned char* rec = ring.rec(0);
                 const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
                 const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
                 const int rowa = s1.x, rowb = s1.y;
-                T pa[K][4], pbv[K][4];
-#pragma unroll
-                for (int j = 0; j < K; ++j) {  // issue this step's operand loads first
-                    if (rowa >= 0) ld4cs(SC(rowa, j), NT, pa[j]);
-                    if (rowb >= 0) ld4cs(SC(rowb, j), NT, pbv[j]);
-                }
                 unsigned ca2 = 0u, cb2 = 0u, d2 = 0u;
                 if (i + 2 < nsteps) {  // operands of step i+2: bytes -> registers, scratch lines -> L2
                     const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
@@ -714,6 +719,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         lds_mat(rec + 64, M);
 #pragma unroll
                         for (int j = 0; j < K; ++j) matTvec(M, Aa[j], tos[j]);
+                    }
+                    if (i + 1 < nsteps) {  // pa / pbv are dead: fetch the next step's operands now
+                        const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(1) + 16);
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                            if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                        }
                     }
                     warp_reduce16_atomic(G, Gd + s2.y, lane);
                 }
