@@ -224,10 +224,13 @@ def run_ours(args):
             dist.all_reduce(out_t)
 
     def e2e_step():
+        if world == 1:  # the call a user (or the Stan shim) makes: phylo_b200_eval_batch on host arrays
+            vg = lik.value_grad(bl, rates, freqs, rs, ps)
+            return np.concatenate([vg.log_P[:, None], vg.grad_blens, vg.grad_subst, vg.grad_freqs, vg.grad_rs,
+                                   vg.grad_ps], axis=1)
         lik.upload(bl, rates, freqs, rs, ps)       # host packing + H2D
         lik.run(B, True)
-        if world > 1:
-            dist.all_reduce(out_t)
+        dist.all_reduce(out_t)
         return lik.download(B)                     # D2H + sync
 
     # ---- device-resident timing (value) with per-kernel CUDA events

@@ -652,17 +652,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                     d2 = ldg_bytes<K>(dlt + n1.z);
                 }
-                T qn[K][4];
+                // q(node) lives in the TOS registers for the whole step: either it is still there (the
+                // node was the previous step's first child) or it is popped from the shared-memory stack
+                T (&qn)[K][4] = tos;
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (rowa < 0) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
                     if (rowb < 0) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
-                    if (s1.w < 0) {  // q(node) is the previous step's first child: still in registers
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) qn[j][s] = tos[j][s];
-                    } else {
-                        ld4(ST(s1.w, j), NT, qn[j]);
-                    }
+                    if (s1.w >= 0) ld4(ST(s1.w, j), NT, qn[j]);
                     if (BYTE_OF(dcur, j)) {  // rare: this node was rescaled in the post-order
                         const T f = R::pow2((int)BYTE_OF(dcur, j));
 #pragma unroll
