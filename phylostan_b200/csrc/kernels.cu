@@ -201,6 +201,14 @@ __device__ __forceinline__ unsigned ldg_bytes(const uint8_t* p) {
     if (K == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
     return __ldg(p);
 }
+// same, through the coherent path: the rescale exponents are written earlier in the SAME kernel, so
+// the read-only (.nc) path of __ldg must not be used for them
+template <int K>
+__device__ __forceinline__ unsigned ld_bytes(const uint8_t* p) {
+    if (K == 4) return __ldcs(reinterpret_cast<const unsigned*>(p));
+    if (K == 2) return __ldcs(reinterpret_cast<const unsigned short*>(p));
+    return __ldcs(p);
+}
 template <int K>
 __device__ __forceinline__ void stcs_bytes(uint8_t* p, unsigned w) {
     if (K == 4) __stcs(reinterpret_cast<unsigned*>(p), w);
@@ -604,12 +612,12 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
                 if (r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
                 if (r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
-                dcur = ldg_bytes<K>(dlt + r0->dl_n);
+                dcur = ld_bytes<K>(dlt + r0->dl_n);
                 if (nsteps > 1) {
                     const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
                     if (r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
                     if (r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
-                    d1 = ldg_bytes<K>(dlt + r1->dl_n);
+                    d1 = ld_bytes<K>(dlt + r1->dl_n);
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
@@ -650,7 +658,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
-                    d2 = ldg_bytes<K>(dlt + n1.z);
+                    d2 = ld_bytes<K>(dlt + n1.z);
                 }
                 // q(node) lives in the TOS registers for the whole step: either it is still there (the
                 // node was the previous step's first child) or it is popped from the shared-memory stack
