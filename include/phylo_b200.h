@@ -130,6 +130,21 @@ PHYLO_B200_API int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t *m
                                            double *g_ps);
 
 /*
+ * The same front end for the autocorrelated clocks (acln, acg, ace, aoup, hsmrf, gmrf; replaces
+ * `heights_to_blens_autocorr`, phylostan/generate_script.py:682-708): the rate of a branch is the mean
+ * of the rates at its two ends,
+ *     blens[node] = 1/2 (substrates[node] + substrates[parent]) * (heights[parent] - heights|lowers[node])
+ * with substrates[map[2,1]] standing in for the root's rate, and the branch above map[2,1] (the first
+ * child of the root in the pre-order map) using substrates[map[2,1]] alone.  nrates must be 2S-2.
+ */
+PHYLO_B200_API int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const int32_t *map, const double *heights,
+                                                    const double *lowers, const double *rates, int nrates,
+                                                    const double *subst, const double *freqs, const double *rs,
+                                                    const double *ps, int want_grad, double *logp,
+                                                    double *g_heights, double *g_rates, double *g_subst,
+                                                    double *g_freqs, double *g_rs, double *g_ps);
+
+/*
  * Split form of eval_batch for callers that keep parameters resident on the device between
  * evaluations (benchmarks, batched drivers, multi-GPU ranks):
  *   upload   host parameters -> device (one H2D copy); also derives the eigen system per draw

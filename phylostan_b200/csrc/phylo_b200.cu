@@ -560,23 +560,44 @@ int phylo_b200_eval(phylo_b200_handle h, const double* blens, const double* subs
                                  g_rs, g_ps);
 }
 
-int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t* map, const double* heights, const double* lowers,
-                            const double* rates, int nrates, const double* subst, const double* freqs,
-                            const double* rs, const double* ps, int want_grad, double* logp, double* g_heights,
-                            double* g_rates, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
-    if (!h || !map || !heights || !rates || !logp) return fail(PHYLO_B200_EINVAL, "eval_heights: NULL argument");
-    if (!h->rooted) return fail(PHYLO_B200_EINVAL, "eval_heights needs a rooted (clock) handle");
+// heights -> branch lengths on the host (O(S)), likelihood on the device, chain rule back on the host.
+// autocorr == 0: generate_script.py:660-679 (strict / uncorrelated clocks);
+// autocorr == 1: generate_script.py:682-708 (branch rate = mean of the rates at its two ends).
+static int eval_heights_impl(phylo_b200_handle h, int autocorr, const int32_t* map, const double* heights,
+                             const double* lowers, const double* rates, int nrates, const double* subst,
+                             const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
+                             double* g_heights, double* g_rates, double* g_subst, double* g_freqs, double* g_rs,
+                             double* g_ps) {
+    const char* who = autocorr ? "eval_heights_autocorr" : "eval_heights";
+    if (!h || !map || !heights || !rates || !logp) return fail(PHYLO_B200_EINVAL, std::string(who) + ": NULL argument");
+    if (!h->rooted) return fail(PHYLO_B200_EINVAL, std::string(who) + " needs a rooted (clock) handle");
     const int S = h->S, nn = h->nn;
-    if (nrates != 1 && nrates != h->bcount) return fail(PHYLO_B200_EINVAL, "eval_heights: nrates must be 1 or 2S-2");
+    if (autocorr ? nrates != h->bcount : (nrates != 1 && nrates != h->bcount))
+        return fail(PHYLO_B200_EINVAL, std::string(who) + (autocorr ? ": nrates must be 2S-2" : ": nrates must be 1 or 2S-2"));
     std::vector<double> blens(h->bcount, 0.0), gb(h->bcount, 0.0);
-    // generate_script.py:660-679: rows 2..nodeCount of the pre-order map
     for (int j = 1; j < nn; ++j) {
         const int node = map[2 * j], par = map[2 * j + 1];
         if (node < 1 || node >= nn || par <= S || par > nn)
-            return fail(PHYLO_B200_EINVAL, "eval_heights: malformed pre-order map row " + std::to_string(j));
-        const double r = nrates == 1 ? rates[0] : rates[node - 1];
+            return fail(PHYLO_B200_EINVAL, std::string(who) + ": malformed pre-order map row " + std::to_string(j));
+    }
+    // rate multiplier of the branch above `node`, and the (up to two) rate slots it reads
+    const int first = map[2] - 1;  // map[2,1] of the Stan program: the first child of the root
+    auto slots = [&](int j, int& s0, int& s1) {
+        const int node = map[2 * j], par = map[2 * j + 1];
+        if (!autocorr) { s0 = nrates == 1 ? 0 : node - 1; s1 = -1; return; }
+        s0 = node - 1;
+        s1 = j == 1 ? -1 : (par == nn ? first : par - 1);
+    };
+    auto span = [&](int j) {
+        const int node = map[2 * j], par = map[2 * j + 1];
         const double lo = node > S ? heights[node - S - 1] : (lowers ? lowers[node - 1] : 0.0);
-        blens[node - 1] = r * (heights[par - S - 1] - lo);
+        return heights[par - S - 1] - lo;
+    };
+    for (int j = 1; j < nn; ++j) {
+        int s0, s1;
+        slots(j, s0, s1);
+        const double r = s1 < 0 ? rates[s0] : 0.5 * (rates[s0] + rates[s1]);
+        blens[map[2 * j] - 1] = r * span(j);
     }
     int rc = phylo_b200_eval(h, blens.data(), subst, freqs, rs, ps, want_grad, logp, gb.data(), g_subst, g_freqs, g_rs,
                              g_ps);
@@ -585,16 +606,38 @@ int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t* map, const doubl
     if (g_rates) std::fill(g_rates, g_rates + nrates, 0.0);
     for (int j = 1; j < nn; ++j) {
         const int node = map[2 * j], par = map[2 * j + 1];
-        const double r = nrates == 1 ? rates[0] : rates[node - 1];
-        const double lo = node > S ? heights[node - S - 1] : (lowers ? lowers[node - 1] : 0.0);
+        int s0, s1;
+        slots(j, s0, s1);
+        const double r = s1 < 0 ? rates[s0] : 0.5 * (rates[s0] + rates[s1]);
         const double g = gb[node - 1];
         if (g_heights) {
             g_heights[par - S - 1] += r * g;
             if (node > S) g_heights[node - S - 1] -= r * g;
         }
-        if (g_rates) g_rates[nrates == 1 ? 0 : node - 1] += (heights[par - S - 1] - lo) * g;
+        if (g_rates) {
+            const double d = span(j) * g;
+            if (s1 < 0) g_rates[s0] += d;
+            else { g_rates[s0] += 0.5 * d; g_rates[s1] += 0.5 * d; }
+        }
     }
     return 0;
+}
+
+int phylo_b200_eval_heights(phylo_b200_handle h, const int32_t* map, const double* heights, const double* lowers,
+                            const double* rates, int nrates, const double* subst, const double* freqs,
+                            const double* rs, const double* ps, int want_grad, double* logp, double* g_heights,
+                            double* g_rates, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+    return eval_heights_impl(h, 0, map, heights, lowers, rates, nrates, subst, freqs, rs, ps, want_grad, logp,
+                             g_heights, g_rates, g_subst, g_freqs, g_rs, g_ps);
+}
+
+int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const int32_t* map, const double* heights,
+                                     const double* lowers, const double* rates, int nrates, const double* subst,
+                                     const double* freqs, const double* rs, const double* ps, int want_grad,
+                                     double* logp, double* g_heights, double* g_rates, double* g_subst,
+                                     double* g_freqs, double* g_rs, double* g_ps) {
+    return eval_heights_impl(h, 1, map, heights, lowers, rates, nrates, subst, freqs, rs, ps, want_grad, logp,
+                             g_heights, g_rates, g_subst, g_freqs, g_rs, g_ps);
 }
 
 // Host-only planning hook (no GPU): exercised by the CPU test-suite.

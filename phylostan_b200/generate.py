@@ -47,6 +47,7 @@ def likelihood_call(params) -> str:
 
 DECLARATION_HEIGHTS = ("\treal phylo_loglik_heights(real[] heights, real[] rates, int[,] map, real[] lowers, "
                        "vector subst, vector freqs, vector rs, vector ps);\n")
+DECLARATION_AUTOCORR = DECLARATION_HEIGHTS.replace("phylo_loglik_heights(", "phylo_loglik_heights_autocorr(")
 AUTOCORRELATED = ("acln", "acg", "ace", "aoup", "hsmrf", "gmrf")  # generate_script.py:1333
 
 
@@ -56,26 +57,29 @@ def heights_call(params) -> str:
     subst = {"GTR": "rates", "HKY": "rep_vector(kappa, 1)", "JC69": "rep_vector(0.0, 0)"}[params.model]
     site = "rs, ps" if is_mixture(params) else "rep_vector(1.0, 1), rep_vector(1.0, 1)"
     strict = params.clock == "strict" or not params.estimate_rate       # generate_script.py:1336
-    rate = "rep_array(rate, 1)" if strict else "substrates"
+    autocorr = params.clock in AUTOCORRELATED
+    rate = "substrates" if autocorr or not strict else "rep_array(rate, 1)"
     lowers = "lowers" if params.heterochronous else "rep_array(0.0, 2*S-1)"
-    return "\ttarget += phylo_loglik_heights(heights, {}, map, {}, {}, freqs, {});\n".format(rate, lowers, subst, site)
+    return "\ttarget += phylo_loglik_heights{}(heights, {}, map, {}, {}, freqs, {});\n".format(
+        "_autocorr" if autocorr else "", rate, lowers, subst, site)
 
 
 def externalize(script: str, params, generate_script=None, heights: bool = False) -> str:
     """Rewrite a program produced by the reference's ``get_model(params)``.
 
-    ``heights=True`` (clock trees with a strict or uncorrelated clock) also moves the
-    heights -> branch-length loop into the library."""
+    ``heights=True`` (clock trees) also moves the heights -> branch-length loop into the library."""
     g = _reference_generator(generate_script)
     mixture, clock = is_mixture(params), params.clock is not None
     like = g.likelihood(mixture, clock)
     if like not in script:
         raise ValueError("the program does not contain the reference's likelihood block")
     if heights:
-        if not clock or params.clock in AUTOCORRELATED:
-            raise ValueError("heights=True needs a clock tree with a strict or uncorrelated clock")
+        if not clock:
+            raise ValueError("heights=True needs a clock tree")
+        autocorr = params.clock in AUTOCORRELATED
         strict = params.clock == "strict" or not params.estimate_rate
-        h2b = g.heights_to_blens(params.heterochronous, strict)
+        h2b = (g.heights_to_blens_autocorr(params.heterochronous) if autocorr
+               else g.heights_to_blens(params.heterochronous, strict))
         if h2b not in script:
             raise ValueError("the program does not contain the reference's heights_to_blens block")
         script = script.replace(h2b, "").replace(like, heights_call(params))
@@ -86,7 +90,8 @@ def externalize(script: str, params, generate_script=None, heights: bool = False
     fn = {"GTR": g.GTR, "HKY": g.HKY, "JC69": g.JC69}[params.model](params.categories, params.invariant)
     if fn not in script:
         raise ValueError("the program does not contain the reference's P-matrix function")
-    script = script.replace(fn, DECLARATION_HEIGHTS if heights else DECLARATION)
+    script = script.replace(fn, DECLARATION if not heights else
+                            DECLARATION_AUTOCORR if params.clock in AUTOCORRELATED else DECLARATION_HEIGHTS)
     kept = []
     for line in script.split("\n"):
         s = line.strip()

@@ -68,6 +68,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_eval_batch.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_eval_heights.argtypes = [vp, ip, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp,
                                           _dp, _dp]
+    L.phylo_b200_eval_heights_autocorr.argtypes = L.phylo_b200_eval_heights.argtypes
     L.phylo_b200_upload.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_run.argtypes = [vp, i, i]
     L.phylo_b200_device_out.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i)]
@@ -220,9 +221,11 @@ class TreeLikelihood:
                                            _ptr(logp), None, None, None, None, None))
         return float(logp[0]) if single else logp
 
-    def value_grad_heights(self, map_, heights, rates, lowers=None, subst=None, freqs=None, rs=None, ps=None):
+    def value_grad_heights(self, map_, heights, rates, lowers=None, subst=None, freqs=None, rs=None, ps=None,
+                           autocorrelated=False):
         """Clock-tree front end (generate_script.py:660-679): node heights + rate(s) in, gradient with
-        respect to heights and rate(s) out.  ``rates``: scalar (strict clock) or [2S-2] substrates."""
+        respect to heights and rate(s) out.  ``rates``: scalar (strict clock) or [2S-2] substrates.
+        ``autocorrelated=True``: branch rate = mean of the rates at both ends (generate_script.py:682-708)."""
         m = np.ascontiguousarray(map_, dtype=np.int32)
         hts = _arr(heights, (self.S - 1,))
         rt = _arr(np.atleast_1d(rates))
@@ -234,9 +237,10 @@ class TreeLikelihood:
         logp = np.zeros(1)
         gh, gr = np.zeros(self.S - 1), np.zeros(rt.size)
         gs, gf, grs, gps = np.zeros(max(self.nsubst, 1)), np.zeros(4), np.zeros(self.C), np.zeros(self.C)
-        _check(lib().phylo_b200_eval_heights(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(hts),
-                                             _ptr(lo), _ptr(rt), rt.size, _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps),
-                                             1, _ptr(logp), _ptr(gh), _ptr(gr), _ptr(gs), _ptr(gf), _ptr(grs), _ptr(gps)))
+        fn = lib().phylo_b200_eval_heights_autocorr if autocorrelated else lib().phylo_b200_eval_heights
+        _check(fn(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(hts), _ptr(lo), _ptr(rt), rt.size,
+                  _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps), 1, _ptr(logp), _ptr(gh), _ptr(gr), _ptr(gs), _ptr(gf),
+                  _ptr(grs), _ptr(gps)))
         return float(logp[0]), gh, gr, ValueGrad(float(logp[0]), None, gs[:self.nsubst], gf, grs, gps)
 
     # ------------------------------------------------------------------ resident / split form

@@ -142,19 +142,20 @@ inline void push_operands(const std::vector<double>&, const double*, std::vector
                           std::vector<double>&) {}
 }  // namespace phylo_b200_stan
 
+namespace phylo_b200_stan {
 template <typename T_h, typename T_r, typename T_su, typename T_fr, typename T_rs, typename T_ps>
-inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_loglik_heights(
-    const std::vector<T_h>& heights, const std::vector<T_r>& rates, const std::vector<std::vector<int> >& map,
-    const std::vector<double>& lowers, const Eigen::Matrix<T_su, Eigen::Dynamic, 1>& subst,
-    const Eigen::Matrix<T_fr, Eigen::Dynamic, 1>& freqs, const Eigen::Matrix<T_rs, Eigen::Dynamic, 1>& rs,
-    const Eigen::Matrix<T_ps, Eigen::Dynamic, 1>& ps, std::ostream* /*pstream__*/) {
+inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type loglik_heights(
+    bool autocorr, const std::vector<T_h>& heights, const std::vector<T_r>& rates,
+    const std::vector<std::vector<int> >& map, const std::vector<double>& lowers,
+    const Eigen::Matrix<T_su, Eigen::Dynamic, 1>& subst, const Eigen::Matrix<T_fr, Eigen::Dynamic, 1>& freqs,
+    const Eigen::Matrix<T_rs, Eigen::Dynamic, 1>& rs, const Eigen::Matrix<T_ps, Eigen::Dynamic, 1>& ps) {
     namespace p = phylo_b200_stan;
     typedef typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type R;
     phylo_b200_handle h = p::handle();
     const int bcount = phylo_b200_bcount(h), nsubst = phylo_b200_nsubst(h), C = phylo_b200_ncat(h);
     const int S = bcount / 2 + 1;
     if ((int)heights.size() != S - 1 || (int)map.size() != 2 * S - 1 || (int)lowers.size() != 2 * S - 1 ||
-        ((int)rates.size() != 1 && (int)rates.size() != bcount) || subst.rows() != nsubst || rs.rows() != C ||
+        ((int)rates.size() != bcount && (autocorr || (int)rates.size() != 1)) || subst.rows() != nsubst || rs.rows() != C ||
         ps.rows() != C || (nsubst > 0 && freqs.rows() != 4))
         throw std::invalid_argument("phylo_loglik_heights: argument sizes do not match the published tree/alignment");
     std::vector<int32_t> fmap(2 * map.size());
@@ -168,10 +169,10 @@ inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_
     const int want_grad = !p::is_double<R>::value;
     double logp = 0.0;
     std::vector<double> gh(S - 1), gr(rates.size()), gs(nsubst > 0 ? nsubst : 1), gf(4), grs(C), gp(C);
-    p::check(phylo_b200_eval_heights(h, fmap.data(), xh.data(), lowers.data(), xr.data(), (int)xr.size(),
-                                     nsubst ? xs.data() : 0, xf.size() == 4 ? xf.data() : 0, xrs.data(), xp.data(),
-                                     want_grad, &logp, gh.data(), gr.data(), gs.data(), gf.data(), grs.data(),
-                                     gp.data()));
+    p::check((autocorr ? phylo_b200_eval_heights_autocorr : phylo_b200_eval_heights)(
+        h, fmap.data(), xh.data(), lowers.data(), xr.data(), (int)xr.size(), nsubst ? xs.data() : 0,
+        xf.size() == 4 ? xf.data() : 0, xrs.data(), xp.data(), want_grad, &logp, gh.data(), gr.data(), gs.data(),
+        gf.data(), grs.data(), gp.data()));
     std::vector<stan::math::var> ops;
     std::vector<double> grads;
     if (want_grad) {
@@ -183,6 +184,28 @@ inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_
         p::push_operands(ps, gp.data(), ops, grads);
     }
     return p::finish<R>::go(logp, ops, grads);
+}
+}  // namespace phylo_b200_stan
+
+template <typename T_h, typename T_r, typename T_su, typename T_fr, typename T_rs, typename T_ps>
+inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_loglik_heights(
+    const std::vector<T_h>& heights, const std::vector<T_r>& rates, const std::vector<std::vector<int> >& map,
+    const std::vector<double>& lowers, const Eigen::Matrix<T_su, Eigen::Dynamic, 1>& subst,
+    const Eigen::Matrix<T_fr, Eigen::Dynamic, 1>& freqs, const Eigen::Matrix<T_rs, Eigen::Dynamic, 1>& rs,
+    const Eigen::Matrix<T_ps, Eigen::Dynamic, 1>& ps, std::ostream* /*pstream__*/) {
+    return phylo_b200_stan::loglik_heights(false, heights, rates, map, lowers, subst, freqs, rs, ps);
+}
+
+// real phylo_loglik_heights_autocorr(real[] heights, real[] substrates, int[,] map, real[] lowers,
+//                                    vector subst, vector freqs, vector rs, vector ps)
+// Autocorrelated clocks: replaces heights_to_blens_autocorr (generate_script.py:682-708) + the likelihood.
+template <typename T_h, typename T_r, typename T_su, typename T_fr, typename T_rs, typename T_ps>
+inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type phylo_loglik_heights_autocorr(
+    const std::vector<T_h>& heights, const std::vector<T_r>& rates, const std::vector<std::vector<int> >& map,
+    const std::vector<double>& lowers, const Eigen::Matrix<T_su, Eigen::Dynamic, 1>& subst,
+    const Eigen::Matrix<T_fr, Eigen::Dynamic, 1>& freqs, const Eigen::Matrix<T_rs, Eigen::Dynamic, 1>& rs,
+    const Eigen::Matrix<T_ps, Eigen::Dynamic, 1>& ps, std::ostream* /*pstream__*/) {
+    return phylo_b200_stan::loglik_heights(true, heights, rates, map, lowers, subst, freqs, rs, ps);
 }
 
 // real pruning_loglik(vector blens) -- the reference's own operator (eigen/prune_stan.hpp:9-17,

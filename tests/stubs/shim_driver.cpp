@@ -3,6 +3,8 @@
 //   shim_driver --no-gpu          : no handle published -> the shim must throw std::runtime_error
 //   shim_driver problem.bin       : value (double overload) and value+gradient (var overload)
 #include <cstdint>
+#include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -114,6 +116,16 @@ int main(int argc, char** argv) {
         std::printf(", \"heights_value\": %.17g, \"heights_nops\": %d, \"heights_grad\": [", r4.val(), (int)r4.vi_->ops.size());
         for (int i = 0; i < S - 1; ++i) std::printf("%s%.17g", i ? ", " : "", vh[i].adj());
         std::printf("], \"rate_grad\": %.17g", vrate[0].adj());
+        // autocorrelated variant with every substrate equal to the strict rate: same branch lengths
+        std::vector<stan::math::var> vh2(hts.begin(), hts.end()), vsub(2 * S - 2, stan::math::var(rate[0]));
+        stan::math::var r5 = model_namespace::phylo_loglik_heights_autocorr(vh2, vsub, m2, lowers, make<VecD>(su), make<VecD>(fr),
+                                                                            make<VecD>(rs), make<VecD>(ps), &std::cout);
+        r5.grad();
+        double hdiff = 0.0, rsum = 0.0;
+        for (int i = 0; i < S - 1; ++i) hdiff = std::max(hdiff, std::fabs(vh2[i].adj() - vh[i].adj()));
+        for (int i = 0; i < 2 * S - 2; ++i) rsum += vsub[i].adj();
+        std::printf(", \"autocorr_value\": %.17g, \"autocorr_heights_maxdiff\": %.17g, \"autocorr_rate_grad_sum\": %.17g",
+                    r5.val(), hdiff, rsum);
     }
     std::printf("}\n");
     phylo_b200_destroy(h);

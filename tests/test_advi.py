@@ -1,0 +1,195 @@
+"""Batched ADVI driver (phylostan_b200/advi.py): transforms, the model block's gradient, the optimiser.
+CPU tests drive the model block with the oracle as likelihood back end; the GPU tests with the library."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from phylostan_b200 import advi, synth
+from phylostan_b200 import encode as E
+
+from conftest import GOLDEN
+
+
+class OracleLikelihood:
+    """The TreeLikelihood surface UnrootedModel uses, answered by the CPU oracle (test infrastructure)."""
+
+    def __init__(self, peel, tipmask, weights, model, C):
+        self.peel, self.tipmask, self.weights = peel, tipmask, weights
+        self.model, self.C = {"JC69": O.JC69, "HKY": O.HKY, "GTR": O.GTR}[model], C
+        self.bcount = 2 * tipmask.shape[0] - 3
+        self.nsubst = {"JC69": 0, "HKY": 1, "GTR": 6}[model]
+        self.calls = 0
+
+    def _each(self, blens, subst, freqs, rs, ps, want_grad):
+        self.calls += 1
+        out = []
+        for b in range(blens.shape[0]):
+            out.append(O.loglik_grad(self.peel, self.tipmask, self.weights, self.model, blens[b],
+                                     None if subst is None else subst[b], None if freqs is None else freqs[b],
+                                     rs[b], ps[b], rooted=False, want_grad=want_grad))
+        return out
+
+    def value_grad(self, blens, subst=None, freqs=None, rs=None, ps=None):
+        from phylostan_b200.likelihood import ValueGrad
+        r = self._each(blens, subst, freqs, rs, ps, True)
+        st = lambda name: np.stack([np.atleast_1d(getattr(x, name)) for x in r])
+        return ValueGrad(np.array([x.logp for x in r]), st("grad_blens"),
+                         st("grad_subst") if self.nsubst else np.zeros((len(r), 0)), st("grad_freqs"), st("grad_rs"),
+                         st("grad_ps"))
+
+    def loglik(self, blens, subst=None, freqs=None, rs=None, ps=None):
+        return np.array([x.logp for x in self._each(blens, subst, freqs, rs, ps, False)])
+
+
+def small_problem(model, C, S=6, L=40, seed=5):
+    prob = synth.make_problem(S, L, C, seed=seed)
+    peel = E.unrooted_swap(prob.peel)
+    return OracleLikelihood(peel, prob.tipmask, prob.weights, model, C)
+
+
+def test_simplex_transform_is_stans_stick_breaking():
+    rng = np.random.default_rng(0)
+    y = rng.normal(0, 1.5, (7, 5))
+    x, logj, cache = advi.simplex_constrain(y)
+    assert np.allclose(x.sum(axis=1), 1.0) and np.all(x > 0)
+    assert np.allclose(advi.simplex_constrain(np.zeros((1, 3)))[0], 0.25)       # y = 0 is the uniform simplex
+    # log|J| against the determinant of the numerical Jacobian of the first K-1 coordinates
+    for b in range(3):
+        J = np.zeros((5, 5))
+        for k in range(5):
+            e = np.zeros(5); e[k] = 1e-6
+            J[:, k] = (advi.simplex_constrain((y[b] + e)[None])[0][0, :5] - advi.simplex_constrain((y[b] - e)[None])[0][0, :5]) / 2e-6
+        assert math.log(abs(np.linalg.det(J))) == pytest.approx(logj[b], abs=1e-6)
+    # adjoint: d/dy [ sum(c * log x) + logJ ]
+    c = rng.uniform(0.5, 2.0, 6)
+    f = lambda yy: (c * np.log(advi.simplex_constrain(yy)[0])).sum(axis=1) + advi.simplex_constrain(yy)[1]
+    g = advi.simplex_adjoint(c / x, cache)
+    for k in range(5):
+        e = np.zeros(5); e[k] = 1e-6
+        assert np.allclose((f(y + e) - f(y - e)) / 2e-6, g[:, k], rtol=1e-6, atol=1e-7)
+
+
+def test_weibull_rates_and_derivative():
+    w = np.array([0.488, 1.3])
+    rs, drs = advi.weibull_rates(w, 4)
+    assert np.allclose(rs[0], E.weibull_rates(0.488, 4)) and np.allclose(rs.mean(axis=1), 1.0)
+    fd = (advi.weibull_rates(w + 1e-6, 4)[0] - advi.weibull_rates(w - 1e-6, 4)[0]) / 2e-6
+    assert np.allclose(drs, fd, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("model,C", [("GTR", 4), ("HKY", 4), ("JC69", 1), ("JC69", 3)])
+def test_model_block_gradient_matches_finite_differences(model, C):
+    lik = small_problem(model, C)
+    m = advi.UnrootedModel(lik, model, rates_alpha=np.array([1, 2, 1, 1, 2, 1.5]), freqs_alpha=np.array([2, 1, 1, 3.0]))
+    assert m.dim == (1 if C > 1 else 0) + lik.bcount + {"GTR": 8, "HKY": 4, "JC69": 0}[model]
+    assert len(m.constrained_names()) == m.constrained_matrix(np.zeros((1, m.dim))).shape[1]
+    rng = np.random.default_rng(3)
+    Z = rng.normal(-1.0, 0.7, (3, m.dim))
+    lp, G = m.log_prob_grad(Z)
+    assert lik.calls == 1                                      # one batched likelihood call for all draws
+    assert np.allclose(lp, m.log_prob(Z), rtol=1e-13)
+    for k in range(m.dim):
+        e = np.zeros(m.dim); e[k] = 1e-6
+        fd = (m.log_prob(Z + e) - m.log_prob(Z - e)) / 2e-6
+        assert np.allclose(fd, G[:, k], rtol=2e-5, atol=2e-5), (k, fd, G[:, k])
+
+
+def test_model_block_value_is_the_stan_program():
+    """log_prob restated literally from tests/golden/DS1-GTR-W4-external.stan for one draw."""
+    lik = small_problem("GTR", 4)
+    m = advi.UnrootedModel(lik, "GTR")
+    rng = np.random.default_rng(11)
+    z = rng.normal(-1.0, 0.5, m.dim)
+    c = m.constrain(z[None])
+    wshape, blens, rates, freqs = c["wshape"][0], c["blens"][0], c["rates"][0], c["freqs"][0]
+    assert wshape == pytest.approx(0.1 + math.exp(z[0]))
+    C = 4
+    rs = np.array([(-math.log(1.0 - (2.0 * i + 1.0) / (2.0 * C))) ** (1.0 / wshape) for i in range(C)])
+    rs /= rs.sum() / C
+    target = -wshape - 10.0 * blens.sum()                    # exponential(1), exponential(10); dirichlet(1) is flat
+    target += O.loglik_grad(lik.peel, lik.tipmask, lik.weights, O.GTR, blens, rates, freqs, rs, np.full(C, 1.0 / C),
+                            rooted=False, want_grad=False).logp
+    assert m.log_prob(z[None])[0] - c["logj"][0] == pytest.approx(target, rel=1e-12)
+    # draws outside the domain are dropped, not fatal
+    bad = np.vstack([z, np.full(m.dim, 800.0)])
+    lp = m.log_prob(bad)
+    assert np.isfinite(lp[0]) and lp[1] == -np.inf
+
+
+class GaussianTarget:
+    """log p(z) = -1/2 sum ((z - m)/s)^2: the mean-field optimum is mu = m, omega = log s."""
+
+    def __init__(self, mean, sd):
+        self.mean, self.sd, self.dim = np.asarray(mean, float), np.asarray(sd, float), len(mean)
+
+    def log_prob(self, Z):
+        return -0.5 * (((Z - self.mean) / self.sd) ** 2).sum(axis=1)
+
+    def log_prob_grad(self, Z, want_grad=True):
+        return self.log_prob(Z), -(Z - self.mean) / self.sd ** 2
+
+    def constrained_names(self):
+        return [f"z.{i + 1}" for i in range(self.dim)]
+
+    def constrained_matrix(self, Z):
+        return Z
+
+
+def test_advi_recovers_a_gaussian():
+    tgt = GaussianTarget([1.0, -2.0, 0.5, 3.0], [0.5, 2.0, 1.0, 0.1])
+    fit = advi.advi_meanfield(tgt, iter=3000, grad_samples=16, elbo_samples=200, tol_rel_obj=1e-4, seed=4, init="zero")
+    assert fit.eta in advi._Advi.ETA_SEQUENCE
+    assert np.allclose(fit.mu, tgt.mean, atol=0.15)
+    assert np.allclose(np.exp(fit.omega), tgt.sd, rtol=0.2)
+    assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
+    assert fit.draws.shape == (1000, 4)
+    # one library call per iteration / per ELBO estimate, regardless of the number of draws
+    assert fit.likelihood_draws > 10 * fit.likelihood_calls
+
+
+def test_advi_on_a_small_tree_with_the_oracle_back_end():
+    lik = small_problem("JC69", 1, S=5, L=30)
+    m = advi.UnrootedModel(lik, "JC69")
+    fit = advi.advi_meanfield(m, iter=60, grad_samples=2, elbo_samples=20, eval_elbo=20, eta=0.1, seed=2,
+                              init=np.full(m.dim, -2.0), output_samples=50)
+    assert fit.iterations <= 60 and len(fit.elbo_trace) >= 2
+    assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
+    assert fit.draws.shape == (50, lik.bcount) and np.all(fit.draws > 0)
+
+
+# --------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_model_block_matches_oracle_back_end_on_ds1():
+    from phylostan_b200 import likelihood as lk
+    d = np.load(GOLDEN + "/DS1.npz")
+    rng = np.random.default_rng(8)
+    ora = OracleLikelihood(d["peel"], d["tipmask"], d["weights"], "GTR", 4)
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=False) as lik:
+        m_gpu, m_cpu = advi.UnrootedModel(lik, "GTR"), advi.UnrootedModel(ora, "GTR")
+        Z = rng.normal(-2.5, 0.5, (6, m_gpu.dim))
+        lp, G = m_gpu.log_prob_grad(Z)
+        lp0, G0 = m_cpu.log_prob_grad(Z)
+        assert np.max(np.abs(lp - lp0) / np.abs(lp0)) <= 1e-10
+        assert np.max(np.abs(G - G0) / np.maximum(1.0, np.abs(G0))) <= 1e-8
+        assert np.max(np.abs(m_gpu.log_prob(Z) - lp0) / np.abs(lp0)) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_batched_advi_on_ds1():
+    """DS1, GTR+W4 (BASELINE config 2's model): the ELBO rises and the fit lands on sensible values."""
+    from phylostan_b200 import likelihood as lk
+    d = np.load(GOLDEN + "/DS1.npz")
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=False) as lik:
+        m = advi.UnrootedModel(lik, "GTR")
+        fit = advi.advi_meanfield(m, iter=1500, grad_samples=8, elbo_samples=100, tol_rel_obj=0.001, seed=3,
+                                  output_samples=200)
+    e0, e1 = fit.elbo_trace[0][1], fit.elbo_trace[-1][1]
+    assert e1 > e0 and e1 > -9000.0            # the alignment's log-likelihood at a fitted tree is about -7100
+    mean = fit.mean()
+    total = sum(v for k, v in mean.items() if k.startswith("blens."))
+    assert 0.5 < total < 10.0
+    assert abs(sum(mean[f"freqs.{i}"] for i in range(1, 5)) - 1.0) < 1e-9
+    assert mean["rates.2"] > mean["rates.1"] and mean["rates.5"] > mean["rates.6"]    # transitions > transversions
+    assert fit.likelihood_calls < fit.iterations + fit.iterations // 100 + 400

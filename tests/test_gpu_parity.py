@@ -371,6 +371,54 @@ def test_gpu_heights_front_end(datasets, strict):
     assert (f(hp, rates) - f(hm, rates)) / (2 * eps) == pytest.approx(got_h[k], rel=1e-5, abs=1e-4)
 
 
+def test_gpu_heights_front_end_autocorrelated(datasets):
+    """heights_to_blens_autocorr (generate_script.py:682-708): the Stan loops restated literally in torch
+    fp64, their reverse sweep by autograd, the likelihood part from the oracle."""
+    import torch
+    d = datasets["fluA"]
+    S = d["tipmask"].shape[0]
+    nn = 2 * S - 1
+    rng = np.random.default_rng(37)
+    blt = d["tree_blens"]
+    depth = {nn: 0.0}
+    for node, par in d["map"][1:]:
+        depth[int(node)] = depth[int(par)] + blt[int(node) - 1]
+    top = max(depth.values())
+    heights = np.array([top - depth[S + 1 + k] for k in range(S - 1)])
+    lowers = np.zeros(nn)
+    for k in range(1, S + 1):
+        lowers[k - 1] = top - depth[k]
+    substrates = rng.lognormal(np.log(0.005), 0.3, 2 * S - 2)
+    subst, fr, rs, ps = rng.dirichlet(np.ones(6)), rng.dirichlet(np.ones(4) * 5), E.weibull_rates(0.5, 4), np.full(4, 0.25)
+    m = [[int(a), int(b)] for a, b in d["map"]]     # m[j-1] = map[j,] of the Stan program (1-based rows)
+
+    ht = torch.tensor(heights, dtype=torch.float64, requires_grad=True)
+    sr = torch.tensor(substrates, dtype=torch.float64, requires_grad=True)
+    bl = [None] * (2 * S - 2)
+    for j in range(2, nn + 1):                      # first loop: time spans
+        node, par = m[j - 1]
+        bl[node - 1] = ht[par - S - 1] - (ht[node - S - 1] if node > S else lowers[node - 1])
+    first = m[1][0]
+    bl[first - 1] = bl[first - 1] * sr[first - 1]
+    for j in range(3, nn + 1):                      # second loop: mean of the rates at both ends
+        node, par = m[j - 1]
+        other = sr[first - 1] if par == nn else sr[par - 1]
+        bl[node - 1] = bl[node - 1] * 0.5 * (sr[node - 1] + other)
+    blens = torch.stack(bl)
+    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, np.maximum(blens.detach().numpy(), 0.0), subst,
+                         fr, rs, ps)
+    blens.backward(torch.tensor(want.grad_blens))
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4) as lik:
+        logp, got_h, got_r, rest = lik.value_grad_heights(d["map"], heights, substrates, lowers, subst, fr, rs, ps,
+                                                          autocorrelated=True)
+        with pytest.raises(lk.PhyloB200Error):      # one rate per branch is mandatory here
+            lik.value_grad_heights(d["map"], heights, 0.005, lowers, subst, fr, rs, ps, autocorrelated=True)
+    assert abs(logp - want.logp) <= RTOL_LOGP * abs(want.logp)
+    for g, w in ((got_h, ht.grad.numpy()), (got_r, sr.grad.numpy()), (rest.grad_subst, want.grad_subst),
+                 (rest.grad_freqs, want.grad_freqs), (rest.grad_rs, want.grad_rs)):
+        assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
+
+
 def _caterpillar(S):
     rows = [[1, 2, S + 1]] + [[S + k, k + 2, S + k + 1] for k in range(1, S - 1)]
     return np.array(rows, dtype=np.int32)

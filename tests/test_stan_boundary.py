@@ -67,7 +67,7 @@ def test_generator_switch_all_model_variants():
 
 
 def test_generator_switch_heights_variant():
-    """heights=True also replaces generate_script.py:660-679 (strict / uncorrelated clocks only)."""
+    """heights=True also replaces generate_script.py:660-679 / 682-708 (the heights -> blens loops)."""
     ref = _ref()
     for kw in (dict(model="HKY"), dict(clock="ucln"), dict(heterochronous=False, estimate_rate=False)):
         p = params(**kw)
@@ -76,9 +76,15 @@ def test_generator_switch_heights_variant():
         assert s.count("phylo_loglik_heights(") == 2 and "blens" not in body and "pmats" not in s
         assert ("lowers" in body) == p.heterochronous or "rep_array(0.0, 2*S-1)" in body
         assert "target += log(heights" in body           # the Jacobian of the height transform stays in Stan
-    for kw in (dict(clock="acln"), dict(clock=None, coalescent=None, heterochronous=False, estimate_rate=False)):
-        with pytest.raises(ValueError):
-            G.get_model(params(**kw), ref, heights=True)
+    for clock in ("acln", "ace", "gmrf"):          # generate_script.py:682-708
+        p = params(clock=clock)
+        s = G.get_model(p, ref, heights=True)
+        body = s.split("model{")[1]
+        assert s.count("phylo_loglik_heights_autocorr(") == 2 and "phylo_loglik_heights(" not in s
+        assert "blens" not in body and "target += phylo_loglik_heights_autocorr(heights, substrates, map," in body
+        assert "substrates" in s.split("model{")[0]                # the clock model itself stays in Stan
+    with pytest.raises(ValueError):
+        G.get_model(params(clock=None, coalescent=None, heterochronous=False, estimate_rate=False), ref, heights=True)
 
 
 def test_stan_model_kwargs_point_at_existing_files():
@@ -164,6 +170,10 @@ def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, mo
             grate += bl[node - 1] / rate * wb[node - 1]
         np.testing.assert_allclose(got["heights_grad"], gh, rtol=1e-7, atol=1e-6)
         assert got["rate_grad"] == pytest.approx(grate, rel=1e-7)
+        # phylo_loglik_heights_autocorr with all substrates equal: identical branch lengths
+        assert got["autocorr_value"] == pytest.approx(got["heights_value"], rel=1e-12)
+        assert got["autocorr_heights_maxdiff"] <= 1e-6
+        assert got["autocorr_rate_grad_sum"] == pytest.approx(grate, rel=1e-7)
         assert got["heights_nops"] == (S - 1) + 1
     want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps, rooted=rooted)
     for key in ("value_double", "value_var"):
