@@ -255,8 +255,10 @@ static void dP_eigen(const subst_t *m, const double *dQ, double tau, double *dP)
     mat4_mul(T, m->m1, X);
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j) {
-            double x = (m->lam[i] - m->lam[j]) * tau;
-            double f = tau * exp(m->lam[j] * tau) * (fabs(x) < 1e-9 ? 1.0 + 0.5 * x : expm1(x) / x);
+            /* factored around the larger exponential: expm1 never overflows on long branches */
+            double x = fabs(m->lam[i] - m->lam[j]) * tau;
+            double hi = exp((m->lam[i] > m->lam[j] ? m->lam[i] : m->lam[j]) * tau);
+            double f = tau * hi * (x < 1e-9 ? 1.0 - 0.5 * x : -expm1(-x) / x);
             X[4 * i + j] *= f;
         }
     mat4_mul(m->m1, X, T);

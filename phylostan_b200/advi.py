@@ -88,8 +88,8 @@ class UnrootedModel:
     """Jacobian-adjusted log density of the unrooted-tree program on Stan's unconstrained space.
 
     ``lik`` is a ``phylostan_b200.likelihood.TreeLikelihood`` created with ``rooted=False`` (anything
-    with the same ``value_grad`` / ``loglik`` / ``bcount`` / ``C`` / ``nsubst`` surface works, which is
-    how the CPU tests drive this class with the oracle).  Parameter order is the Stan program's:
+    with the same ``value_grad`` / ``loglik`` / ``bcount`` / ``C`` / ``nsubst`` surface works; the CPU
+    tests use that to check the model block without a GPU).  Parameter order is the Stan program's:
     ``wshape`` (when C > 1), ``blens``, then ``rates`` (GTR) or ``kappa`` (HKY), then ``freqs``.
     """
 

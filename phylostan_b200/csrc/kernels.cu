@@ -858,8 +858,10 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) s = fma(Tm[4 * i + k], m2[4 * j + k], s);
-                    const double x = (lam[i] - lam[j]) * tau;
-                    const double f = tau * ex[j] * (fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x);
+                    // F_ij = (e^{l_i tau} - e^{l_j tau}) / (l_i - l_j), factored around the LARGER exponential so
+                    // that expm1 only ever sees a non-positive argument (long branches: 0 * inf otherwise)
+                    const double x = fabs(lam[i] - lam[j]) * tau;
+                    const double f = tau * fmax(ex[i], ex[j]) * (x < 1e-8 ? 1.0 - 0.5 * x : -expm1(-x) / x);
                     H[4 * i + j] = s * f;
                 }
 #pragma unroll

@@ -117,7 +117,8 @@ int main(int argc, char** argv) {
         for (int i = 0; i < S - 1; ++i) std::printf("%s%.17g", i ? ", " : "", vh[i].adj());
         std::printf("], \"rate_grad\": %.17g", vrate[0].adj());
         // autocorrelated variant with every substrate equal to the strict rate: same branch lengths
-        std::vector<stan::math::var> vh2(hts.begin(), hts.end()), vsub(2 * S - 2, stan::math::var(rate[0]));
+        std::vector<stan::math::var> vh2(hts.begin(), hts.end()), vsub;
+        for (int i = 0; i < 2 * S - 2; ++i) vsub.push_back(stan::math::var(rate[0]));  // distinct operands
         stan::math::var r5 = model_namespace::phylo_loglik_heights_autocorr(vh2, vsub, m2, lowers, make<VecD>(su), make<VecD>(fr),
                                                                             make<VecD>(rs), make<VecD>(ps), &std::cout);
         r5.grad();

@@ -371,6 +371,23 @@ def test_gpu_heights_front_end(datasets, strict):
     assert (f(hp, rates) - f(hm, rates)) / (2 * eps) == pytest.approx(got_h[k], rel=1e-5, abs=1e-4)
 
 
+def test_gpu_long_branches_skewed_frequencies(datasets):
+    """A draw ADVI's random initialisation produces on DS1: branch lengths up to 19 substitutions/site and
+    frequencies down to 0.007, so (l_i - l_j) tau is in the hundreds (regression: d/dsubst, d/dfreqs)."""
+    d = datasets["DS1"]
+    rng = np.random.default_rng(2)
+    bl = rng.exponential(3.0, 2 * d["tipmask"].shape[0] - 3) + 0.03
+    bl[5] = 18.9
+    rates = np.array([0.02597748, 0.52534685, 0.02513972, 0.06528041, 0.32244615, 0.03580939])
+    freqs = np.array([0.59239554, 0.38125913, 0.00654059, 0.01980474])
+    rs, ps = E.weibull_rates(0.4590802211249382, 4), np.full(4, 0.25)
+    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.GTR, bl, rates, freqs, rs, ps, rooted=False)
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4, rooted=False) as lik:
+        got = lik.value_grad(bl, rates, freqs, rs, ps)
+    assert np.all(np.isfinite(got.grad))
+    assert_parity(got, want)
+
+
 def test_gpu_heights_front_end_autocorrelated(datasets):
     """heights_to_blens_autocorr (generate_script.py:682-708): the Stan loops restated literally in torch
     fp64, their reverse sweep by autograd, the likelihood part from the oracle."""
