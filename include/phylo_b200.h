@@ -167,6 +167,11 @@ PHYLO_B200_API int phylo_b200_sync(phylo_b200_handle h);
  * 0 = automatic.  Takes effect on the next run. */
 PHYLO_B200_API int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int pattern_blocks);
 
+/* Tuning / testing: shared-memory stack slots for gradient runs (0 = automatic).  Fewer slots than the
+ * tree's stack depth park the top stack positions in the per-CTA HBM scratch (phylo_b200_info 0 =
+ * depth, 11 = slots used by the last run).  Value-only runs always keep the whole stack on chip. */
+PHYLO_B200_API int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots);
+
 /* Arithmetic of the sweeps: 64 (default; the parity-tested product path) or 32, the optional
  * "fp32 with scaling" mode: partials, transition matrices and 4x4 statistics in float with
  * power-of-two rescaling in units of 2^24, log-likelihood and gradient sums in double.  Its error is

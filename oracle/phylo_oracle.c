@@ -155,16 +155,26 @@ static void subst_setup(subst_t *m, int model, int flags, const double *subst, c
 }
 
 static void subst_pmatrix(const subst_t *m, double tau, double *P) {
-    if (m->jc_closed) { /* generate_script.py:765-766 */
-        double e = exp(-tau / 0.75);
-        for (int i = 0; i < 16; ++i) P[i] = 0.25 - 0.25 * e;
-        for (int i = 0; i < 4; ++i) P[5 * i] = 0.25 + 0.75 * e;
+    if (m->jc_closed) { /* generate_script.py:765-766; expm1 form: 1/4 - 1/4 e^{-x} cancels when x is tiny */
+        double e1 = expm1(-tau / 0.75);
+        for (int i = 0; i < 16; ++i) P[i] = -0.25 * e1;
+        for (int i = 0; i < 4; ++i) P[5 * i] = 1.0 + 0.75 * e1;
         return;
     }
-    double T[16];
+    /* generate_script.py:824-829.  Short branches (max|lambda| tau < 1): the mathematically identical
+     * P = I + m1 diag(expm1(lambda tau)) m2; the plain form computes the O(tau) off-diagonal entries by
+     * cancelling m1 m2 against the identity (absolute error 1e-16 on entries of size tau), which no
+     * two implementations round alike -- see DESIGN.md "reference quirks". */
+    double T[16], lmax = 0;
+    for (int j = 0; j < 4; ++j)
+        if (fabs(m->lam[j]) > lmax) lmax = fabs(m->lam[j]);
+    int small = lmax * tau < 1.0;
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) T[4 * i + j] = m->m1[4 * i + j] * exp(m->lam[j] * tau);
+        for (int j = 0; j < 4; ++j)
+            T[4 * i + j] = m->m1[4 * i + j] * (small ? expm1(m->lam[j] * tau) : exp(m->lam[j] * tau));
     mat4_mul(T, m->m2, P);
+    if (small)
+        for (int i = 0; i < 4; ++i) P[5 * i] += 1.0;
 }
 
 /* dQ/dtheta_k (unconstrained partials).  k < ntheta: exchangeability parameter;

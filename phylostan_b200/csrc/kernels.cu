@@ -233,15 +233,24 @@ __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const Pa
         return;
     }
     const double tau = prm[lay.off_t + node] * prm[lay.off_rs + c];
-    if (jc_closed) {  // generate_script.py:765-766
-        const double e = exp(-tau / 0.75);
+    if (jc_closed) {  // generate_script.py:765-766, written with expm1: 1/4 - 1/4 e^{-x} cancels for short branches
+        const double e1 = expm1(-tau / 0.75);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 0.25 + 0.75 * e : 0.25 - 0.25 * e;
+        for (int i = 0; i < 16; ++i) m[i] = (i % 5 == 0) ? 1.0 + 0.75 * e1 : -0.25 * e1;
         return;
     }
-    double ex[4];  // generate_script.py:824-829
+    // generate_script.py:824-829: P = m1 diag(e^{lambda tau}) m2.  For short branches (max |lambda| tau < 1) the
+    // identical P = I + m1 diag(expm1(lambda tau)) m2 is used: the plain form gets the O(tau) off-diagonals
+    // by cancelling m1 m2 against the identity, i.e. with absolute error 1e-16 on values of size tau.
+    double lam[4], ex[4], lmax = 0.0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ex[j] = exp(prm[lay.off_lam + j] * tau);
+    for (int j = 0; j < 4; ++j) {
+        lam[j] = prm[lay.off_lam + j];
+        lmax = fmax(lmax, fabs(lam[j]));
+    }
+    const bool small = lmax * tau < 1.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ex[j] = small ? expm1(lam[j] * tau) : exp(lam[j] * tau);
     const double* m1 = prm + lay.off_m1;
     const double* m2 = prm + lay.off_m2;
 #pragma unroll
@@ -251,7 +260,7 @@ __device__ __forceinline__ void pmatrix(const double* __restrict__ prm, const Pa
             double s = 0.0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) s += (m1[4 * i + q] * ex[q]) * m2[4 * q + j];
-            m[4 * i + j] = s;
+            m[4 * i + j] = (small && i == j) ? 1.0 + s : s;
         }
 }
 
@@ -312,11 +321,12 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             PostRec pr;
             pr.tip_a = (long long)na * a.Lpad;
             pr.tip_b = (long long)nb * a.Lpad;
-            pr.off_a = s0.z >= 0 ? s0.z * a.SS : 0;
-            pr.off_b = s0.w >= 0 ? s0.w * a.SS : 0;
-            pr.off_spill = spill >= 0 ? spill * a.SS : -1;
+            const bool a_hbm = s0.z >= a.slots;  // parked above the capped shared-memory stack
+            pr.off_a = s0.z < 0 ? 0 : a_hbm ? __ldg(a.node_row + na) * a.SS : s0.z * a.SS;
+            pr.off_b = 0;  // an internal second child is always the previous result (TOS)
+            pr.off_spill = spill >= 0 && spill < a.slots ? spill * a.SS : -1;
             pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
-                       (s0.w == kSrcTos ? 8 : 0);
+                       (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0);
             const int4* src = reinterpret_cast<const int4*>(&pr);
             rd[0] = src[0]; rd[1] = src[1]; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
         }
@@ -333,11 +343,12 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.row_a = s1.w >= 0 ? s1.w * a.SS : -1;
             pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
             pr.dl_n = s1.z * a.KNT;
-            pr.off_n = s0.w >= 0 ? s0.w * a.SS : -1;
-            pr.off_b = s1.x >= 0 ? s1.x * a.SS : -1;
+            const bool n_hbm = s0.w >= a.slots, b_hbm = s1.x >= a.slots;
+            pr.off_n = s0.w < 0 ? -1 : n_hbm ? s1.z * a.SS : s0.w * a.SS;   // s1.z = rown
+            pr.off_b = s1.x < 0 ? -1 : b_hbm ? rowb * a.SS : s1.x * a.SS;
             pr.g_a = na * a.lay.C * 16;
             pr.g_b = nb * a.lay.C * 16;
-            pr.flags = s1.y ? 1 : 0;
+            pr.flags = (s1.y ? 1 : 0) | (n_hbm ? 2 : 0) | (b_hbm ? 4 : 0);
             const int4* src = reinterpret_cast<const int4*>(&pr);
             rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
         }
@@ -410,7 +421,8 @@ struct Ring {
 
 // NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
 // immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
-template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB>
+// DEEP (gradient runs of deep trees): stack entries flagged by the stream live in the HBM scratch.
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -487,7 +499,16 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (nf & 2) cb2 = ldg_bytes<K>(tipp + n->tip_b);
             }
             T ma[K][4], mb[K][4];
-            if (TIPS && (fl & 1)) {  // tip child: its message is a column of P_a
+            if (DEEP && (fl & 16)) {  // rare: child a was parked above the capped stack, in its scratch row
+                T M[16];
+                lds_mat(rec + 64, M);
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    T p[4];
+                    ld4cs(SC(s1.x, j), NT, p);
+                    matvec(M, p, ma[j]);
+                }
+            } else if (TIPS && (fl & 1)) {  // tip child: its message is a column of P_a
 #pragma unroll
                 for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, BYTE_OF(ca, j), ma[j]);
             } else {
@@ -663,11 +684,16 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 // q(node) lives in the TOS registers for the whole step: either it is still there (the
                 // node was the previous step's first child) or it is popped from the shared-memory stack
                 T (&qn)[K][4] = tos;
+                if (DEEP && (s2.w & 2)) {  // rare: q(node) was parked above the capped stack, in p(node)'s scratch row
+#pragma unroll
+                    for (int j = 0; j < K; ++j) ld4cs(SC(s1.w, j), NT, qn[j]);
+                }
+                const bool pop = s1.w >= 0 && !(DEEP && (s2.w & 2));
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (rowa < 0) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
                     if (rowb < 0) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
-                    if (s1.w >= 0) ld4(ST(s1.w, j), NT, qn[j]);
+                    if (pop) ld4(ST(s1.w, j), NT, qn[j]);
                     if (BYTE_OF(dcur, j)) {  // rare: this node was rescaled in the post-order
                         const T f = R::pow2((int)BYTE_OF(dcur, j));
 #pragma unroll
@@ -703,7 +729,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         if (s2.x >= 0) {
                             T q[4];
                             matTvec(M, Ab[j], q);  // eigen.j2:151-153
-                            st4(ST(s2.x, j), NT, q);
+                            if (DEEP && (s2.w & 4)) st4cs(SC(s2.x, j), NT, q);  // over p(b)'s scratch row (just consumed)
+                            else st4(ST(s2.x, j), NT, q);
                         }
                     }
                     warp_reduce16_atomic(G, Gd + s2.z, lane);
@@ -913,28 +940,32 @@ template <> struct Cfg<float, 4> { static constexpr int minb = 3; };
 
 typedef void (*SweepFn)(const SweepArgs);
 
-template <typename T, int K, bool GRAD, bool TIPS>
+template <typename T, int K, bool GRAD, bool TIPS, bool DEEP>
 SweepFn pick_kernel(int nthreads) {
-    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb>;
-    return sweep_kernel<T, K, GRAD, TIPS, 0, 1>;
+    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP>;
+    return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP>;
 }
 
 template <typename T, bool TIPS>
-SweepFn pick_kernel_k(int K, bool grad, int nthreads) {
-    switch (K * 2 + (grad ? 1 : 0)) {
-        case 2: return pick_kernel<T, 1, false, TIPS>(nthreads);
-        case 3: return pick_kernel<T, 1, true, TIPS>(nthreads);
-        case 4: return pick_kernel<T, 2, false, TIPS>(nthreads);
-        case 5: return pick_kernel<T, 2, true, TIPS>(nthreads);
-        case 8: return pick_kernel<T, 4, false, TIPS>(nthreads);
-        case 9: return pick_kernel<T, 4, true, TIPS>(nthreads);
+SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
+    switch (K * 4 + (grad ? (deep ? 2 : 1) : 0)) {
+        case 4: return pick_kernel<T, 1, false, TIPS, false>(nthreads);
+        case 5: return pick_kernel<T, 1, true, TIPS, false>(nthreads);
+        case 6: return pick_kernel<T, 1, true, TIPS, true>(nthreads);
+        case 8: return pick_kernel<T, 2, false, TIPS, false>(nthreads);
+        case 9: return pick_kernel<T, 2, true, TIPS, false>(nthreads);
+        case 10: return pick_kernel<T, 2, true, TIPS, true>(nthreads);
+        case 16: return pick_kernel<T, 4, false, TIPS, false>(nthreads);
+        case 17: return pick_kernel<T, 4, true, TIPS, false>(nthreads);
+        case 18: return pick_kernel<T, 4, true, TIPS, true>(nthreads);
     }
     return nullptr;
 }
 
-SweepFn pick(int prec, bool tips, int K, bool grad, int nthreads) {
-    if (prec == 32) return tips ? pick_kernel_k<float, true>(K, grad, nthreads) : pick_kernel_k<float, false>(K, grad, nthreads);
-    return tips ? pick_kernel_k<double, true>(K, grad, nthreads) : pick_kernel_k<double, false>(K, grad, nthreads);
+SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads) {
+    if (prec == 32)
+        return tips ? pick_kernel_k<float, true>(K, grad, deep, nthreads) : pick_kernel_k<float, false>(K, grad, deep, nthreads);
+    return tips ? pick_kernel_k<double, true>(K, grad, deep, nthreads) : pick_kernel_k<double, false>(K, grad, deep, nthreads);
 }
 
 }  // namespace
@@ -955,9 +986,9 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
     else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
-cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, int grid, int nthreads,
+cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
                          size_t smem, cudaStream_t stream) {
-    SweepFn kern = pick(prec, tips, K, grad, nthreads);
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -965,8 +996,8 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool gr
     return cudaGetLastError();
 }
 
-cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, int nthreads, size_t smem, int* n) {
-    SweepFn kern = pick(prec, tips, K, grad, nthreads);
+cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -79,6 +79,12 @@ struct StreamArgs {
     int nsteps, bcount, jc_closed, B;
     int Lpad, SS, KNT;        // tile geometry baked into the descriptors
     int S, tips_simple;       // tips_simple: tip children get the column-major 4x5 matrix layout
+    // Capped shared-memory stack (gradient runs only): stack positions >= slots (the top of a deep
+    // stack, reached rarely and briefly) live in the CTA's HBM scratch instead -- a parked partial is
+    // there anyway (every partial is written to its scratch row), a parked q(node) takes over the row
+    // of p(node), which nobody reads any more by then.
+    const int* node_row;      // [2S-1] node id -> its own post-order step (= scratch row), -1 for tips
+    int slots;
 };
 
 struct SweepArgs {
@@ -110,9 +116,11 @@ struct ContractArgs {
 
 // prec: 64 (product path) or 32 (optional fp32-with-scaling mode); K in {1,2,4}; nthreads <= 512
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
-cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, int grid, int nthreads,
+// deep: the stream parks stack entries in the HBM scratch (gradient runs only)
+cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
                          size_t smem, cudaStream_t stream);
-cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, int nthreads, size_t smem, int* blocks_per_sm);
+cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
+                            int* blocks_per_sm);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
 
 size_t sweep_smem_bytes(int D, int K, int nthreads, int prec);

@@ -97,15 +97,16 @@ struct phylo_b200_ctx {
     // per-batch device data
     DevBuf<double> d_params, d_G, d_out;
     DevBuf<unsigned char> d_spost, d_spre;  // per-(draw, category) instruction streams
-    DevBuf<int32_t> d_node_pos;
+    DevBuf<int32_t> d_node_pos, d_node_row;
     DevBuf<double2> d_scratch;
     DevBuf<uint8_t> d_dscr;
     PinnedBuf<double> h_params, h_out;
 
     // tiling (user request, 0 = auto) and the resolved launch shape of the last run
     int prec = 64;  // 64: product path; 32: optional fp32-with-scaling mode
-    int req_K = 0, req_PB = 0;
+    int req_K = 0, req_PB = 0, req_cap = 0;
     int K = 1, PB = 1, NT = 0, grid = 0, ntiles = 0;
+    int slots = 0;  // shared-memory stack slots of the last run (< plan.depth(): the rest is parked in HBM)
     size_t smem = 0;
     int last_launches = 0;
 
@@ -118,7 +119,7 @@ struct phylo_b200_ctx {
         cudaSetDevice(device);
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
         d_params.release(); d_G.release(); d_out.release();
-        d_spost.release(); d_spre.release(); d_node_pos.release();
+        d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
         h_params.release(); h_out.release();
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -130,7 +131,27 @@ namespace {
 
 // Resolve (K, PB) -> launch shape.
 int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
-    const int C = h->C, D = h->plan.depth();
+    const int C = h->C, Dfull = h->plan.depth();
+    // Gradient runs may cap the shared-memory stack: the top stack positions (reached rarely, and only
+    // briefly) are parked in the CTA's HBM scratch, which holds every partial anyway.  A deep tree
+    // (stack depth 7+, thousands of taxa) then still gets the widest tile twice per SM.
+    // Value-only runs have no scratch and keep the whole stack in shared memory.
+    const int kMaxParked = 2;
+    int Dmin = Dfull;
+    if (grad) Dmin = h->req_cap > 0 ? std::min(Dfull, h->req_cap) : std::max(std::min(Dfull, 2), Dfull - kMaxParked);
+    const int Dmax = grad && h->req_cap > 0 ? Dmin : Dfull;
+    // largest slot count in [Dmin, Dmax] reaching `want` CTAs per SM; 0 when none does
+    auto slots_for = [&](int k, int nt, int want) {
+        for (int dd = Dmax; dd >= Dmin; --dd) {
+            int occ = 0;
+            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec);
+            if (sm <= h->smem_optin &&
+                sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sm, &occ) == cudaSuccess && occ >= want)
+                return dd;
+            if (dd == 0) break;
+        }
+        return -1;
+    };
     int K = h->req_K, PB = h->req_PB;
     if (K == 0) {
         // Small problems spread thin (K = 1).  Large ones take the largest K that still keeps two
@@ -139,16 +160,11 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
         const long long work = (long long)B * ((h->L + 31) / 32);  // warps of patterns per category
         K = 1;
         if (work >= 8LL * h->num_sms && 32 * C * (PB ? PB : 1) <= 128) {
-            for (int k : {4, 2}) {
-                int occ = 0;
-                const size_t sm = sweep_smem_bytes(D, k, 32 * C * (PB ? PB : 1), h->prec);
-                if (sm <= h->smem_optin &&
-                    sweep_occupancy(h->prec, h->tips_simple, k, grad, 32 * C * (PB ? PB : 1), sm, &occ) == cudaSuccess &&
-                    occ >= 2) {
+            for (int k : {4, 2})
+                if (slots_for(k, 32 * C * (PB ? PB : 1), 2) >= 0) {
                     K = k;
                     break;
                 }
-            }
         } else if (work >= 8LL * h->num_sms) {
             K = 2;
         }
@@ -160,16 +176,23 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     while (K > 1 && 32 * C * PB > sweep_max_threads(K)) K >>= 1;
     int NT = 32 * C * PB;
     if (NT > sweep_max_threads(K)) return fail(PHYLO_B200_EINVAL, "too many rate categories for one CTA");
-    size_t smem = sweep_smem_bytes(D, K, NT, h->prec);
-    while (smem > h->smem_optin && K > 1) { K >>= 1; smem = sweep_smem_bytes(D, K, NT, h->prec); }
-    while (smem > h->smem_optin && PB > 1) { PB >>= 1; NT = 32 * C * PB; smem = sweep_smem_bytes(D, K, NT, h->prec); }
-    if (smem > h->smem_optin)
-        return fail(PHYLO_B200_EINVAL, "tree too deep for the shared-memory stack (depth " + std::to_string(D) + ")");
+    int D = -1;
+    for (;;) {
+        D = slots_for(K, NT, 2);                 // two CTAs per SM if any allowed slot count gives that
+        if (D < 0) D = slots_for(K, NT, 1);
+        if (D >= 0) break;
+        if (K > 1) K >>= 1;
+        else if (PB > 1) { PB >>= 1; NT = 32 * C * PB; }
+        else
+            return fail(PHYLO_B200_EINVAL,
+                        "tree too deep for the shared-memory stack (depth " + std::to_string(Dfull) + ")");
+    }
+    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec);
     const int tpat = PB * 32 * K;
-    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem;
+    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D;
     h->ntiles = (h->L + tpat - 1) / tpat;
     int occ = 0;
-    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, NT, smem, &occ));
+    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -285,9 +308,11 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
         node_pos[h->plan.post[i].a] = (int32_t)(2 * i);
         node_pos[h->plan.post[i].b] = (int32_t)(2 * i + 1);
     }
+    std::vector<int32_t> node_row((size_t)h->nn, -1);  // internal node -> its own post-order step = scratch row
+    for (size_t i = 0; i < h->plan.post.size(); ++i) node_row[h->plan.post[i].node] = (int32_t)i;
     cudaError_t e = cudaSuccess;
     if ((e = up(h->d_tips, tips)) != cudaSuccess || (e = up(h->d_weights, w)) != cudaSuccess ||
-        (e = up(h->d_node_pos, node_pos)) != cudaSuccess ||
+        (e = up(h->d_node_pos, node_pos)) != cudaSuccess || (e = up(h->d_node_row, node_row)) != cudaSuccess ||
         (e = up(h->d_post, h->plan.post)) != cudaSuccess || (e = up(h->d_pre, h->plan.pre)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
@@ -387,6 +412,13 @@ int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int patt
     return 0;
 }
 
+int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    if (slots < 0) return fail(PHYLO_B200_EINVAL, "slots must be >= 0 (0 = automatic)");
+    h->req_cap = slots;
+    return 0;
+}
+
 int phylo_b200_set_precision(phylo_b200_handle h, int bits) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     if (bits != 32 && bits != 64) return fail(PHYLO_B200_EINVAL, "precision must be 64 or 32");
@@ -429,6 +461,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 8: return h->plan.depth_post;
         case 9: return h->plan.depth_pre;
         case 10: return h->ntiles;
+        case 11: return h->slots;
     }
     return PHYLO_B200_EINVAL;
 }
@@ -476,6 +509,8 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     const int VP = h->prec == 32 ? 1 : 2;  // 16-byte vectors per 4-state entry
     sa.Lpad = h->Lpad; sa.SS = h->K * VP * h->NT; sa.KNT = h->K * h->NT;
     sa.S = h->S; sa.tips_simple = h->tips_simple;
+    sa.node_row = h->d_node_row.p;
+    sa.slots = grad ? h->slots : h->plan.depth();
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
@@ -488,9 +523,10 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     a.scratch_stride = (long long)(h->S - 1) * h->K * VP * h->NT;
     a.dscr_stride = (long long)(h->S - 1) * h->K * h->NT;
     a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
-    a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->plan.depth();
+    a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->slots;
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
-    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, h->grid, h->NT, h->smem, st));
+    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, grad && h->slots < h->plan.depth(), h->grid, h->NT,
+                        h->smem, st));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {

@@ -76,6 +76,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_set_stream.argtypes = [vp, vp]
     L.phylo_b200_set_tiling.argtypes = [vp, i, i]
     L.phylo_b200_set_precision.argtypes = [vp, i]
+    L.phylo_b200_set_stack_slots.argtypes = [vp, i]
     L.phylo_b200_set_timing.argtypes = [vp, i]
     L.phylo_b200_get_timing.argtypes = [vp, _dp]
     L.phylo_b200_info.argtypes = [vp, i]
@@ -272,6 +273,11 @@ class TreeLikelihood:
     def set_tiling(self, patterns_per_thread: int = 0, pattern_blocks: int = 0) -> None:
         _check(lib().phylo_b200_set_tiling(self._h, patterns_per_thread, pattern_blocks))
 
+    def set_stack_slots(self, slots: int = 0) -> None:
+        """Shared-memory stack slots for gradient runs (0 = automatic); fewer than ``info()['stack_depth']``
+        parks the top stack positions in the per-CTA HBM scratch."""
+        _check(lib().phylo_b200_set_stack_slots(self._h, int(slots)))
+
     def set_precision(self, bits: int) -> None:
         """64 (default, parity-tested) or 32 (optional fp32-with-scaling mode, error reported separately)."""
         _check(lib().phylo_b200_set_precision(self._h, int(bits)))
@@ -286,7 +292,7 @@ class TreeLikelihood:
 
     def info(self) -> dict:
         names = ["stack_depth", "patterns_per_thread", "threads_per_cta", "grid", "smem_bytes", "padded_patterns",
-                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles"]
+                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots"]
         return {n: int(lib().phylo_b200_info(self._h, k)) for k, n in enumerate(names)}
 
     def unpack(self, out: np.ndarray) -> ValueGrad:

@@ -388,6 +388,87 @@ def test_gpu_long_branches_skewed_frequencies(datasets):
     assert_parity(got, want)
 
 
+def _extreme_draws(model, S, rooted, C, rng, n):
+    """Parameter draws at the edges of what an optimiser or a sampler visits during warm-up."""
+    nb = 2 * S - 2 if rooted else 2 * S - 3
+    out = []
+    for i in range(n):
+        kind = i % 6
+        bl = {0: rng.exponential(0.05, nb), 1: 10.0 ** rng.uniform(-9, 1.5, nb), 2: rng.exponential(5.0, nb),
+              3: np.where((rng.random(nb) < 0.5) & (np.arange(nb) >= S), 0.0, rng.exponential(0.1, nb)),  # internal zeros
+              4: np.full(nb, 1e-10),
+              5: rng.exponential(0.02, nb)}[kind]
+        if kind == 5:
+            bl[rng.integers(nb)] = 60.0
+        conc = [5.0, 0.3, 0.2, 1.0, 50.0, 0.15][kind]
+        fr = np.maximum(rng.dirichlet(np.ones(4) * conc), 1e-5); fr /= fr.sum()
+        if model == O.GTR:
+            su = np.maximum(rng.dirichlet(np.ones(6) * conc), 1e-6); su /= su.sum()
+        elif model == O.HKY:
+            su = np.array([10.0 ** rng.uniform(-2, 2)])
+        else:
+            su = np.zeros(0)
+        w = [0.5, 0.11, 8.0, 1.0, 0.2, 0.3][kind]
+        rs = E.weibull_rates(w, C) if C > 1 else np.ones(1)
+        ps = rng.dirichlet(np.ones(C) * (0.5 if kind % 2 else 5.0)) if C > 1 else np.ones(1)
+        out.append((bl, su, fr, rs, ps))
+    return out
+
+
+@pytest.mark.parametrize("name,model,C", [("DS1", O.GTR, 4), ("fluA", O.HKY, 4), ("HCV", O.GTR, 1), ("DS1", O.JC69, 3)])
+def test_gpu_extreme_parameters(datasets, name, model, C):
+    """Zero / tiny / very long branches, near-degenerate frequencies and exchangeabilities, extreme Weibull
+    shapes: finite, and equal to the oracle.  Parity bar against the oracle's eigen route; its Van Loan
+    route (block exponential by scaling and squaring, independent of the F matrix) loses digits itself
+    when |tau Q| is in the hundreds, so it is held to 1e-5 here."""
+    d = datasets[name]
+    rooted = bool(d["rooted"])
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(101)
+    draws = _extreme_draws(model, S, rooted, C, rng, 12)
+    with make(d["peel"], d["tipmask"], d["weights"], model, C, rooted=rooted) as lik:
+        B = len(draws)
+        batch = lik.value_grad(np.stack([x[0] for x in draws]), np.stack([x[1] for x in draws]) if model else None,
+                               np.stack([x[2] for x in draws]), np.stack([x[3] for x in draws]),
+                               np.stack([x[4] for x in draws]))
+        for i, (bl, su, fr, rs, ps) in enumerate(draws):
+            want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, su, fr, rs, ps, rooted=rooted,
+                                 dp_eigen=True)
+            loan = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, su, fr, rs, ps, rooted=rooted)
+            assert np.all(np.isfinite(want.flat())), i
+            got = lk.ValueGrad(batch.log_P[i], batch.grad_blens[i], batch.grad_subst[i], batch.grad_freqs[i],
+                               batch.grad_rs[i], batch.grad_ps[i])
+            assert np.all(np.isfinite(got.grad)), i
+            flat = np.concatenate([[got.log_P], got.grad_blens, got.grad_subst, got.grad_freqs, got.grad_rs, got.grad_ps])
+            # logL to the parity bar; gradient components to the parity bar plus the rounding floor of a sum
+            # whose terms are as large as the largest component (saturated branches with frequencies of 1e-3:
+            # d/drs is ~0 as a sum of +-1e8 terms, and neither side can do better than eps times that)
+            assert abs(got.log_P - want.logp) <= RTOL_LOGP * abs(want.logp), i
+            w = want.flat()
+            floor = 1e-13 * np.abs(w[1:]).max()
+            assert np.all(np.abs(flat - w)[1:] <= TOL_GRAD * np.maximum(1.0, np.abs(w[1:])) + floor), i
+            assert np.max(np.abs(flat - loan.flat()) / np.maximum(1.0, np.abs(loan.flat()))) <= 1e-5, i
+
+
+def test_gpu_zero_likelihood_is_not_finite(datasets):
+    """All branch lengths zero: sites with two different observed states have likelihood 0, logL = -inf.
+    The library reports that (the Stan shim turns it into std::domain_error, i.e. a rejected draw)."""
+    d = datasets["DS1"]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(0)
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4, rooted=False) as lik:
+        try:
+            lp = lik.loglik(np.zeros(2 * S - 3), rng.dirichlet(np.ones(6)), np.full(4, 0.25), E.weibull_rates(0.5, 4),
+                            np.full(4, 0.25))
+            assert not np.isfinite(lp)
+        except lk.PhyloDomainError:
+            pass
+        # and the handle is still usable afterwards
+        bl = rng.exponential(0.05, 2 * S - 3)
+        ok = lik.loglik(bl, np.full(6, 1 / 6), np.full(4, 0.25), E.weibull_rates(0.5, 4), np.full(4, 0.25))
+        assert np.isfinite(ok)
+
+
 def test_gpu_heights_front_end_autocorrelated(datasets):
     """heights_to_blens_autocorr (generate_script.py:682-708): the Stan loops restated literally in torch
     fp64, their reverse sweep by autograd, the likelihood part from the oracle."""
@@ -434,6 +515,56 @@ def test_gpu_heights_front_end_autocorrelated(datasets):
     for g, w in ((got_h, ht.grad.numpy()), (got_r, sr.grad.numpy()), (rest.grad_subst, want.grad_subst),
                  (rest.grad_freqs, want.grad_freqs), (rest.grad_rs, want.grad_rs)):
         assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
+
+
+@pytest.mark.parametrize("prec", [64, 32])
+def test_gpu_capped_stack_parks_entries_in_hbm(prec):
+    """Gradient runs with fewer shared-memory stack slots than the tree's stack depth: the top stack
+    positions live in the HBM scratch (post-order: the partial's own row; pre-order: q(node) over
+    p(node)'s row).  Results must not depend on the number of slots."""
+    prob = synth.make_problem(150, 700, 4, seed=77)
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 3)
+    want = [O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[i], rates[i], freqs[i], rs[i], ps[i])
+            for i in range(3)]
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        lik.set_precision(prec)
+        depth = lik.info()["stack_depth"]
+        assert depth >= 3
+        ref = None
+        for K in (1, 2, 4):
+            ref = None
+            for slots in (0, depth, depth - 1, 1):
+                lik.set_tiling(K, 1)
+                lik.set_stack_slots(slots)
+                got = lik.value_grad(bl, rates, freqs, rs, ps)
+                assert lik.info()["stack_slots"] == (slots if slots else depth)
+                if prec == 64:
+                    for i in range(3):
+                        assert_parity(lk.ValueGrad(got.log_P[i], got.grad_blens[i], got.grad_subst[i], got.grad_freqs[i],
+                                                   got.grad_rs[i], got.grad_ps[i]), want[i])
+                else:       # fp32 mode: every slot count does the same arithmetic per pattern
+                    if ref is None:
+                        ref = got
+                        assert np.max(np.abs(got.log_P - [w.logp for w in want]) / np.abs(got.log_P)) < 2e-6
+                    assert np.allclose(got.log_P, ref.log_P, rtol=1e-12, atol=0)     # sums go through atomics
+                    assert np.allclose(got.grad_blens, ref.grad_blens, rtol=1e-4, atol=1e-3)
+                # value-only runs ignore the cap (no scratch to park in)
+                lp = lik.loglik(bl, rates, freqs, rs, ps)
+                assert lik.info()["stack_slots"] == depth
+                assert np.max(np.abs(lp - got.log_P) / np.abs(lp)) < (1e-12 if prec == 64 else 1e-5)
+
+
+def test_gpu_deep_tree_gets_the_widest_tile():
+    """3000 taxa: stack depth 7 does not fit the K = 4 tile twice per SM; the capped stack does."""
+    prob = synth.make_problem(3000, 2048, 4)
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 20)       # enough work for the automatic K > 1 path
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        got = lik.value_grad(bl, rates, freqs, rs, ps)
+        info = lik.info()
+        assert info["stack_depth"] == 7 and info["patterns_per_thread"] == 4 and info["stack_slots"] == 6
+        want = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[7], rates[7], freqs[7], rs[7], ps[7])
+        assert_parity(lk.ValueGrad(got.log_P[7], got.grad_blens[7], got.grad_subst[7], got.grad_freqs[7], got.grad_rs[7],
+                                   got.grad_ps[7]), want)
 
 
 def _caterpillar(S):

@@ -21,6 +21,7 @@ print(f"problem {S}x{L} built in {time.time() - t0:.1f}s", flush=True)
 lik = lk.TreeLikelihood(prob.peel, prob.tipmask, prob.weights, model="GTR", categories=4)
 PREC = int(os.environ.get("PHYLO_PREC", "64"))
 lik.set_precision(PREC)
+lik.set_stack_slots(int(os.environ.get("PHYLO_SLOTS", "0")))
 print("precision", PREC, flush=True)
 lik.upload(*draws)
 alg = (32.0 * L * 4 * (5 * S - 9) + 2.0 * S * L + 8.0 * L) * B
