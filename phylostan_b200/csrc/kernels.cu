@@ -689,16 +689,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     for (int j = 0; j < K; ++j) ld4cs(SC(s1.w, j), NT, qn[j]);
                 }
                 const bool pop = s1.w >= 0 && !(DEEP && (s2.w & 2));
+                // one (warp-uniform) branch per operand kind rather than one per pattern
+                if (rowa < 0) {
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    if (rowa < 0) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
-                    if (rowb < 0) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
+                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
+                }
+                if (rowb < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < K; ++j)
                     if (pop) ld4(ST(s1.w, j), NT, qn[j]);
-                    if (BYTE_OF(dcur, j)) {  // rare: this node was rescaled in the post-order
-                        const T f = R::pow2((int)BYTE_OF(dcur, j));
+                if (dcur) {  // rare: this node was rescaled in the post-order for some pattern of this lane
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) qn[j][s] *= f;
-                    }
+                    for (int j = 0; j < K; ++j)
+                        if (BYTE_OF(dcur, j)) {
+                            const T f = R::pow2((int)BYTE_OF(dcur, j));
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) qn[j][s] *= f;
+                        }
                 }
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
                 T Aa[K][4], Ab[K][4];
@@ -726,9 +736,12 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         for (int x = 0; x < 4; ++x)
 #pragma unroll
                             for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
-                        if (s2.x >= 0) {
+                    }
+                    if (s2.x >= 0) {  // b is internal: q(b) = P_b^T A_b   (eigen.j2:151-153)
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
                             T q[4];
-                            matTvec(M, Ab[j], q);  // eigen.j2:151-153
+                            matTvec(M, Ab[j], q);
                             if (DEEP && (s2.w & 4)) st4cs(SC(s2.x, j), NT, q);  // over p(b)'s scratch row (just consumed)
                             else st4(ST(s2.x, j), NT, q);
                         }
