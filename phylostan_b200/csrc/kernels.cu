@@ -551,28 +551,34 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 for (int j = 0; j < K; ++j) st4(ST(s1.z, j), NT, tos[j]);
             }
             unsigned kpack = 0u;
+            bool tiny = false;
+            const T kTiny = R::tiny();
 #pragma unroll
             for (int j = 0; j < K; ++j) {
-                T p[4];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) p[s] = ma[j][s] * mb[j][s];
-                // per-(pattern,category) rescaling by exact powers of two
-                int kexp = 0;
-                const T kTiny = R::tiny();
-                if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {  // rare
-                    const T mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
-                    if (mx > T(0)) {
-                        kexp = min((-R::exponent(mx)) / R::kUnit, R::kMaxK);
-                        const T f = R::pow2(kexp);
+                for (int s = 0; s < 4; ++s) tos[j][s] = ma[j][s] * mb[j][s];
+                tiny |= tos[j][0] < kTiny && tos[j][1] < kTiny && tos[j][2] < kTiny && tos[j][3] < kTiny;
+            }
+            if (tiny) {  // rare: per-(pattern,category) rescaling by exact powers of two
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) p[s] *= f;
-                        etot[j] += kexp;
-                        kpack |= (unsigned)kexp << (8 * j);
+                for (int j = 0; j < K; ++j) {
+                    T (&p)[4] = tos[j];
+                    if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {
+                        const T mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+                        if (mx > T(0)) {
+                            const int kexp = min((-R::exponent(mx)) / R::kUnit, R::kMaxK);
+                            const T f = R::pow2(kexp);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) p[s] *= f;
+                            etot[j] += kexp;
+                            kpack |= (unsigned)kexp << (8 * j);
+                        }
                     }
                 }
+            }
+            if (GRAD) {
 #pragma unroll
-                for (int s = 0; s < 4; ++s) tos[j][s] = p[s];
-                if (GRAD) st4cs(srow + j * (VP * NT), NT, p);
+                for (int j = 0; j < K; ++j) st4cs(srow + j * (VP * NT), NT, tos[j]);
             }
             if (GRAD) stcs_bytes<K>(drow, kpack);
             srow += SS;
