@@ -186,6 +186,51 @@ __device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* _
     if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), (double)a1);
 }
 
+// The same reduction split in two so that the low-parallelism tail of TWO reductions can be
+// interleaved: head = the xor-16 and xor-8 levels (16 -> 4 values per lane), tail = xor-4, -2, -1 of
+// both and the two REDs.
+template <typename T>
+__device__ __forceinline__ void warp_reduce16_head(const T (&v)[16], T (&a4)[4], int lane) {
+    T a8[8];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        T send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        T send = hi ? a8[i] : a8[i + 4], keep = hi ? a8[i + 4] : a8[i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void warp_reduce4x2_tail_atomic(const T (&x4)[4], const T (&y4)[4], double* __restrict__ dx,
+                                                           double* __restrict__ dy, int lane) {
+    T x2[2], y2[2], x1, y1;
+    bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        T sx = hi ? x4[i] : x4[i + 2], kx = hi ? x4[i + 2] : x4[i];
+        T sy = hi ? y4[i] : y4[i + 2], ky = hi ? y4[i + 2] : y4[i];
+        x2[i] = kx + __shfl_xor_sync(0xffffffffu, sx, 4);
+        y2[i] = ky + __shfl_xor_sync(0xffffffffu, sy, 4);
+    }
+    hi = lane & 2;
+    {
+        T sx = hi ? x2[0] : x2[1], kx = hi ? x2[1] : x2[0];
+        T sy = hi ? y2[0] : y2[1], ky = hi ? y2[1] : y2[0];
+        x1 = kx + __shfl_xor_sync(0xffffffffu, sx, 2);
+        y1 = ky + __shfl_xor_sync(0xffffffffu, sy, 2);
+    }
+    // last level: the even lane finishes x, the odd lane finishes y -- one shuffle serves both
+    const bool odd = lane & 1;
+    const T mine = odd ? y1 : x1, other = odd ? x1 : y1;
+    const T tot = mine + __shfl_xor_sync(0xffffffffu, other, 1);
+    atomicAdd((odd ? dy : dx) + ((lane >> 1) & 15), (double)tot);
+}
+
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
@@ -728,6 +773,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
                     }
                 }
+                T gb4[4];  // child b's statistics after the first two reduction levels
                 {   // child b: q(b) waits in shared memory
                     T M[16], m[4], G[16];
                     lds_mat(rec + 64 + R::kMat, M);
@@ -752,7 +798,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             else st4(ST(s2.x, j), NT, q);
                         }
                     }
-                    warp_reduce16_atomic(G, Gd + s2.z, lane);
+                    warp_reduce16_head(G, gb4, lane);
                 }
                 {   // child a: processed next when internal, so q(a) stays in the TOS registers
                     T G[16];
@@ -779,7 +825,9 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                         }
                     }
-                    warp_reduce16_atomic(G, Gd + s2.y, lane);
+                    T ga4[4];
+                    warp_reduce16_head(G, ga4, lane);
+                    warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
                 }
                 ca = ca1; cb = cb1; dcur = d1; ca1 = ca2; cb1 = cb2; d1 = d2;
             }
