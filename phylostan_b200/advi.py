@@ -5,12 +5,14 @@ iteration, ``elbo_samples`` value-only calls per ELBO estimate; phylostan/phylos
 Here all draws of an iteration go through ONE ``phylo_b200_eval_batch`` call, which is the only way
 the batch parallelism of the likelihood library (BASELINE config 3) reaches a user.
 
-Scope: the program phylostan generates for an unconstrained, unrooted tree (``clock is None``;
-tests/golden/DS1-GTR-W4-external.stan; phylostan/generate_script.py:1186-1457): parameters
-``wshape`` (Weibull categories), ``blens``, and ``rates``/``kappa`` + ``freqs``; priors
-``wshape ~ exponential(1)``, ``blens ~ exponential(10)``, ``rates ~ dirichlet(rates_alpha)``,
-``freqs ~ dirichlet(frequencies_alpha)``, ``kappa ~ lognormal(1, 1.25)``.  Clock trees keep their
-coalescent / clock priors in Stan and use the external-function route.
+Scope: two of the programs phylostan generates (phylostan/generate_script.py:1186-1457).
+``UnrootedModel``: an unconstrained, unrooted tree (``clock is None``; tests/golden/DS1-GTR-W4-external.stan):
+``wshape`` (Weibull categories), ``blens``, ``rates``/``kappa`` + ``freqs``; priors ``wshape ~ exponential(1)``,
+``blens ~ exponential(10)``, ``rates ~ dirichlet(rates_alpha)``, ``freqs ~ dirichlet(frequencies_alpha)``,
+``kappa ~ lognormal(1, 1.25)``.  ``StrictClockModel``: a time tree with a strict clock and a constant-size
+coalescent, tips dated or not -- the fluA quick start (tests/golden/fluA-HKY-W4-external.stan): ratio-transformed
+node heights, ``rate ~ exponential(1000)``, ``theta ~ 1/x``, ``heights ~ constant_coalescent(theta)``.  The other
+clocks and demographic priors stay in Stan and use the external-function route.
 
 The algorithm follows Stan 2.19's ``stan::variational::advi`` with a ``normal_meanfield`` family
 (third-party, not under /root/reference; restated from its published description: Kucukelbir et al.
@@ -31,7 +33,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["UnrootedModel", "MeanFieldFit", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
+__all__ = ["UnrootedModel", "StrictClockModel", "MeanFieldFit", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -84,57 +86,45 @@ def weibull_rates(wshape: np.ndarray, C: int) -> Tuple[np.ndarray, np.ndarray]:
 # ---------------------------------------------------------------------------------------------------
 # the model block
 # ---------------------------------------------------------------------------------------------------
-class UnrootedModel:
-    """Jacobian-adjusted log density of the unrooted-tree program on Stan's unconstrained space.
-
-    ``lik`` is a ``phylostan_b200.likelihood.TreeLikelihood`` created with ``rooted=False`` (anything
-    with the same ``value_grad`` / ``loglik`` / ``bcount`` / ``C`` / ``nsubst`` surface works; the CPU
-    tests use that to check the model block without a GPU).  Parameter order is the Stan program's:
-    ``wshape`` (when C > 1), ``blens``, then ``rates`` (GTR) or ``kappa`` (HKY), then ``freqs``.
-    """
+class _ModelBase:
+    """Pieces shared by the model blocks: parameter layout in the Stan program's order, the site model
+    (``wshape`` -> Weibull ``rs``), the substitution-model parameters with their priors
+    (generate_script.py:1416-1457), and the reverse sweep through the constraining transforms."""
 
     WSHAPE_LOWER = 0.1           # real<lower=0.1> wshape   (generate_script.py:1212)
 
-    def __init__(self, lik, model: str = "GTR", rates_alpha=None, freqs_alpha=None):
+    def __init__(self, lik, model, rates_alpha, freqs_alpha):
         if model not in ("JC69", "HKY", "GTR"):
             raise ValueError("model must be JC69, HKY or GTR")
         self.lik, self.model, self.C, self.bcount = lik, model, int(lik.C), int(lik.bcount)
         self.rates_alpha = np.ones(6) if rates_alpha is None else np.asarray(rates_alpha, dtype=np.float64)
         self.freqs_alpha = np.ones(4) if freqs_alpha is None else np.asarray(freqs_alpha, dtype=np.float64)
         self.slices: Dict[str, slice] = {}
+        self.dim = 0
+
+    def _layout(self, blocks) -> None:
         o = 0
-        for name, n in (("wshape", 1 if self.C > 1 else 0), ("blens", self.bcount),
-                        ("rates", 5 if model == "GTR" else 0), ("kappa", 1 if model == "HKY" else 0),
-                        ("freqs", 3 if model != "JC69" else 0)):
+        for name, n in blocks:
             if n:
                 self.slices[name] = slice(o, o + n)
                 o += n
         self.dim = o
 
-    # -- names of the constrained quantities, Stan CSV style
-    def constrained_names(self) -> List[str]:
-        names = ["wshape"] if self.C > 1 else []
-        names += [f"blens.{i + 1}" for i in range(self.bcount)]
-        if self.model == "GTR":
-            names += [f"rates.{i + 1}" for i in range(6)]
-        if self.model == "HKY":
-            names += ["kappa"]
-        if self.model != "JC69":
-            names += [f"freqs.{i + 1}" for i in range(4)]
-        return names
+    def _subst_blocks(self):
+        return (("rates", 5 if self.model == "GTR" else 0), ("kappa", 1 if self.model == "HKY" else 0),
+                ("freqs", 3 if self.model != "JC69" else 0))
 
-    def constrain(self, Z: np.ndarray) -> Dict[str, np.ndarray]:
-        """Unconstrained [B, dim] -> dict of constrained arrays plus ``logj`` and transform caches."""
-        Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
-        B = Z.shape[0]
-        out: Dict[str, np.ndarray] = {"logj": np.zeros(B)}
+    def _subst_names(self) -> List[str]:
+        names = [f"rates.{i + 1}" for i in range(6)] if self.model == "GTR" else []
+        names += ["kappa"] if self.model == "HKY" else []
+        return names + ([f"freqs.{i + 1}" for i in range(4)] if self.model != "JC69" else [])
+
+    # -- constrain: shared parameters
+    def _constrain_common(self, Z, out) -> None:
         if "wshape" in self.slices:
             u = Z[:, self.slices["wshape"]][:, 0]
             out["wshape"] = self.WSHAPE_LOWER + np.exp(u)
             out["logj"] += u
-        u = Z[:, self.slices["blens"]]
-        out["blens"] = np.exp(u)
-        out["logj"] += u.sum(axis=1)
         if self.model == "GTR":
             out["rates"], lj, out["_rates"] = simplex_constrain(Z[:, self.slices["rates"]])
             out["logj"] += lj
@@ -145,6 +135,92 @@ class UnrootedModel:
         if self.model != "JC69":
             out["freqs"], lj, out["_freqs"] = simplex_constrain(Z[:, self.slices["freqs"]])
             out["logj"] += lj
+
+    def _ok_common(self, c, rs) -> np.ndarray:
+        ok = np.isfinite(c["logj"]) & np.all(np.isfinite(rs), axis=1) & np.all(rs > 0, axis=1)
+        for k in ("rates", "freqs"):
+            if k in c:
+                ok &= np.all(c[k] > 0, axis=1)
+        if "kappa" in c:
+            ok &= np.isfinite(c["kappa"]) & (c["kappa"] > 0)
+        return ok
+
+    def _site_model(self, c, B):
+        if self.C > 1:
+            rs, drs = weibull_rates(c["wshape"], self.C)
+        else:
+            rs, drs = np.ones((B, 1)), np.zeros((B, 1))
+        return rs, drs, np.full((B, self.C), 1.0 / self.C)
+
+    def _subst_arg(self, c):
+        return c["rates"] if self.model == "GTR" else c["kappa"][:, None] if self.model == "HKY" else None
+
+    @staticmethod
+    def _take(c, idx):
+        return {k: (v[idx] if isinstance(v, np.ndarray) else tuple(a[idx] for a in v)) for k, v in c.items()}
+
+    # -- `~` statements of the shared parameters; constants dropped exactly as Stan does
+    def _prior_common(self, sub) -> np.ndarray:
+        n = sub["logj"].shape[0]
+        prior = np.zeros(n)
+        if self.C > 1:
+            prior += -sub["wshape"]                                     # wshape ~ exponential(1.0)
+        if self.model == "GTR":
+            prior += ((self.rates_alpha - 1.0) * np.log(sub["rates"])).sum(axis=1)
+        if self.model == "HKY":
+            lk = np.log(sub["kappa"])
+            prior += -lk - (lk - 1.0) ** 2 / (2.0 * 1.25 ** 2)          # kappa ~ lognormal(1.0, 1.25)
+        if self.model != "JC69":
+            prior += ((self.freqs_alpha - 1.0) * np.log(sub["freqs"])).sum(axis=1)
+        return prior
+
+    # -- gradient w.r.t. the unconstrained shared parameters (likelihood + prior + log-Jacobian)
+    def _grad_common(self, g, sub, vg, drs) -> None:
+        n = g.shape[0]
+        if self.C > 1:                                                  # x = 0.1 + exp(u)
+            gw = (np.reshape(vg.grad_rs, (n, self.C)) * drs).sum(axis=1) - 1.0
+            g[:, self.slices["wshape"]] = (gw * (sub["wshape"] - self.WSHAPE_LOWER) + 1.0)[:, None]
+        if self.model == "GTR":
+            gr = np.reshape(vg.grad_subst, (n, 6)) + (self.rates_alpha - 1.0) / sub["rates"]
+            g[:, self.slices["rates"]] = simplex_adjoint(gr, sub["_rates"])
+        if self.model == "HKY":
+            k = sub["kappa"]
+            gk = np.reshape(vg.grad_subst, (n,)) - 1.0 / k - (np.log(k) - 1.0) / (1.25 ** 2 * k)
+            g[:, self.slices["kappa"]] = (gk * k + 1.0)[:, None]
+        if self.model != "JC69":
+            gf = np.reshape(vg.grad_freqs, (n, 4)) + (self.freqs_alpha - 1.0) / sub["freqs"]
+            g[:, self.slices["freqs"]] = simplex_adjoint(gf, sub["_freqs"])
+
+    def log_prob(self, Z: np.ndarray) -> np.ndarray:
+        """Value only, [B]; draws whose constrained values are not finite get -inf (Stan drops them)."""
+        return self.log_prob_grad(Z, want_grad=False)[0]
+
+
+class UnrootedModel(_ModelBase):
+    """Jacobian-adjusted log density of the unrooted-tree program on Stan's unconstrained space.
+
+    ``lik`` is a ``phylostan_b200.likelihood.TreeLikelihood`` created with ``rooted=False`` (anything
+    with the same ``value_grad`` / ``loglik`` / ``bcount`` / ``C`` / ``nsubst`` surface works; the CPU
+    tests use that to check the model block without a GPU).  Parameter order is the Stan program's:
+    ``wshape`` (when C > 1), ``blens``, then ``rates`` (GTR) or ``kappa`` (HKY), then ``freqs``.
+    """
+
+    def __init__(self, lik, model: str = "GTR", rates_alpha=None, freqs_alpha=None):
+        super().__init__(lik, model, rates_alpha, freqs_alpha)
+        self._layout((("wshape", 1 if self.C > 1 else 0), ("blens", self.bcount)) + self._subst_blocks())
+
+    # -- names of the constrained quantities, Stan CSV style
+    def constrained_names(self) -> List[str]:
+        return (["wshape"] if self.C > 1 else []) + [f"blens.{i + 1}" for i in range(self.bcount)] + self._subst_names()
+
+    def constrain(self, Z: np.ndarray) -> Dict[str, np.ndarray]:
+        """Unconstrained [B, dim] -> dict of constrained arrays plus ``logj`` and transform caches."""
+        Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+        out: Dict[str, np.ndarray] = {"logj": np.zeros(Z.shape[0])}
+        u = Z[:, self.slices["blens"]]
+        out["blens"] = np.exp(u)
+        out["logj"] += u.sum(axis=1)
+        self._constrain_common(Z, out)
         return out
 
     def constrained_matrix(self, Z: np.ndarray) -> np.ndarray:
@@ -156,20 +232,130 @@ class UnrootedModel:
                 cols.append(c[k] if c[k].ndim == 2 else c[k][:, None])
         return np.concatenate(cols, axis=1)
 
-    def _site_model(self, c, B):
-        if self.C > 1:
-            rs, drs = weibull_rates(c["wshape"], self.C)
+    def log_prob_grad(self, Z: np.ndarray, want_grad: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+        B = Z.shape[0]
+        with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+            c = self.constrain(Z)
+            rs, drs, ps = self._site_model(c, B)
+            ok = self._ok_common(c, rs) & np.all(np.isfinite(c["blens"]), axis=1) & np.all(c["blens"] < 1e6, axis=1)
+        lp = np.full(B, -np.inf)
+        G = np.zeros((B, self.dim)) if want_grad else None
+        if not ok.any():
+            return lp, G
+        idx = np.nonzero(ok)[0]
+        sub = self._take(c, idx)
+        rs_, drs_, ps_ = rs[idx], drs[idx], ps[idx]
+        args = (sub["blens"], self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
+        if want_grad:
+            vg = self.lik.value_grad(*args)
+            ll = np.atleast_1d(vg.log_P)
         else:
-            rs, drs = np.ones((B, 1)), np.zeros((B, 1))
-        return rs, drs, np.full((B, self.C), 1.0 / self.C)
+            ll = np.atleast_1d(self.lik.loglik(*args))
+        prior = self._prior_common(sub) - 10.0 * sub["blens"].sum(axis=1)          # blens ~ exponential(10)
+        lp[idx] = ll + prior + sub["logj"]
+        if not want_grad:
+            return lp, None
+        g = np.zeros((idx.size, self.dim))
+        gb = np.reshape(vg.grad_blens, (idx.size, self.bcount)) - 10.0
+        g[:, self.slices["blens"]] = gb * sub["blens"] + 1.0
+        self._grad_common(g, sub, vg, drs_)
+        G[idx] = g
+        return lp, G
 
-    def _lik_args(self, c, rs, ps):
-        subst = c["rates"] if self.model == "GTR" else c["kappa"][:, None] if self.model == "HKY" else None
-        return c["blens"], subst, c.get("freqs"), rs, ps
 
-    def log_prob(self, Z: np.ndarray) -> np.ndarray:
-        """Value only, [B]; draws whose constrained values are not finite get -inf (Stan drops them)."""
-        return self.log_prob_grad(Z, want_grad=False)[0]
+class StrictClockModel(_ModelBase):
+    """The program phylostan generates for a time tree with a strict clock and a constant-size
+    coalescent prior -- the fluA quick start (BASELINE config 1; tests/golden/fluA-HKY-W4-external.stan;
+    generate_script.py:285-349 coalescent, :660-679 heights -> blens, :711-752 ratio transform + Jacobian).
+
+    Parameters in the Stan program's order: ``wshape`` (C > 1), ``props[S-2]`` in (0,1), ``rate`` > 0
+    (``rate ~ exponential(1000)``), root ``height`` > ``lower_root``, ``theta`` > 0 (``theta ~ 1/x``),
+    then ``rates``/``kappa`` and ``freqs``.  ``map_`` is the pre-order [node, parent] table and ``lowers``
+    the per-node lower bounds (tip dates) of ``phylostan_b200.encode`` (utils.py:84-104); ``lowers=None``
+    means contemporaneous tips.  Needs a ``rooted=True`` likelihood handle.
+    """
+
+    def __init__(self, lik, model: str, map_, lowers=None, lower_root: Optional[float] = None, rates_alpha=None,
+                 freqs_alpha=None):
+        super().__init__(lik, model, rates_alpha, freqs_alpha)
+        m = np.asarray(map_, dtype=np.int64)
+        self.S = S = (m.shape[0] + 1) // 2
+        if m.shape != (2 * S - 1, 2) or self.bcount != 2 * S - 2:
+            raise ValueError("map must be [2S-1, 2] and the likelihood handle rooted")
+        self.nn = nn = 2 * S - 1
+        self.lowers = np.zeros(nn) if lowers is None else np.asarray(lowers, dtype=np.float64)
+        self.lower_root = float(self.lowers.max() if lower_root is None else max(lower_root, self.lowers.max()))
+        self.root = int(m[0, 0])
+        self.node = m[1:, 0] - 1                                 # 0-based node of every non-root pre-order row
+        self.parent_h = m[1:, 1] - S - 1                         # index of its parent in heights[]
+        self.internal = m[1:, 0] > S
+        self.node_h = np.where(self.internal, m[1:, 0] - S - 1, 0)
+        # internal non-root nodes in pre-order: (heights index, parent heights index, lower bound); prop j = position
+        rows = np.nonzero(self.internal)[0]
+        self.tr_node, self.tr_parent, self.tr_lo = self.node_h[rows], self.parent_h[rows], self.lowers[self.node[rows]]
+        self.is_tip_time = np.arange(nn) < S                     # times[] is indexed by node: tips first
+        self._layout((("wshape", 1 if self.C > 1 else 0), ("props", S - 2), ("rate", 1), ("height", 1), ("theta", 1))
+                     + self._subst_blocks())
+
+    def constrained_names(self) -> List[str]:
+        return ((["wshape"] if self.C > 1 else []) + [f"props.{i + 1}" for i in range(self.S - 2)]
+                + ["rate", "height", "theta"] + self._subst_names() + [f"heights.{i + 1}" for i in range(self.S - 1)])
+
+    def constrain(self, Z: np.ndarray) -> Dict[str, np.ndarray]:
+        Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+        B = Z.shape[0]
+        out: Dict[str, np.ndarray] = {"logj": np.zeros(B)}
+        u = Z[:, self.slices["props"]]
+        out["props"] = 1.0 / (1.0 + np.exp(-u))
+        out["logj"] += -(np.logaddexp(0.0, u) + np.logaddexp(0.0, -u)).sum(axis=1)      # log p(1-p)
+        for name, lower in (("rate", 0.0), ("height", self.lower_root), ("theta", 0.0)):
+            u = Z[:, self.slices[name]][:, 0]
+            out[name] = lower + np.exp(u)
+            out["logj"] += u
+        self._constrain_common(Z, out)
+        # heights = transform(props, height, map, lowers)   (generate_script.py:711-735)
+        h = np.empty((B, self.S - 1))
+        h[:, self.root - self.S - 1] = out["height"]
+        for j in range(self.S - 2):
+            lo = self.tr_lo[j]
+            h[:, self.tr_node[j]] = lo + (h[:, self.tr_parent[j]] - lo) * out["props"][:, j]
+        out["heights"] = h
+        return out
+
+    def constrained_matrix(self, Z: np.ndarray) -> np.ndarray:
+        c = self.constrain(Z)
+        cols = [c["wshape"][:, None]] if self.C > 1 else []
+        cols += [c["props"], c["rate"][:, None], c["height"][:, None], c["theta"][:, None]]
+        for k in ("rates", "kappa", "freqs"):
+            if k in c:
+                cols.append(c[k] if c[k].ndim == 2 else c[k][:, None])
+        cols.append(c["heights"])
+        return np.concatenate(cols, axis=1)
+
+    # span of every branch in time units: heights[parent] - (heights[node] | lowers[node])
+    def _spans(self, h):
+        return h[:, self.parent_h] - np.where(self.internal[None, :], h[:, self.node_h], self.lowers[self.node][None, :])
+
+    def _coalescent(self, h, theta, want_grad):
+        """constant_coalescent_log (generate_script.py:285-349), batched; gradient w.r.t. heights, theta."""
+        B, S = h.shape[0], self.S
+        times = np.concatenate([np.broadcast_to(self.lowers[:S], (B, S)), h], axis=1)     # indexed by node
+        order = np.argsort(times, axis=1, kind="stable")
+        ts = np.take_along_axis(times, order, axis=1)
+        delta = np.where(order < S, 1.0, -1.0)                   # sampling event +1, coalescent event -1
+        k_before = np.cumsum(delta, axis=1) - delta
+        c = 0.5 * k_before * (k_before - 1.0)
+        interval = np.diff(ts, axis=1, prepend=ts[:, :1])
+        tot = (interval * c).sum(axis=1)
+        logp = -tot / theta - (S - 1) * np.log(theta)
+        if not want_grad:
+            return logp, None, None
+        # event i ends the interval weighted by c_i and starts the one weighted by c_{i+1}
+        gt_sorted = (-c + np.concatenate([c[:, 1:], np.zeros((B, 1))], axis=1)) / theta[:, None]
+        gt = np.empty_like(gt_sorted)
+        np.put_along_axis(gt, order, gt_sorted, axis=1)
+        return logp, gt[:, S:], tot / theta ** 2 - (S - 1) / theta
 
     def log_prob_grad(self, Z: np.ndarray, want_grad: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
         Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
@@ -177,57 +363,54 @@ class UnrootedModel:
         with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
             c = self.constrain(Z)
             rs, drs, ps = self._site_model(c, B)
-            ok = np.isfinite(c["logj"]) & np.all(np.isfinite(c["blens"]), axis=1) & np.all(np.isfinite(rs), axis=1) \
-                & np.all(rs > 0, axis=1) & np.all(c["blens"] < 1e6, axis=1)
-            for k in ("rates", "freqs"):
-                if k in c:
-                    ok &= np.all(c[k] > 0, axis=1)
-            if "kappa" in c:
-                ok &= np.isfinite(c["kappa"]) & (c["kappa"] > 0)
+            span = self._spans(c["heights"])
+            ok = self._ok_common(c, rs) & np.all(np.isfinite(c["heights"]), axis=1) & np.all(span > 0, axis=1) \
+                & np.isfinite(c["rate"]) & (c["rate"] > 0) & np.isfinite(c["theta"]) & (c["theta"] > 0) \
+                & np.all(c["rate"][:, None] * span < 1e6, axis=1)
         lp = np.full(B, -np.inf)
         G = np.zeros((B, self.dim)) if want_grad else None
         if not ok.any():
             return lp, G
         idx = np.nonzero(ok)[0]
-        sub = {k: (v[idx] if isinstance(v, np.ndarray) else tuple(a[idx] for a in v)) for k, v in c.items()}
-        rs_, drs_, ps_ = rs[idx], drs[idx], ps[idx]
-        args = self._lik_args(sub, rs_, ps_)
+        n = idx.size
+        sub = self._take(c, idx)
+        rs_, drs_, ps_, span = rs[idx], drs[idx], ps[idx], span[idx]
+        h, rate, theta = sub["heights"], sub["rate"], sub["theta"]
+        blens = np.empty((n, self.bcount))
+        blens[:, self.node] = rate[:, None] * span                                   # generate_script.py:660-679
+        args = (blens, self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
         if want_grad:
             vg = self.lik.value_grad(*args)
             ll = np.atleast_1d(vg.log_P)
         else:
             ll = np.atleast_1d(self.lik.loglik(*args))
-        # priors, `~` statements: constants dropped exactly as Stan does
-        prior = -10.0 * sub["blens"].sum(axis=1)
-        if self.C > 1:
-            prior += -sub["wshape"]
-        if self.model == "GTR":
-            prior += ((self.rates_alpha - 1.0) * np.log(sub["rates"])).sum(axis=1)
-        if self.model == "HKY":
-            lk = np.log(sub["kappa"])
-            prior += -lk - (lk - 1.0) ** 2 / (2.0 * 1.25 ** 2)
-        if self.model != "JC69":
-            prior += ((self.freqs_alpha - 1.0) * np.log(sub["freqs"])).sum(axis=1)
-        lp[idx] = ll + prior + sub["logj"]
+        coal, g_coal_h, g_coal_theta = self._coalescent(h, theta, want_grad)
+        # Jacobian of the ratio transform: sum over internal non-root nodes of log(heights[parent] - lowers[node])
+        tr_span = h[:, self.tr_parent] - self.tr_lo[None, :]
+        prior = self._prior_common(sub) - 1000.0 * rate - np.log(theta) + coal           # exponential(1000), oneOnX
+        lp[idx] = ll + prior + np.log(tr_span).sum(axis=1) + sub["logj"]
         if not want_grad:
             return lp, None
-        g = np.zeros((idx.size, self.dim))
-        n = idx.size
-        if self.C > 1:                                                  # x = 0.1 + exp(u)
-            gw = (np.reshape(vg.grad_rs, (n, self.C)) * drs_).sum(axis=1) - 1.0
-            g[:, self.slices["wshape"]] = (gw * (sub["wshape"] - self.WSHAPE_LOWER) + 1.0)[:, None]
-        gb = np.reshape(vg.grad_blens, (n, self.bcount)) - 10.0
-        g[:, self.slices["blens"]] = gb * sub["blens"] + 1.0
-        if self.model == "GTR":
-            gr = np.reshape(vg.grad_subst, (n, 6)) + (self.rates_alpha - 1.0) / sub["rates"]
-            g[:, self.slices["rates"]] = simplex_adjoint(gr, sub["_rates"])
-        if self.model == "HKY":
-            k = sub["kappa"]
-            gk = np.reshape(vg.grad_subst, (n,)) - 1.0 / k - (np.log(k) - 1.0) / (1.25 ** 2 * k)
-            g[:, self.slices["kappa"]] = (gk * k + 1.0)[:, None]
-        if self.model != "JC69":
-            gf = np.reshape(vg.grad_freqs, (n, 4)) + (self.freqs_alpha - 1.0) / sub["freqs"]
-            g[:, self.slices["freqs"]] = simplex_adjoint(gf, sub["_freqs"])
+        g = np.zeros((n, self.dim))
+        gb = np.reshape(vg.grad_blens, (n, self.bcount))[:, self.node]               # per pre-order row
+        hbar = g_coal_h.copy()
+        w = rate[:, None] * gb
+        np.add.at(hbar.T, self.parent_h, w.T)
+        np.add.at(hbar.T, self.node_h[self.internal], -w[:, self.internal].T)
+        np.add.at(hbar.T, self.tr_parent, (1.0 / tr_span).T)
+        g_rate = (gb * span).sum(axis=1) - 1000.0
+        # reverse sweep of the ratio transform (children before parents = reverse pre-order)
+        gp = np.empty((n, self.S - 2))
+        for j in range(self.S - 3, -1, -1):
+            nb = hbar[:, self.tr_node[j]]
+            gp[:, j] = nb * (h[:, self.tr_parent[j]] - self.tr_lo[j])
+            hbar[:, self.tr_parent[j]] += nb * sub["props"][:, j]
+        p = sub["props"]
+        g[:, self.slices["props"]] = gp * p * (1.0 - p) + (1.0 - 2.0 * p)
+        g[:, self.slices["rate"]] = (g_rate * rate + 1.0)[:, None]
+        g[:, self.slices["height"]] = (hbar[:, self.root - self.S - 1] * (sub["height"] - self.lower_root) + 1.0)[:, None]
+        g[:, self.slices["theta"]] = ((g_coal_theta - 1.0 / theta) * theta + 1.0)[:, None]
+        self._grad_common(g, sub, vg, drs_)
         G[idx] = g
         return lp, G
 
@@ -360,14 +543,19 @@ def advi_meanfield(model: UnrootedModel, *, iter: int = 10000, grad_samples: int
 # ---------------------------------------------------------------------------------------------------
 def main(argv=None) -> int:
     import argparse
+    import csv
 
     from . import encode, likelihood
 
-    ap = argparse.ArgumentParser(description="batched mean-field ADVI for an unrooted tree on one B200")
+    ap = argparse.ArgumentParser(description="batched mean-field ADVI on one B200: unrooted tree, or time tree with a "
+                                             "strict clock and a constant-size coalescent (option names of `phylostan run`)")
     ap.add_argument("-t", "--tree", required=True)
     ap.add_argument("-i", "--input", required=True, help="alignment (FASTA or NEXUS)")
     ap.add_argument("-m", "--model", default="GTR", choices=("JC69", "HKY", "GTR"))
     ap.add_argument("-C", "--categories", type=int, default=1)
+    ap.add_argument("--clock", choices=("strict",), help="time tree: strict clock + constant coalescent")
+    ap.add_argument("--heterochronous", action="store_true", help="tip dates from the tree's root-to-tip distances")
+    ap.add_argument("--dates", help="csv file with header name,date")
     ap.add_argument("-o", "--output", required=True, help="CSV of draws from the approximation")
     ap.add_argument("--iter", type=int, default=10000)
     ap.add_argument("--grad_samples", type=int, default=1)
@@ -377,12 +565,23 @@ def main(argv=None) -> int:
     ap.add_argument("--samples", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args(argv)
-    enc = encode.encode(encode.read_tree(a.tree), encode.read_alignment(a.input), rooted=False)
-    with likelihood.TreeLikelihood(enc.peel, enc.tipmask, enc.weights, model=a.model,
-                                   categories=a.categories, rooted=False) as lik:
-        fit = advi_meanfield(UnrootedModel(lik, a.model), iter=a.iter, grad_samples=a.grad_samples,
-                             elbo_samples=a.elbo_samples, tol_rel_obj=a.tol_rel_obj, eta=a.eta,
-                             output_samples=a.samples, seed=a.seed, verbose=True)
+    tree, seqs = encode.read_tree(a.tree), encode.read_alignment(a.input)
+    rooted = a.clock is not None
+    enc = encode.encode(tree, seqs, rooted=rooted)
+    with likelihood.TreeLikelihood(enc.peel, enc.tipmask, enc.weights, model=a.model, categories=a.categories,
+                                   rooted=rooted) as lik:
+        if rooted:
+            dates = None
+            if a.dates:
+                with open(a.dates) as f:
+                    dates = {row["name"]: float(row["date"].strip()) for row in csv.DictReader(f)}
+            oldest = encode.setup_dates(tree, dates, a.heterochronous)
+            lowers = encode.get_lowers(tree) if oldest is not None else None
+            model = StrictClockModel(lik, a.model, enc.map, lowers)
+        else:
+            model = UnrootedModel(lik, a.model)
+        fit = advi_meanfield(model, iter=a.iter, grad_samples=a.grad_samples, elbo_samples=a.elbo_samples,
+                             tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples, seed=a.seed, verbose=True)
     with open(a.output, "w") as f:
         f.write(",".join(fit.names) + "\n")
         for row in fit.draws:

@@ -231,6 +231,32 @@ def get_preorder(tree: Tree) -> np.ndarray:
     return np.asarray(rows, dtype=np.int32)
 
 
+def setup_dates(tree: Tree, dates: Optional[Dict[str, float]] = None, heterochronous: bool = False) -> Optional[float]:
+    """phylostan/utils.py:5-57: sampling dates -> ``node.date`` = time before the most recent tip.
+
+    ``dates``: taxon -> date (what the reference reads from its csv file); None with
+    ``heterochronous=True`` takes the root-to-tip distances of the (time) tree, as ``get_dates`` does.
+    Returns ``oldest`` (None for contemporaneous tips)."""
+    if dates:
+        heterochronous = True
+    if not heterochronous:
+        for node in tree.postorder():
+            node.date = 0.0
+        return None
+    if not dates:
+        dist = {id(tree.root): 0.0}
+        dates = {}
+        for node in tree.preorder():
+            if node.parent is not None:
+                dist[id(node)] = dist[id(node.parent)] + (node.edge_length or 0.0)
+                if node.is_leaf():
+                    dates[node.label] = dist[id(node)]
+    hi, lo = max(dates.values()), min(dates.values())
+    for node in tree.leaves():
+        node.date = dates[node.label] if lo == 0 else hi - dates[node.label]      # utils.py:42-52
+    return hi if lo == 0 else hi - lo
+
+
 def get_lowers(tree: Tree) -> np.ndarray:
     """phylostan/utils.py:93-104: lower bound of each node height = max date below it."""
     ll: Dict[int, float] = {}

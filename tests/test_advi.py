@@ -193,3 +193,180 @@ def test_gpu_batched_advi_on_ds1():
     assert abs(sum(mean[f"freqs.{i}"] for i in range(1, 5)) - 1.0) < 1e-9
     assert mean["rates.2"] > mean["rates.1"] and mean["rates.5"] > mean["rates.6"]    # transitions > transversions
     assert fit.likelihood_calls < fit.iterations + fit.iterations // 100 + 400
+
+
+# --------------------------------------------------------------------------------------------------- clock trees
+def flua_clock_problem():
+    """fluA golden data + tip dates / lower bounds derived from the time tree (utils.py:5-16, 93-104)."""
+    d = np.load(GOLDEN + "/fluA.npz")
+    S = d["tipmask"].shape[0]
+    nn = 2 * S - 1
+    depth = {nn: 0.0}
+    for node, par in d["map"][1:]:
+        depth[int(node)] = depth[int(par)] + float(d["tree_blens"][int(node) - 1])
+    top = max(depth[k] for k in range(1, S + 1))
+    lowers = np.zeros(nn)
+    for k in range(1, S + 1):
+        lowers[k - 1] = top - depth[k]
+    for node, par in d["map"][:0:-1]:                         # reverse pre-order: children before parents
+        lowers[int(par) - 1] = max(lowers[int(par) - 1], lowers[int(node) - 1])
+    heights = np.array([top - depth[S + 1 + k] for k in range(S - 1)])
+    return d, S, lowers, heights
+
+
+class OracleRooted(OracleLikelihood):
+    def __init__(self, peel, tipmask, weights, model, C):
+        super().__init__(peel, tipmask, weights, model, C)
+        self.bcount = 2 * tipmask.shape[0] - 2
+
+    def _each(self, blens, subst, freqs, rs, ps, want_grad):
+        self.calls += 1
+        return [O.loglik_grad(self.peel, self.tipmask, self.weights, self.model, blens[b],
+                              None if subst is None else subst[b], None if freqs is None else freqs[b], rs[b], ps[b],
+                              rooted=True, want_grad=want_grad) for b in range(blens.shape[0])]
+
+
+def _unconstrained_from_tree(m, heights, lowers, rate=0.004, theta=5.0, wshape=0.6, kappa=4.0):
+    """Unconstrained point whose heights are the time tree's (inverse of the ratio transform)."""
+    z = np.zeros(m.dim)
+    h = heights
+    props = np.array([(h[m.tr_node[j]] - m.tr_lo[j]) / (h[m.tr_parent[j]] - m.tr_lo[j]) for j in range(m.S - 2)])
+    props = np.clip(props, 1e-6, 1 - 1e-6)
+    z[m.slices["props"]] = np.log(props) - np.log1p(-props)
+    z[m.slices["rate"]] = math.log(rate)
+    z[m.slices["height"]] = math.log(h[m.root - m.S - 1] - m.lower_root)
+    z[m.slices["theta"]] = math.log(theta)
+    if "wshape" in m.slices:
+        z[m.slices["wshape"]] = math.log(wshape - 0.1)
+    if "kappa" in m.slices:
+        z[m.slices["kappa"]] = math.log(kappa)
+    return z
+
+
+def test_strict_clock_model_is_the_stan_program():
+    """One draw of tests/golden/fluA-HKY-W4-external.stan restated literally: transform(), the
+    heights -> blens loop, constant_coalescent_log, the priors and the log-det-Jacobian loop."""
+    d, S, lowers, heights = flua_clock_problem()
+    lik = OracleRooted(d["peel"], d["tipmask"], d["weights"], "HKY", 4)
+    m = advi.StrictClockModel(lik, "HKY", d["map"], lowers)
+    assert m.dim == 1 + (S - 2) + 3 + 1 + 3
+    z = _unconstrained_from_tree(m, heights, lowers) + np.random.default_rng(0).normal(0, 0.05, m.dim)
+    c = m.constrain(z[None])
+    props, rate, height, theta = c["props"][0], c["rate"][0], c["height"][0], c["theta"][0]
+    kappa, freqs, wshape = c["kappa"][0], c["freqs"][0], c["wshape"][0]
+    mp = [[int(a), int(b)] for a, b in d["map"]]
+    nodeCount = 2 * S - 1
+    # transform (generate_script.py:711-735)
+    hs = [0.0] * (S - 1)
+    hs[mp[0][0] - S - 1] = height
+    j = 0
+    for i in range(1, nodeCount):
+        if mp[i][0] > S:
+            lo = lowers[mp[i][0] - 1]
+            hs[mp[i][0] - S - 1] = lo + (hs[mp[i][1] - S - 1] - lo) * props[j]
+            j += 1
+    assert np.allclose(hs, c["heights"][0], rtol=1e-14)
+    # heights -> blens (generate_script.py:660-679)
+    blens = np.zeros(2 * S - 2)
+    for i in range(1, nodeCount):
+        node, par = mp[i]
+        blens[node - 1] = rate * (hs[par - S - 1] - (hs[node - S - 1] if node > S else lowers[node - 1]))
+    # constant_coalescent_log (generate_script.py:285-349)
+    times = [lowers[k] for k in range(S)] + hs
+    child = [0] * S + [2] * (S - 1)
+    order = sorted(range(nodeCount), key=lambda k: times[k])
+    logP, lineages, start = 0.0, 0.0, times[order[0]]
+    for k in order:
+        interval = times[k] - start
+        if interval != 0.0:
+            logP -= interval * (lineages * (lineages - 1.0)) / 2.0 / theta
+        if child[k] == 0:
+            lineages += 1.0
+        else:
+            lineages -= 1.0
+            logP -= math.log(theta)
+        start = times[k]
+    C = 4
+    rs = np.array([(-math.log(1.0 - (2.0 * i + 1.0) / (2.0 * C))) ** (1.0 / wshape) for i in range(C)])
+    rs /= rs.sum() / C
+    target = -wshape - 1000.0 * rate - math.log(theta) + logP
+    lk = math.log(kappa)
+    target += -lk - (lk - 1.0) ** 2 / (2 * 1.25 ** 2)
+    target += O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.HKY, blens, np.array([kappa]), freqs, rs,
+                            np.full(C, 0.25), rooted=True, want_grad=False).logp
+    for i in range(1, nodeCount):
+        if mp[i][0] > S:
+            target += math.log(hs[mp[i][1] - S - 1] - lowers[mp[i][0] - 1])
+    assert m.log_prob(z[None])[0] - c["logj"][0] == pytest.approx(target, rel=1e-12)
+
+
+def test_strict_clock_model_gradient_matches_finite_differences():
+    d, S, lowers, heights = flua_clock_problem()
+    L = 40                                                    # a slice of the patterns keeps the oracle fast
+    lik = OracleRooted(d["peel"], d["tipmask"][:, :L].copy(), d["weights"][:L].copy(), "HKY", 4)
+    m = advi.StrictClockModel(lik, "HKY", d["map"], lowers, freqs_alpha=np.array([2.0, 1, 1, 3]))
+    rng = np.random.default_rng(4)
+    Z = _unconstrained_from_tree(m, heights, lowers)[None] + rng.normal(0, 0.1, (2, m.dim))
+    lp, G = m.log_prob_grad(Z)
+    assert np.all(np.isfinite(lp)) and lik.calls == 1
+    for k in range(m.dim):
+        e = np.zeros(m.dim); e[k] = 1e-6
+        fd = (m.log_prob(Z + e) - m.log_prob(Z - e)) / 2e-6
+        assert np.allclose(fd, G[:, k], rtol=5e-5, atol=5e-5), (k, fd, G[:, k])
+    # contemporaneous tips, JC69, one category: the other branch of every `if heterochronous`
+    lik1 = OracleRooted(d["peel"], d["tipmask"][:, :L].copy(), d["weights"][:L].copy(), "JC69", 1)
+    m1 = advi.StrictClockModel(lik1, "JC69", d["map"])
+    assert m1.lower_root == 0.0 and m1.dim == (S - 2) + 3
+    Z1 = rng.normal(0, 0.3, (2, m1.dim))
+    Z1[:, m1.slices["rate"]] -= 5.0
+    lp1, G1 = m1.log_prob_grad(Z1)
+    for k in range(0, m1.dim, 3):
+        e = np.zeros(m1.dim); e[k] = 1e-6
+        fd = (m1.log_prob(Z1 + e) - m1.log_prob(Z1 - e)) / 2e-6
+        assert np.allclose(fd, G1[:, k], rtol=5e-5, atol=5e-5), (k, fd, G1[:, k])
+
+
+@pytest.mark.gpu
+def test_gpu_flua_quickstart_batched_advi():
+    """BASELINE config 1 without Stan: fluA, HKY + W4, heterochronous strict clock, constant coalescent,
+    mean-field ADVI with all draws of an iteration in one library call."""
+    from phylostan_b200 import likelihood as lk
+    d, S, lowers, heights = flua_clock_problem()
+    ora = OracleRooted(d["peel"], d["tipmask"], d["weights"], "HKY", 4)
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="HKY", categories=4, rooted=True) as lik:
+        m = advi.StrictClockModel(lik, "HKY", d["map"], lowers)
+        z0 = _unconstrained_from_tree(m, heights, lowers)
+        Z = z0[None] + np.random.default_rng(1).normal(0, 0.1, (4, m.dim))
+        lp, G = m.log_prob_grad(Z)
+        lp0, G0 = advi.StrictClockModel(ora, "HKY", d["map"], lowers).log_prob_grad(Z)
+        assert np.max(np.abs(lp - lp0) / np.abs(lp0)) <= 1e-10
+        assert np.max(np.abs(G - G0) / np.maximum(1.0, np.abs(G0))) <= 1e-7
+        fit = advi.advi_meanfield(m, iter=2000, grad_samples=8, elbo_samples=100, tol_rel_obj=0.001, seed=5, init=z0,
+                                  output_samples=300)
+    mean = fit.mean()
+    assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
+    assert 1e-3 < mean["rate"] < 1e-2                     # influenza A/H3N2 HA: a few 1e-3 substitutions/site/year
+    assert mean["height"] > lowers.max() and 2.0 < mean["kappa"] < 12.0
+    assert abs(sum(mean[f"freqs.{i}"] for i in range(1, 5)) - 1.0) < 1e-9
+
+
+def test_setup_dates_and_lowers_from_the_time_tree():
+    """encode.setup_dates / get_lowers (utils.py:5-57, 93-104) on the reference's fluA files."""
+    import os
+    ref = "/root/reference/examples/fluA"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted (GPU box)")
+    tree = E.read_tree(ref + "/fluA.tree")
+    enc = E.encode(tree, E.read_alignment(ref + "/fluA.fa"), rooted=True)
+    oldest = E.setup_dates(tree, None, True)
+    lowers = E.get_lowers(tree)
+    d, S, want, heights = flua_clock_problem()
+    assert np.array_equal(enc.map, d["map"])
+    assert np.allclose(lowers, want, atol=1e-9) and oldest == pytest.approx(want.max(), abs=1e-9)
+    assert lowers[:S].min() == pytest.approx(0.0, abs=1e-9)          # the most recent tip defines time 0
+    # contemporaneous: all dates zero, no lower bounds
+    assert E.setup_dates(tree, None, False) is None and E.get_lowers(tree).max() == 0.0
+    # dates given explicitly as calendar years
+    years = {n.label: 2000.0 + i % 7 for i, n in enumerate(tree.leaves())}
+    assert E.setup_dates(tree, years, False) == pytest.approx(6.0)
+    assert max(n.date for n in tree.leaves()) == pytest.approx(6.0) and min(n.date for n in tree.leaves()) == 0.0
