@@ -341,32 +341,15 @@ def test_gpu_flua_quickstart_batched_advi():
         lp0, G0 = advi.StrictClockModel(ora, "HKY", d["map"], lowers).log_prob_grad(Z)
         assert np.max(np.abs(lp - lp0) / np.abs(lp0)) <= 1e-10
         assert np.max(np.abs(G - G0) / np.maximum(1.0, np.abs(G0))) <= 1e-7
-        fit = advi.advi_meanfield(m, iter=2000, grad_samples=8, elbo_samples=100, tol_rel_obj=0.001, seed=5, init=z0,
-                                  output_samples=300)
+        fit = advi.advi_meanfield(m, iter=10000, grad_samples=8, elbo_samples=100, tol_rel_obj=0.001, seed=5, init=z0,
+                                  output_samples=1000)
     mean = fit.mean()
-    assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
-    assert 1e-3 < mean["rate"] < 1e-2                     # influenza A/H3N2 HA: a few 1e-3 substitutions/site/year
-    assert mean["height"] > lowers.max() and 2.0 < mean["kappa"] < 12.0
+    assert fit.converged and fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
+    # The reference publishes this run's outcome (README.md:103-108, `phylostan run ... -q meanfield`):
+    # posterior means with 95 % intervals.  Every mean of the batched driver must fall inside them.
+    published = {"wshape": (0.488, 0.383, 0.616), "rate": (0.00499, 0.00432, 0.00577), "theta": (4.03, 3.14, 5.05),
+                 "kappa": (5.58, 4.37, 7.039), "height": (18.96, 18.36, 19.74)}
+    for name, (ref_mean, lo, hi) in published.items():
+        assert lo < mean[name] < hi, (name, mean[name], ref_mean)
+        assert abs(mean[name] - ref_mean) < 0.5 * (hi - lo), (name, mean[name], ref_mean)
     assert abs(sum(mean[f"freqs.{i}"] for i in range(1, 5)) - 1.0) < 1e-9
-
-
-def test_setup_dates_and_lowers_from_the_time_tree():
-    """encode.setup_dates / get_lowers (utils.py:5-57, 93-104) on the reference's fluA files."""
-    import os
-    ref = "/root/reference/examples/fluA"
-    if not os.path.exists(ref):
-        pytest.skip("reference tree not mounted (GPU box)")
-    tree = E.read_tree(ref + "/fluA.tree")
-    enc = E.encode(tree, E.read_alignment(ref + "/fluA.fa"), rooted=True)
-    oldest = E.setup_dates(tree, None, True)
-    lowers = E.get_lowers(tree)
-    d, S, want, heights = flua_clock_problem()
-    assert np.array_equal(enc.map, d["map"])
-    assert np.allclose(lowers, want, atol=1e-9) and oldest == pytest.approx(want.max(), abs=1e-9)
-    assert lowers[:S].min() == pytest.approx(0.0, abs=1e-9)          # the most recent tip defines time 0
-    # contemporaneous: all dates zero, no lower bounds
-    assert E.setup_dates(tree, None, False) is None and E.get_lowers(tree).max() == 0.0
-    # dates given explicitly as calendar years
-    years = {n.label: 2000.0 + i % 7 for i, n in enumerate(tree.leaves())}
-    assert E.setup_dates(tree, years, False) == pytest.approx(6.0)
-    assert max(n.date for n in tree.leaves()) == pytest.approx(6.0) and min(n.date for n in tree.leaves()) == 0.0
