@@ -353,3 +353,25 @@ def test_gpu_flua_quickstart_batched_advi():
         assert lo < mean[name] < hi, (name, mean[name], ref_mean)
         assert abs(mean[name] - ref_mean) < 0.5 * (hi - lo), (name, mean[name], ref_mean)
     assert abs(sum(mean[f"freqs.{i}"] for i in range(1, 5)) - 1.0) < 1e-9
+
+
+def test_setup_dates_and_lowers_from_the_time_tree():
+    """encode.setup_dates / get_lowers (utils.py:5-57, 93-104) on the reference's fluA files."""
+    import os
+    ref = "/root/reference/examples/fluA"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted (GPU box)")
+    tree = E.read_tree(ref + "/fluA.tree")
+    enc = E.encode(tree, E.read_alignment(ref + "/fluA.fa"), rooted=True)
+    oldest = E.setup_dates(tree, None, True)
+    lowers = E.get_lowers(tree)
+    d, S, want, heights = flua_clock_problem()
+    assert np.array_equal(enc.map, d["map"])
+    assert np.allclose(lowers, want, atol=1e-9) and oldest == pytest.approx(want.max(), abs=1e-9)
+    assert lowers[:S].min() == pytest.approx(0.0, abs=1e-9)          # the most recent tip defines time 0
+    # contemporaneous: all dates zero, no lower bounds
+    assert E.setup_dates(tree, None, False) is None and E.get_lowers(tree).max() == 0.0
+    # dates given explicitly as calendar years
+    years = {n.label: 2000.0 + i % 7 for i, n in enumerate(tree.leaves())}
+    assert E.setup_dates(tree, years, False) == pytest.approx(6.0)
+    assert max(n.date for n in tree.leaves()) == pytest.approx(6.0) and min(n.date for n in tree.leaves()) == 0.0
