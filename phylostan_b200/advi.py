@@ -1,4 +1,4 @@
-"""Batched mean-field ADVI over the GPU likelihood.
+"""Batched ADVI (mean-field or full-rank) over the GPU likelihood.
 
 Stan's ADVI evaluates ``log_prob`` one draw at a time (``grad_samples`` value+gradient calls per
 iteration, ``elbo_samples`` value-only calls per ELBO estimate; phylostan/phylostan.py:47-50,311-313).
@@ -14,7 +14,8 @@ coalescent, tips dated or not -- the fluA quick start (tests/golden/fluA-HKY-W4-
 node heights, ``rate ~ exponential(1000)``, ``theta ~ 1/x``, ``heights ~ constant_coalescent(theta)``.  The other
 clocks and demographic priors stay in Stan and use the external-function route.
 
-The algorithm follows Stan 2.19's ``stan::variational::advi`` with a ``normal_meanfield`` family
+The algorithm follows Stan 2.19's ``stan::variational::advi`` with the ``normal_meanfield`` (zeta = mu +
+exp(omega) * eta) or ``normal_fullrank`` (zeta = mu + L eta, L lower triangular) family
 (third-party, not under /root/reference; restated from its published description: Kucukelbir et al.
 2017, "Automatic Differentiation Variational Inference", Alg. 1 and the adaptive step-size sequence
 of section 2.6 / Stan reference manual "ADVI algorithm"):  unconstrained parameters zeta = mu +
@@ -33,7 +34,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["UnrootedModel", "StrictClockModel", "MeanFieldFit", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
+__all__ = ["UnrootedModel", "StrictClockModel", "MeanFieldFit", "advi", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -416,12 +417,13 @@ class StrictClockModel(_ModelBase):
 
 
 # ---------------------------------------------------------------------------------------------------
-# mean-field ADVI
+# mean-field and full-rank ADVI
 # ---------------------------------------------------------------------------------------------------
 @dataclass
 class MeanFieldFit:
+    """Result of ``advi`` (either family; ``omega`` is None for full rank, ``L`` None for mean field)."""
     mu: np.ndarray
-    omega: np.ndarray
+    omega: Optional[np.ndarray]
     eta: float
     iterations: int
     converged: bool
@@ -430,57 +432,100 @@ class MeanFieldFit:
     names: List[str] = field(default_factory=list)
     likelihood_calls: int = 0                    # library calls (each one a whole batch of draws)
     likelihood_draws: int = 0                    # draws evaluated in total
+    L: Optional[np.ndarray] = None               # Cholesky factor of the covariance (full rank)
 
     def mean(self) -> Dict[str, float]:
         return dict(zip(self.names, self.draws.mean(axis=0))) if self.draws is not None else {}
+
+
+class _MeanFieldFamily:
+    """zeta = mu + exp(omega) * eta   (stan::variational::normal_meanfield); theta = [mu | omega]."""
+
+    def __init__(self, dim):
+        self.d = dim
+
+    def init(self, mu):
+        return np.concatenate([mu, np.zeros(self.d)])
+
+    def transform(self, th, eta):
+        return th[:self.d] + np.exp(th[self.d:]) * eta
+
+    def entropy(self, th):
+        return 0.5 * self.d * (1.0 + math.log(2.0 * math.pi)) + th[self.d:].sum()
+
+    def grad(self, th, g, eta):
+        return np.concatenate([g.mean(axis=0), (g * eta).mean(axis=0) * np.exp(th[self.d:]) + 1.0])
+
+
+class _FullRankFamily:
+    """zeta = mu + L eta, L lower triangular, initialised to I  (stan::variational::normal_fullrank);
+    theta = [mu | L row-major]; entries above the diagonal have zero gradient and stay zero."""
+
+    def __init__(self, dim):
+        self.d = dim
+
+    def init(self, mu):
+        return np.concatenate([mu, np.eye(self.d).ravel()])
+
+    def _L(self, th):
+        return th[self.d:].reshape(self.d, self.d)
+
+    def transform(self, th, eta):
+        return th[:self.d] + eta @ self._L(th).T
+
+    def entropy(self, th):
+        return 0.5 * self.d * (1.0 + math.log(2.0 * math.pi)) + np.log(np.abs(np.diag(self._L(th)))).sum()
+
+    def grad(self, th, g, eta):
+        gl = np.tril(g.T @ eta / g.shape[0])
+        gl[np.diag_indices(self.d)] += 1.0 / np.diag(self._L(th))
+        return np.concatenate([g.mean(axis=0), gl.ravel()])
 
 
 class _Advi:
     ALPHA, TAU = 0.1, 1.0
     ETA_SEQUENCE = (100.0, 10.0, 1.0, 0.1, 0.01)
 
-    def __init__(self, model, grad_samples, elbo_samples, rng):
-        self.m, self.ng, self.ne, self.rng = model, int(grad_samples), int(elbo_samples), rng
+    def __init__(self, model, family, grad_samples, elbo_samples, rng):
+        self.m, self.f, self.ng, self.ne, self.rng = model, family, int(grad_samples), int(elbo_samples), rng
         self.calls = self.draws = 0
 
-    def elbo(self, mu, omega) -> float:
+    def elbo(self, th) -> float:
         eta = self.rng.standard_normal((self.ne, self.m.dim))
-        lp = self.m.log_prob(mu + np.exp(omega) * eta)
+        lp = self.m.log_prob(self.f.transform(th, eta))
         self.calls += 1
         self.draws += self.ne
         lp = lp[np.isfinite(lp)]                                         # Stan drops failed draws
         if lp.size == 0:
             return -np.inf
-        return float(lp.mean() + 0.5 * self.m.dim * (1.0 + math.log(2.0 * math.pi)) + omega.sum())
+        return float(lp.mean() + self.f.entropy(th))
 
-    def elbo_grad(self, mu, omega):
+    def elbo_grad(self, th):
         eta = self.rng.standard_normal((self.ng, self.m.dim))
-        lp, g = self.m.log_prob_grad(mu + np.exp(omega) * eta)
+        lp, g = self.m.log_prob_grad(self.f.transform(th, eta))
         self.calls += 1
         self.draws += self.ng
         if not np.all(np.isfinite(lp)) or not np.all(np.isfinite(g)):
             raise FloatingPointError("non-finite log density or gradient in an ELBO gradient draw")
-        return g.mean(axis=0), (g * eta).mean(axis=0) * np.exp(omega) + 1.0
+        return self.f.grad(th, g, eta)
 
-    def ascend(self, mu, omega, eta, iters, hist=None, start=1, on_check=None, eval_elbo=0):
-        for it in range(start, start + iters):
-            gm, go = self.elbo_grad(mu, omega)
-            g2 = np.concatenate([gm, go]) ** 2
-            hist = g2 if hist is None else self.ALPHA * g2 + (1.0 - self.ALPHA) * hist
-            step = eta / math.sqrt(it) / (self.TAU + np.sqrt(hist))
-            mu = mu + step[:self.m.dim] * gm
-            omega = omega + step[self.m.dim:] * go
-            if eval_elbo and it % eval_elbo == 0 and on_check(it, mu, omega):
-                return mu, omega, hist, it, True
-        return mu, omega, hist, start + iters - 1, False
+    def ascend(self, th, eta, iters, on_check=None, eval_elbo=0):
+        hist = None
+        for it in range(1, iters + 1):
+            g = self.elbo_grad(th)
+            hist = g * g if hist is None else self.ALPHA * g * g + (1.0 - self.ALPHA) * hist
+            th = th + eta / math.sqrt(it) / (self.TAU + np.sqrt(hist)) * g
+            if eval_elbo and it % eval_elbo == 0 and on_check(it, th):
+                return th, it, True
+        return th, iters, False
 
-    def adapt_eta(self, mu0, omega0, adapt_iter):
-        elbo_init = self.elbo(mu0, omega0)
+    def adapt_eta(self, th0, adapt_iter):
+        elbo_init = self.elbo(th0)
         best, eta_best = -np.inf, None
         for k, eta in enumerate(self.ETA_SEQUENCE):
             try:
-                mu, omega, _, _, _ = self.ascend(mu0.copy(), omega0.copy(), eta, adapt_iter)
-                e = self.elbo(mu, omega)
+                th, _, _ = self.ascend(th0.copy(), eta, adapt_iter)
+                e = self.elbo(th)
             except FloatingPointError:
                 e = -np.inf
             if e < best and best > elbo_init:
@@ -492,15 +537,17 @@ class _Advi:
         return eta_best
 
 
-def advi_meanfield(model: UnrootedModel, *, iter: int = 10000, grad_samples: int = 1, elbo_samples: int = 100,
-                   eval_elbo: int = 100, tol_rel_obj: float = 0.001, eta: Optional[float] = None,
-                   adapt_iter: int = 50, output_samples: int = 1000, seed: int = 1, init="random",
-                   verbose: bool = False) -> MeanFieldFit:
-    """Mean-field ADVI; keyword names follow ``pystan.StanModel.vb`` (phylostan/phylostan.py:311-313).
+def advi(model, *, algorithm: str = "meanfield", iter: int = 10000, grad_samples: int = 1, elbo_samples: int = 100,
+         eval_elbo: int = 100, tol_rel_obj: float = 0.001, eta: Optional[float] = None, adapt_iter: int = 50,
+         output_samples: int = 1000, seed: int = 1, init="random", verbose: bool = False) -> MeanFieldFit:
+    """ADVI with a mean-field or full-rank Gaussian family; keyword names follow ``pystan.StanModel.vb``
+    (phylostan/phylostan.py:311-313; ``algorithm`` is phylostan's ``-q/--variational``).
 
     ``init``: "random" (Stan's uniform(-2, 2) on the unconstrained scale), "zero", or an unconstrained
     vector.  ``grad_samples`` draws per iteration and ``elbo_samples`` draws per ELBO estimate are each
     evaluated by one batched library call."""
+    if algorithm not in ("meanfield", "fullrank"):
+        raise ValueError("algorithm must be meanfield or fullrank")
     rng = np.random.default_rng(seed)
     if isinstance(init, str):
         mu = rng.uniform(-2.0, 2.0, model.dim) if init == "random" else np.zeros(model.dim)
@@ -508,18 +555,19 @@ def advi_meanfield(model: UnrootedModel, *, iter: int = 10000, grad_samples: int
         mu = np.asarray(init, dtype=np.float64).copy()
         if mu.shape != (model.dim,):
             raise ValueError(f"init must have {model.dim} entries")
-    omega = np.zeros(model.dim)
-    A = _Advi(model, grad_samples, elbo_samples, rng)
+    fam = _MeanFieldFamily(model.dim) if algorithm == "meanfield" else _FullRankFamily(model.dim)
+    th = fam.init(mu)
+    A = _Advi(model, fam, grad_samples, elbo_samples, rng)
     if eta is None:
-        eta = A.adapt_eta(mu, omega, adapt_iter)
+        eta = A.adapt_eta(th, adapt_iter)
     trace: List[Tuple[int, float]] = []
     cb_size = max(int(0.1 * iter / eval_elbo), 2)
     ring: List[float] = []
-    state = {"prev": A.elbo(mu, omega)}
+    state = {"prev": A.elbo(th)}
     trace.append((0, state["prev"]))
 
-    def on_check(it, mu_, omega_):
-        e = A.elbo(mu_, omega_)
+    def on_check(it, th_):
+        e = A.elbo(th_)
         trace.append((it, e))
         delta = abs((e - state["prev"]) / e) if e != 0 else np.inf
         state["prev"] = e
@@ -529,13 +577,19 @@ def advi_meanfield(model: UnrootedModel, *, iter: int = 10000, grad_samples: int
             print(f"  {it:6d}  ELBO {e:.3f}  delta_mean {np.mean(ring):.5f}  delta_med {np.median(ring):.5f}")
         return np.mean(ring) < tol_rel_obj or np.median(ring) < tol_rel_obj
 
-    mu, omega, _, its, conv = A.ascend(mu, omega, eta, iter, on_check=on_check, eval_elbo=eval_elbo)
-    fit = MeanFieldFit(mu, omega, float(eta), its, conv, trace, names=model.constrained_names(),
-                       likelihood_calls=A.calls, likelihood_draws=A.draws)
+    th, its, conv = A.ascend(th, eta, iter, on_check=on_check, eval_elbo=eval_elbo)
+    d = model.dim
+    fit = MeanFieldFit(th[:d].copy(), th[d:].copy() if algorithm == "meanfield" else None, float(eta), its, conv, trace,
+                       names=model.constrained_names(), likelihood_calls=A.calls, likelihood_draws=A.draws,
+                       L=th[d:].reshape(d, d).copy() if algorithm == "fullrank" else None)
     if output_samples:
-        Z = mu + np.exp(omega) * rng.standard_normal((output_samples, model.dim))
-        fit.draws = model.constrained_matrix(Z)
+        fit.draws = model.constrained_matrix(fam.transform(th, rng.standard_normal((output_samples, d))))
     return fit
+
+
+def advi_meanfield(model, **kw) -> MeanFieldFit:
+    """``advi(model, algorithm="meanfield", ...)``."""
+    return advi(model, algorithm="meanfield", **kw)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -562,6 +616,7 @@ def main(argv=None) -> int:
     ap.add_argument("--elbo_samples", type=int, default=100)
     ap.add_argument("--tol_rel_obj", type=float, default=0.001)
     ap.add_argument("-e", "--eta", type=float)
+    ap.add_argument("-q", "--variational", default="meanfield", choices=("meanfield", "fullrank"))
     ap.add_argument("--samples", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
     a = ap.parse_args(argv)
@@ -580,8 +635,9 @@ def main(argv=None) -> int:
             model = StrictClockModel(lik, a.model, enc.map, lowers)
         else:
             model = UnrootedModel(lik, a.model)
-        fit = advi_meanfield(model, iter=a.iter, grad_samples=a.grad_samples, elbo_samples=a.elbo_samples,
-                             tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples, seed=a.seed, verbose=True)
+        fit = advi(model, algorithm=a.variational, iter=a.iter, grad_samples=a.grad_samples,
+                   elbo_samples=a.elbo_samples, tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples,
+                   seed=a.seed, verbose=True)
     with open(a.output, "w") as f:
         f.write(",".join(fit.names) + "\n")
         for row in fit.draws:

@@ -375,3 +375,35 @@ def test_setup_dates_and_lowers_from_the_time_tree():
     years = {n.label: 2000.0 + i % 7 for i, n in enumerate(tree.leaves())}
     assert E.setup_dates(tree, years, False) == pytest.approx(6.0)
     assert max(n.date for n in tree.leaves()) == pytest.approx(6.0) and min(n.date for n in tree.leaves()) == 0.0
+
+
+class CorrelatedGaussian(GaussianTarget):
+    """log p(z) = -1/2 (z - m)^T P (z - m): the full-rank optimum is mu = m, L L^T = P^-1."""
+
+    def __init__(self, mean, cov):
+        self.mean, self.cov, self.dim = np.asarray(mean, float), np.asarray(cov, float), len(mean)
+        self.prec = np.linalg.inv(self.cov)
+
+    def log_prob(self, Z):
+        dz = Z - self.mean
+        return -0.5 * np.einsum("bi,ij,bj->b", dz, self.prec, dz)
+
+    def log_prob_grad(self, Z, want_grad=True):
+        return self.log_prob(Z), -(Z - self.mean) @ self.prec
+
+
+def test_fullrank_advi_recovers_a_correlated_gaussian():
+    cov = np.array([[1.0, 0.8, 0.0], [0.8, 1.0, -0.3], [0.0, -0.3, 0.5]])
+    tgt = CorrelatedGaussian([0.5, -1.0, 2.0], cov)
+    fit = advi.advi(tgt, algorithm="fullrank", iter=4000, grad_samples=32, elbo_samples=200, tol_rel_obj=1e-5, seed=7,
+                    init="zero")
+    assert fit.omega is None and fit.L.shape == (3, 3) and np.allclose(np.triu(fit.L, 1), 0.0)
+    assert np.allclose(fit.mu, tgt.mean, atol=0.15)
+    assert np.allclose(fit.L @ fit.L.T, cov, atol=0.2)
+    # the mean-field family cannot represent the correlation: its variances are the conditional ones, 1 / P_ii
+    mf = advi.advi(tgt, algorithm="meanfield", iter=4000, grad_samples=32, elbo_samples=200, tol_rel_obj=1e-5, seed=7,
+                   init="zero")
+    assert np.allclose(np.exp(2 * mf.omega), 1.0 / np.diag(tgt.prec), rtol=0.3)
+    assert fit.elbo_trace[-1][1] > mf.elbo_trace[-1][1] - 0.05
+    with pytest.raises(ValueError):
+        advi.advi(tgt, algorithm="lowrank")
