@@ -616,6 +616,7 @@ def main(argv=None) -> int:
     ap.add_argument("--elbo_samples", type=int, default=100)
     ap.add_argument("--tol_rel_obj", type=float, default=0.001)
     ap.add_argument("-e", "--eta", type=float)
+    ap.add_argument("-a", "--algorithm", default="vb", choices=("vb", "nuts"))
     ap.add_argument("-q", "--variational", default="meanfield", choices=("meanfield", "fullrank"))
     ap.add_argument("--samples", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
@@ -635,15 +636,21 @@ def main(argv=None) -> int:
             model = StrictClockModel(lik, a.model, enc.map, lowers)
         else:
             model = UnrootedModel(lik, a.model)
-        fit = advi(model, algorithm=a.variational, iter=a.iter, grad_samples=a.grad_samples,
-                   elbo_samples=a.elbo_samples, tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples,
-                   seed=a.seed, verbose=True)
+        if a.algorithm == "nuts":           # pystan's convention: iter = warm-up + sampling, half each
+            from .sampling import nuts
+            fit = nuts(model, num_warmup=a.iter // 2, num_samples=a.iter - a.iter // 2, seed=a.seed, verbose=True)
+            print(f"step size {fit.stepsize:.4g}  mean tree depth {fit.treedepth.mean():.2f}  "
+                  f"divergent {int(fit.divergent.sum())}  gradient evaluations {fit.gradient_evaluations}")
+        else:
+            fit = advi(model, algorithm=a.variational, iter=a.iter, grad_samples=a.grad_samples,
+                       elbo_samples=a.elbo_samples, tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples,
+                       seed=a.seed, verbose=True)
+            print(f"eta {fit.eta}  iterations {fit.iterations}  converged {fit.converged}  "
+                  f"library calls {fit.likelihood_calls} ({fit.likelihood_draws} draws)")
     with open(a.output, "w") as f:
         f.write(",".join(fit.names) + "\n")
         for row in fit.draws:
             f.write(",".join(f"{v:.9g}" for v in row) + "\n")
-    print(f"eta {fit.eta}  iterations {fit.iterations}  converged {fit.converged}  "
-          f"library calls {fit.likelihood_calls} ({fit.likelihood_draws} draws)")
     return 0
 
 
