@@ -145,6 +145,21 @@ PHYLO_B200_API int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const i
                                                     double *g_freqs, double *g_rs, double *g_ps);
 
 /*
+ * Host-only helpers (no GPU) for drivers that keep the ratio parametrisation of the node heights outside
+ * Stan: heights = transform(props, root_height, map, lowers) of phylostan/generate_script.py:711-735
+ * with its log-Jacobian (:738-752), for B draws, and the reverse sweep through it.  props [B][S-2] are
+ * consumed in pre-order of the internal non-root nodes; lowers may be NULL (contemporaneous tips).
+ * ratios_reverse: hbar [B][S-1] holds d(everything downstream)/dheights on entry and is used as scratch;
+ * the log-Jacobian's own derivative is added inside.
+ */
+PHYLO_B200_API int phylo_b200_ratios_forward(int S, const int32_t *map, const double *lowers, int B,
+                                             const double *props, const double *root_height, double *heights,
+                                             double *logjac);
+PHYLO_B200_API int phylo_b200_ratios_reverse(int S, const int32_t *map, const double *lowers, int B,
+                                             const double *props, const double *heights, double *hbar,
+                                             double *g_props, double *g_root);
+
+/*
  * Split form of eval_batch for callers that keep parameters resident on the device between
  * evaluations (benchmarks, batched drivers, multi-GPU ranks):
  *   upload   host parameters -> device (one H2D copy); also derives the eigen system per draw

@@ -295,7 +295,16 @@ class StrictClockModel(_ModelBase):
         # internal non-root nodes in pre-order: (heights index, parent heights index, lower bound); prop j = position
         rows = np.nonzero(self.internal)[0]
         self.tr_node, self.tr_parent, self.tr_lo = self.node_h[rows], self.parent_h[rows], self.lowers[self.node[rows]]
-        self.is_tip_time = np.arange(nn) < S                     # times[] is indexed by node: tips first
+        self.map32 = np.ascontiguousarray(m, dtype=np.int32)
+        self.lowers_or_none = None if lowers is None else self.lowers
+        # scatter of the reverse sweep d blens -> d heights: +1 at the parent, -1 at an internal node itself
+        from scipy import sparse
+        nb = 2 * S - 2
+        rows = np.concatenate([np.arange(nb), np.nonzero(self.internal)[0]])
+        cols = np.concatenate([self.parent_h, self.node_h[self.internal]])
+        vals = np.concatenate([np.ones(nb), -np.ones(int(self.internal.sum()))])
+        sc = sparse.csr_matrix((vals, (rows, cols)), shape=(nb, S - 1))
+        self.scatter_blens = sc.toarray() if S <= 2000 else sc.T.tocsr()
         self._layout((("wshape", 1 if self.C > 1 else 0), ("props", S - 2), ("rate", 1), ("height", 1), ("theta", 1))
                      + self._subst_blocks())
 
@@ -315,13 +324,15 @@ class StrictClockModel(_ModelBase):
             out[name] = lower + np.exp(u)
             out["logj"] += u
         self._constrain_common(Z, out)
-        # heights = transform(props, height, map, lowers)   (generate_script.py:711-735)
-        h = np.empty((B, self.S - 1))
-        h[:, self.root - self.S - 1] = out["height"]
-        for j in range(self.S - 2):
-            lo = self.tr_lo[j]
-            h[:, self.tr_node[j]] = lo + (h[:, self.tr_parent[j]] - lo) * out["props"][:, j]
-        out["heights"] = h
+        # heights = transform(props, height, map, lowers) and the log-det-Jacobian loop
+        # (generate_script.py:711-752), in the library's host code: O(B S), no Python loop over nodes
+        from .likelihood import ratios_forward
+        with np.errstate(invalid="ignore"):
+            ok = np.isfinite(out["props"]).all(axis=1) & np.isfinite(out["height"])
+        out["heights"], out["logjac_heights"] = ratios_forward(
+            self.map32, self.lowers_or_none, np.where(ok[:, None], out["props"], 0.5),
+            np.where(ok, out["height"], self.lower_root + 1.0))
+        out["heights"][~ok] = np.nan
         return out
 
     def constrained_matrix(self, Z: np.ndarray) -> np.ndarray:
@@ -386,30 +397,23 @@ class StrictClockModel(_ModelBase):
         else:
             ll = np.atleast_1d(self.lik.loglik(*args))
         coal, g_coal_h, g_coal_theta = self._coalescent(h, theta, want_grad)
-        # Jacobian of the ratio transform: sum over internal non-root nodes of log(heights[parent] - lowers[node])
-        tr_span = h[:, self.tr_parent] - self.tr_lo[None, :]
         prior = self._prior_common(sub) - 1000.0 * rate - np.log(theta) + coal           # exponential(1000), oneOnX
-        lp[idx] = ll + prior + np.log(tr_span).sum(axis=1) + sub["logj"]
+        lp[idx] = ll + prior + sub["logjac_heights"] + sub["logj"]
         if not want_grad:
             return lp, None
         g = np.zeros((n, self.dim))
         gb = np.reshape(vg.grad_blens, (n, self.bcount))[:, self.node]               # per pre-order row
-        hbar = g_coal_h.copy()
         w = rate[:, None] * gb
-        np.add.at(hbar.T, self.parent_h, w.T)
-        np.add.at(hbar.T, self.node_h[self.internal], -w[:, self.internal].T)
-        np.add.at(hbar.T, self.tr_parent, (1.0 / tr_span).T)
+        hbar = g_coal_h + (w @ self.scatter_blens if isinstance(self.scatter_blens, np.ndarray)
+                           else (self.scatter_blens @ w.T).T)
         g_rate = (gb * span).sum(axis=1) - 1000.0
-        # reverse sweep of the ratio transform (children before parents = reverse pre-order)
-        gp = np.empty((n, self.S - 2))
-        for j in range(self.S - 3, -1, -1):
-            nb = hbar[:, self.tr_node[j]]
-            gp[:, j] = nb * (h[:, self.tr_parent[j]] - self.tr_lo[j])
-            hbar[:, self.tr_parent[j]] += nb * sub["props"][:, j]
+        # reverse sweep of the ratio transform and of its log-Jacobian (library host code)
+        from .likelihood import ratios_reverse
+        gp, g_root = ratios_reverse(self.map32, self.lowers_or_none, sub["props"], h, hbar)
         p = sub["props"]
         g[:, self.slices["props"]] = gp * p * (1.0 - p) + (1.0 - 2.0 * p)
         g[:, self.slices["rate"]] = (g_rate * rate + 1.0)[:, None]
-        g[:, self.slices["height"]] = (hbar[:, self.root - self.S - 1] * (sub["height"] - self.lower_root) + 1.0)[:, None]
+        g[:, self.slices["height"]] = (g_root * (sub["height"] - self.lower_root) + 1.0)[:, None]
         g[:, self.slices["theta"]] = ((g_coal_theta - 1.0 / theta) * theta + 1.0)[:, None]
         self._grad_common(g, sub, vg, drs_)
         G[idx] = g

@@ -676,6 +676,66 @@ int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const int32_t* map, co
                              g_heights, g_rates, g_subst, g_freqs, g_rs, g_ps);
 }
 
+// Host-only: the ratio transform of the node heights (generate_script.py:711-735) and its log-Jacobian
+// (:738-752) for B draws, and the reverse sweep through it.  O(B S); no GPU.
+// props [B][S-2] are consumed in pre-order of the internal non-root nodes, as the Stan loop does.
+int phylo_b200_ratios_forward(int S, const int32_t* map, const double* lowers, int B, const double* props,
+                              const double* root_height, double* heights, double* logjac) {
+    if (S < 2 || !map || B < 1 || !props || !root_height || !heights) return fail(PHYLO_B200_EINVAL, "ratios_forward: bad arguments");
+    const int nn = 2 * S - 1;
+    for (int j = 1; j < nn; ++j) {
+        const int node = map[2 * j], par = map[2 * j + 1];
+        if (node < 1 || node >= nn || par <= S || par > nn)
+            return fail(PHYLO_B200_EINVAL, "ratios_forward: malformed pre-order map row " + std::to_string(j));
+    }
+    if (map[0] <= S || map[0] > nn) return fail(PHYLO_B200_EINVAL, "ratios_forward: map row 0 must hold the root");
+    for (int b = 0; b < B; ++b) {
+        double* h = heights + (size_t)b * (S - 1);
+        const double* p = props + (size_t)b * (S - 2);
+        h[map[0] - S - 1] = root_height[b];
+        double lj = 0.0;
+        int k = 0;
+        for (int j = 1; j < nn; ++j) {
+            const int node = map[2 * j], par = map[2 * j + 1];
+            if (node <= S) continue;
+            const double lo = lowers ? lowers[node - 1] : 0.0, span = h[par - S - 1] - lo;
+            h[node - S - 1] = lo + span * p[k++];
+            lj += std::log(span);
+        }
+        if (logjac) logjac[b] = lj;
+    }
+    return 0;
+}
+
+// hbar [B][S-1]: adjoint of the heights coming from everything downstream (likelihood, tree prior); the
+// log-Jacobian's own contribution is added here.  Outputs d/dprops [B][S-2], d/droot_height [B].
+int phylo_b200_ratios_reverse(int S, const int32_t* map, const double* lowers, int B, const double* props,
+                              const double* heights, double* hbar, double* g_props, double* g_root) {
+    if (S < 2 || !map || B < 1 || !props || !heights || !hbar || !g_props || !g_root)
+        return fail(PHYLO_B200_EINVAL, "ratios_reverse: bad arguments");
+    const int nn = 2 * S - 1;
+    std::vector<int> slot(nn, -1);
+    int k = 0;
+    for (int j = 1; j < nn; ++j)
+        if (map[2 * j] > S) slot[j] = k++;
+    for (int b = 0; b < B; ++b) {
+        const double* h = heights + (size_t)b * (S - 1);
+        const double* p = props + (size_t)b * (S - 2);
+        double* hb = hbar + (size_t)b * (S - 1);
+        double* gp = g_props + (size_t)b * (S - 2);
+        for (int j = nn - 1; j >= 1; --j) {  // reverse pre-order: children before parents
+            if (slot[j] < 0) continue;
+            const int node = map[2 * j], par = map[2 * j + 1];
+            const double lo = lowers ? lowers[node - 1] : 0.0, span = h[par - S - 1] - lo;
+            const double nb = hb[node - S - 1];
+            gp[slot[j]] = nb * span;
+            hb[par - S - 1] += nb * p[slot[j]] + 1.0 / span;
+        }
+        g_root[b] = hb[map[0] - S - 1];
+    }
+    return 0;
+}
+
 // Host-only planning hook (no GPU): exercised by the CPU test-suite.
 // post/pre receive S-1 rows of 8 / 12 int32 (the PostStep / PreStep fields); depth[2] = {post, pre}.
 int phylo_b200_plan(int S, const int32_t* peel, int32_t* post, int32_t* pre, int32_t* depth) {

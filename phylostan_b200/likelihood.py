@@ -84,6 +84,8 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_last_error.restype = ctypes.c_char_p
     L.phylo_b200_set_default.argtypes = [vp]
     L.phylo_b200_get_default.restype = vp
+    L.phylo_b200_ratios_forward.argtypes = [i, ip, _dp, i, _dp, _dp, _dp, _dp]
+    L.phylo_b200_ratios_reverse.argtypes = [i, ip, _dp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_plan.argtypes = [i, ip, ip, ip, ip]
     L.phylo_b200_derive.argtypes = [i, i, _dp, _dp, _dp]
     _lib = L
@@ -320,6 +322,35 @@ def plan(peel) -> dict:
     _check(lib().phylo_b200_plan(S, peel.ctypes.data_as(ip), post.ctypes.data_as(ip), pre.ctypes.data_as(ip),
                                  depth.ctypes.data_as(ip)))
     return {"post": post, "pre": pre, "depth_post": int(depth[0]), "depth_pre": int(depth[1])}
+
+
+def ratios_forward(map_, lowers, props, root_height):
+    """heights [B, S-1] and log-Jacobian [B] of the ratio transform (generate_script.py:711-752); no GPU."""
+    m = np.ascontiguousarray(map_, dtype=np.int32)
+    S = (m.shape[0] + 1) // 2
+    props = _arr(np.atleast_2d(props))
+    B = props.shape[0]
+    root = _arr(np.reshape(root_height, (B,)))
+    lo = None if lowers is None else _arr(lowers, (2 * S - 1,))
+    heights, logjac = np.empty((B, S - 1)), np.empty(B)
+    _check(lib().phylo_b200_ratios_forward(S, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(lo), B, _ptr(props),
+                                           _ptr(root), _ptr(heights), _ptr(logjac)))
+    return heights, logjac
+
+
+def ratios_reverse(map_, lowers, props, heights, hbar):
+    """Reverse sweep of ``ratios_forward``: hbar [B, S-1] = d(downstream)/dheights (consumed);
+    returns d/dprops [B, S-2] and d/droot_height [B], the log-Jacobian's derivative included."""
+    m = np.ascontiguousarray(map_, dtype=np.int32)
+    S = (m.shape[0] + 1) // 2
+    props, heights = _arr(np.atleast_2d(props)), _arr(np.atleast_2d(heights))
+    B = props.shape[0]
+    hb = np.array(np.atleast_2d(hbar), dtype=np.float64, order="C")
+    lo = None if lowers is None else _arr(lowers, (2 * S - 1,))
+    gp, gr = np.empty((B, S - 2)), np.empty(B)
+    _check(lib().phylo_b200_ratios_reverse(S, m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(lo), B, _ptr(props),
+                                           _ptr(heights), _ptr(hb), _ptr(gp), _ptr(gr)))
+    return gp, gr
 
 
 def derive(model, subst=None, freqs=None, normalize: bool = True) -> dict:
