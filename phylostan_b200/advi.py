@@ -5,14 +5,15 @@ iteration, ``elbo_samples`` value-only calls per ELBO estimate; phylostan/phylos
 Here all draws of an iteration go through ONE ``phylo_b200_eval_batch`` call, which is the only way
 the batch parallelism of the likelihood library (BASELINE config 3) reaches a user.
 
-Scope: two of the programs phylostan generates (phylostan/generate_script.py:1186-1457).
+Scope: model blocks of the programs phylostan generates (phylostan/generate_script.py:1186-1457).
 ``UnrootedModel``: an unconstrained, unrooted tree (``clock is None``; tests/golden/DS1-GTR-W4-external.stan):
 ``wshape`` (Weibull categories), ``blens``, ``rates``/``kappa`` + ``freqs``; priors ``wshape ~ exponential(1)``,
 ``blens ~ exponential(10)``, ``rates ~ dirichlet(rates_alpha)``, ``freqs ~ dirichlet(frequencies_alpha)``,
-``kappa ~ lognormal(1, 1.25)``.  ``StrictClockModel``: a time tree with a strict clock and a constant-size
-coalescent, tips dated or not -- the fluA quick start (tests/golden/fluA-HKY-W4-external.stan): ratio-transformed
-node heights, ``rate ~ exponential(1000)``, ``theta ~ 1/x``, ``heights ~ constant_coalescent(theta)``.  The other
-clocks and demographic priors stay in Stan and use the external-function route.
+``kappa ~ lognormal(1, 1.25)``.  ``ClockModel``: a time tree (tips dated or not) with ratio-transformed node
+heights, a strict or uncorrelated-lognormal clock and a constant-size or skygrid coalescent;
+``StrictClockModel`` = strict + constant, the fluA quick start (tests/golden/fluA-HKY-W4-external.stan);
+ucln + skygrid is BASELINE config 5's program (HCV).  The remaining clocks (uced, autocorrelated) and
+demographic priors (skyride, birth-death) stay in Stan and use the external-function route.
 
 The algorithm follows Stan 2.19's ``stan::variational::advi`` with the ``normal_meanfield`` (zeta = mu +
 exp(omega) * eta) or ``normal_fullrank`` (zeta = mu + L eta, L lower triangular) family
@@ -34,7 +35,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-__all__ = ["UnrootedModel", "StrictClockModel", "MeanFieldFit", "advi", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
+__all__ = ["UnrootedModel", "ClockModel", "StrictClockModel", "MeanFieldFit", "advi", "advi_meanfield", "simplex_constrain", "simplex_adjoint", "weibull_rates"]
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -265,21 +266,29 @@ class UnrootedModel(_ModelBase):
         return lp, G
 
 
-class StrictClockModel(_ModelBase):
-    """The program phylostan generates for a time tree with a strict clock and a constant-size
-    coalescent prior -- the fluA quick start (BASELINE config 1; tests/golden/fluA-HKY-W4-external.stan;
-    generate_script.py:285-349 coalescent, :660-679 heights -> blens, :711-752 ratio transform + Jacobian).
+class ClockModel(_ModelBase):
+    """The programs phylostan generates for a time tree (generate_script.py:1290-1415): ratio-transformed
+    node heights (:711-752), a clock, a coalescent prior, and the likelihood of the branch lengths
+    ``rate * time`` (:660-679).
 
-    Parameters in the Stan program's order: ``wshape`` (C > 1), ``props[S-2]`` in (0,1), ``rate`` > 0
-    (``rate ~ exponential(1000)``), root ``height`` > ``lower_root``, ``theta`` > 0 (``theta ~ 1/x``),
-    then ``rates``/``kappa`` and ``freqs``.  ``map_`` is the pre-order [node, parent] table and ``lowers``
-    the per-node lower bounds (tip dates) of ``phylostan_b200.encode`` (utils.py:84-104); ``lowers=None``
-    means contemporaneous tips.  Needs a ``rooted=True`` likelihood handle.
+    ``clock``: "strict" (one ``rate``, ``rate ~ exponential(1000)``) or "ucln" (one rate per branch,
+    ``substrates ~ lognormal(log(ucln_mean) - ucln_stdev^2/2, ucln_stdev)``, ``ucln_mean ~ exponential(1000)``,
+    ``ucln_stdev ~ gamma(0.5396, 2.6184)``; :1311-1318).  ``coalescent``: "constant" (``theta ~ 1/x``,
+    ``constant_coalescent_log`` :285-349) or "skygrid" (log population sizes ``thetas[G]`` on the grid
+    ``linspace(0, cutoff, grid)[1:]``, ``skygrid_coalescent_log`` :440-520, ``thetas ~ gmrf(tau)``,
+    ``tau ~ gamma(0.001, 0.001)``).  Parameters in the Stan program's order: ``wshape`` (C > 1),
+    ``props[S-2]``, clock parameters, root ``height``, coalescent parameters, ``rates``/``kappa``, ``freqs``.
+    ``map_`` is the pre-order [node, parent] table and ``lowers`` the per-node lower bounds (tip dates) of
+    ``phylostan_b200.encode`` (utils.py:84-104); ``lowers=None`` means contemporaneous tips.  Needs a
+    ``rooted=True`` likelihood handle.
     """
 
     def __init__(self, lik, model: str, map_, lowers=None, lower_root: Optional[float] = None, rates_alpha=None,
-                 freqs_alpha=None):
+                 freqs_alpha=None, clock: str = "strict", coalescent: str = "constant", grid=None):
         super().__init__(lik, model, rates_alpha, freqs_alpha)
+        if clock not in ("strict", "ucln") or coalescent not in ("constant", "skygrid"):
+            raise ValueError("clock must be strict or ucln, coalescent constant or skygrid")
+        self.clock, self.coalescent = clock, coalescent
         m = np.asarray(map_, dtype=np.int64)
         self.S = S = (m.shape[0] + 1) // 2
         if m.shape != (2 * S - 1, 2) or self.bcount != 2 * S - 2:
@@ -305,12 +314,30 @@ class StrictClockModel(_ModelBase):
         vals = np.concatenate([np.ones(nb), -np.ones(int(self.internal.sum()))])
         sc = sparse.csr_matrix((vals, (rows, cols)), shape=(nb, S - 1))
         self.scatter_blens = sc.toarray() if S <= 2000 else sc.T.tocsr()
-        self._layout((("wshape", 1 if self.C > 1 else 0), ("props", S - 2), ("rate", 1), ("height", 1), ("theta", 1))
-                     + self._subst_blocks())
+        if coalescent == "skygrid":
+            if grid is None or len(grid) < 2:
+                raise ValueError("skygrid needs the grid points linspace(0, cutoff, grid)[1:]")
+            self.grid = np.asarray(grid, dtype=np.float64)
+            self.G = self.grid.size
+        clock_blocks = (("rate", 1),) if clock == "strict" else (("substrates", nb), ("ucln_mean", 1), ("ucln_stdev", 1))
+        coal_blocks = (("theta", 1),) if coalescent == "constant" else (("thetas", self.G), ("tau", 1))
+        self._layout((("wshape", 1 if self.C > 1 else 0), ("props", S - 2)) + clock_blocks + (("height", 1),)
+                     + coal_blocks + self._subst_blocks())
+
+    def _scalar_names(self):
+        clock = ["rate"] if self.clock == "strict" else ["ucln_mean", "ucln_stdev"]
+        coal = ["theta"] if self.coalescent == "constant" else ["tau"]
+        return clock, coal
 
     def constrained_names(self) -> List[str]:
-        return ((["wshape"] if self.C > 1 else []) + [f"props.{i + 1}" for i in range(self.S - 2)]
-                + ["rate", "height", "theta"] + self._subst_names() + [f"heights.{i + 1}" for i in range(self.S - 1)])
+        names = (["wshape"] if self.C > 1 else []) + [f"props.{i + 1}" for i in range(self.S - 2)]
+        if self.clock == "strict":
+            names += ["rate"]
+        else:
+            names += [f"substrates.{i + 1}" for i in range(self.bcount)] + ["ucln_mean", "ucln_stdev"]
+        names += ["height"]
+        names += ["theta"] if self.coalescent == "constant" else [f"thetas.{i + 1}" for i in range(self.G)] + ["tau"]
+        return names + self._subst_names() + [f"heights.{i + 1}" for i in range(self.S - 1)]
 
     def constrain(self, Z: np.ndarray) -> Dict[str, np.ndarray]:
         Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
@@ -319,10 +346,17 @@ class StrictClockModel(_ModelBase):
         u = Z[:, self.slices["props"]]
         out["props"] = 1.0 / (1.0 + np.exp(-u))
         out["logj"] += -(np.logaddexp(0.0, u) + np.logaddexp(0.0, -u)).sum(axis=1)      # log p(1-p)
-        for name, lower in (("rate", 0.0), ("height", self.lower_root), ("theta", 0.0)):
+        clock, coal = self._scalar_names()
+        for name in clock + ["height"] + coal:
             u = Z[:, self.slices[name]][:, 0]
-            out[name] = lower + np.exp(u)
+            out[name] = (self.lower_root if name == "height" else 0.0) + np.exp(u)
             out["logj"] += u
+        if self.clock == "ucln":
+            u = Z[:, self.slices["substrates"]]
+            out["substrates"] = np.exp(u)
+            out["logj"] += u.sum(axis=1)
+        if self.coalescent == "skygrid":
+            out["thetas"] = Z[:, self.slices["thetas"]]                 # vector[G] thetas: unconstrained (log space)
         self._constrain_common(Z, out)
         # heights = transform(props, height, map, lowers) and the log-det-Jacobian loop
         # (generate_script.py:711-752), in the library's host code: O(B S), no Python loop over nodes
@@ -338,7 +372,11 @@ class StrictClockModel(_ModelBase):
     def constrained_matrix(self, Z: np.ndarray) -> np.ndarray:
         c = self.constrain(Z)
         cols = [c["wshape"][:, None]] if self.C > 1 else []
-        cols += [c["props"], c["rate"][:, None], c["height"][:, None], c["theta"][:, None]]
+        cols.append(c["props"])
+        cols += [c["rate"][:, None]] if self.clock == "strict" else [c["substrates"], c["ucln_mean"][:, None],
+                                                                      c["ucln_stdev"][:, None]]
+        cols.append(c["height"][:, None])
+        cols += [c["theta"][:, None]] if self.coalescent == "constant" else [c["thetas"], c["tau"][:, None]]
         for k in ("rates", "kappa", "freqs"):
             if k in c:
                 cols.append(c[k] if c[k].ndim == 2 else c[k][:, None])
@@ -349,10 +387,15 @@ class StrictClockModel(_ModelBase):
     def _spans(self, h):
         return h[:, self.parent_h] - np.where(self.internal[None, :], h[:, self.node_h], self.lowers[self.node][None, :])
 
-    def _coalescent(self, h, theta, want_grad):
-        """constant_coalescent_log (generate_script.py:285-349), batched; gradient w.r.t. heights, theta."""
+    def _events(self, h):
         B, S = h.shape[0], self.S
         times = np.concatenate([np.broadcast_to(self.lowers[:S], (B, S)), h], axis=1)     # indexed by node
+        return times
+
+    def _constant_coalescent(self, h, theta, want_grad):
+        """constant_coalescent_log (generate_script.py:285-349), batched; gradient w.r.t. heights, theta."""
+        B, S = h.shape[0], self.S
+        times = self._events(h)
         order = np.argsort(times, axis=1, kind="stable")
         ts = np.take_along_axis(times, order, axis=1)
         delta = np.where(order < S, 1.0, -1.0)                   # sampling event +1, coalescent event -1
@@ -369,16 +412,64 @@ class StrictClockModel(_ModelBase):
         np.put_along_axis(gt, order, gt_sorted, axis=1)
         return logp, gt[:, S:], tot / theta ** 2 - (S - 1) / theta
 
+    def _skygrid_coalescent(self, h, thetas, want_grad):
+        """skygrid_coalescent_log (generate_script.py:440-520), batched: the time axis is cut at the sampling
+        / coalescent events AND at the grid points grid[0..G-2]; a segment starting at s has lineage count
+        k(s) and population size exp(thetas[#grid points <= s])."""
+        B, S, G = h.shape[0], self.S, self.G
+        nn = self.nn
+        times = self._events(h)
+        cuts = np.broadcast_to(self.grid[:G - 1], (B, G - 1))
+        allt = np.concatenate([times, cuts], axis=1)
+        kind = np.concatenate([np.where(np.arange(nn) < S, 1.0, -1.0), np.zeros(G - 1)])      # +1 tip, -1 coalescence, 0 grid
+        # ties: a grid point sorts AFTER an event at the same time (Stan switches only when finish > grid[index])
+        order = np.lexsort((np.broadcast_to(kind == 0, allt.shape), allt), axis=1)
+        ts = np.take_along_axis(allt, order, axis=1)
+        kd = kind[order]
+        k_after = np.cumsum(kd, axis=1)                           # lineages after the point
+        g_after = np.cumsum(kd == 0, axis=1)                      # grid index (0-based) after the point
+        seg = np.diff(ts, axis=1)                                 # segment i: from point i to point i+1
+        ka, ga = k_after[:, :-1], g_after[:, :-1]
+        c = 0.5 * ka * (ka - 1.0)
+        inv_pop = np.exp(-np.take_along_axis(thetas, ga, axis=1))
+        w = c * inv_pop                                           # rate of the segment
+        coal = kd == -1
+        g_at = np.concatenate([np.zeros((B, 1), dtype=np.int64), g_after[:, :-1]], axis=1)   # grid index before the point
+        logp = -(seg * w).sum(axis=1) - (np.take_along_axis(thetas, g_at, axis=1) * coal).sum(axis=1)
+        if not want_grad:
+            return logp, None, None
+        # d/d(time of point i) = -w_{i-1} + w_i  (end of segment i-1, start of segment i)
+        zero = np.zeros((B, 1))
+        gpt = -np.concatenate([zero, w], axis=1) + np.concatenate([w, zero], axis=1)
+        gt = np.zeros_like(allt)
+        np.put_along_axis(gt, order, gpt, axis=1)
+        gth = np.zeros((B, G))
+        contrib = seg * w                                          # d/dtheta_g of -(seg c exp(-theta_g)) = +seg w
+        for b in range(B) if B <= 4 else ():                      # tiny batches: bincount per row is cheapest
+            gth[b] = np.bincount(ga[b], weights=contrib[b], minlength=G) - np.bincount(g_at[b], weights=coal[b], minlength=G)
+        if B > 4:
+            rows = np.repeat(np.arange(B), ga.shape[1])
+            gth = np.bincount(rows * G + ga.ravel(), weights=contrib.ravel(), minlength=B * G).reshape(B, G)
+            rows = np.repeat(np.arange(B), g_at.shape[1])
+            gth -= np.bincount(rows * G + g_at.ravel(), weights=coal.ravel().astype(float), minlength=B * G).reshape(B, G)
+        return logp, gt[:, S:nn], gth
+
     def log_prob_grad(self, Z: np.ndarray, want_grad: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
         Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
         B = Z.shape[0]
+        strict, constant = self.clock == "strict", self.coalescent == "constant"
         with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
             c = self.constrain(Z)
             rs, drs, ps = self._site_model(c, B)
             span = self._spans(c["heights"])
+            rate_b = c["rate"][:, None] if strict else c["substrates"]
             ok = self._ok_common(c, rs) & np.all(np.isfinite(c["heights"]), axis=1) & np.all(span > 0, axis=1) \
-                & np.isfinite(c["rate"]) & (c["rate"] > 0) & np.isfinite(c["theta"]) & (c["theta"] > 0) \
-                & np.all(c["rate"][:, None] * span < 1e6, axis=1)
+                & np.all(np.isfinite(rate_b) & (rate_b > 0), axis=1) & np.all(rate_b * span < 1e6, axis=1)
+            clock_names, coal_names = self._scalar_names()
+            for name in clock_names + coal_names:
+                ok &= np.isfinite(c[name]) & (c[name] > 0)
+            if not constant:
+                ok &= np.all(np.abs(c["thetas"]) < 700.0, axis=1)
         lp = np.full(B, -np.inf)
         G = np.zeros((B, self.dim)) if want_grad else None
         if not ok.any():
@@ -387,37 +478,86 @@ class StrictClockModel(_ModelBase):
         n = idx.size
         sub = self._take(c, idx)
         rs_, drs_, ps_, span = rs[idx], drs[idx], ps[idx], span[idx]
-        h, rate, theta = sub["heights"], sub["rate"], sub["theta"]
+        h = sub["heights"]
+        rate_b = sub["rate"][:, None] if strict else sub["substrates"][:, self.node]     # per pre-order row
         blens = np.empty((n, self.bcount))
-        blens[:, self.node] = rate[:, None] * span                                   # generate_script.py:660-679
+        blens[:, self.node] = rate_b * span                                          # generate_script.py:660-679
         args = (blens, self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
         if want_grad:
             vg = self.lik.value_grad(*args)
             ll = np.atleast_1d(vg.log_P)
         else:
             ll = np.atleast_1d(self.lik.loglik(*args))
-        coal, g_coal_h, g_coal_theta = self._coalescent(h, theta, want_grad)
-        prior = self._prior_common(sub) - 1000.0 * rate - np.log(theta) + coal           # exponential(1000), oneOnX
+        prior = self._prior_common(sub)
+        if constant:
+            theta = sub["theta"]
+            coal, g_coal_h, g_coal_theta = self._constant_coalescent(h, theta, want_grad)
+            prior += -np.log(theta) + coal                                           # theta ~ oneOnX()
+        else:
+            thetas, tau = sub["thetas"], sub["tau"]
+            coal, g_coal_h, g_coal_thetas = self._skygrid_coalescent(h, thetas, want_grad)
+            dth = np.diff(thetas, axis=1)
+            ssq = (dth ** 2).sum(axis=1)
+            prior += coal + np.log(tau) * (self.G - 1.0) / 2.0 - ssq * tau / 2.0 \
+                - (self.G - 1.0) / 2.0 * math.log(2.0 * math.pi)                     # thetas ~ gmrf(tau): user function, constant kept
+            prior += (0.001 - 1.0) * np.log(tau) - 0.001 * tau                      # tau ~ gamma(0.001, 0.001)
+        if strict:
+            prior += -1000.0 * sub["rate"]                                           # rate ~ exponential(1000)
+        else:
+            s_, mean, sd = sub["substrates"], sub["ucln_mean"], sub["ucln_stdev"]
+            mu = np.log(mean) - 0.5 * sd ** 2
+            ls = np.log(s_)
+            resid = ls - mu[:, None]
+            prior += (-ls - resid ** 2 / (2.0 * sd[:, None] ** 2)).sum(axis=1) - self.bcount * np.log(sd)
+            prior += -1000.0 * mean + (0.5396 - 1.0) * np.log(sd) - 2.6184 * sd
         lp[idx] = ll + prior + sub["logjac_heights"] + sub["logj"]
         if not want_grad:
             return lp, None
         g = np.zeros((n, self.dim))
         gb = np.reshape(vg.grad_blens, (n, self.bcount))[:, self.node]               # per pre-order row
-        w = rate[:, None] * gb
+        w = rate_b * gb
         hbar = g_coal_h + (w @ self.scatter_blens if isinstance(self.scatter_blens, np.ndarray)
                            else (self.scatter_blens @ w.T).T)
-        g_rate = (gb * span).sum(axis=1) - 1000.0
         # reverse sweep of the ratio transform and of its log-Jacobian (library host code)
         from .likelihood import ratios_reverse
         gp, g_root = ratios_reverse(self.map32, self.lowers_or_none, sub["props"], h, hbar)
         p = sub["props"]
         g[:, self.slices["props"]] = gp * p * (1.0 - p) + (1.0 - 2.0 * p)
-        g[:, self.slices["rate"]] = (g_rate * rate + 1.0)[:, None]
         g[:, self.slices["height"]] = (g_root * (sub["height"] - self.lower_root) + 1.0)[:, None]
-        g[:, self.slices["theta"]] = ((g_coal_theta - 1.0 / theta) * theta + 1.0)[:, None]
+        if strict:
+            g_rate = (gb * span).sum(axis=1) - 1000.0
+            g[:, self.slices["rate"]] = (g_rate * sub["rate"] + 1.0)[:, None]
+        else:
+            gs = np.zeros((n, self.bcount))
+            gs[:, self.node] = gb * span                                             # likelihood, node order
+            gs += -1.0 / s_ - resid / (sd[:, None] ** 2 * s_)
+            g[:, self.slices["substrates"]] = gs * s_ + 1.0
+            r1 = resid.sum(axis=1) / sd ** 2                                         # d prior / d mu
+            g_mean = r1 / mean - 1000.0
+            g_sd = -r1 * sd + (resid ** 2).sum(axis=1) / sd ** 3 - self.bcount / sd + (0.5396 - 1.0) / sd - 2.6184
+            g[:, self.slices["ucln_mean"]] = (g_mean * mean + 1.0)[:, None]
+            g[:, self.slices["ucln_stdev"]] = (g_sd * sd + 1.0)[:, None]
+        if constant:
+            g[:, self.slices["theta"]] = ((g_coal_theta - 1.0 / theta) * theta + 1.0)[:, None]
+        else:
+            gth = g_coal_thetas.copy()
+            gth[:, :-1] += tau[:, None] * dth
+            gth[:, 1:] -= tau[:, None] * dth
+            g[:, self.slices["thetas"]] = gth
+            g_tau = (self.G - 1.0) / (2.0 * tau) - ssq / 2.0 + (0.001 - 1.0) / tau - 0.001
+            g[:, self.slices["tau"]] = (g_tau * tau + 1.0)[:, None]
         self._grad_common(g, sub, vg, drs_)
         G[idx] = g
         return lp, G
+
+
+class StrictClockModel(ClockModel):
+    """``ClockModel`` with a strict clock and a constant-size coalescent -- the fluA quick start
+    (BASELINE config 1; tests/golden/fluA-HKY-W4-external.stan)."""
+
+    def __init__(self, lik, model: str, map_, lowers=None, lower_root: Optional[float] = None, rates_alpha=None,
+                 freqs_alpha=None):
+        super().__init__(lik, model, map_, lowers, lower_root, rates_alpha, freqs_alpha, "strict", "constant")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -605,13 +745,17 @@ def main(argv=None) -> int:
 
     from . import encode, likelihood
 
-    ap = argparse.ArgumentParser(description="batched mean-field ADVI on one B200: unrooted tree, or time tree with a "
-                                             "strict clock and a constant-size coalescent (option names of `phylostan run`)")
+    ap = argparse.ArgumentParser(description="batched ADVI / NUTS on one B200: unrooted tree, or time tree with a strict or "
+                                             "uncorrelated-lognormal clock and a constant or skygrid coalescent "
+                                             "(option names of `phylostan run`)")
     ap.add_argument("-t", "--tree", required=True)
     ap.add_argument("-i", "--input", required=True, help="alignment (FASTA or NEXUS)")
     ap.add_argument("-m", "--model", default="GTR", choices=("JC69", "HKY", "GTR"))
     ap.add_argument("-C", "--categories", type=int, default=1)
-    ap.add_argument("--clock", choices=("strict",), help="time tree: strict clock + constant coalescent")
+    ap.add_argument("--clock", choices=("strict", "ucln"), help="time tree with this clock (omit: unrooted tree)")
+    ap.add_argument("-c", "--coalescent", default="constant", choices=("constant", "skygrid"))
+    ap.add_argument("--grid", type=int, help="number of grid points in skygrid")
+    ap.add_argument("--cutoff", type=float, help="a cutoff for skygrid")
     ap.add_argument("--heterochronous", action="store_true", help="tip dates from the tree's root-to-tip distances")
     ap.add_argument("--dates", help="csv file with header name,date")
     ap.add_argument("-o", "--output", required=True, help="CSV of draws from the approximation")
@@ -637,7 +781,8 @@ def main(argv=None) -> int:
                     dates = {row["name"]: float(row["date"].strip()) for row in csv.DictReader(f)}
             oldest = encode.setup_dates(tree, dates, a.heterochronous)
             lowers = encode.get_lowers(tree) if oldest is not None else None
-            model = StrictClockModel(lik, a.model, enc.map, lowers)
+            grid = np.linspace(0, a.cutoff, a.grid)[1:] if a.coalescent == "skygrid" else None   # phylostan.py:275-277
+            model = ClockModel(lik, a.model, enc.map, lowers, clock=a.clock, coalescent=a.coalescent, grid=grid)
         else:
             model = UnrootedModel(lik, a.model)
         if a.algorithm == "nuts":           # pystan's convention: iter = warm-up + sampling, half each

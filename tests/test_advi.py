@@ -196,9 +196,9 @@ def test_gpu_batched_advi_on_ds1():
 
 
 # --------------------------------------------------------------------------------------------------- clock trees
-def flua_clock_problem():
-    """fluA golden data + tip dates / lower bounds derived from the time tree (utils.py:5-16, 93-104)."""
-    d = np.load(GOLDEN + "/fluA.npz")
+def flua_clock_problem(name="fluA"):
+    """Golden data + tip dates / lower bounds derived from the time tree (utils.py:5-16, 93-104)."""
+    d = np.load(GOLDEN + "/" + name + ".npz")
     S = d["tipmask"].shape[0]
     nn = 2 * S - 1
     depth = {nn: 0.0}
@@ -407,3 +407,123 @@ def test_fullrank_advi_recovers_a_correlated_gaussian():
     assert fit.elbo_trace[-1][1] > mf.elbo_trace[-1][1] - 0.05
     with pytest.raises(ValueError):
         advi.advi(tgt, algorithm="lowrank")
+
+
+# --------------------------------------------------------------------------------------------------- ucln + skygrid
+def _hcv_model(lik_cls=None, L=None, model="GTR", C=4):
+    d, S, lowers, heights = flua_clock_problem("HCV")
+    tm, w = (d["tipmask"], d["weights"]) if L is None else (d["tipmask"][:, :L].copy(), d["weights"][:L].copy())
+    lik = OracleRooted(d["peel"], tm, w, model, C)
+    grid = np.linspace(0, 400.0, 6)[1:]                        # phylostan.py:275-277 with --grid 6 --cutoff 400
+    m = advi.ClockModel(lik, model, d["map"], lowers, clock="ucln", coalescent="skygrid", grid=grid)
+    return d, S, lowers, heights, lik, grid, m
+
+
+def _ucln_point(m, heights, lowers, rng):
+    z = rng.normal(0, 0.1, m.dim)
+    h = heights
+    props = np.array([(h[m.tr_node[j]] - m.tr_lo[j]) / (h[m.tr_parent[j]] - m.tr_lo[j]) for j in range(m.S - 2)])
+    props = np.clip(props, 1e-4, 1 - 1e-4)
+    z[m.slices["props"]] += np.log(props) - np.log1p(-props)
+    z[m.slices["height"]] += math.log(h[m.root - m.S - 1] - m.lower_root)
+    z[m.slices["substrates"]] += math.log(8e-4)
+    z[m.slices["ucln_mean"]] += math.log(8e-4)
+    z[m.slices["ucln_stdev"]] += math.log(0.4)
+    z[m.slices["thetas"]] += 5.0
+    z[m.slices["wshape"]] += math.log(0.4)
+    return z
+
+
+def test_ucln_skygrid_model_is_the_stan_program():
+    """BASELINE config 5's program (ucln clock + skygrid, HCV) for one draw, restated literally from the
+    generator's text: skygrid_coalescent_log, gmrf_log, the lognormal clock prior, the per-branch rates."""
+    d, S, lowers, heights, lik, grid, m = _hcv_model(L=30)
+    G = grid.size
+    assert m.dim == 1 + (S - 2) + (2 * S - 2) + 2 + 1 + G + 1 + 5 + 3
+    z = _ucln_point(m, heights, lowers, np.random.default_rng(3))
+    c = m.constrain(z[None])
+    hs, sub, mean, sd = list(c["heights"][0]), c["substrates"][0], c["ucln_mean"][0], c["ucln_stdev"][0]
+    pop, tau, wshape, rates, freqs = c["thetas"][0], c["tau"][0], c["wshape"][0], c["rates"][0], c["freqs"][0]
+    mp = [[int(a), int(b)] for a, b in d["map"]]
+    nodeCount = 2 * S - 1
+    blens = np.zeros(2 * S - 2)
+    for i in range(1, nodeCount):
+        node, par = mp[i]
+        blens[node - 1] = sub[node - 1] * (hs[par - S - 1] - (hs[node - S - 1] if node > S else lowers[node - 1]))
+    # skygrid_coalescent_log, 1-based indices of the Stan text mapped to 0-based
+    times = [lowers[k] for k in range(S)] + hs
+    child = [0] * S + [2] * (S - 1)
+    order = sorted(range(nodeCount), key=lambda k: times[k])
+    logP, index, lineages, start = 0.0, 1, 0.0, times[order[0]]
+    logPop = pop[index - 1]; popSize = math.exp(logPop)
+    for k in order:
+        finish = times[k]
+        while index < G and finish > grid[index - 1]:
+            end = min(grid[index - 1], finish)
+            logP -= (end - start) * (lineages * (lineages - 1.0)) / 2.0 / popSize
+            start = end
+            if index < G:
+                index += 1
+                logPop = pop[index - 1]; popSize = math.exp(logPop)
+        logP -= (finish - start) * (lineages * (lineages - 1.0)) / 2.0 / popSize
+        if child[k] != 0:
+            logP -= logPop
+        lineages += 1.0 if child[k] == 0 else -1.0
+        start = finish
+    gmrf = math.log(tau) * (G - 1.0) / 2.0 - sum((pop[i] - pop[i - 1]) ** 2 for i in range(1, G)) * tau / 2.0
+    C = 4
+    rs = np.array([(-math.log(1.0 - (2.0 * i + 1.0) / (2.0 * C))) ** (1.0 / wshape) for i in range(C)])
+    rs /= rs.sum() / C
+    mu = math.log(mean) - sd * sd * 0.5
+    target = -wshape
+    target += sum(-math.log(sd) - math.log(x) - (math.log(x) - mu) ** 2 / (2 * sd * sd) for x in sub)   # lognormal
+    target += -1000.0 * mean + (0.5396 - 1.0) * math.log(sd) - 2.6184 * sd
+    target += logP + gmrf + (0.001 - 1.0) * math.log(tau) - 0.001 * tau
+    target += O.loglik_grad(lik.peel, lik.tipmask, lik.weights, O.GTR, blens, rates, freqs, rs, np.full(C, 0.25),
+                            rooted=True, want_grad=False).logp
+    for i in range(1, nodeCount):
+        if mp[i][0] > S:
+            target += math.log(hs[mp[i][1] - S - 1] - lowers[mp[i][0] - 1])
+    # gmrf_log keeps its -(G-1)/2 log(2 pi) constant (a user-defined function, not a built-in `~`)
+    target += -(G - 1.0) / 2.0 * math.log(2.0 * math.pi)
+    assert m.log_prob(z[None])[0] - c["logj"][0] == pytest.approx(target, rel=1e-12)
+
+
+def test_ucln_skygrid_model_gradient_matches_finite_differences():
+    d, S, lowers, heights, lik, grid, m = _hcv_model(L=30)
+    rng = np.random.default_rng(9)
+    Z = np.stack([_ucln_point(m, heights, lowers, rng) for _ in range(2)])
+    lp, Gd = m.log_prob_grad(Z)
+    assert np.all(np.isfinite(lp)) and lik.calls == 1
+    for k in list(range(0, m.dim, 4)) + list(range(m.slices["thetas"].start, m.slices["tau"].stop)) + \
+            [m.slices["ucln_mean"].start, m.slices["ucln_stdev"].start, m.slices["height"].start]:
+        e = np.zeros(m.dim); e[k] = 1e-6
+        fd = (m.log_prob(Z + e) - m.log_prob(Z - e)) / 2e-6
+        assert np.allclose(fd, Gd[:, k], rtol=1e-4, atol=1e-4), (k, fd, Gd[:, k])
+    # large batches take the vectorised bincount path of the skygrid gradient
+    Z8 = np.stack([_ucln_point(m, heights, lowers, rng) for _ in range(6)])
+    lp8, G8 = m.log_prob_grad(Z8)
+    lp1, G1 = m.log_prob_grad(Z8[4:5])
+    assert np.allclose(lp8[4], lp1[0], rtol=1e-13) and np.allclose(G8[4], G1[0], rtol=1e-10, atol=1e-10)
+    assert len(m.constrained_names()) == m.constrained_matrix(Z).shape[1]
+
+
+@pytest.mark.gpu
+def test_gpu_hcv_ucln_skygrid_model_block():
+    """BASELINE config 5's model (HCV, GTR + W4, heterochronous, ucln clock, skygrid): the model block on the
+    library equals the one on the oracle back end, and a short batched ADVI run raises the ELBO."""
+    from phylostan_b200 import likelihood as lk
+    d, S, lowers, heights, ora, grid, m_cpu = _hcv_model()
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=True) as lik:
+        m = advi.ClockModel(lik, "GTR", d["map"], lowers, clock="ucln", coalescent="skygrid", grid=grid)
+        rng = np.random.default_rng(2)
+        Z = np.stack([_ucln_point(m, heights, lowers, rng) for _ in range(4)])
+        lp, Gd = m.log_prob_grad(Z)
+        lp0, G0 = m_cpu.log_prob_grad(Z)
+        assert np.max(np.abs(lp - lp0) / np.abs(lp0)) <= 1e-10
+        assert np.max(np.abs(Gd - G0) / np.maximum(1.0, np.abs(G0))) <= 1e-7
+        fit = advi.advi(m, iter=600, grad_samples=8, elbo_samples=50, eval_elbo=100, eta=0.1, seed=1, init=Z[0],
+                        output_samples=100)
+    assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
+    mean = fit.mean()
+    assert mean["height"] > lowers.max() and 1e-5 < mean["ucln_mean"] < 1e-1
