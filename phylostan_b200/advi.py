@@ -764,7 +764,9 @@ def main(argv=None) -> int:
     ap.add_argument("--elbo_samples", type=int, default=100)
     ap.add_argument("--tol_rel_obj", type=float, default=0.001)
     ap.add_argument("-e", "--eta", type=float)
-    ap.add_argument("-a", "--algorithm", default="vb", choices=("vb", "nuts"))
+    ap.add_argument("-a", "--algorithm", default="vb", choices=("vb", "nuts", "hmc"))
+    ap.add_argument("--chains", type=int, default=8, help="chains of -a hmc, advanced in lock step (one batched "
+                                                              "library call per leapfrog step)")
     ap.add_argument("-q", "--variational", default="meanfield", choices=("meanfield", "fullrank"))
     ap.add_argument("--samples", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=1)
@@ -790,6 +792,13 @@ def main(argv=None) -> int:
             fit = nuts(model, num_warmup=a.iter // 2, num_samples=a.iter - a.iter // 2, seed=a.seed, verbose=True)
             print(f"step size {fit.stepsize:.4g}  mean tree depth {fit.treedepth.mean():.2f}  "
                   f"divergent {int(fit.divergent.sum())}  gradient evaluations {fit.gradient_evaluations}")
+        elif a.algorithm == "hmc":
+            from .sampling import hmc
+            fit = hmc(model, chains=a.chains, num_warmup=a.iter // 2, num_samples=a.iter - a.iter // 2, seed=a.seed,
+                      verbose=True)
+            print(f"step size {fit.stepsize:.4g}  leapfrog steps {fit.n_leapfrog}  accept {fit.accept_stat.mean():.2f}  "
+                  f"batched library calls {fit.gradient_calls}")
+            fit.draws = fit.draws.reshape(-1, fit.draws.shape[-1])
         else:
             fit = advi(model, algorithm=a.variational, iter=a.iter, grad_samples=a.grad_samples,
                        elbo_samples=a.elbo_samples, tol_rel_obj=a.tol_rel_obj, eta=a.eta, output_samples=a.samples,

@@ -1,4 +1,4 @@
-"""NUTS over the model blocks of ``phylostan_b200.advi`` (phylostan's ``-a nuts``).
+"""NUTS and lock-step multi-chain HMC over the model blocks of ``phylostan_b200.advi`` (phylostan's ``-a nuts`` / ``-a hmc``).
 
 phylostan hands sampling to Stan (``sm.sampling(algorithm='NUTS')``, phylostan/phylostan.py:318-321), where
 every leapfrog step is one value-and-gradient evaluation of the model block -- the call the GPU library
@@ -24,7 +24,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-__all__ = ["NutsFit", "nuts"]
+__all__ = ["NutsFit", "nuts", "HmcFit", "hmc"]
 
 
 @dataclass
@@ -255,3 +255,119 @@ def nuts(model, *, num_warmup: int = 1000, num_samples: int = 1000, seed: int = 
             print(f"  iteration {it + 1}/{total}  eps {S.eps:.4g}  treedepth {depth}  accept {a:.2f}")
     return NutsFit(model.constrained_matrix(out_q), model.constrained_names(), out_q, out_lp, float(S.eps), S.inv.copy(),
                    acc, td, nl, dv, gradient_evaluations=S.ngrad)
+
+
+# ---------------------------------------------------------------------------------------------------
+# static HMC, many chains in lock step (one batched library call per leapfrog step)
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class HmcFit:
+    draws: np.ndarray                  # [chains, num_samples, n constrained]
+    names: List[str]
+    unconstrained: np.ndarray          # [chains, num_samples, dim]
+    lp: np.ndarray                     # [chains, num_samples]
+    stepsize: float
+    n_leapfrog: int
+    inv_metric: np.ndarray
+    accept_stat: np.ndarray            # [chains, num_samples]
+    gradient_calls: int = 0            # batched library calls (each evaluates every chain)
+
+    def mean(self) -> Dict[str, float]:
+        return dict(zip(self.names, self.draws.reshape(-1, self.draws.shape[-1]).mean(axis=0)))
+
+
+def hmc(model, *, chains: int = 8, num_warmup: int = 1000, num_samples: int = 1000, int_time: float = 2.0 * math.pi,
+        seed: int = 1, init="random", delta: float = 0.8, stepsize: float = 1.0, max_leapfrog: int = 256,
+        verbose: bool = False) -> HmcFit:
+    """Static HMC (phylostan's ``-a hmc``; Stan's ``static`` engine: integration time ``int_time`` = 2 pi,
+    at most L = int_time / eps leapfrog steps -- the count is jittered uniformly in 1..L -- diagonal metric) for ``chains`` chains advanced in LOCK STEP: every
+    leapfrog step is one batched ``log_prob_grad`` call, i.e. one ``phylo_b200_eval_batch`` for all chains --
+    what Stan's one-process-per-chain sampling (``--chains``, phylostan/phylostan.py:319-321) cannot do.
+    Step size (dual averaging on the mean acceptance probability) and metric (windowed variance pooled
+    over the chains) are shared by the chains.  ``init``: "random", "zero" or an unconstrained vector /
+    [chains, dim] array."""
+    rng = np.random.default_rng(seed)
+    d = model.dim
+    if isinstance(init, str):
+        q = rng.uniform(-2.0, 2.0, (chains, d)) if init == "random" else np.zeros((chains, d))
+    else:
+        q = np.broadcast_to(np.asarray(init, dtype=np.float64), (chains, d)).copy()
+    calls = 0
+
+    def potential(qq):
+        nonlocal calls
+        lp, g = model.log_prob_grad(qq)
+        calls += 1
+        bad = ~np.isfinite(lp) | ~np.all(np.isfinite(g), axis=1)
+        return np.where(bad, np.inf, -lp), np.where(bad[:, None], 0.0, -g)
+
+    V, g = potential(q)
+    if not np.all(np.isfinite(V)):
+        raise ValueError("an initial point has zero density")
+    inv = np.ones(d)
+    eps = float(stepsize)
+
+    def trajectory(q, V, g, eps, L):
+        p = rng.standard_normal((chains, d)) / np.sqrt(inv)
+        H0 = V + 0.5 * (p * p * inv).sum(axis=1)
+        qn, pn, Vn, gn = q.copy(), p, V, g
+        for _ in range(L):
+            pn = pn - 0.5 * eps * gn
+            qn = qn + eps * inv * pn
+            Vn, gn = potential(qn)
+            pn = pn - 0.5 * eps * gn
+        H1 = Vn + 0.5 * (pn * pn * inv).sum(axis=1)
+        with np.errstate(over="ignore", invalid="ignore"):
+            a = np.where(np.isfinite(H1), np.minimum(1.0, np.exp(H0 - H1)), 0.0)
+        acc = rng.uniform(size=chains) < a
+        return (np.where(acc[:, None], qn, q), np.where(acc, Vn, V), np.where(acc[:, None], gn, g), a)
+
+    def find_eps(eps):
+        """Stan's heuristic on the mean one-step acceptance probability of the chains."""
+        def one(e):
+            return float(trajectory(q, V, g, e, 1)[3].mean())
+        direction = 1 if one(eps) > 0.8 else -1
+        for _ in range(60):
+            a = one(eps)
+            if (direction == 1 and not a > 0.8) or (direction == -1 and not a < 0.8):
+                break
+            eps = 2.0 * eps if direction == 1 else 0.5 * eps
+        return eps
+
+    eps = find_eps(eps)
+    da = _DualAveraging(delta)
+    da.restart(eps)
+    ends, init_buffer = _windows(num_warmup)
+    win_n, win_mean, win_m2 = 0, np.zeros(d), np.zeros(d)
+    out_q = np.empty((chains, num_samples, d))
+    out_lp, acc = np.empty((chains, num_samples)), np.empty((chains, num_samples))
+    L = 1
+    for it in range(num_warmup + num_samples):
+        L = int(min(max(1, math.floor(int_time / eps)), max_leapfrog))
+        # the number of steps is drawn uniformly from 1..L: a fixed integration time resonates with the
+        # period of a well-adapted Gaussian-like posterior (2 pi is exactly one period)
+        q, V, g, a = trajectory(q, V, g, eps, int(rng.integers(1, L + 1)))
+        if it < num_warmup:
+            eps = da.learn(float(a.mean()))
+            if ends and init_buffer <= it < ends[-1]:
+                for cq in q:                                            # Welford, pooled over the chains
+                    win_n += 1
+                    dlt = cq - win_mean
+                    win_mean += dlt / win_n
+                    win_m2 += dlt * (cq - win_mean)
+                if it + 1 in ends:
+                    var = win_m2 / max(win_n - 1, 1)
+                    inv = (win_n / (win_n + 5.0)) * var + 1e-3 * (5.0 / (win_n + 5.0))
+                    win_n, win_mean, win_m2 = 0, np.zeros(d), np.zeros(d)
+                    eps = find_eps(eps)
+                    da.restart(eps)
+            if it + 1 == num_warmup:
+                eps = da.final()
+        else:
+            k = it - num_warmup
+            out_q[:, k], out_lp[:, k], acc[:, k] = q, -V, a
+        if verbose and (it + 1) % max((num_warmup + num_samples) // 10, 1) == 0:
+            print(f"  iteration {it + 1}  eps {eps:.4g}  L {L}  accept {a.mean():.2f}")
+    draws = model.constrained_matrix(out_q.reshape(-1, d))
+    return HmcFit(draws.reshape(chains, num_samples, -1), model.constrained_names(), out_q, out_lp, float(eps), L,
+                  inv.copy(), acc, gradient_calls=calls)

@@ -76,3 +76,45 @@ def test_gpu_nuts_flua_quickstart():
     for name, (lo, hi) in {"wshape": (0.383, 0.616), "rate": (0.00432, 0.00577), "theta": (3.14, 5.05),
                            "kappa": (4.37, 7.039), "height": (18.36, 19.74)}.items():
         assert lo < mean[name] < hi, (name, mean[name])
+
+
+def test_lockstep_hmc_recovers_a_gaussian_with_one_call_per_leapfrog_step():
+    tgt = GaussianTarget([1.0, -2.0, 0.5], [0.5, 2.0, 0.05])
+    calls = {"n": 0, "rows": 0}
+    orig = tgt.log_prob_grad
+
+    def counted(Z, want_grad=True):
+        calls["n"] += 1
+        calls["rows"] += Z.shape[0]
+        return orig(Z, want_grad)
+
+    tgt.log_prob_grad = counted
+    fit = sampling.hmc(tgt, chains=16, num_warmup=300, num_samples=300, seed=2, init="zero")
+    assert fit.draws.shape == (16, 300, 3) and fit.gradient_calls == calls["n"]
+    assert calls["rows"] == 16 * calls["n"]                      # every call advances all chains together
+    flat = fit.draws.reshape(-1, 3)
+    assert np.allclose(flat.mean(axis=0), tgt.mean, atol=4 * tgt.sd / np.sqrt(400))
+    assert np.allclose(flat.std(axis=0), tgt.sd, rtol=0.12)
+    assert np.allclose(np.sqrt(fit.inv_metric), tgt.sd, rtol=0.3)
+    assert 0.6 < fit.accept_stat.mean() <= 1.0
+    # chains agree with each other (potential scale reduction close to 1)
+    w = fit.draws.var(axis=1, ddof=1).mean(axis=0)
+    b = fit.draws.mean(axis=1).var(axis=0, ddof=1) * 300
+    assert np.all(np.sqrt(((299 / 300) * w + b / 300) / w) < 1.1), np.sqrt(((299 / 300) * w + b / 300) / w)
+
+
+@pytest.mark.gpu
+def test_gpu_lockstep_hmc_flua_quickstart():
+    """16 chains of static HMC advanced by one phylo_b200_eval_batch per leapfrog step; the pooled posterior means
+    land inside the reference's published intervals (README.md:103-108)."""
+    from phylostan_b200 import likelihood as lk
+    d, S, lowers, heights = flua_clock_problem()
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="HKY", categories=4, rooted=True) as lik:
+        m = advi.StrictClockModel(lik, "HKY", d["map"], lowers)
+        fit = sampling.hmc(m, chains=16, num_warmup=300, num_samples=150, seed=3,
+                           init=_unconstrained_from_tree(m, heights, lowers), max_leapfrog=64)
+    mean = fit.mean()
+    assert fit.accept_stat.mean() > 0.5
+    for name, (lo, hi) in {"wshape": (0.383, 0.616), "rate": (0.00432, 0.00577), "theta": (3.14, 5.05),
+                           "kappa": (4.37, 7.039), "height": (18.36, 19.74)}.items():
+        assert lo < mean[name] < hi, (name, mean[name])
