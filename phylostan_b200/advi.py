@@ -193,6 +193,32 @@ class _ModelBase:
             gf = np.reshape(vg.grad_freqs, (n, 4)) + (self.freqs_alpha - 1.0) / sub["freqs"]
             g[:, self.slices["freqs"]] = simplex_adjoint(gf, sub["_freqs"])
 
+    def _likelihood(self, args, want_grad):
+        """One batched library call; if the library rejects the batch (a draw with a non-finite likelihood --
+        its ``std::domain_error`` case), the draws are evaluated one by one and the offending ones get -inf
+        and a zero gradient, which is what Stan does with a rejected draw."""
+        from .likelihood import ValueGrad
+        try:
+            if want_grad:
+                vg = self.lik.value_grad(*args)
+                return np.atleast_1d(vg.log_P), vg
+            return np.atleast_1d(self.lik.loglik(*args)), None
+        except Exception as e:                                   # PhyloDomainError of the library (or a back end's own)
+            if type(e).__name__ != "PhyloDomainError" or args[0].shape[0] == 1:
+                if type(e).__name__ != "PhyloDomainError":
+                    raise
+                n = args[0].shape[0]
+                zero = ValueGrad(np.full(n, -np.inf), np.zeros((n, self.bcount)), np.zeros((n, max(self.lik.nsubst, 0))),
+                                 np.zeros((n, 4)), np.zeros((n, self.C)), np.zeros((n, self.C)))
+                return zero.log_P, (zero if want_grad else None)
+        parts = [self._likelihood(tuple(None if a is None else a[i:i + 1] for a in args), want_grad)
+                 for i in range(args[0].shape[0])]
+        ll = np.concatenate([p[0] for p in parts])
+        if not want_grad:
+            return ll, None
+        cat = lambda name: np.concatenate([np.reshape(getattr(p[1], name), (1, -1)) for p in parts])
+        return ll, ValueGrad(ll, cat("grad_blens"), cat("grad_subst"), cat("grad_freqs"), cat("grad_rs"), cat("grad_ps"))
+
     def log_prob(self, Z: np.ndarray) -> np.ndarray:
         """Value only, [B]; draws whose constrained values are not finite get -inf (Stan drops them)."""
         return self.log_prob_grad(Z, want_grad=False)[0]
@@ -249,11 +275,7 @@ class UnrootedModel(_ModelBase):
         sub = self._take(c, idx)
         rs_, drs_, ps_ = rs[idx], drs[idx], ps[idx]
         args = (sub["blens"], self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
-        if want_grad:
-            vg = self.lik.value_grad(*args)
-            ll = np.atleast_1d(vg.log_P)
-        else:
-            ll = np.atleast_1d(self.lik.loglik(*args))
+        ll, vg = self._likelihood(args, want_grad)
         prior = self._prior_common(sub) - 10.0 * sub["blens"].sum(axis=1)          # blens ~ exponential(10)
         lp[idx] = ll + prior + sub["logj"]
         if not want_grad:
@@ -483,11 +505,7 @@ class ClockModel(_ModelBase):
         blens = np.empty((n, self.bcount))
         blens[:, self.node] = rate_b * span                                          # generate_script.py:660-679
         args = (blens, self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
-        if want_grad:
-            vg = self.lik.value_grad(*args)
-            ll = np.atleast_1d(vg.log_P)
-        else:
-            ll = np.atleast_1d(self.lik.loglik(*args))
+        ll, vg = self._likelihood(args, want_grad)
         prior = self._prior_common(sub)
         if constant:
             theta = sub["theta"]

@@ -527,3 +527,28 @@ def test_gpu_hcv_ucln_skygrid_model_block():
     assert fit.elbo_trace[-1][1] > fit.elbo_trace[0][1]
     mean = fit.mean()
     assert mean["height"] > lowers.max() and 1e-5 < mean["ucln_mean"] < 1e-1
+
+
+def test_a_rejected_batch_is_retried_draw_by_draw():
+    """The library answers a batch containing a draw with a non-finite likelihood with its domain error; the
+    model block then isolates that draw (-inf, like a draw Stan rejects) and keeps the others."""
+    class PhyloDomainError(Exception):
+        pass
+
+    class Picky(OracleLikelihood):
+        def _each(self, blens, subst, freqs, rs, ps, want_grad):
+            if np.any(blens > 50.0):
+                self.calls += 1
+                raise PhyloDomainError("log-likelihood is not finite")
+            return super()._each(blens, subst, freqs, rs, ps, want_grad)
+
+    prob = synth.make_problem(6, 40, 4, seed=5)
+    lik = Picky(E.unrooted_swap(prob.peel), prob.tipmask, prob.weights, "GTR", 4)
+    m = advi.UnrootedModel(lik, "GTR")
+    Z = np.random.default_rng(0).normal(-1.0, 0.3, (3, m.dim))
+    Z[1, m.slices["blens"].start] = 5.0                                  # exp(5) > 50
+    lp, G = m.log_prob_grad(Z)
+    assert np.isfinite(lp[0]) and np.isfinite(lp[2]) and lp[1] == -np.inf
+    good = m.log_prob_grad(Z[[0, 2]])
+    assert np.allclose(lp[[0, 2]], good[0], rtol=1e-13) and np.allclose(G[[0, 2]], good[1], rtol=1e-12)
+    assert np.array_equal(m.log_prob(Z) == -np.inf, [False, True, False])
