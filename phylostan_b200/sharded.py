@@ -41,11 +41,41 @@ class ShardedLikelihood:
     """Rank-local likelihood + all-reduce.  ``local`` is a TreeLikelihood built on this rank's pattern
     slice (production) or any callable ``(params...) -> packed rows [B, nout]`` (host-side tests)."""
 
-    def __init__(self, local, group=None):
+    def __init__(self, local, group=None, layout: Optional[Tuple[int, int, int]] = None):
+        """``layout`` = (bcount, nsubst, C) is needed only when ``local`` is a callable."""
         import torch.distributed as dist
         self.local, self.group, self.dist = local, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._is_gpu = hasattr(local, "device_out")
+        if self._is_gpu:
+            self.bcount, self.nsubst, self.C = local.bcount, local.nsubst, local.C
+        elif layout is not None:
+            self.bcount, self.nsubst, self.C = layout
+
+    # -- the TreeLikelihood surface the model blocks of phylostan_b200.advi / .sampling call, so that ADVI,
+    #    NUTS and lock-step HMC run unchanged over pattern shards (every rank runs the same driver with the
+    #    same seed; after the all-reduce every rank holds the same log-likelihood and gradient)
+    def _unpack(self, rows: np.ndarray):
+        from .likelihood import ValueGrad
+        o = 1
+        gb = rows[:, o:o + self.bcount]; o += self.bcount
+        gs = rows[:, o:o + self.nsubst]; o += self.nsubst
+        gf = rows[:, o:o + 4]; o += 4
+        gr = rows[:, o:o + self.C]; o += self.C
+        return ValueGrad(rows[:, 0].copy(), gb, gs, gf, gr, rows[:, o:o + self.C])
+
+    def value_grad(self, blens, subst=None, freqs=None, rs=None, ps=None):
+        blens = np.asarray(blens, dtype=np.float64)
+        vg = self._unpack(self.packed(np.atleast_2d(blens), subst, freqs, rs, ps, want_grad=True))
+        if blens.ndim == 1:
+            return type(vg)(float(vg.log_P[0]), vg.grad_blens[0], vg.grad_subst[0], vg.grad_freqs[0], vg.grad_rs[0],
+                            vg.grad_ps[0])
+        return vg
+
+    def loglik(self, blens, subst=None, freqs=None, rs=None, ps=None):
+        blens = np.asarray(blens, dtype=np.float64)
+        lp = self.packed(np.atleast_2d(blens), subst, freqs, rs, ps, want_grad=False)[:, 0].copy()
+        return float(lp[0]) if blens.ndim == 1 else lp
 
     def packed(self, blens, subst=None, freqs=None, rs=None, ps=None, want_grad: bool = True) -> np.ndarray:
         """All-reduced packed rows [B, nout] on every rank."""
@@ -58,6 +88,8 @@ class ShardedLikelihood:
                 self.dist.all_reduce(device_out_tensor(lik, B), group=self.group)  # same stream as the kernels
             return lik.download(B)
         rows = np.atleast_2d(np.asarray(self.local(blens, subst, freqs, rs, ps), dtype=np.float64))
+        if not want_grad:
+            rows = rows[:, :1]
         if self.world > 1:
             t = torch.from_numpy(rows.copy())
             self.dist.all_reduce(t, group=self.group)

@@ -71,6 +71,57 @@ def test_two_rank_gloo_allreduce_matches_unsharded():
         assert shape == (3, 1 + 51 + 6 + 4 + 4 + 4)
 
 
+def _advi_worker(rank, world, port, q):
+    """Every rank runs the same ADVI driver on its pattern shard; the all-reduce makes them agree."""
+    import torch.distributed as dist
+    from conftest import load_dataset
+    from oracle import oracle as O
+    from phylostan_b200 import advi
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = load_dataset("DS1")
+    S, L = d["tipmask"].shape
+    L = 120                                                    # a slice keeps the oracle quick
+    lo, hi = sharded.shard_bounds(L, world, rank)
+
+    def local(bl, rates, freqs, rs, ps, sl=slice(lo, hi)):
+        return np.stack([O.loglik_grad(d["peel"], d["tipmask"][:, sl], d["weights"][sl], O.GTR, bl[i], rates[i], freqs[i],
+                                       rs[i], ps[i], rooted=False, nthreads=1).flat() for i in range(len(bl))])
+
+    lik = sharded.ShardedLikelihood(local, layout=(2 * S - 3, 6, 4))
+    m = advi.UnrootedModel(lik, "GTR")
+    z0 = np.full(m.dim, -2.5)
+    fit = advi.advi(m, iter=12, grad_samples=2, elbo_samples=4, eval_elbo=6, eta=0.1, seed=5, init=z0, output_samples=0)
+    # the same run on the unsharded alignment, in this process
+    whole = sharded.ShardedLikelihood.__new__(sharded.ShardedLikelihood)
+    whole.local, whole.world, whole._is_gpu = (lambda *a: local(*a, sl=slice(0, L))), 1, False
+    whole.bcount, whole.nsubst, whole.C = 2 * S - 3, 6, 4
+    ref = advi.advi(advi.UnrootedModel(whole, "GTR"), iter=12, grad_samples=2, elbo_samples=4, eval_elbo=6, eta=0.1, seed=5,
+                    init=z0, output_samples=0)
+    q.put((rank, fit.mu, float(np.max(np.abs(fit.mu - ref.mu))), fit.elbo_trace[-1][1], ref.elbo_trace[-1][1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_advi_over_pattern_shards():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_advi_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][1], res[1][1])                  # both ranks hold the same variational mean
+    for rank, mu, err, e_sharded, e_whole in res:
+        assert err < 1e-8 and abs(e_sharded - e_whole) < 1e-6 * abs(e_whole), (rank, err, e_sharded, e_whole)
+
+
 def _gpu_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
