@@ -552,3 +552,54 @@ def test_a_rejected_batch_is_retried_draw_by_draw():
     good = m.log_prob_grad(Z[[0, 2]])
     assert np.allclose(lp[[0, 2]], good[0], rtol=1e-13) and np.allclose(G[[0, 2]], good[1], rtol=1e-12)
     assert np.array_equal(m.log_prob(Z) == -np.inf, [False, True, False])
+
+
+def _write_newick_and_fasta(tmp_path, S=8, L=300, seed=3):
+    """A small simulated data set as the files `phylostan run -t ... -i ...` takes."""
+    prob = synth.make_problem(S, L, 4, seed=seed)
+    names = [f"t{k + 1}_{2000 + (k * 3) % 11}" for k in range(S)]
+    sub = {k: names[k] for k in range(S)}
+    for a, b, p in prob.peel:
+        sub[p - 1] = "(%s:%.6f,%s:%.6f)" % (sub[a - 1], max(prob.blens[a - 1], 1e-4) * 50, sub[b - 1],
+                                             max(prob.blens[b - 1], 1e-4) * 50)
+    tree = tmp_path / "sim.tree"
+    tree.write_text(sub[2 * S - 2] + ";\n")
+    code = {1: "A", 2: "C", 4: "G", 8: "T", 15: "N"}
+    fasta = tmp_path / "sim.fa"
+    with open(fasta, "w") as f:
+        for k in range(S):
+            seq = "".join(code.get(int(m), "N") * int(w) for m, w in zip(prob.tipmask[k], prob.weights))
+            f.write(f">{names[k]}\n{seq}\n")
+    return tree, fasta
+
+
+def test_command_line_reads_tree_and_alignment(tmp_path):
+    """The file front end of the drivers (no GPU needed up to the encoders)."""
+    tree, fasta = _write_newick_and_fasta(tmp_path)
+    t = E.read_tree(str(tree))
+    enc = E.encode(t, E.read_alignment(str(fasta)), rooted=True)
+    assert enc.S == 8 and enc.peel.shape == (7, 3) and enc.tipmask.shape[0] == 8 and enc.weights.sum() > 300
+    assert E.setup_dates(t, None, True) > 0 and E.get_lowers(t).shape == (15,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("argv", [
+    ["-m", "HKY", "-C", "4", "--iter", "300", "--grad_samples", "4"],
+    ["-m", "GTR", "-C", "4", "--clock", "strict", "--heterochronous", "--iter", "300", "--grad_samples", "4", "-q", "fullrank"],
+    ["-m", "JC69", "--clock", "ucln", "-c", "skygrid", "--grid", "5", "--cutoff", "30", "--iter", "200"],
+    ["-m", "HKY", "--clock", "strict", "-a", "nuts", "--iter", "60"],
+    ["-m", "HKY", "--clock", "strict", "--heterochronous", "-a", "hmc", "--chains", "4", "--iter", "60"],
+])
+def test_gpu_command_line_end_to_end(tmp_path, argv):
+    """python -m phylostan_b200.advi: tree + alignment files in, CSV of posterior draws out."""
+    tree, fasta = _write_newick_and_fasta(tmp_path)
+    out = tmp_path / "draws.csv"
+    assert advi.main(["-t", str(tree), "-i", str(fasta), "-o", str(out), "--samples", "50"] + argv) == 0
+    rows = out.read_text().strip().split("\n")
+    header = rows[0].split(",")
+    data = np.array([[float(x) for x in r.split(",")] for r in rows[1:]])
+    assert data.shape[1] == len(header) and data.shape[0] >= 30 and np.all(np.isfinite(data))
+    if "--clock" in argv:
+        assert "height" in header and np.all(data[:, header.index("height")] > 0)
+    else:
+        assert "blens.1" in header and np.all(data[:, header.index("blens.1")] > 0)
