@@ -482,6 +482,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                         // [K][NT]
     Ring<R::kRec> ring;
     ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * (R::kRec * kRecChunk * kRecBufs);
+    // K == 1 (small, latency-bound problems): the two 4x4 statistics of a step are summed over the warp
+    // through shared memory -- 32 values per lane in, one entry per lane out -- instead of the
+    // shuffle/select exchange, which K = 1 cannot amortise over several patterns.  [32 entries][33] per warp.
+    T* const red = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ex_e + K * NT) +
+                                        (NT / 32) * (R::kRec * kRecChunk * kRecBufs)) + warp * (32 * 33);
     ring.sbuf = (unsigned)__cvta_generic_to_shared(ring.buf);
     ring.lane = lane;
     ring.next = nullptr;
@@ -803,7 +808,12 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             else st4(ST(s2.x, j), NT, q);
                         }
                     }
-                    warp_reduce16_head(G, gb4, lane);
+                    if (K == 1) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) red[x * 33 + lane] = G[x];
+                    } else {
+                        warp_reduce16_head(G, gb4, lane);
+                    }
                 }
                 {   // child a: processed next when internal, so q(a) stays in the TOS registers
                     T G[16];
@@ -830,9 +840,27 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                         }
                     }
-                    T ga4[4];
-                    warp_reduce16_head(G, ga4, lane);
-                    warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
+                    if (K == 1) {
+#pragma unroll
+                        for (int x = 0; x < 16; ++x) red[(16 + x) * 33 + lane] = G[x];
+                        __syncwarp();
+                        // lane l owns entry l: 0..15 of child b, 16..31 of child a; four partial sums keep the chain short
+                        const T* row = red + lane * 33;
+                        T s0 = T(0), s1 = T(0), s2s = T(0), s3 = T(0);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            s0 += row[j];
+                            s1 += row[j + 1];
+                            s2s += row[j + 2];
+                            s3 += row[j + 3];
+                        }
+                        atomicAdd(Gd + (lane < 16 ? s2.z + lane : s2.y + lane - 16), (double)((s0 + s1) + (s2s + s3)));
+                        __syncwarp();  // the rows are rewritten by the next step
+                    } else {
+                        T ga4[4];
+                        warp_reduce16_head(G, ga4, lane);
+                        warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
+                    }
                 }
                 ca = ca1; cb = cb1; dcur = d1; ca1 = ca2; cb1 = cb2; d1 = d2;
             }
@@ -1048,8 +1076,9 @@ int record_bytes(int prec) { return prec == 32 ? kRecBytesF32 : kRecBytes; }
 
 size_t sweep_smem_bytes(int D, int K, int nthreads, int prec) {
     const size_t entry = prec == 32 ? 16 : 32;  // bytes per 4-state vector
+    const size_t red = K == 1 ? (size_t)(nthreads / 32) * 32 * 33 * (entry / 4) : 0;  // K = 1: reduction through smem
     return (size_t)D * K * nthreads * entry + (size_t)K * nthreads * (sizeof(double) + sizeof(int)) +
-           (size_t)(nthreads / 32) * record_bytes(prec) * kRecChunk * kRecBufs;
+           (size_t)(nthreads / 32) * record_bytes(prec) * kRecChunk * kRecBufs + red;
 }
 
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
