@@ -6,7 +6,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -111,6 +113,11 @@ struct phylo_b200_ctx {
     int last_launches = 0;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // eval_batch replays a captured CUDA graph (H2D copy, memsets, the three kernels, D2H copy): for
+    // fluA-sized problems the six stream calls cost more CPU time than the GPU needs to run them
+    struct EvalGraph { cudaGraphExec_t exec = nullptr; std::vector<unsigned long long> sig; };
+    std::map<std::pair<int, int>, EvalGraph> graphs;  // (B, want_grad) -> executable graph + what it baked in
+    bool use_graphs = true;
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false, ev_has_contract = false;
@@ -122,6 +129,7 @@ struct phylo_b200_ctx {
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
         h_params.release(); h_out.release();
+        for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -319,6 +327,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
         return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
     }
     h->stream = h->own_stream;
+    if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
             delete h;
@@ -466,8 +475,10 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
     return PHYLO_B200_EINVAL;
 }
 
-int phylo_b200_upload(phylo_b200_handle h, int B, const double* blens, const double* subst, const double* freqs,
-                      const double* rs, const double* ps) {
+namespace {
+// validate, size the per-batch buffers and pack the draws into the pinned staging buffer (no copy yet)
+int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subst, const double* freqs,
+               const double* rs, const double* ps) {
     if (!h || B < 1 || !blens) return fail(PHYLO_B200_EINVAL, "upload: bad arguments");
     if (h->nsubst > 0 && !subst) return fail(PHYLO_B200_EINVAL, "upload: subst is NULL");
     if (h->model != PHYLO_B200_JC69 && !freqs) return fail(PHYLO_B200_EINVAL, "upload: freqs is NULL");
@@ -482,22 +493,47 @@ int phylo_b200_upload(phylo_b200_handle h, int B, const double* blens, const dou
                        ps ? ps + (size_t)d * h->C : nullptr, h->h_params.p + (size_t)d * h->lay.stride, why))
             return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": " + why);
     }
+    return 0;
+}
+}  // namespace
+
+int phylo_b200_upload(phylo_b200_handle h, int B, const double* blens, const double* subst, const double* freqs,
+                      const double* rs, const double* ps) {
+    if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps)) return rc;
     CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, sizeof(double) * B * h->lay.stride, cudaMemcpyHostToDevice,
                            h->stream));
     return 0;
 }
 
-int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
-    if (!h || B < 1) return fail(PHYLO_B200_EINVAL, "run: bad arguments");
-    CU_TRY(cudaSetDevice(h->device));
+namespace {
+
+// launch shape + scratch for B draws: everything that allocates or queries, i.e. all that may not
+// happen while a stream is being captured
+int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
     if ((size_t)B * h->lay.stride > h->d_params.n) return fail(PHYLO_B200_EINVAL, "run: upload B draws first");
-    const bool grad = want_grad != 0;
     if (int rc = resolve_tiling(h, B, grad)) return rc;
     if (grad) {
         const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
         CU_TRY(h->d_scratch.ensure(rows * 2));  // 16-byte vectors; fp32 uses half of them
         CU_TRY(h->d_dscr.ensure(rows));
     }
+    return 0;
+}
+
+int run_enqueue(phylo_b200_ctx* h, int B, bool grad);
+
+}  // namespace
+
+int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
+    if (!h || B < 1) return fail(PHYLO_B200_EINVAL, "run: bad arguments");
+    CU_TRY(cudaSetDevice(h->device));
+    if (int rc = run_prepare(h, B, want_grad != 0)) return rc;
+    return run_enqueue(h, B, want_grad != 0);
+}
+
+namespace {
+
+int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     cudaStream_t st = h->stream;
     CU_TRY(cudaMemsetAsync(h->d_out.p, 0, sizeof(double) * B * h->nout, st));
     if (grad) CU_TRY(cudaMemsetAsync(h->d_G.p, 0, sizeof(double) * B * h->nn * h->C * 16, st));
@@ -548,6 +584,65 @@ int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     return 0;
 }
 
+// everything a captured eval graph has baked into its nodes; any change means capture again
+std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
+    auto u = [](const void* p) { return (unsigned long long)(uintptr_t)p; };
+    return {u(h->d_params.p), u(h->d_spost.p), u(h->d_spre.p), u(h->d_G.p), u(h->d_out.p), u(h->d_scratch.p),
+            u(h->d_dscr.p), u(h->h_params.p), u(h->h_out.p), u(h->stream), (unsigned long long)h->K,
+            (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
+            (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles};
+}
+
+// H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
+int eval_enqueue(phylo_b200_ctx* h, int B, bool grad) {
+    const size_t in_bytes = sizeof(double) * B * h->lay.stride, out_bytes = sizeof(double) * B * h->nout;
+    const bool graphable = h->use_graphs && !h->timing && h->stream != nullptr;
+    if (!graphable) {
+        CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = run_enqueue(h, B, grad)) return rc;
+        CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        return 0;
+    }
+    auto& g = h->graphs[{B, grad ? 1 : 0}];
+    const auto sig = graph_signature(h);
+    if (!g.exec || g.sig != sig) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        if (h->graphs.size() > 16) {  // a caller cycling through many batch sizes: keep the cache small
+            for (auto it = h->graphs.begin(); it != h->graphs.end();) {
+                if (&it->second != &g) { if (it->second.exec) cudaGraphExecDestroy(it->second.exec); it = h->graphs.erase(it); }
+                else ++it;
+            }
+        }
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            (void)cudaGetLastError();  // a stream that cannot be captured (e.g. the legacy default stream): plain launches
+            h->use_graphs = false;
+            h->graphs.erase({B, grad ? 1 : 0});
+            return eval_enqueue(h, B, grad);
+        }
+        int rc = 0;
+        cudaError_t e = cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) rc = run_enqueue(h, B, grad);
+        if (e == cudaSuccess && rc == 0)
+            e = cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess || e2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return fail(PHYLO_B200_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g.exec = nullptr; return fail(PHYLO_B200_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+        g.sig = sig;
+    }
+    CU_TRY(cudaGraphLaunch(g.exec, h->stream));
+    h->last_launches = grad ? 3 : 2;
+    return 0;
+}
+
+}  // namespace
+
 int phylo_b200_device_out(phylo_b200_handle h, void** dptr, int* ld) {
     if (!h || !dptr) return fail(PHYLO_B200_EINVAL, "NULL argument");
     *dptr = h->d_out.p;
@@ -569,9 +664,9 @@ int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double* blens, const
                           const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
                           double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
     if (!h || !logp) return fail(PHYLO_B200_EINVAL, "eval: NULL handle or logp");
-    if (int rc = phylo_b200_upload(h, B, blens, subst, freqs, rs, ps)) return rc;
-    if (int rc = phylo_b200_run(h, B, want_grad)) return rc;
-    CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * B * h->nout, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps)) return rc;
+    if (int rc = run_prepare(h, B, want_grad != 0)) return rc;
+    if (int rc = eval_enqueue(h, B, want_grad != 0)) return rc;
     CU_TRY(cudaStreamSynchronize(h->stream));
     bool finite = true;
     for (int d = 0; d < B; ++d) {
