@@ -978,6 +978,19 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                     for (int k = 0; k < 4; ++k) s = fma(m1[4 * k + i], G[4 * k + j], s);
                     Tm[4 * i + j] = s;
                 }
+            // F_ij = (e^{l_i tau} - e^{l_j tau}) / (l_i - l_j), factored around the LARGER exponential so that
+            // expm1 only ever sees a non-positive argument (long branches: 0 * inf otherwise).  F is
+            // symmetric: six expm1 for the off-diagonal pairs, F_ii = tau e^{l_i tau}.
+            double F[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                F[5 * i] = tau * ex[i];
+#pragma unroll
+                for (int j = i + 1; j < 4; ++j) {
+                    const double x = fabs(lam[i] - lam[j]) * tau;
+                    F[4 * i + j] = F[4 * j + i] = tau * fmax(ex[i], ex[j]) * (x < 1e-8 ? 1.0 - 0.5 * x : -expm1(-x) / x);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -985,11 +998,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                     double s = 0.0;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) s = fma(Tm[4 * i + k], m2[4 * j + k], s);
-                    // F_ij = (e^{l_i tau} - e^{l_j tau}) / (l_i - l_j), factored around the LARGER exponential so
-                    // that expm1 only ever sees a non-positive argument (long branches: 0 * inf otherwise)
-                    const double x = fabs(lam[i] - lam[j]) * tau;
-                    const double f = tau * fmax(ex[i], ex[j]) * (x < 1e-8 ? 1.0 - 0.5 * x : -expm1(-x) / x);
-                    H[4 * i + j] = s * f;
+                    H[4 * i + j] = s * F[4 * i + j];
                 }
 #pragma unroll
             for (int k = 0; k < 10; ++k)
