@@ -10,10 +10,11 @@ Scope: model blocks of the programs phylostan generates (phylostan/generate_scri
 ``wshape`` (Weibull categories), ``blens``, ``rates``/``kappa`` + ``freqs``; priors ``wshape ~ exponential(1)``,
 ``blens ~ exponential(10)``, ``rates ~ dirichlet(rates_alpha)``, ``freqs ~ dirichlet(frequencies_alpha)``,
 ``kappa ~ lognormal(1, 1.25)``.  ``ClockModel``: a time tree (tips dated or not) with ratio-transformed node
-heights, a strict or uncorrelated-lognormal clock and a constant-size or skygrid coalescent;
-``StrictClockModel`` = strict + constant, the fluA quick start (tests/golden/fluA-HKY-W4-external.stan);
-ucln + skygrid is BASELINE config 5's program (HCV).  The remaining clocks (uced, autocorrelated) and
-demographic priors (skyride, birth-death) stay in Stan and use the external-function route.
+heights, a strict or uncorrelated (lognormal / exponential) clock and a constant-size, skyride or skygrid
+coalescent; ``StrictClockModel`` = strict + constant, the fluA quick start
+(tests/golden/fluA-HKY-W4-external.stan); ucln + skygrid is BASELINE config 5's program (HCV).  The
+autocorrelated clocks and the birth-death prior stay in Stan and use the external-function route
+(INTEGRATION.md).
 
 The algorithm follows Stan 2.19's ``stan::variational::advi`` with the ``normal_meanfield`` (zeta = mu +
 exp(omega) * eta) or ``normal_fullrank`` (zeta = mu + L eta, L lower triangular) family
@@ -293,12 +294,14 @@ class ClockModel(_ModelBase):
     node heights (:711-752), a clock, a coalescent prior, and the likelihood of the branch lengths
     ``rate * time`` (:660-679).
 
-    ``clock``: "strict" (one ``rate``, ``rate ~ exponential(1000)``) or "ucln" (one rate per branch,
+    ``clock``: "strict" (one ``rate``, ``rate ~ exponential(1000)``), "ucln" (one rate per branch,
     ``substrates ~ lognormal(log(ucln_mean) - ucln_stdev^2/2, ucln_stdev)``, ``ucln_mean ~ exponential(1000)``,
-    ``ucln_stdev ~ gamma(0.5396, 2.6184)``; :1311-1318).  ``coalescent``: "constant" (``theta ~ 1/x``,
-    ``constant_coalescent_log`` :285-349) or "skygrid" (log population sizes ``thetas[G]`` on the grid
-    ``linspace(0, cutoff, grid)[1:]``, ``skygrid_coalescent_log`` :440-520, ``thetas ~ gmrf(tau)``,
-    ``tau ~ gamma(0.001, 0.001)``).  Parameters in the Stan program's order: ``wshape`` (C > 1),
+    ``ucln_stdev ~ gamma(0.5396, 2.6184)``; :1311-1318) or "uced" (``substrates ~ exponential(1/uced_mean)``,
+    ``uced_mean ~ exponential(1000)``; :1319-1322).  ``coalescent``: "constant" (``theta ~ 1/x``,
+    ``constant_coalescent_log`` :285-349), "skyride" (one log population size per coalescent interval,
+    ``skyride_coalescent_log`` :352-414) or "skygrid" (log population sizes ``thetas[G]`` on the grid
+    ``linspace(0, cutoff, grid)[1:]``, ``skygrid_coalescent_log`` :422-520), the last two with
+    ``thetas ~ gmrf(tau)``, ``tau ~ gamma(0.001, 0.001)``.  Parameters in the Stan program's order: ``wshape`` (C > 1),
     ``props[S-2]``, clock parameters, root ``height``, coalescent parameters, ``rates``/``kappa``, ``freqs``.
     ``map_`` is the pre-order [node, parent] table and ``lowers`` the per-node lower bounds (tip dates) of
     ``phylostan_b200.encode`` (utils.py:84-104); ``lowers=None`` means contemporaneous tips.  Needs a
@@ -308,8 +311,8 @@ class ClockModel(_ModelBase):
     def __init__(self, lik, model: str, map_, lowers=None, lower_root: Optional[float] = None, rates_alpha=None,
                  freqs_alpha=None, clock: str = "strict", coalescent: str = "constant", grid=None):
         super().__init__(lik, model, rates_alpha, freqs_alpha)
-        if clock not in ("strict", "ucln") or coalescent not in ("constant", "skygrid"):
-            raise ValueError("clock must be strict or ucln, coalescent constant or skygrid")
+        if clock not in ("strict", "ucln", "uced") or coalescent not in ("constant", "skyride", "skygrid"):
+            raise ValueError("clock must be strict, ucln or uced; coalescent constant, skyride or skygrid")
         self.clock, self.coalescent = clock, coalescent
         m = np.asarray(map_, dtype=np.int64)
         self.S = S = (m.shape[0] + 1) // 2
@@ -341,13 +344,16 @@ class ClockModel(_ModelBase):
                 raise ValueError("skygrid needs the grid points linspace(0, cutoff, grid)[1:]")
             self.grid = np.asarray(grid, dtype=np.float64)
             self.G = self.grid.size
-        clock_blocks = (("rate", 1),) if clock == "strict" else (("substrates", nb), ("ucln_mean", 1), ("ucln_stdev", 1))
+        elif coalescent == "skyride":
+            self.G = S - 1                                        # data['I']: one log population size per coalescent interval
+        clock_blocks = {"strict": (("rate", 1),), "ucln": (("substrates", nb), ("ucln_mean", 1), ("ucln_stdev", 1)),
+                        "uced": (("substrates", nb), ("uced_mean", 1))}[clock]
         coal_blocks = (("theta", 1),) if coalescent == "constant" else (("thetas", self.G), ("tau", 1))
         self._layout((("wshape", 1 if self.C > 1 else 0), ("props", S - 2)) + clock_blocks + (("height", 1),)
                      + coal_blocks + self._subst_blocks())
 
     def _scalar_names(self):
-        clock = ["rate"] if self.clock == "strict" else ["ucln_mean", "ucln_stdev"]
+        clock = {"strict": ["rate"], "ucln": ["ucln_mean", "ucln_stdev"], "uced": ["uced_mean"]}[self.clock]
         coal = ["theta"] if self.coalescent == "constant" else ["tau"]
         return clock, coal
 
@@ -356,7 +362,7 @@ class ClockModel(_ModelBase):
         if self.clock == "strict":
             names += ["rate"]
         else:
-            names += [f"substrates.{i + 1}" for i in range(self.bcount)] + ["ucln_mean", "ucln_stdev"]
+            names += [f"substrates.{i + 1}" for i in range(self.bcount)] + self._scalar_names()[0]
         names += ["height"]
         names += ["theta"] if self.coalescent == "constant" else [f"thetas.{i + 1}" for i in range(self.G)] + ["tau"]
         return names + self._subst_names() + [f"heights.{i + 1}" for i in range(self.S - 1)]
@@ -373,11 +379,11 @@ class ClockModel(_ModelBase):
             u = Z[:, self.slices[name]][:, 0]
             out[name] = (self.lower_root if name == "height" else 0.0) + np.exp(u)
             out["logj"] += u
-        if self.clock == "ucln":
+        if self.clock != "strict":
             u = Z[:, self.slices["substrates"]]
             out["substrates"] = np.exp(u)
             out["logj"] += u.sum(axis=1)
-        if self.coalescent == "skygrid":
+        if self.coalescent != "constant":
             out["thetas"] = Z[:, self.slices["thetas"]]                 # vector[G] thetas: unconstrained (log space)
         self._constrain_common(Z, out)
         # heights = transform(props, height, map, lowers) and the log-det-Jacobian loop
@@ -395,8 +401,8 @@ class ClockModel(_ModelBase):
         c = self.constrain(Z)
         cols = [c["wshape"][:, None]] if self.C > 1 else []
         cols.append(c["props"])
-        cols += [c["rate"][:, None]] if self.clock == "strict" else [c["substrates"], c["ucln_mean"][:, None],
-                                                                      c["ucln_stdev"][:, None]]
+        cols += [c["rate"][:, None]] if self.clock == "strict" else \
+            [c["substrates"]] + [c[k][:, None] for k in self._scalar_names()[0]]
         cols.append(c["height"][:, None])
         cols += [c["theta"][:, None]] if self.coalescent == "constant" else [c["thetas"], c["tau"][:, None]]
         for k in ("rates", "kappa", "freqs"):
@@ -433,6 +439,31 @@ class ClockModel(_ModelBase):
         gt = np.empty_like(gt_sorted)
         np.put_along_axis(gt, order, gt_sorted, axis=1)
         return logp, gt[:, S:], tot / theta ** 2 - (S - 1) / theta
+
+    def _skyride_coalescent(self, h, thetas, want_grad):
+        """skyride_coalescent_log (generate_script.py:352-414), batched: the interval that ends at the j-th
+        coalescent event (and the sampling intervals before it) has population size exp(thetas[j])."""
+        B, S = h.shape[0], self.S
+        times = self._events(h)
+        order = np.argsort(times, axis=1, kind="stable")
+        ts = np.take_along_axis(times, order, axis=1)
+        coal = order >= S
+        delta = np.where(coal, -1.0, 1.0)
+        k_before = np.cumsum(delta, axis=1) - delta
+        c = 0.5 * k_before * (k_before - 1.0)
+        idx = np.minimum(np.cumsum(coal, axis=1) - coal, S - 2)          # coalescent events strictly before the event
+        interval = np.diff(ts, axis=1, prepend=ts[:, :1])
+        w = c * np.exp(-np.take_along_axis(thetas, idx, axis=1))
+        logp = -(interval * w).sum(axis=1) - (np.take_along_axis(thetas, idx, axis=1) * coal).sum(axis=1)
+        if not want_grad:
+            return logp, None, None
+        gt_sorted = -w + np.concatenate([w[:, 1:], np.zeros((B, 1))], axis=1)
+        gt = np.empty_like(gt_sorted)
+        np.put_along_axis(gt, order, gt_sorted, axis=1)
+        rows = np.repeat(np.arange(B), idx.shape[1])
+        gth = np.bincount(rows * (S - 1) + idx.ravel(), weights=(interval * w - coal).ravel(),
+                          minlength=B * (S - 1)).reshape(B, S - 1)
+        return logp, gt[:, S:], gth
 
     def _skygrid_coalescent(self, h, thetas, want_grad):
         """skygrid_coalescent_log (generate_script.py:440-520), batched: the time axis is cut at the sampling
@@ -513,7 +544,8 @@ class ClockModel(_ModelBase):
             prior += -np.log(theta) + coal                                           # theta ~ oneOnX()
         else:
             thetas, tau = sub["thetas"], sub["tau"]
-            coal, g_coal_h, g_coal_thetas = self._skygrid_coalescent(h, thetas, want_grad)
+            coal, g_coal_h, g_coal_thetas = (self._skygrid_coalescent if self.coalescent == "skygrid"
+                                             else self._skyride_coalescent)(h, thetas, want_grad)
             dth = np.diff(thetas, axis=1)
             ssq = (dth ** 2).sum(axis=1)
             prior += coal + np.log(tau) * (self.G - 1.0) / 2.0 - ssq * tau / 2.0 \
@@ -521,6 +553,10 @@ class ClockModel(_ModelBase):
             prior += (0.001 - 1.0) * np.log(tau) - 0.001 * tau                      # tau ~ gamma(0.001, 0.001)
         if strict:
             prior += -1000.0 * sub["rate"]                                           # rate ~ exponential(1000)
+        elif self.clock == "uced":
+            s_, mean = sub["substrates"], sub["uced_mean"]
+            prior += -self.bcount * np.log(mean) - s_.sum(axis=1) / mean             # substrates ~ exponential(1/uced_mean)
+            prior += -1000.0 * mean                                                  # uced_mean ~ exponential(1000)
         else:
             s_, mean, sd = sub["substrates"], sub["ucln_mean"], sub["ucln_stdev"]
             mu = np.log(mean) - 0.5 * sd ** 2
@@ -545,6 +581,13 @@ class ClockModel(_ModelBase):
         if strict:
             g_rate = (gb * span).sum(axis=1) - 1000.0
             g[:, self.slices["rate"]] = (g_rate * sub["rate"] + 1.0)[:, None]
+        elif self.clock == "uced":
+            gs = np.zeros((n, self.bcount))
+            gs[:, self.node] = gb * span
+            gs += -1.0 / mean[:, None]
+            g[:, self.slices["substrates"]] = gs * s_ + 1.0
+            g_mean = -self.bcount / mean + s_.sum(axis=1) / mean ** 2 - 1000.0
+            g[:, self.slices["uced_mean"]] = (g_mean * mean + 1.0)[:, None]
         else:
             gs = np.zeros((n, self.bcount))
             gs[:, self.node] = gb * span                                             # likelihood, node order
@@ -770,8 +813,8 @@ def main(argv=None) -> int:
     ap.add_argument("-i", "--input", required=True, help="alignment (FASTA or NEXUS)")
     ap.add_argument("-m", "--model", default="GTR", choices=("JC69", "HKY", "GTR"))
     ap.add_argument("-C", "--categories", type=int, default=1)
-    ap.add_argument("--clock", choices=("strict", "ucln"), help="time tree with this clock (omit: unrooted tree)")
-    ap.add_argument("-c", "--coalescent", default="constant", choices=("constant", "skygrid"))
+    ap.add_argument("--clock", choices=("strict", "ucln", "uced"), help="time tree with this clock (omit: unrooted tree)")
+    ap.add_argument("-c", "--coalescent", default="constant", choices=("constant", "skyride", "skygrid"))
     ap.add_argument("--grid", type=int, help="number of grid points in skygrid")
     ap.add_argument("--cutoff", type=float, help="a cutoff for skygrid")
     ap.add_argument("--heterochronous", action="store_true", help="tip dates from the tree's root-to-tip distances")

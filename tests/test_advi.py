@@ -603,3 +603,62 @@ def test_gpu_command_line_end_to_end(tmp_path, argv):
         assert "height" in header and np.all(data[:, header.index("height")] > 0)
     else:
         assert "blens.1" in header and np.all(data[:, header.index("blens.1")] > 0)
+
+
+def test_uced_skyride_model_is_the_stan_program_and_its_gradient():
+    """uced clock + skyride coalescent: skyride_coalescent_log (generate_script.py:352-414) and the exponential
+    clock prior (:1319-1322) restated literally for one draw; gradient against finite differences."""
+    d, S, lowers, heights = flua_clock_problem("HCV")
+    L = 30
+    lik = OracleRooted(d["peel"], d["tipmask"][:, :L].copy(), d["weights"][:L].copy(), "JC69", 1)
+    m = advi.ClockModel(lik, "JC69", d["map"], lowers, clock="uced", coalescent="skyride")
+    assert m.dim == (S - 2) + (2 * S - 2) + 1 + 1 + (S - 1) + 1
+    rng = np.random.default_rng(6)
+    z = rng.normal(0, 0.1, m.dim)
+    props = np.array([(heights[m.tr_node[j]] - m.tr_lo[j]) / (heights[m.tr_parent[j]] - m.tr_lo[j]) for j in range(S - 2)])
+    props = np.clip(props, 1e-4, 1 - 1e-4)
+    z[m.slices["props"]] += np.log(props) - np.log1p(-props)
+    z[m.slices["height"]] += math.log(heights[m.root - S - 1] - m.lower_root)
+    z[m.slices["substrates"]] += math.log(8e-4)
+    z[m.slices["uced_mean"]] += math.log(8e-4)
+    z[m.slices["thetas"]] += 5.0
+    c = m.constrain(z[None])
+    hs, sub, mean, pop, tau = list(c["heights"][0]), c["substrates"][0], c["uced_mean"][0], c["thetas"][0], c["tau"][0]
+    mp = [[int(a), int(b)] for a, b in d["map"]]
+    nodeCount = 2 * S - 1
+    blens = np.zeros(2 * S - 2)
+    for i in range(1, nodeCount):
+        node, par = mp[i]
+        blens[node - 1] = sub[node - 1] * (hs[par - S - 1] - (hs[node - S - 1] if node > S else lowers[node - 1]))
+    # skyride_coalescent_log: times / childCounts indexed by pre-order row, as in the Stan text
+    times = [hs[mp[i][0] - S - 1] if mp[i][0] > S else lowers[mp[i][0] - 1] for i in range(nodeCount)]
+    child = [2 if mp[i][0] > S else 0 for i in range(nodeCount)]
+    order = sorted(range(nodeCount), key=lambda k: times[k])
+    logP, index, lineages, start = 0.0, 1, 0.0, times[order[0]]
+    for k in order:
+        finish = times[k]
+        interval = finish - start
+        if interval != 0.0:
+            logP -= interval * (lineages * (lineages - 1.0)) / 2.0 / math.exp(pop[index - 1])
+            if child[k] != 0:
+                logP -= pop[index - 1]
+                index += 1
+        lineages += 1.0 if child[k] == 0 else -1.0
+        start = finish
+    I = S - 1
+    gmrf = math.log(tau) * (I - 1.0) / 2.0 - sum((pop[i] - pop[i - 1]) ** 2 for i in range(1, I)) * tau / 2.0 \
+        - (I - 1.0) / 2.0 * math.log(2.0 * math.pi)
+    target = sum(math.log(1.0 / mean) - x / mean for x in sub) - 1000.0 * mean        # exponential(1/uced_mean)
+    target += logP + gmrf + (0.001 - 1.0) * math.log(tau) - 0.001 * tau
+    target += O.loglik_grad(lik.peel, lik.tipmask, lik.weights, O.JC69, blens, None, None, np.ones(1), np.ones(1),
+                            rooted=True, want_grad=False).logp
+    for i in range(1, nodeCount):
+        if mp[i][0] > S:
+            target += math.log(hs[mp[i][1] - S - 1] - lowers[mp[i][0] - 1])
+    assert m.log_prob(z[None])[0] - c["logj"][0] == pytest.approx(target, rel=1e-12)
+    Z = np.stack([z, z + rng.normal(0, 0.05, m.dim)])
+    lp, G = m.log_prob_grad(Z)
+    for k in list(range(0, m.dim, 5)) + [m.slices["uced_mean"].start, m.slices["tau"].start, m.slices["height"].start]:
+        e = np.zeros(m.dim); e[k] = 1e-6
+        fd = (m.log_prob(Z + e) - m.log_prob(Z - e)) / 2e-6
+        assert np.allclose(fd, G[:, k], rtol=1e-4, atol=1e-4), (k, fd, G[:, k])
