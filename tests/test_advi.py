@@ -587,6 +587,7 @@ def test_command_line_reads_tree_and_alignment(tmp_path):
     ["-m", "HKY", "-C", "4", "--iter", "300", "--grad_samples", "4"],
     ["-m", "GTR", "-C", "4", "--clock", "strict", "--heterochronous", "--iter", "300", "--grad_samples", "4", "-q", "fullrank"],
     ["-m", "JC69", "--clock", "ucln", "-c", "skygrid", "--grid", "5", "--cutoff", "30", "--iter", "200"],
+    ["-m", "HKY", "-C", "4", "--clock", "uced", "-c", "skyride", "--heterochronous", "--iter", "200", "--grad_samples", "2"],
     ["-m", "HKY", "--clock", "strict", "-a", "nuts", "--iter", "60"],
     ["-m", "HKY", "--clock", "strict", "--heterochronous", "-a", "hmc", "--chains", "4", "--iter", "60"],
 ])
