@@ -272,8 +272,8 @@ class UnrootedModel(_ModelBase):
         G = np.zeros((B, self.dim)) if want_grad else None
         if not ok.any():
             return lp, G
-        idx = np.nonzero(ok)[0]
-        sub = self._take(c, idx)
+        idx = slice(None) if ok.all() else np.nonzero(ok)[0]                     # the usual case: no copy
+        sub = c if isinstance(idx, slice) else self._take(c, idx)
         rs_, drs_, ps_ = rs[idx], drs[idx], ps[idx]
         args = (sub["blens"], self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
         ll, vg = self._likelihood(args, want_grad)
@@ -281,8 +281,9 @@ class UnrootedModel(_ModelBase):
         lp[idx] = ll + prior + sub["logj"]
         if not want_grad:
             return lp, None
-        g = np.zeros((idx.size, self.dim))
-        gb = np.reshape(vg.grad_blens, (idx.size, self.bcount)) - 10.0
+        n = ll.shape[0]
+        g = np.zeros((n, self.dim))
+        gb = np.reshape(vg.grad_blens, (n, self.bcount)) - 10.0
         g[:, self.slices["blens"]] = gb * sub["blens"] + 1.0
         self._grad_common(g, sub, vg, drs_)
         G[idx] = g
@@ -527,10 +528,10 @@ class ClockModel(_ModelBase):
         G = np.zeros((B, self.dim)) if want_grad else None
         if not ok.any():
             return lp, G
-        idx = np.nonzero(ok)[0]
-        n = idx.size
-        sub = self._take(c, idx)
+        idx = slice(None) if ok.all() else np.nonzero(ok)[0]                     # the usual case: no copy
+        sub = c if isinstance(idx, slice) else self._take(c, idx)
         rs_, drs_, ps_, span = rs[idx], drs[idx], ps[idx], span[idx]
+        n = span.shape[0]
         h = sub["heights"]
         rate_b = sub["rate"][:, None] if strict else sub["substrates"][:, self.node]     # per pre-order row
         blens = np.empty((n, self.bcount))
