@@ -162,18 +162,30 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     };
     int K = h->req_K, PB = h->req_PB;
     if (K == 0) {
-        // Small problems spread thin (K = 1).  Large ones take the largest K that still keeps two
-        // CTAs per SM resident: per-step work (record decode, matrix loads, the 4x4 reduction) is
-        // shared by K patterns, but the shared-memory stack grows with K.
-        const long long work = (long long)B * ((h->L + 31) / 32);  // warps of patterns per category
+        // K patterns per lane share the per-step work (record decode, matrix loads, the 4x4 reduction) but
+        // lengthen a warp's instruction chain and shrink the number of CTAs.  Estimate the run time of each
+        // K as (waves of CTAs) x (time of one tile): measured tile times relative to K = 1 are 1 : 1.1 : 1.35
+        // when everything runs in a single wave (latency-bound) and 1 : 1.40 : 1.62 with the SMs saturated
+        // (142 / 123 / 86 evaluations/s at K = 4 / 2 / 1 on the 1000 x 100k bench).  K > 1 wants two CTAs
+        // per SM; gradient runs may park stack positions to get there.
+        const int nt = 32 * C * (PB ? PB : 1);
         K = 1;
-        if (work >= 8LL * h->num_sms && 32 * C * (PB ? PB : 1) <= 128) {
-            for (int k : {4, 2})
-                if (slots_for(k, 32 * C * (PB ? PB : 1), 2) >= 0) {
-                    K = k;
-                    break;
-                }
-        } else if (work >= 8LL * h->num_sms) {
+        if (nt <= 128) {
+            static const double kLat[5] = {0, 1.0, 1.1, 0, 1.35}, kSat[5] = {0, 1.0, 1.40, 0, 1.62};
+            double best = 1e300;
+            for (int k : {1, 2, 4}) {
+                const int dd = slots_for(k, nt, k == 1 ? 1 : 2);
+                if (dd < 0) continue;
+                int occ = 0;
+                if (sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sweep_smem_bytes(dd, k, nt, h->prec),
+                                    &occ) != cudaSuccess || occ < 1)
+                    continue;
+                const double items = (double)B * ((h->L + 32 * k - 1) / (32 * k));
+                const double w = items / ((double)occ * h->num_sms);
+                const double est = w <= 1.0 ? kLat[k] : std::ceil(w) * kSat[k];  // items are dealt out statically
+                if (est < best) { best = est; K = k; }
+            }
+        } else if ((long long)B * ((h->L + 31) / 32) >= 8LL * h->num_sms) {
             K = 2;
         }
     }

@@ -557,7 +557,7 @@ def test_gpu_capped_stack_parks_entries_in_hbm(prec):
 def test_gpu_deep_tree_gets_the_widest_tile():
     """3000 taxa: stack depth 7 does not fit the K = 4 tile twice per SM; the capped stack does."""
     prob = synth.make_problem(3000, 2048, 4)
-    bl, rates, freqs, rs, ps = synth.make_draws(prob, 20)       # enough work for the automatic K > 1 path
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 37)       # 37 x 16 tiles = two full waves of K = 4 CTAs
     with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
         got = lik.value_grad(bl, rates, freqs, rs, ps)
         info = lik.info()

@@ -1,5 +1,5 @@
 """Single-draw latency on mid-size problems (one chain of NUTS / one Stan gradient): the regime where the
-sweep leaves most schedulers with one warp.   python tools/midsize_latency.py"""
+sweep leaves most schedulers with one warp.   [PHYLO_K=1|2|4] python tools/midsize_latency.py"""
 import os
 import sys
 import time
@@ -13,6 +13,7 @@ for S, L, B in ((100, 1000, 1), (200, 3000, 1), (500, 5000, 1), (500, 20000, 1),
     prob = synth.make_problem(S, L, 4, structured=False)
     draws = synth.make_draws(prob, B)
     with lk.TreeLikelihood(prob.peel, prob.tipmask, prob.weights, model="GTR", categories=4) as lik:
+        lik.set_tiling(int(os.environ.get("PHYLO_K", "0")), 0)
         for _ in range(5):
             lik.value_grad(*draws)
         t0 = time.perf_counter()
