@@ -467,7 +467,12 @@ struct Ring {
 // NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
 // immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
 // DEEP (gradient runs of deep trees): stack entries flagged by the stream live in the HBM scratch.
-template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP>
+// JC (gradient runs of JC69 handles): Q = mu (J/4 - I), so Q P p = mu (mean(p) 1 - P p) and the branch
+// derivative needs ONE number per (pattern, branch) -- the reference's own formula, eigen.j2:160-167 --
+// instead of the 4x4 statistic: with T = sum_x q_n(x) (P_a p_a)(x) (P_b p_b)(x),
+//   <A_b p_b^T, Q P_b> / mu = mean(p_b) sum(A_b) - T,   <A_a p_a^T, Q P_a> / mu = mean(p_a) sum(A_a) - T.
+// The scalar goes to entry 0 of the branch's G block; the contraction multiplies by mu.
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -784,6 +789,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                 }
                 T gb4[4];  // child b's statistics after the first two reduction levels
+                T jb = T(0), ja = T(0);  // JC: the scalar statistics of both branches
                 {   // child b: q(b) waits in shared memory
                     T M[16], m[4], G[16];
                     lds_mat(rec + 64 + R::kMat, M);
@@ -794,10 +800,20 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         matvec(M, pbv[j], m);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) Aa[j][s] = qn[j][s] * m[s];
+                        if (JC) {
+                            const T t = fma(Ab[j][3], m[3], fma(Ab[j][2], m[2], fma(Ab[j][1], m[1], Ab[j][0] * m[0])));
+                            const T sAb = (Ab[j][0] + Ab[j][1]) + (Ab[j][2] + Ab[j][3]);
+                            const T sAa = (Aa[j][0] + Aa[j][1]) + (Aa[j][2] + Aa[j][3]);
+                            const T mb_ = T(0.25) * ((pbv[j][0] + pbv[j][1]) + (pbv[j][2] + pbv[j][3]));
+                            const T ma_ = T(0.25) * ((pa[j][0] + pa[j][1]) + (pa[j][2] + pa[j][3]));
+                            jb += fma(mb_, sAb, -t);
+                            ja += fma(ma_, sAa, -t);
+                        } else {
 #pragma unroll
-                        for (int x = 0; x < 4; ++x)
+                            for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
+                                for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
+                        }
                     }
                     if (s2.x >= 0) {  // b is internal: q(b) = P_b^T A_b   (eigen.j2:151-153)
 #pragma unroll
@@ -808,7 +824,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             else st4(ST(s2.x, j), NT, q);
                         }
                     }
-                    if (K == 1) {
+                    if (JC) {
+                    } else if (K == 1) {
 #pragma unroll
                         for (int x = 0; x < 16; ++x) red[x * 33 + lane] = G[x];
                     } else {
@@ -819,12 +836,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     T G[16];
 #pragma unroll
                     for (int x = 0; x < 16; ++x) G[x] = T(0);
+                    if (!JC) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j)
+                        for (int j = 0; j < K; ++j)
 #pragma unroll
-                        for (int x = 0; x < 4; ++x)
+                            for (int x = 0; x < 4; ++x)
 #pragma unroll
-                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
+                                for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
+                    }
                     if (s2.w & 1) {
                         T M[16];
                         asm volatile("" ::: "memory");  // reload P_a instead of keeping it alive in registers
@@ -840,7 +859,13 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                         }
                     }
-                    if (K == 1) {
+                    if (JC) {  // two scalars per lane: lanes 0..15 finish child b's sum, lanes 16..31 child a's
+                        const bool hi = lane & 16;
+                        T v = (hi ? ja : jb) + __shfl_xor_sync(0xffffffffu, hi ? jb : ja, 16);
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if ((lane & 15) == 0) atomicAdd(Gd + (hi ? s2.y : s2.z), (double)v);
+                    } else if (K == 1) {
 #pragma unroll
                         for (int x = 0; x < 16; ++x) red[(16 + x) * 33 + lane] = G[x];
                         __syncwarp();
@@ -949,15 +974,19 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         }
         // d logL / d tau = <G, Q P>   (dP/dtau = Q P)
         const double* Q = prm + a.lay.off_Q;
+        if (a.jc_scalar) {  // the sweep already contracted with (J/4 - P): entry 0 holds <G, Q P> / mu, mu = -4/3 Q_00
+            g = G[0] * (-Q[0] * (4.0 / 3.0));
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double qp = 0.0;
+                for (int j = 0; j < 4; ++j) {
+                    double qp = 0.0;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) qp = fma(Q[4 * i + k], P[4 * k + j], qp);
-                g = fma(G[4 * i + j], qp, g);
-            }
+                    for (int k = 0; k < 4; ++k) qp = fma(Q[4 * i + k], P[4 * k + j], qp);
+                    g = fma(G[4 * i + j], qp, g);
+                }
+        }
         if (a.lay.ntheta > 0) {
             // H = m1^T G m2^T ; d logL/dtheta += sum_ij H_ij F_ij X_ij
             const double* m1 = prm + a.lay.off_m1;
@@ -1049,10 +1078,21 @@ template <> struct Cfg<float, 4> { static constexpr int minb = 3; };
 
 typedef void (*SweepFn)(const SweepArgs);
 
-template <typename T, int K, bool GRAD, bool TIPS, bool DEEP>
+template <typename T, int K, bool GRAD, bool TIPS, bool DEEP, bool JC = false>
 SweepFn pick_kernel(int nthreads) {
-    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP>;
-    return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP>;
+    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP, JC>;
+    return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC>;
+}
+
+// scalar-statistic gradient kernels (JC69, fp64, whole stack on chip)
+template <bool TIPS>
+SweepFn pick_kernel_jc(int K, int nthreads) {
+    switch (K) {
+        case 1: return pick_kernel<double, 1, true, TIPS, false, true>(nthreads);
+        case 2: return pick_kernel<double, 2, true, TIPS, false, true>(nthreads);
+        case 4: return pick_kernel<double, 4, true, TIPS, false, true>(nthreads);
+    }
+    return nullptr;
 }
 
 template <typename T, bool TIPS>
@@ -1071,7 +1111,8 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
     return nullptr;
 }
 
-SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads) {
+SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false) {
+    if (jc && prec == 64 && grad && !deep) return tips ? pick_kernel_jc<true>(K, nthreads) : pick_kernel_jc<false>(K, nthreads);
     if (prec == 32)
         return tips ? pick_kernel_k<float, true>(K, grad, deep, nthreads) : pick_kernel_k<float, false>(K, grad, deep, nthreads);
     return tips ? pick_kernel_k<double, true>(K, grad, deep, nthreads) : pick_kernel_k<double, false>(K, grad, deep, nthreads);
@@ -1097,8 +1138,8 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
 }
 
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads);
+                         size_t smem, cudaStream_t stream, bool jc) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -111,14 +111,16 @@ struct ContractArgs {
     double* out;
     ParamLayout lay;
     int bcount, C, nn, nout, nsubst, nsteps, S, tips_simple;
+    int jc_scalar;            // entry 0 of a G block holds <G, Q P> / mu (JC69 scalar-statistic sweep)
     int off_out_subst, off_out_freqs, off_out_rs;
 };
 
 // prec: 64 (product path) or 32 (optional fp32-with-scaling mode); K in {1,2,4}; nthreads <= 512
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
 // deep: the stream parks stack entries in the HBM scratch (gradient runs only)
+// jc: scalar-statistic gradient kernel of JC69 handles (fp64, gradient, not deep; ContractArgs::jc_scalar must agree)
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream);
+                         size_t smem, cudaStream_t stream, bool jc = false);
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
                             int* blocks_per_sm);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);

@@ -118,6 +118,7 @@ struct phylo_b200_ctx {
     struct EvalGraph { cudaGraphExec_t exec = nullptr; std::vector<unsigned long long> sig; };
     std::map<std::pair<int, int>, EvalGraph> graphs;  // (B, want_grad) -> executable graph + what it baked in
     bool use_graphs = true;
+    bool use_jc_scalar = true;  // JC69 gradient runs use the scalar-statistic sweep (PHYLO_B200_NO_JC_SCALAR=1: generic)
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false, ev_has_contract = false;
@@ -340,6 +341,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     }
     h->stream = h->own_stream;
     if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
+    if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
             delete h;
@@ -573,14 +575,15 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
     a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->slots;
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
-    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, grad && h->slots < h->plan.depth(), h->grid, h->NT,
-                        h->smem, st));
+    const bool deep = grad && h->slots < h->plan.depth();
+    const bool jc = grad && !deep && h->prec == 64 && h->model == PHYLO_B200_JC69 && h->use_jc_scalar;
+    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {
         ContractArgs ca{};
         ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
-        ca.S = h->S; ca.tips_simple = h->tips_simple;
+        ca.S = h->S; ca.tips_simple = h->tips_simple; ca.jc_scalar = jc ? 1 : 0;
         ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
         ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
         launch_contract(ca, h->prec, B, st);
