@@ -244,3 +244,43 @@ def test_derive_rejects_out_of_domain():
         lk.derive("HKY", [float("nan")], [0.25] * 4)
     with pytest.raises(lk.PhyloDomainError):
         lk.derive("GTR", np.ones(6), [0.5, 0.5, 0.0, 0.0])
+
+
+def test_ratio_transform_helpers_match_the_stan_loops():
+    """phylo_b200_ratios_forward / _reverse (host only): generate_script.py:711-752 restated in Python, the
+    reverse sweep against finite differences of  sum(c * heights) + log-Jacobian."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "fluA.npz"))
+    S = d["tipmask"].shape[0]
+    nn = 2 * S - 1
+    rng = np.random.default_rng(4)
+    lowers = np.zeros(nn)
+    lowers[:S] = rng.uniform(0, 5, S)
+    for node, par in d["map"][:0:-1]:
+        lowers[int(par) - 1] = max(lowers[int(par) - 1], lowers[int(node) - 1])
+    B = 3
+    props, root = rng.uniform(0.05, 0.95, (B, S - 2)), lowers.max() + rng.uniform(1, 5, B)
+    h, lj = lk.ratios_forward(d["map"], lowers, props, root)
+    for b in range(B):                                       # the Stan function `transform` + the Jacobian loop
+        hs, j, logj = np.zeros(S - 1), 0, 0.0
+        hs[int(d["map"][0, 0]) - S - 1] = root[b]
+        for node, par in d["map"][1:]:
+            if node > S:
+                lo = lowers[node - 1]
+                hs[node - S - 1] = lo + (hs[par - S - 1] - lo) * props[b, j]
+                logj += np.log(hs[par - S - 1] - lo)
+                j += 1
+        assert np.allclose(h[b], hs, rtol=1e-14) and lj[b] == pytest.approx(logj, rel=1e-13)
+    c = rng.normal(0, 1, S - 1)
+    f = lambda p, r: (lk.ratios_forward(d["map"], lowers, p, r)[0] * c).sum(axis=1) + lk.ratios_forward(d["map"], lowers, p, r)[1]
+    gp, gr = lk.ratios_reverse(d["map"], lowers, props, h, np.tile(c, (B, 1)))
+    for k in (0, 7, S - 3):
+        e = np.zeros((B, S - 2)); e[:, k] = 1e-5
+        assert np.allclose((f(props + e, root) - f(props - e, root)) / 2e-5, gp[:, k], rtol=1e-5, atol=1e-6)
+    assert np.allclose((f(props, root + 1e-4) - f(props, root - 1e-4)) / 2e-4, gr, rtol=1e-5, atol=1e-6)
+    # contemporaneous tips: lowers = NULL
+    h0, _ = lk.ratios_forward(d["map"], None, props, root)
+    assert np.all(h0 > 0) and np.all(h0 <= root[:, None] + 1e-12)
+    bad = np.array(d["map"]).copy()
+    bad[5, 1] = 1                                            # a tip as parent
+    with pytest.raises(lk.PhyloB200Error):
+        lk.ratios_forward(bad, lowers, props, root)
