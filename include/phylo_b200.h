@@ -82,6 +82,14 @@ PHYLO_B200_API int phylo_b200_create_tipdata(phylo_b200_handle *out, int S, int 
                               const int32_t *peel, const double *tipdata, const double *weights,
                               int device);
 
+/* Same as phylo_b200_create, with the alignment already resident on the GPU: d_tipmask uint8 [S][L] and
+ * d_weights double [L] (NULL = all 1) are DEVICE pointers on `device` (the "device-resident buffers" of the
+ * data plumbing; phylostan/phylostan.py:183-204 builds the same arrays on the host).  Padding, the
+ * one-hot / all-ones classification and the re-coding run on the device; the inputs are not kept. */
+PHYLO_B200_API int phylo_b200_create_device(phylo_b200_handle *out, int S, int L, int C, int model, int flags,
+                                            const int32_t *peel, const uint8_t *d_tipmask, const double *d_weights,
+                                            int device);
+
 PHYLO_B200_API void phylo_b200_destroy(phylo_b200_handle h);
 
 /* sizes of the per-evaluation arrays */
@@ -98,7 +106,8 @@ PHYLO_B200_API int phylo_b200_nout(phylo_b200_handle h);
  * Outputs: logp[1]; with want_grad != 0 any non-NULL g_* array is filled:
  * g_blens[bcount], g_subst[nsubst], g_freqs[4], g_rs[C], g_ps[C].  d/dsubst and d/dfreqs are the
  * unconstrained partial derivatives of the formulas at generate_script.py:799-812 / 855-868;
- * d/dfreqs includes the root term of generate_script.py:1007.
+ * d/dfreqs includes the root term of generate_script.py:1007.  JC69 handles fix the frequencies to 1/4
+ * (generate_script.py:755-780 takes no freqs argument): freqs is not read and g_freqs is returned as zeros.
  */
 PHYLO_B200_API int phylo_b200_eval(phylo_b200_handle h, const double *blens, const double *subst,
                     const double *freqs, const double *rs, const double *ps, int want_grad,

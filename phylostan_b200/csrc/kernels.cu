@@ -1,8 +1,27 @@
 // kernels.cu -- see kernels.cuh.  sm_100a only.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 #ifndef PHYLO_ABLATE
 #define PHYLO_ABLATE 0  // profiling experiments only: 1 = skip the cross-lane G reduction, 2 = skip only its RED
+#endif
+// Build-time switches kept for A/B measurements (profiles/README.md, round 2); the defaults are the product.
+// Measured on the 1000 x 100k bench shape, 16 draws, K = 4 (r2_ab_*.log): the shared-memory reduction and the
+// cp.async byte ring remove ~130 / ~40 instructions per warp-step but lengthen the step's dependency chain and
+// cost shared memory (a stack slot, i.e. the DEEP variant): 134 vs 146 evaluations/s; the pre-order tip
+// shortcut removes 13 % of the FP64 work and is neutral to slower (register spills).
+#ifndef PHYLO_RSM
+#define PHYLO_RSM 0     // K > 1: 4x4 statistics summed over the warp through shared memory (0: shuffle exchange)
+#endif
+#ifndef PHYLO_BYTECP
+#define PHYLO_BYTECP 0  // byte operands through a cp.async shared-memory ring (1) or a two-step register look-ahead (0)
+#endif
+#ifndef PHYLO_PF
+#define PHYLO_PF 1      // pre-order: L2 prefetch of the scratch lines two steps ahead
+#endif
+#ifndef PHYLO_PRETIP
+#define PHYLO_PRETIP 0  // pre-order: a simple tip child's message is a column of P (tip records column-major)
 #endif
 
 namespace phylo {
@@ -191,6 +210,10 @@ __device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* _
 // both and the two REDs.
 template <typename T>
 __device__ __forceinline__ void warp_reduce16_head(const T (&v)[16], T (&a4)[4], int lane) {
+#if PHYLO_ABLATE == 7
+    a4[0] = a4[1] = a4[2] = a4[3] = v[0];
+    return;
+#endif
     T a8[8];
     bool hi = lane & 16;
 #pragma unroll
@@ -208,6 +231,10 @@ __device__ __forceinline__ void warp_reduce16_head(const T (&v)[16], T (&a4)[4],
 template <typename T>
 __device__ __forceinline__ void warp_reduce4x2_tail_atomic(const T (&x4)[4], const T (&y4)[4], double* __restrict__ dx,
                                                            double* __restrict__ dy, int lane) {
+#if PHYLO_ABLATE == 7
+    if (x4[0] == T(1.2345e-30)) atomicAdd(dx, (double)y4[0]);
+    return;
+#endif
     T x2[2], y2[2], x1, y1;
     bool hi = lane & 4;
 #pragma unroll
@@ -242,6 +269,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // K consecutive bytes (K = 1, 2, 4) of a lane as one packed word: byte j = (w >> 8 j) & 0xff
 template <int K>
 __device__ __forceinline__ unsigned ldg_bytes(const uint8_t* p) {
+#if PHYLO_ABLATE == 4
+    return (unsigned)(reinterpret_cast<uintptr_t>(p) & 0x03030303u);  // experiment: no tip-code traffic
+#endif
     if (K == 4) return __ldg(reinterpret_cast<const unsigned*>(p));
     if (K == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
     return __ldg(p);
@@ -401,7 +431,7 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     double m[16];
     const int node = child ? nb : na;
     pmatrix(prm, a.lay, node, c, a.bcount, a.jc_closed, m);
-    if (a.tips_simple && which == 0 && node < a.S) store_tipmat(rec + 64 + Real<T>::kMat * child, m, T());
+    if (a.tips_simple && (which == 0 || PHYLO_PRETIP) && node < a.S) store_tipmat(rec + 64 + Real<T>::kMat * child, m, T());
     else store_mat(rec + 64 + Real<T>::kMat * child, m, T());
 }
 
@@ -447,7 +477,8 @@ struct Ring {
         issue();
         issue();
     }
-    // top of step i: afterwards the records of steps i, i+1, i+2 are readable
+    // top of step i: afterwards the records of steps i, i+1, i+2 (even i: and i+3) are readable, and so
+    // is every byte-operand block committed before this call
     __device__ __forceinline__ void step(int i) {
         if (i) slot = slot == kRecChunk * kRecBufs - 1 ? 0 : slot + 1;
         if ((i & 1) == 0) {
@@ -463,6 +494,71 @@ struct Ring {
         return buf + s * REC;
     }
 };
+
+// Per-warp ring of BYTE operands (tip codes of both children, rescale exponents of the node): the
+// 32 K bytes a warp needs for one operand of one step are contiguous in global memory, so 2 K lanes
+// copy them with one 16-byte cp.async each, two to three steps before they are used, in the same
+// commit-group cadence as the record ring.  Nothing waits in a register (the register look-ahead this
+// replaces stalled every post-order step on its rotation: a tip-code line takes longer to arrive than
+// a step runs) and nothing passes through L1 (.cg), so the exponents written earlier by this kernel
+// are read coherently.  Step i uses slot i & 3: steps i, i+1 are being consumed while i+2, i+3 land.
+template <int K>
+struct ByteRing {
+    static constexpr int kBlk = 32 * K;     // bytes of one operand block
+    static constexpr int kSlot = 3 * kBlk;  // operands 0, 1: children's tip codes; 2: rescale exponents
+    static constexpr int kBytes = 4 * kSlot;
+    const unsigned char* buf;
+    unsigned sbuf;
+    int lane;
+    __device__ __forceinline__ void fetch(int step, int op, const uint8_t* src) const {
+        if (lane < 2 * K) cp_async16(sbuf + (step & 3) * kSlot + op * kBlk + lane * 16, src + lane * 16);
+    }
+    // this lane's K bytes as one packed word: byte j = (w >> 8 j) & 0xff
+    __device__ __forceinline__ unsigned get(int step, int op) const {
+        const unsigned char* p = buf + (step & 3) * kSlot + op * kBlk + lane * K;
+        if (K == 4) return *reinterpret_cast<const unsigned*>(p);
+        if (K == 2) return *reinterpret_cast<const unsigned short*>(p);
+        return *p;
+    }
+};
+
+// Sum 16 per-lane values over the warp through shared memory: every lane parks its 16 values
+// (row x of red holds entry x of all lanes, rows padded to 34), then lane l adds up entry l & 15 over
+// the 16 source lanes of its half (8 conflict-free 16-byte loads), one shuffle joins the halves and
+// lanes 0..15 issue one 128-byte RED.  ~45 instructions and a short dependency chain instead of the
+// ~110 of the select/shuffle exchange.
+template <typename T>
+__device__ __forceinline__ void warp_reduce16_smem(const T (&v)[16], T* __restrict__ red, double* __restrict__ dst,
+                                                   int lane) {
+#pragma unroll
+    for (int x = 0; x < 16; ++x) red[x * 34 + lane] = v[x];
+    __syncwarp();
+    const T* row = red + (lane & 15) * 34 + (lane & 16);
+    T s[4] = {T(0), T(0), T(0), T(0)};
+    if (sizeof(T) == 8) {
+        const double2* r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double2 u = r2[k];
+            s[(2 * k) & 3] += (T)u.x;
+            s[(2 * k + 1) & 3] += (T)u.y;
+        }
+    } else {
+        const float4* r4 = reinterpret_cast<const float4*>(row);  // rows start 8-byte aligned only: see below
+        (void)r4;
+        const float2* r2 = reinterpret_cast<const float2*>(row);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 u = r2[k];
+            s[(2 * k) & 3] += (T)u.x;
+            s[(2 * k + 1) & 3] += (T)u.y;
+        }
+    }
+    T t = (s[0] + s[1]) + (s[2] + s[3]);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (lane < 16) atomicAdd(dst + lane, (double)t);
+    __syncwarp();  // the rows are rewritten by the next reduction
+}
 
 // NTC > 0: the CTA size is the compile-time constant NTC (all shared/scratch offsets fold into
 // immediates); NTC == 0: generic CTA size read from blockDim (up to 512 threads).
@@ -482,16 +578,23 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = a.C, nsteps = a.nsteps;
     const int c = warp % C, pb = warp / C;
+    // shared memory: [stack | ring | byte ring | reduction rows]; the root's category exchange borrows the
+    // head of the stack region, which is empty between the two sweeps (see sweep_smem_bytes)
     V* st = reinterpret_cast<V*>(smem_raw);                                    // [D][K][VP][NT]
-    double* ex_l = reinterpret_cast<double*>(st + (size_t)a.D * K * VP * NT);  // [K][NT]
+    double* ex_l = reinterpret_cast<double*>(smem_raw);                        // [K][NT]
     int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                         // [K][NT]
+    unsigned char* sm_p = smem_raw + a.stack_bytes;
     Ring<R::kRec> ring;
-    ring.buf = reinterpret_cast<unsigned char*>(ex_e + K * NT) + warp * (R::kRec * kRecChunk * kRecBufs);
+    ring.buf = sm_p + warp * (R::kRec * kRecChunk * kRecBufs);
+    sm_p += (NT / 32) * (R::kRec * kRecChunk * kRecBufs);
+    ByteRing<K> bytes;
+    bytes.buf = sm_p + warp * ByteRing<K>::kBytes;
+    bytes.sbuf = (unsigned)__cvta_generic_to_shared(bytes.buf);
+    bytes.lane = lane;
+    if (PHYLO_BYTECP) sm_p += (NT / 32) * ByteRing<K>::kBytes;
     // K == 1 (small, latency-bound problems): the two 4x4 statistics of a step are summed over the warp
-    // through shared memory -- 32 values per lane in, one entry per lane out -- instead of the
-    // shuffle/select exchange, which K = 1 cannot amortise over several patterns.  [32 entries][33] per warp.
-    T* const red = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(ex_e + K * NT) +
-                                        (NT / 32) * (R::kRec * kRecChunk * kRecBufs)) + warp * (32 * 33);
+    // in one pass, [32 entries][33] per warp; K > 1: one child at a time, [16 entries][34] per warp
+    T* const red = reinterpret_cast<T*>(sm_p) + warp * (K == 1 ? 32 * 33 : 16 * 34);
     ring.sbuf = (unsigned)__cvta_generic_to_shared(ring.buf);
     ring.lane = lane;
     ring.next = nullptr;
@@ -504,6 +607,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     V* const stt = st + tid;
     V* const sct = reinterpret_cast<V*>(a.scratch) + (size_t)blockIdx.x * a.scratch_stride + tid;
     uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid * K;  // K exponents per lane, packed
+    const uint8_t* const dlw = a.dscr + (size_t)blockIdx.x * a.dscr_stride + (tid - lane) * K;  // the warp's block
 
     // entry j of the stack slot / scratch row at vector offset `off`
 #define ST(off, j) (stt + (off) + (j) * (VP * NT))
@@ -513,7 +617,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         const int d = item / a.ntiles, tile = item - d * a.ntiles;
         const double* prm = a.params + (size_t)d * a.lay.stride;
         const int pat0 = tile * tpat + pb * 32 * K + lane * K;  // this lane's K consecutive patterns: pat0 + j
-        const uint8_t* tipp = a.tips + pat0;
+        const uint8_t* tipw = a.tips + (pat0 - lane * K);       // the warp's 32 K tip codes of a row start here
         const size_t stream_off = ((size_t)d * C + c) * nsteps * R::kRec;
 
         // -------------------------------------------------------------- post-order
@@ -526,8 +630,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         }
         ring.start(a.spost + stream_off, nsteps);
         ring.step(0);
+#if PHYLO_BYTECP
+        // tip codes of the children of steps 0..3 -> byte ring (two commit groups)
+        {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (u < nsteps) {
+                    const PostRec* r = reinterpret_cast<const PostRec*>(ring.rec(u));
+                    if (r->flags & 1) bytes.fetch(u, 0, tipw + r->tip_a);
+                    if (r->flags & 2) bytes.fetch(u, 1, tipw + r->tip_b);
+                    if (u == 1) cp_async_commit();
+                }
+            if (nsteps < 2) cp_async_commit();
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+        }
+#else
         // tip codes of the children of steps i (ca, cb), i+1 (ca1, cb1) and, inside the loop, i+2:
         // K codes per lane packed in one word, loaded two steps ahead of their use
+        const uint8_t* tipp = tipw + lane * K;
         unsigned ca = 0u, cb = 0u, ca1 = 0u, cb1 = 0u;
         {
             const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
@@ -539,14 +661,33 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (r1->flags & 2) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
             }
         }
+#endif
         V* srow = sct;  // scratch row of step i
         uint8_t* drow = dlt;
-        // value-only kernels unroll by two: the look-ahead registers then alternate roles instead of being
-        // rotated by moves (a move of a still-pending load result waits for it a whole step early);
-        // measured +6 % (K = 4) / +13 % (K = 2) there, nothing in the gradient kernels (larger code)
+        // value-only kernels unroll by two (measured +6 % at K = 4, +13 % at K = 2; nothing in the gradient
+        // kernels, whose code is larger)
         constexpr int kPostUnroll = GRAD ? 1 : 2;
 #pragma unroll kPostUnroll
         for (int i = 0; i < nsteps; ++i) {
+#if PHYLO_BYTECP
+            if (i) {
+                ring.step(i);
+                if ((i & 1) == 0) {  // records i+2, i+3 just became readable: their tip codes -> byte ring
+#pragma unroll
+                    for (int u = 2; u < 4; ++u)
+                        if (i + u < nsteps) {
+                            const PostRec* r = reinterpret_cast<const PostRec*>(ring.rec(u));
+                            if (r->flags & 1) bytes.fetch(i + u, 0, tipw + r->tip_a);
+                            if (r->flags & 2) bytes.fetch(i + u, 1, tipw + r->tip_b);
+                        }
+                    cp_async_commit();
+                }
+            }
+            const unsigned char* rec = ring.rec(0);
+            const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
+            const int fl = s1.w;
+            const unsigned ca = (fl & 1) ? bytes.get(i, 0) : 0u, cb = (fl & 2) ? bytes.get(i, 1) : 0u;
+#else
             if (i) ring.step(i);
             const unsigned char* rec = ring.rec(0);
             const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
@@ -558,6 +699,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (nf & 1) ca2 = ldg_bytes<K>(tipp + n->tip_a);
                 if (nf & 2) cb2 = ldg_bytes<K>(tipp + n->tip_b);
             }
+#endif
             T ma[K][4], mb[K][4];
             if (DEEP && (fl & 16)) {  // rare: child a was parked above the capped stack, in its scratch row
                 T M[16];
@@ -638,12 +780,15 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             }
             if (GRAD) {
 #pragma unroll
-                for (int j = 0; j < K; ++j) st4cs(srow + j * (VP * NT), NT, tos[j]);
+                for (int j = 0; j < K; ++j)
+                    if (PHYLO_ABLATE != 3 && PHYLO_ABLATE != 6) st4cs(srow + j * (VP * NT), NT, tos[j]);
             }
-            if (GRAD) stcs_bytes<K>(drow, kpack);
+            if (GRAD && PHYLO_ABLATE != 3 && PHYLO_ABLATE != 6) stcs_bytes<K>(drow, kpack);
             srow += SS;
             drow += K * NT;
+#if !PHYLO_BYTECP
             ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2;
+#endif
         }
 
         // -------------------------------------------------------------- root: site likelihoods
@@ -653,7 +798,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
         if (GRAD) ring.start(a.spre + stream_off, nsteps);  // overlaps the root exchange
         double rdot[K];
-        __syncthreads();  // previous item's readers of ex_* are done
+        __syncthreads();  // every warp has emptied its stack: the exchange arrays may borrow it
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             rdot[j] = pi[0] * (double)tos[j][0] + pi[1] * (double)tos[j][1] + pi[2] * (double)tos[j][2] +
@@ -688,10 +833,29 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 }
             }
         }
+        __syncthreads();  // the exchange has been read: the stack region is a stack again
 
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
             ring.step(0);
+#if PHYLO_BYTECP
+            // byte operands of steps n: tip codes of the children (0, 1), rescale exponents of the node (2)
+            {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (u < nsteps) {
+                        const PreRec* r = reinterpret_cast<const PreRec*>(ring.rec(u));
+                        if (r->row_a < 0) bytes.fetch(u, 0, tipw + r->tip_a);
+                        if (r->row_b < 0) bytes.fetch(u, 1, tipw + r->tip_b);
+                        bytes.fetch(u, 2, dlw + r->dl_n);
+                        if (u == 1) cp_async_commit();
+                    }
+                if (nsteps < 2) cp_async_commit();
+                cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+            }
+#else
             // packed byte operands of steps i (ca, cb, dcur = rescale exponents of the node) and i+1
             unsigned dcur, d1 = 0u;
             ca = cb = ca1 = cb1 = 0u;
@@ -707,45 +871,81 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     d1 = ld_bytes<K>(dlt + r1->dl_n);
                 }
             }
+#endif
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
             // children's partials of the current step; loaded from scratch during the previous step's
             // tail (after their last use there), so no extra registers and a reduction's worth of cover
             T pa[K][4], pbv[K][4];
             {
+                const int i_abl = 0;
+                (void)i_abl;
                 const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(0) + 16);  // row_a, row_b, ...
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
-                    if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                    if (PHYLO_ABLATE != 5 && PHYLO_ABLATE != 6) {
+                        if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                        if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                    } else if (i_abl == 0) {
+                        pa[j][0] = pa[j][1] = pa[j][2] = pa[j][3] = T(0.25);
+                        pbv[j][0] = pbv[j][1] = pbv[j][2] = pbv[j][3] = T(0.25);
+                    }
                 }
             }
             for (int i = 0; i < nsteps; ++i) {
+#if PHYLO_BYTECP
+                if (i) {
+                    ring.step(i);
+                    if ((i & 1) == 0) {
+#pragma unroll
+                        for (int u = 2; u < 4; ++u)
+                            if (i + u < nsteps) {
+                                const PreRec* r = reinterpret_cast<const PreRec*>(ring.rec(u));
+                                if (r->row_a < 0) bytes.fetch(i + u, 0, tipw + r->tip_a);
+                                if (r->row_b < 0) bytes.fetch(i + u, 1, tipw + r->tip_b);
+                                bytes.fetch(i + u, 2, dlw + r->dl_n);
+                            }
+                        cp_async_commit();
+                    }
+                }
+#else
                 if (i) ring.step(i);
+#endif
                 const unsigned char* rec = ring.rec(0);
                 const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
                 const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
                 const int rowa = s1.x, rowb = s1.y;
+#if PHYLO_BYTECP
+                const unsigned ca = rowa < 0 ? bytes.get(i, 0) : 0u, cb = rowb < 0 ? bytes.get(i, 1) : 0u;
+                const unsigned dcur = bytes.get(i, 2);
+#else
                 unsigned ca2 = 0u, cb2 = 0u, d2 = 0u;
+#endif
                 if (i + 2 < nsteps) {  // operands of step i+2: bytes -> registers, scratch lines -> L2
                     const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
                     const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
                     if (n1.x < 0) {
+#if !PHYLO_BYTECP
                         ca2 = ldg_bytes<K>(tipp + n->tip_a);
-                    } else {
+#endif
+                    } else if (PHYLO_PF) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.x, j) + h * NT);
                     }
                     if (n1.y < 0) {
+#if !PHYLO_BYTECP
                         cb2 = ldg_bytes<K>(tipp + n->tip_b);
-                    } else {
+#endif
+                    } else if (PHYLO_PF) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
+#if !PHYLO_BYTECP
                     d2 = ld_bytes<K>(dlt + n1.z);
+#endif
                 }
                 // q(node) lives in the TOS registers for the whole step: either it is still there (the
                 // node was the previous step's first child) or it is popped from the shared-memory stack
@@ -755,15 +955,6 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     for (int j = 0; j < K; ++j) ld4cs(SC(s1.w, j), NT, qn[j]);
                 }
                 const bool pop = s1.w >= 0 && !(DEEP && (s2.w & 2));
-                // one (warp-uniform) branch per operand kind rather than one per pattern
-                if (rowa < 0) {
-#pragma unroll
-                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
-                }
-                if (rowb < 0) {
-#pragma unroll
-                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
-                }
 #pragma unroll
                 for (int j = 0; j < K; ++j)
                     if (pop) ld4(ST(s1.w, j), NT, qn[j]);
@@ -776,9 +967,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             for (int s = 0; s < 4; ++s) qn[j][s] *= f;
                         }
                 }
-                // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
+                // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148).  One (warp-uniform)
+                // branch per operand kind; a simple tip's message is a column of P (PRETIP streams).
                 T Aa[K][4], Ab[K][4];
-                {
+                if (rowa < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
+                }
+                if (rowb < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
+                }
+                if (PHYLO_PRETIP && TIPS && rowa < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T m[4];
+                        tip_msg<V>(rec + 64, BYTE_OF(ca, j), m);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
+                    }
+                } else {
                     T M[16], m[4];
                     lds_mat(rec + 64, M);
 #pragma unroll
@@ -788,16 +996,21 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
                     }
                 }
-                T gb4[4];  // child b's statistics after the first two reduction levels
+                T gb4[4];  // child b's statistics after the first two reduction levels (shuffle exchange)
                 T jb = T(0), ja = T(0);  // JC: the scalar statistics of both branches
+                (void)gb4;
                 {   // child b: q(b) waits in shared memory
-                    T M[16], m[4], G[16];
-                    lds_mat(rec + 64 + R::kMat, M);
+                    T G[16];
 #pragma unroll
                     for (int x = 0; x < 16; ++x) G[x] = T(0);
+                    const bool btip = PHYLO_PRETIP && TIPS && rowb < 0;  // tip: the message is a column of P_b
+                    T M[16];
+                    if (!btip) lds_mat(rec + 64 + R::kMat, M);
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
-                        matvec(M, pbv[j], m);
+                        T m[4];
+                        if (btip) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), m);
+                        else matvec(M, pbv[j], m);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) Aa[j][s] = qn[j][s] * m[s];
                         if (JC) {
@@ -812,7 +1025,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
+                                for (int y = 0; y < 4; ++y)
+                                    if (PHYLO_ABLATE != 7) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
                         }
                     }
                     if (s2.x >= 0) {  // b is internal: q(b) = P_b^T A_b   (eigen.j2:151-153)
@@ -828,6 +1042,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     } else if (K == 1) {
 #pragma unroll
                         for (int x = 0; x < 16; ++x) red[x * 33 + lane] = G[x];
+                    } else if (PHYLO_RSM) {
+                        warp_reduce16_smem(G, red, Gd + s2.z, lane);
                     } else {
                         warp_reduce16_head(G, gb4, lane);
                     }
@@ -842,7 +1058,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
-                                for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
+                                for (int y = 0; y < 4; ++y)
+                                    if (PHYLO_ABLATE != 7) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
                     }
                     if (s2.w & 1) {
                         T M[16];
@@ -855,8 +1072,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(1) + 16);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
-                            if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
-                            if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                            if (PHYLO_ABLATE != 5 && PHYLO_ABLATE != 6) {
+                                if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                                if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                            }
                         }
                     }
                     if (JC) {  // two scalars per lane: lanes 0..15 finish child b's sum, lanes 16..31 child a's
@@ -871,23 +1090,27 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         __syncwarp();
                         // lane l owns entry l: 0..15 of child b, 16..31 of child a; four partial sums keep the chain short
                         const T* row = red + lane * 33;
-                        T s0 = T(0), s1 = T(0), s2s = T(0), s3 = T(0);
+                        T s0 = T(0), s1_ = T(0), s2s = T(0), s3 = T(0);
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             s0 += row[j];
-                            s1 += row[j + 1];
+                            s1_ += row[j + 1];
                             s2s += row[j + 2];
                             s3 += row[j + 3];
                         }
-                        atomicAdd(Gd + (lane < 16 ? s2.z + lane : s2.y + lane - 16), (double)((s0 + s1) + (s2s + s3)));
+                        atomicAdd(Gd + (lane < 16 ? s2.z + lane : s2.y + lane - 16), (double)((s0 + s1_) + (s2s + s3)));
                         __syncwarp();  // the rows are rewritten by the next step
+                    } else if (PHYLO_RSM) {
+                        warp_reduce16_smem(G, red, Gd + s2.y, lane);
                     } else {
                         T ga4[4];
                         warp_reduce16_head(G, ga4, lane);
                         warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
                     }
                 }
+#if !PHYLO_BYTECP
                 ca = ca1; cb = cb1; dcur = d1; ca1 = ca2; cb1 = cb2; d1 = d2;
+#endif
             }
         }
 
@@ -903,8 +1126,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             for (int s = 0; s < 4; ++s) acc_dpi[s] = warp_sum(acc_dpi[s]);
             if (lane == 0) {
                 atomicAdd(od + a.off_out_ps + c, acc_dps);
+                if (a.lay.ntheta > 0) {  // JC69 fixes the frequencies: no derivative to report
 #pragma unroll
-                for (int s = 0; s < 4; ++s) atomicAdd(od + a.off_out_freqs + s, acc_dpi[s]);
+                    for (int s = 0; s < 4; ++s) atomicAdd(od + a.off_out_freqs + s, acc_dpi[s]);
+                }
             }
         }
     }
@@ -1063,6 +1288,43 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// K0: device-resident tip data -> the handle's padded code rows (phylo_b200_create_device)
+// ------------------------------------------------------------------------------------------
+
+// [S][L] 4-bit masks -> [S][Lpad] masks (padding = all ones); flags[0] is raised when some cell is neither
+// one-hot nor all ones, i.e. when the column-index fast path does not apply
+__global__ void __launch_bounds__(256) tips_pad_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                        int L, int Lpad, size_t total, int* __restrict__ flags) {
+    bool odd = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i / (size_t)Lpad;
+        const int l = (int)(i - s * (size_t)Lpad);
+        const uint8_t m = l < L ? (uint8_t)(src[s * (size_t)L + l] & 0xF) : (uint8_t)0xF;
+        dst[i] = m;
+        odd |= !(m == 15 || m == 1 || m == 2 || m == 4 || m == 8);
+    }
+    if (__any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+}
+
+// masks -> column indices 0..3 / 4 (all ones), in place
+__global__ void __launch_bounds__(256) tips_index_kernel(uint8_t* __restrict__ t, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t m = t[i];
+        t[i] = m == 15 ? 4 : (m == 1 ? 0 : (m == 2 ? 1 : (m == 4 ? 2 : 3)));
+    }
+}
+
+// weights [L] (or NULL: ones) -> [Lpad] (padding = 0); flags[1] is raised on a non-finite weight
+__global__ void __launch_bounds__(256) weights_pad_kernel(const double* __restrict__ w, double* __restrict__ dst, int L,
+                                                           int Lpad, int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lpad) return;
+    const double v = i < L ? (w ? w[i] : 1.0) : 0.0;
+    dst[i] = v;
+    if (!isfinite(v)) atomicOr(flags + 1, 1);
+}
+
+// ------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------
 
@@ -1112,10 +1374,17 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
 }
 
 SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false) {
+#ifdef PHYLO_FAST_BUILD  // compile-time experiments only: the fp64 K = 4 / 2 gradient kernels of simple-tip handles
+    if (prec != 64 || !tips || !grad || jc || nthreads != 128) return nullptr;
+    if (K == 4) return deep ? pick_kernel<double, 4, true, true, true>(128) : pick_kernel<double, 4, true, true, false>(128);
+    if (K == 2) return deep ? pick_kernel<double, 2, true, true, true>(128) : pick_kernel<double, 2, true, true, false>(128);
+    return nullptr;
+#else
     if (jc && prec == 64 && grad && !deep) return tips ? pick_kernel_jc<true>(K, nthreads) : pick_kernel_jc<false>(K, nthreads);
     if (prec == 32)
         return tips ? pick_kernel_k<float, true>(K, grad, deep, nthreads) : pick_kernel_k<float, false>(K, grad, deep, nthreads);
     return tips ? pick_kernel_k<double, true>(K, grad, deep, nthreads) : pick_kernel_k<double, false>(K, grad, deep, nthreads);
+#endif
 }
 
 }  // namespace
@@ -1124,11 +1393,21 @@ int sweep_max_threads(int) { return 512; }
 
 int record_bytes(int prec) { return prec == 32 ? kRecBytesF32 : kRecBytes; }
 
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec) {
+size_t sweep_stack_bytes(int D, int K, int nthreads, int prec) {
     const size_t entry = prec == 32 ? 16 : 32;  // bytes per 4-state vector
-    const size_t red = K == 1 ? (size_t)(nthreads / 32) * 32 * 33 * (entry / 4) : 0;  // K = 1: reduction through smem
-    return (size_t)D * K * nthreads * entry + (size_t)K * nthreads * (sizeof(double) + sizeof(int)) +
-           (size_t)(nthreads / 32) * record_bytes(prec) * kRecChunk * kRecBufs + red;
+    // the root's category exchange (a double and an int per thread and pattern) borrows the stack region
+    return std::max((size_t)D * K * nthreads * entry, (size_t)K * nthreads * (sizeof(double) + sizeof(int)));
+}
+
+// [stack | record rings | byte rings | reduction rows], all per warp except the stack
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc) {
+    const size_t val = prec == 32 ? 4 : 8;
+    const size_t warps = nthreads / 32;
+    size_t red = 0;
+    if (K == 1) red = warps * 32 * 33 * val;                       // both children in one pass
+    else if (PHYLO_RSM && !jc) red = warps * 16 * 34 * val;        // one child at a time
+    return sweep_stack_bytes(D, K, nthreads, prec) + warps * record_bytes(prec) * kRecChunk * kRecBufs +
+           (PHYLO_BYTECP ? warps * (4 * 3 * 32 * K) : 0) + red;
 }
 
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
@@ -1147,12 +1426,27 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool gr
     return cudaGetLastError();
 }
 
-cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads);
+cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n,
+                            bool jc) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, nthreads, smem);
+}
+
+void launch_tips_prepare(const uint8_t* d_src, uint8_t* d_dst, int S, int L, int Lpad, const double* d_w, double* d_wdst,
+                         int* d_flags, cudaStream_t stream) {
+    const size_t total = (size_t)S * Lpad;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+    tips_pad_kernel<<<grid, 256, 0, stream>>>(d_src, d_dst, L, Lpad, total, d_flags);
+    weights_pad_kernel<<<(Lpad + 255) / 256, 256, 0, stream>>>(d_w, d_wdst, L, Lpad, d_flags);
+}
+
+void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream) {
+    const size_t total = (size_t)S * Lpad;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+    tips_index_kernel<<<grid, 256, 0, stream>>>(d_tips, total);
 }
 
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream) {

@@ -4,7 +4,7 @@
 //   stream_kernel    P(t_b r_c) = m1 diag(exp(lambda t_b r_c)) m2 for both children of every step
 //                    (phylostan/generate_script.py:824-829, 880-885; JC69 closed form :765-766),
 //                    written as per-(draw, category) INSTRUCTION STREAMS in traversal order:
-//                    one 320-byte record [step descriptor with ready-made offsets | P_a | P_b] per
+//                    one 384-byte record [step descriptor with ready-made offsets | P_a | P_b] per
 //                    internal node, one stream for the post-order and one for the pre-order sweep
 //   sweep_kernel     per (draw, pattern tile): depth-first post-order partials
 //                    (eigen/eigen.j2:122-141, generate_script.py:998-1005), root likelihood with
@@ -100,6 +100,7 @@ struct SweepArgs {
     ParamLayout lay;
     long long scratch_stride, dscr_stride;   // per CTA, in 16-byte vectors / bytes
     int S, nsteps, Lpad, ntiles, nitems, C, nn, nout, D;
+    int stack_bytes;          // size of the stack region at the head of dynamic shared memory
     int off_out_freqs, off_out_ps;
 };
 
@@ -122,10 +123,17 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
                          size_t smem, cudaStream_t stream, bool jc = false);
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
-                            int* blocks_per_sm);
+                            int* blocks_per_sm, bool jc = false);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
+// device-resident tip masks [S][L] / weights [L] (NULL: ones) -> padded rows; d_flags[2]: {some cell is not
+// simple, some weight is not finite}
+void launch_tips_prepare(const uint8_t* d_src, uint8_t* d_dst, int S, int L, int Lpad, const double* d_w, double* d_wdst,
+                         int* d_flags, cudaStream_t stream);
+void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream);  // masks -> column indices
 
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec);
+// jc: the scalar-statistic kernel needs no reduction rows
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false);
+size_t sweep_stack_bytes(int D, int K, int nthreads, int prec);  // first region of the above
 int record_bytes(int prec);
 int sweep_max_threads(int K);  // largest CTA the K-variant is compiled for
 

@@ -109,6 +109,7 @@ struct phylo_b200_ctx {
     int req_K = 0, req_PB = 0, req_cap = 0;
     int K = 1, PB = 1, NT = 0, grid = 0, ntiles = 0;
     int slots = 0;  // shared-memory stack slots of the last run (< plan.depth(): the rest is parked in HBM)
+    bool jc_run = false;  // the last resolved launch is the JC69 scalar-statistic kernel
     size_t smem = 0;
     int last_launches = 0;
 
@@ -138,9 +139,12 @@ struct phylo_b200_ctx {
 
 namespace {
 
-// Resolve (K, PB) -> launch shape.
+// Resolve (K, PB) -> launch shape.  Everything (occupancy, slots, grid, scratch) is derived for the kernel
+// instantiation that run_enqueue launches, the JC69 scalar-statistic variant included.
 int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     const int C = h->C, Dfull = h->plan.depth();
+    // JC69 gradient runs use the scalar-statistic sweep when the whole stack fits on chip
+    bool jc = grad && h->prec == 64 && h->model == PHYLO_B200_JC69 && h->use_jc_scalar && h->req_cap == 0;
     // Gradient runs may cap the shared-memory stack: the top stack positions (reached rarely, and only
     // briefly) are parked in the CTA's HBM scratch, which holds every partial anyway.  A deep tree
     // (stack depth 7+, thousands of taxa) then still gets the widest tile twice per SM.
@@ -149,13 +153,14 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     int Dmin = Dfull;
     if (grad) Dmin = h->req_cap > 0 ? std::min(Dfull, h->req_cap) : std::max(std::min(Dfull, 2), Dfull - kMaxParked);
     const int Dmax = grad && h->req_cap > 0 ? Dmin : Dfull;
-    // largest slot count in [Dmin, Dmax] reaching `want` CTAs per SM; 0 when none does
-    auto slots_for = [&](int k, int nt, int want) {
-        for (int dd = Dmax; dd >= Dmin; --dd) {
+    // largest slot count in [Dmin, Dmax] reaching `want` CTAs per SM; -1 when none does
+    auto slots_for = [&](int k, int nt, int want, bool j) {
+        for (int dd = Dmax; dd >= (j ? Dfull : Dmin); --dd) {
             int occ = 0;
-            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec);
+            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec, j);
             if (sm <= h->smem_optin &&
-                sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sm, &occ) == cudaSuccess && occ >= want)
+                sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sm, &occ, j) == cudaSuccess &&
+                occ >= want)
                 return dd;
             if (dd == 0) break;
         }
@@ -175,11 +180,13 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             static const double kLat[5] = {0, 1.0, 1.1, 0, 1.35}, kSat[5] = {0, 1.0, 1.40, 0, 1.62};
             double best = 1e300;
             for (int k : {1, 2, 4}) {
-                const int dd = slots_for(k, nt, k == 1 ? 1 : 2);
+                int dd = jc ? slots_for(k, nt, k == 1 ? 1 : 2, true) : -1;
+                const bool j = dd >= 0;
+                if (!j) dd = slots_for(k, nt, k == 1 ? 1 : 2, false);
                 if (dd < 0) continue;
                 int occ = 0;
-                if (sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sweep_smem_bytes(dd, k, nt, h->prec),
-                                    &occ) != cudaSuccess || occ < 1)
+                if (sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt,
+                                    sweep_smem_bytes(dd, k, nt, h->prec, j), &occ, j) != cudaSuccess || occ < 1)
                     continue;
                 const double items = (double)B * ((h->L + 32 * k - 1) / (32 * k));
                 const double w = items / ((double)occ * h->num_sms);
@@ -198,9 +205,15 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     int NT = 32 * C * PB;
     if (NT > sweep_max_threads(K)) return fail(PHYLO_B200_EINVAL, "too many rate categories for one CTA");
     int D = -1;
+    bool jrun = false;
     for (;;) {
-        D = slots_for(K, NT, 2);                 // two CTAs per SM if any allowed slot count gives that
-        if (D < 0) D = slots_for(K, NT, 1);
+        if (jc) {  // the scalar-statistic kernel keeps the whole stack on chip
+            D = slots_for(K, NT, 2, true);
+            if (D < 0) D = slots_for(K, NT, 1, true);
+            jrun = D >= 0;
+        }
+        if (D < 0) D = slots_for(K, NT, 2, false);  // two CTAs per SM if any allowed slot count gives that
+        if (D < 0) D = slots_for(K, NT, 1, false);
         if (D >= 0) break;
         if (K > 1) K >>= 1;
         else if (PB > 1) { PB >>= 1; NT = 32 * C * PB; }
@@ -208,12 +221,12 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             return fail(PHYLO_B200_EINVAL,
                         "tree too deep for the shared-memory stack (depth " + std::to_string(Dfull) + ")");
     }
-    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec);
+    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun);
     const int tpat = PB * 32 * K;
-    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D;
+    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun;
     h->ntiles = (h->L + tpat - 1) / tpat;
     int occ = 0;
-    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ));
+    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -231,8 +244,10 @@ int ensure_batch(phylo_b200_ctx* h, int B) {
     return 0;
 }
 
+// on_device: tipmask / weights are DEVICE pointers on `device` (phylo_b200_create_device)
 int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
-                  const uint8_t* tipmask, const double* tipdata, const double* weights, int device) {
+                  const uint8_t* tipmask, const double* tipdata, const double* weights, int device,
+                  bool on_device = false) {
     if (!out) return fail(PHYLO_B200_EINVAL, "out handle is NULL");
     *out = nullptr;
     if (S < 2 || L < 1 || C < 1) return fail(PHYLO_B200_EINVAL, "need S >= 2, L >= 1, C >= 1");
@@ -295,35 +310,69 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
 
     // static data: tip codes [S][Lpad] (padding = all-ambiguous, weight 0), weights, step lists
     h->Lpad = ((L + kPadPatterns - 1) / kPadPatterns) * kPadPatterns;
-    std::vector<uint8_t> tips((size_t)S * h->Lpad, 0xF);
-    for (int s = 0; s < S; ++s)
-        for (int l = 0; l < L; ++l) {
-            uint8_t m;
-            if (tipmask) {
-                m = tipmask[(size_t)s * L + l] & 0xF;
-            } else {
-                const double* t = tipdata + ((size_t)s * L + l) * 4;
-                m = (uint8_t)((t[0] != 0.0) | ((t[1] != 0.0) << 1) | ((t[2] != 0.0) << 2) | ((t[3] != 0.0) << 3));
-            }
-            tips[(size_t)s * h->Lpad + l] = m;
-        }
-    // reference-encoded alignments only hold one-hot or all-ones cells (phylostan/utils.py:180-188):
-    // store the column index 0..3 / 4 instead of the mask and use the tip fast path
-    h->tips_simple = true;
-    for (uint8_t m : tips)
-        if (!(m == 15 || m == 1 || m == 2 || m == 4 || m == 8)) { h->tips_simple = false; break; }
-    if (h->tips_simple)
-        for (uint8_t& m : tips) m = m == 15 ? 4 : (m == 1 ? 0 : (m == 2 ? 1 : (m == 4 ? 2 : 3)));
-    std::vector<double> w((size_t)h->Lpad, 0.0);
-    for (int l = 0; l < L; ++l) {
-        w[l] = weights ? weights[l] : 1.0;
-        if (!std::isfinite(w[l])) { delete h; return fail(PHYLO_B200_EDOMAIN, "non-finite pattern weight"); }
-    }
     auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
         cudaError_t e = buf.ensure(vec.size());
         if (e != cudaSuccess) return e;
         return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
     };
+    if (on_device) {
+        // the alignment already lives on this GPU: pad / classify / re-code it there
+        DevBuf<int> d_flags;
+        int hf[2] = {0, 0};
+        cudaError_t e = cudaSuccess;
+        if ((e = h->d_tips.ensure((size_t)S * h->Lpad)) != cudaSuccess ||
+            (e = h->d_weights.ensure((size_t)h->Lpad)) != cudaSuccess || (e = d_flags.ensure(2)) != cudaSuccess ||
+            (e = cudaMemset(d_flags.p, 0, 2 * sizeof(int))) != cudaSuccess) {
+            d_flags.release(); delete h;
+            return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
+        }
+        launch_tips_prepare(tipmask, h->d_tips.p, S, L, h->Lpad, weights, h->d_weights.p, d_flags.p, nullptr);
+        if ((e = cudaGetLastError()) != cudaSuccess ||
+            (e = cudaMemcpy(hf, d_flags.p, sizeof hf, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+            d_flags.release(); delete h;
+            return fail(PHYLO_B200_ECUDA, std::string("tip preparation: ") + cudaGetErrorString(e));
+        }
+        d_flags.release();
+        if (hf[1]) { delete h; return fail(PHYLO_B200_EDOMAIN, "non-finite pattern weight"); }
+        h->tips_simple = hf[0] == 0;
+        if (h->tips_simple) {
+            launch_tips_index(h->d_tips.p, S, h->Lpad, nullptr);
+            if ((e = cudaGetLastError()) != cudaSuccess || (e = cudaDeviceSynchronize()) != cudaSuccess) {
+                delete h;
+                return fail(PHYLO_B200_ECUDA, std::string("tip preparation: ") + cudaGetErrorString(e));
+            }
+        }
+    } else {
+        std::vector<uint8_t> tips((size_t)S * h->Lpad, 0xF);
+        for (int s = 0; s < S; ++s)
+            for (int l = 0; l < L; ++l) {
+                uint8_t m;
+                if (tipmask) {
+                    m = tipmask[(size_t)s * L + l] & 0xF;
+                } else {
+                    const double* t = tipdata + ((size_t)s * L + l) * 4;
+                    m = (uint8_t)((t[0] != 0.0) | ((t[1] != 0.0) << 1) | ((t[2] != 0.0) << 2) | ((t[3] != 0.0) << 3));
+                }
+                tips[(size_t)s * h->Lpad + l] = m;
+            }
+        // reference-encoded alignments only hold one-hot or all-ones cells (phylostan/utils.py:180-188):
+        // store the column index 0..3 / 4 instead of the mask and use the tip fast path
+        h->tips_simple = true;
+        for (uint8_t m : tips)
+            if (!(m == 15 || m == 1 || m == 2 || m == 4 || m == 8)) { h->tips_simple = false; break; }
+        if (h->tips_simple)
+            for (uint8_t& m : tips) m = m == 15 ? 4 : (m == 1 ? 0 : (m == 2 ? 1 : (m == 4 ? 2 : 3)));
+        std::vector<double> w((size_t)h->Lpad, 0.0);
+        for (int l = 0; l < L; ++l) {
+            w[l] = weights ? weights[l] : 1.0;
+            if (!std::isfinite(w[l])) { delete h; return fail(PHYLO_B200_EDOMAIN, "non-finite pattern weight"); }
+        }
+        cudaError_t e = cudaSuccess;
+        if ((e = up(h->d_tips, tips)) != cudaSuccess || (e = up(h->d_weights, w)) != cudaSuccess) {
+            delete h;
+            return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
+        }
+    }
     std::vector<int32_t> node_pos((size_t)h->nn, 0);  // non-root node -> 2 * post step + child slot
     for (size_t i = 0; i < h->plan.post.size(); ++i) {
         node_pos[h->plan.post[i].a] = (int32_t)(2 * i);
@@ -332,8 +381,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     std::vector<int32_t> node_row((size_t)h->nn, -1);  // internal node -> its own post-order step = scratch row
     for (size_t i = 0; i < h->plan.post.size(); ++i) node_row[h->plan.post[i].node] = (int32_t)i;
     cudaError_t e = cudaSuccess;
-    if ((e = up(h->d_tips, tips)) != cudaSuccess || (e = up(h->d_weights, w)) != cudaSuccess ||
-        (e = up(h->d_node_pos, node_pos)) != cudaSuccess || (e = up(h->d_node_row, node_row)) != cudaSuccess ||
+    if ((e = up(h->d_node_pos, node_pos)) != cudaSuccess || (e = up(h->d_node_row, node_row)) != cudaSuccess ||
         (e = up(h->d_post, h->plan.post)) != cudaSuccess || (e = up(h->d_pre, h->plan.pre)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
         delete h;
@@ -399,6 +447,12 @@ int phylo_b200_create(phylo_b200_handle* out, int S, int L, int C, int model, in
 int phylo_b200_create_tipdata(phylo_b200_handle* out, int S, int L, int C, int model, int flags,
                               const int32_t* peel, const double* tipdata, const double* weights, int device) {
     return create_common(out, S, L, C, model, flags, peel, nullptr, tipdata, weights, device);
+}
+
+int phylo_b200_create_device(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
+                             const uint8_t* d_tipmask, const double* d_weights, int device) {
+    if (!d_tipmask) return fail(PHYLO_B200_EINVAL, "create_device: tip masks are NULL");
+    return create_common(out, S, L, C, model, flags, peel, d_tipmask, nullptr, d_weights, device, true);
 }
 
 void phylo_b200_destroy(phylo_b200_handle h) {
@@ -574,9 +628,10 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     a.dscr_stride = (long long)(h->S - 1) * h->K * h->NT;
     a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
     a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->slots;
+    a.stack_bytes = (int)sweep_stack_bytes(h->slots, h->K, h->NT, h->prec);
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
     const bool deep = grad && h->slots < h->plan.depth();
-    const bool jc = grad && !deep && h->prec == 64 && h->model == PHYLO_B200_JC69 && h->use_jc_scalar;
+    const bool jc = grad && h->jc_run;
     CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
@@ -605,7 +660,8 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
     return {u(h->d_params.p), u(h->d_spost.p), u(h->d_spre.p), u(h->d_G.p), u(h->d_out.p), u(h->d_scratch.p),
             u(h->d_dscr.p), u(h->h_params.p), u(h->h_out.p), u(h->stream), (unsigned long long)h->K,
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
-            (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles};
+            (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
+            (unsigned long long)h->jc_run};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible

@@ -60,6 +60,8 @@ def lib() -> ctypes.CDLL:
     ip, bp = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_uint8)
     L.phylo_b200_create.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, bp, _dp, i]
     L.phylo_b200_create_tipdata.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, _dp, _dp, i]
+    if hasattr(L, "phylo_b200_create_device"):  # absent from older A/B builds (tools/ab_sweep.py)
+        L.phylo_b200_create_device.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, vp, vp, i]
     L.phylo_b200_destroy.argtypes = [vp]
     L.phylo_b200_destroy.restype = None
     for name in ("bcount", "nsubst", "ncat", "nout", "sync"):
@@ -138,8 +140,11 @@ class TreeLikelihood:
     """
 
     def __init__(self, peel, tipmask=None, weights=None, *, tipdata=None, model="GTR", categories: int = 1,
-                 rooted: bool = True, normalize: bool = True, device: int = 0):
+                 rooted: bool = True, normalize: bool = True, device: int = 0, device_tips=None):
+        """``device_tips`` = (tipmask_ptr, L, weights_ptr or None): the alignment is already resident on
+        ``device`` as uint8 [S, L] masks / float64 [L] weights (e.g. torch tensors' ``data_ptr()``)."""
         L_ = lib()
+        self._h = None
         self.model = MODELS[model] if isinstance(model, str) else int(model)
         peel = np.ascontiguousarray(peel, dtype=np.int32)
         self.S = peel.shape[0] + 1
@@ -147,26 +152,37 @@ class TreeLikelihood:
             raise ValueError("peel must be [S-1, 3]")
         flags = (ROOTED if rooted else 0) | (0 if normalize else NO_NORMQ)
         self.rooted, self.normalize, self.C, self.device = rooted, normalize, int(categories), int(device)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        # every shape is checked BEFORE the library reads the arrays
         w = _arr(weights)
         h = ctypes.c_void_p()
-        if tipdata is not None:
+        if device_tips is not None:
+            tip_ptr, self.L, w_ptr = device_tips
+            self.L = int(self.L)
+            if self.L < 1 or not tip_ptr:
+                raise ValueError("device_tips must be (tipmask_ptr, L >= 1, weights_ptr or None)")
+            rc = L_.phylo_b200_create_device(ctypes.byref(h), self.S, self.L, self.C, self.model, flags,
+                                             peel.ctypes.data_as(ip), ctypes.c_void_p(int(tip_ptr)),
+                                             ctypes.c_void_p(int(w_ptr) if w_ptr else 0), self.device)
+        elif tipdata is not None:
             td = _arr(tipdata)
             if td.ndim != 3 or td.shape[0] != self.S or td.shape[2] != 4:
                 raise ValueError("tipdata must be [S, L, 4]")
             self.L = td.shape[1]
+            if w is not None and w.shape != (self.L,):
+                raise ValueError("weights must be [L]")
             rc = L_.phylo_b200_create_tipdata(ctypes.byref(h), self.S, self.L, self.C, self.model, flags,
-                                              peel.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), _ptr(td), _ptr(w),
-                                              self.device)
+                                              peel.ctypes.data_as(ip), _ptr(td), _ptr(w), self.device)
         else:
             tm = np.ascontiguousarray(tipmask, dtype=np.uint8)
             if tm.ndim != 2 or tm.shape[0] != self.S:
                 raise ValueError("tipmask must be [S, L]")
             self.L = tm.shape[1]
+            if w is not None and w.shape != (self.L,):
+                raise ValueError("weights must be [L]")
             rc = L_.phylo_b200_create(ctypes.byref(h), self.S, self.L, self.C, self.model, flags,
-                                      peel.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                      peel.ctypes.data_as(ip),
                                       tm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _ptr(w), self.device)
-        if w is not None and w.shape != (self.L,):
-            raise ValueError("weights must be [L]")
         _check(rc)
         self._h = h
         self.bcount = L_.phylo_b200_bcount(h)

@@ -47,8 +47,15 @@ class ShardedLikelihood:
         self.local, self.group, self.dist = local, group, dist
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._is_gpu = hasattr(local, "device_out")
+        self._stream = None
         if self._is_gpu:
             self.bcount, self.nsubst, self.C = local.bcount, local.nsubst, local.C
+            # The library launches on the handle's stream and NCCL on torch's current stream: bind both to ONE
+            # stream owned by this object, so the all-reduce can neither overtake the kernels nor be overtaken
+            # by the download.  (Whatever stream the caller had set on the handle is replaced.)
+            import torch
+            self._stream = torch.cuda.Stream(device=local.device)
+            local.set_stream(self._stream.cuda_stream)
         elif layout is not None:
             self.bcount, self.nsubst, self.C = layout
 
@@ -85,8 +92,9 @@ class ShardedLikelihood:
             B = lik.upload(blens, subst, freqs, rs, ps)
             lik.run(B, want_grad)
             if self.world > 1:
-                self.dist.all_reduce(device_out_tensor(lik, B), group=self.group)  # same stream as the kernels
-            return lik.download(B)
+                with torch.cuda.stream(self._stream):  # the stream the kernels were launched on
+                    self.dist.all_reduce(device_out_tensor(lik, B), group=self.group)
+            return lik.download(B)                     # copies on, then synchronises, the same stream
         rows = np.atleast_2d(np.asarray(self.local(blens, subst, freqs, rs, ps), dtype=np.float64))
         if not want_grad:
             rows = rows[:, :1]

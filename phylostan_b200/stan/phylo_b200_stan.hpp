@@ -114,7 +114,7 @@ inline typename stan::return_type<T_bl, T_su, T_fr, T_rs, T_ps>::type phylo_logl
     if (want_grad) {
         p::push_operands(blens, gb.data(), ops, grads);
         p::push_operands(subst, gs.data(), ops, grads);
-        if (freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);
+        if (nsubst > 0 && freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);  // JC69 fixes freqs: no operand
         p::push_operands(rs, gr.data(), ops, grads);
         p::push_operands(ps, gp.data(), ops, grads);
     }
@@ -179,7 +179,7 @@ inline typename stan::return_type<T_h, T_r, T_su, T_fr, T_rs, T_ps>::type loglik
         p::push_operands(heights, gh.data(), ops, grads);
         p::push_operands(rates, gr.data(), ops, grads);
         p::push_operands(subst, gs.data(), ops, grads);
-        if (freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);
+        if (nsubst > 0 && freqs.rows() == 4) p::push_operands(freqs, gf.data(), ops, grads);  // JC69 fixes freqs: no operand
         p::push_operands(rs, grs.data(), ops, grads);
         p::push_operands(ps, gp.data(), ops, grads);
     }

@@ -54,6 +54,44 @@ def coalescent_peel(S: int, rng: np.random.Generator) -> np.ndarray:
     return np.asarray(rows, dtype=np.int32)
 
 
+def coalescent_peel_fast(S: int, rng: np.random.Generator) -> np.ndarray:
+    """Same distribution as ``coalescent_peel`` in O(S) list work (swap-remove instead of rebuilding the active
+    list), for the 10 000-taxon shape.  Not the same tree for the same seed."""
+    left, right = {}, {}
+    active = list(range(S))
+    nxt = S
+    for _ in range(S - 1):
+        n = len(active)
+        i = int(rng.integers(n))
+        j = int(rng.integers(n - 1))
+        if j >= i:
+            j += 1
+        a, b = active[i], active[j]
+        left[nxt], right[nxt] = a, b
+        for k in sorted((i, j), reverse=True):
+            active[k] = active[-1]
+            active.pop()
+        active.append(nxt)
+        nxt += 1
+    root = nxt - 1
+    new_id, rows, counter = {}, [], S
+    stack = [(root, 0)]
+    while stack:
+        node, stage = stack.pop()
+        if node < S:
+            new_id[node] = node
+            continue
+        if stage == 0:
+            stack.append((node, 1))
+            stack.append((right[node], 0))
+            stack.append((left[node], 0))
+        else:
+            new_id[node] = counter
+            counter += 1
+            rows.append((new_id[left[node]] + 1, new_id[right[node]] + 1, new_id[node] + 1))
+    return np.asarray(rows, dtype=np.int32)
+
+
 def gtr_q(rates: np.ndarray, freqs: np.ndarray) -> np.ndarray:
     R = np.zeros((4, 4))
     R[np.triu_indices(4, 1)] = rates
@@ -101,6 +139,51 @@ def simulate_alignment(peel: np.ndarray, blens: np.ndarray, L: int, C: int, rng:
     tipmask[rng.random((S, L)) < ambiguous] = 0xF
     weights = 1.0 + rng.poisson(1.0, size=L)
     return tipmask, weights.astype(np.float64)
+
+
+def simulate_alignment_device(peel: np.ndarray, blens: np.ndarray, L: int, C: int, device, seed: int,
+                              rates=RATES0, freqs=FREQS0, wshape=WSHAPE0, ambiguous: float = 0.01):
+    """``simulate_alignment`` on a CUDA device with torch (same model: one independent GTR + Weibull(C) column
+    per pattern, ``ambiguous`` of the tip cells set to all ones, weights 1 + Poisson(1)); torch's generator, so
+    not the same columns as the numpy version.  Returns device tensors (tipmask uint8 [S, L], weights float64
+    [L]) -- the alignment never touches the host, which is what the 10 000 x 1 000 000 shape needs."""
+    import torch
+    S = peel.shape[0] + 1
+    freqs = np.asarray(freqs)
+    Q = gtr_q(np.asarray(rates), freqs)
+    sq = np.sqrt(freqs)
+    A = sq[:, None] * Q / sq[None, :]
+    lam, U = np.linalg.eigh((A + A.T) / 2)
+    m1, m2 = U / sq[:, None], U.T * sq[None, :]
+    rs = weibull_rates(wshape, C)
+    tau = blens[:, None] * rs[None, :]                                              # [2S-2, C]
+    P = np.einsum("ik,bck,kj->bcij", m1, np.exp(lam[None, None, :] * tau[:, :, None]), m2)
+    cum = np.cumsum(P, axis=3)[:, :, :, :3].reshape(2 * S - 2, C * 4, 3)              # [branch, cat*4 + parent, 3]
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    cum_d = torch.from_numpy(np.ascontiguousarray(cum)).to(device)
+    cat4 = torch.randint(0, C, (L,), generator=g, device=device) * 4
+    tips = torch.empty((S, L), dtype=torch.uint8, device=device)
+    internal = torch.empty((S - 1, L), dtype=torch.uint8, device=device)               # states of nodes S .. 2S-2
+    pi_cum = torch.from_numpy(np.cumsum(freqs)[:3].copy()).to(device)
+    internal[S - 2] = (torch.rand(L, generator=g, device=device, dtype=torch.float64)[:, None] > pi_cum).sum(1).to(torch.uint8)
+    for row in peel[::-1]:  # parents before children
+        par = internal[row[2] - 1 - S].long() + cat4
+        for child in (int(row[0]) - 1, int(row[1]) - 1):
+            u = torch.rand(L, generator=g, device=device, dtype=torch.float64)
+            st = (u[:, None] > cum_d[child][par]).sum(1).to(torch.uint8)
+            if child < S:
+                tips[child] = st
+            else:
+                internal[child - S] = st
+    del internal
+    tipmask = torch.bitwise_left_shift(torch.ones((), dtype=torch.uint8, device=device), tips)
+    del tips
+    for s0 in range(0, S, 256):   # ambiguity in slabs: no [S, L] float temporary
+        blk = tipmask[s0:s0 + 256]
+        blk[torch.rand(blk.shape, generator=g, device=device) < ambiguous] = 0xF
+    weights = 1.0 + torch.poisson(torch.ones(L, device=device, dtype=torch.float64), generator=g)
+    return tipmask, weights
 
 
 @dataclass
