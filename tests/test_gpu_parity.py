@@ -84,6 +84,36 @@ def test_gpu_eigen_operator_surface_and_quirk():
         lk.set_default(None)
 
 
+def test_gpu_gtr_transition_matrices_match_reference_numpy_gtr():
+    """The device P-matrix kernel against the reference's NumPy GTR class (scripts/phylo.py:4-61 via
+    tests/golden/gtr_pt.json).  A two-taxon tree with tip states (x, y) and branch lengths (t, 0) has
+    L = pi_x P(t)[x, y], so every entry of P(t) is read back from a log-likelihood."""
+    cases = json.load(open(os.path.join(GOLDEN, "gtr_pt.json")))["cases"]
+    peel2 = np.array([[1, 2, 3]], dtype=np.int32)
+    # all 16 tip-state pairs as 16 patterns; weights pick one pattern at a time via 16 handles of one pattern
+    handles = {}
+    try:
+        for x in range(4):
+            for y in range(4):
+                handles[x, y] = lk.TreeLikelihood(peel2, np.array([[1 << x], [1 << y]], dtype=np.uint8), None,
+                                                  model="GTR", categories=1)
+        groups = {}
+        for c in cases:
+            groups.setdefault((tuple(c["rates"]), tuple(c["pi"])), []).append(c)
+        for (rates, pi), cs in groups.items():
+            B = len(cs)
+            bl = np.array([[c["t"], 0.0] for c in cs])
+            P = np.zeros((B, 4, 4))
+            for (x, y), h in handles.items():
+                lp = h.loglik(bl, np.tile(rates, (B, 1)), np.tile(pi, (B, 1)), np.ones((B, 1)), np.ones((B, 1)))
+                P[:, x, y] = np.exp(lp) / pi[x]
+            for i, c in enumerate(cs):
+                np.testing.assert_allclose(P[i], np.array(c["P"]), rtol=1e-10, atol=2e-14, err_msg=str((c["tag"], c["t"])))
+    finally:
+        for h in handles.values():
+            h.close()
+
+
 # --------------------------------------------------------------------------- real data sets
 
 @pytest.mark.parametrize("name,model,rooted", [("fluA", O.HKY, True), ("DS1", O.GTR, False), ("HCV", O.GTR, True),
