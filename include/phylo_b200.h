@@ -90,6 +90,22 @@ PHYLO_B200_API int phylo_b200_create_device(phylo_b200_handle *out, int S, int L
                                             const int32_t *peel, const uint8_t *d_tipmask, const double *d_weights,
                                             int device);
 
+/*
+ * One handle, N devices of this box (`devices, ndev`): the site patterns are cut into ndev
+ * contiguous shards (shard i = patterns [L i / ndev, L (i+1) / ndev) on devices[i]), every device holds the
+ * full tree, and every evaluation entry point of this header (eval, eval_batch, eval_heights*, upload / run /
+ * download) runs all shards concurrently on their own streams and adds the shards' result rows on
+ * devices[0] -- peer loads over NVLink when the devices can access each other, staged peer copies otherwise
+ * -- so the Stan-facing call shape (eigen/prune_stan.hpp:9-17) reaches every GPU from one process.  The
+ * exchange is the one the pattern sum `target += log(...) * weights[i]` (generate_script.py:1010) needs:
+ * [B][nout] doubles per evaluation.  device_out / download / get_timing refer to devices[0]; a device may be
+ * listed more than once (two shards on one GPU; used by the single-GPU tests).  ndev == 1 is phylo_b200_create.
+ * phylo_b200_info(h, 12) returns the number of shards.
+ */
+PHYLO_B200_API int phylo_b200_create_multi(phylo_b200_handle *out, int S, int L, int C, int model, int flags,
+                                           const int32_t *peel, const uint8_t *tipmask, const double *weights,
+                                           const int *devices, int ndev);
+
 PHYLO_B200_API void phylo_b200_destroy(phylo_b200_handle h);
 
 /* sizes of the per-evaluation arrays */
@@ -210,7 +226,8 @@ PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
 
 /* Introspection: what = 0 stack depth D, 1 patterns per thread, 2 threads per CTA, 3 grid size,
  * 4 dynamic shared memory bytes, 5 padded pattern count, 6 kernels launched by the last run,
- * 7 scratch bytes allocated on the device, 8 / 9 post- / pre-order stack depth, 10 pattern tiles. */
+ * 7 scratch bytes allocated on the device, 8 / 9 post- / pre-order stack depth, 10 pattern tiles,
+ * 11 shared-memory stack slots of the last run, 12 pattern shards (devices) behind the handle. */
 PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 
 /*

@@ -1325,6 +1325,18 @@ __global__ void __launch_bounds__(256) weights_pad_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// K5: multi-device handles -- add the other shards' result rows (peer memory) to this device's
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) peer_sum_kernel(double* __restrict__ out, const PeerRows peers, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        double s = out[i];
+        for (int p = 0; p < peers.n; ++p) s += peers.src[p][i];  // shard order: the sum is reproducible
+        out[i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------
 
@@ -1447,6 +1459,11 @@ void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream) {
     const size_t total = (size_t)S * Lpad;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
     tips_index_kernel<<<grid, 256, 0, stream>>>(d_tips, total);
+}
+
+void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStream_t stream) {
+    const int grid = (int)std::min<size_t>((count + 255) / 256, 148);
+    peer_sum_kernel<<<grid, 256, 0, stream>>>(out, peers, count);
 }
 
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream) {

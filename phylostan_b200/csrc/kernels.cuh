@@ -131,6 +131,15 @@ void launch_tips_prepare(const uint8_t* d_src, uint8_t* d_dst, int S, int L, int
                          int* d_flags, cudaStream_t stream);
 void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream);  // masks -> column indices
 
+// multi-device handles: out[i] += sum_p src[p][i]; the sources are the other shards' result blocks (peer
+// memory read over NVLink, or staged copies of them on this device)
+constexpr int kMaxPeers = 15;
+struct PeerRows {
+    const double* src[kMaxPeers];
+    int n;
+};
+void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStream_t stream);
+
 // jc: the scalar-statistic kernel needs no reduction rows
 size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false);
 size_t sweep_stack_bytes(int D, int K, int nthreads, int prec);  // first region of the above

@@ -124,8 +124,25 @@ struct phylo_b200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false, ev_has_contract = false;
 
+    // multi-device handle (phylo_b200_create_multi): this context is pattern shard 0, `peers` are the shards on
+    // the other devices.  Every evaluation forks from this context's stream (fork_ev), runs all shards on their
+    // own streams and joins on peer_ev[i]; the peers' result rows are then added to d_out here -- read in place
+    // over NVLink (peer_direct[i]) or from d_stage after a peer copy.
+    std::vector<phylo_b200_ctx*> peers;
+    std::vector<cudaEvent_t> peer_ev;
+    std::vector<char> peer_direct;
+    cudaEvent_t fork_ev = nullptr;
+    DevBuf<double> d_stage;
+    bool is_peer = false;  // peers need no pinned staging buffers of their own
+
     ~phylo_b200_ctx() {
+        for (size_t i = 0; i < peers.size(); ++i) {
+            if (i < peer_ev.size() && peer_ev[i]) { cudaSetDevice(peers[i]->device); cudaEventDestroy(peer_ev[i]); }
+            delete peers[i];
+        }
         cudaSetDevice(device);
+        if (fork_ev) cudaEventDestroy(fork_ev);
+        d_stage.release();
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
@@ -239,8 +256,11 @@ int ensure_batch(phylo_b200_ctx* h, int B) {
     CU_TRY(h->d_spre.ensure((size_t)B * h->C * (h->S - 1) * kRecBytes));
     CU_TRY(h->d_G.ensure((size_t)B * h->nn * h->C * 16));
     CU_TRY(h->d_out.ensure((size_t)B * h->nout));
-    CU_TRY(h->h_params.ensure((size_t)B * h->lay.stride));
-    CU_TRY(h->h_out.ensure((size_t)B * h->nout));
+    if (!h->is_peer) {
+        CU_TRY(h->h_params.ensure((size_t)B * h->lay.stride));
+        CU_TRY(h->h_out.ensure((size_t)B * h->nout));
+        if (!h->peers.empty()) CU_TRY(h->d_stage.ensure(h->peers.size() * (size_t)B * h->nout));
+    }
     return 0;
 }
 
@@ -455,6 +475,67 @@ int phylo_b200_create_device(phylo_b200_handle* out, int S, int L, int C, int mo
     return create_common(out, S, L, C, model, flags, peel, d_tipmask, nullptr, d_weights, device, true);
 }
 
+int phylo_b200_create_multi(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
+                            const uint8_t* tipmask, const double* weights, const int* devices, int ndev) {
+    if (!out) return fail(PHYLO_B200_EINVAL, "out handle is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > kMaxPeers + 1)
+        return fail(PHYLO_B200_EINVAL, "create_multi: need 1 <= ndev <= " + std::to_string(kMaxPeers + 1) + " devices");
+    if (ndev == 1) return create_common(out, S, L, C, model, flags, peel, tipmask, nullptr, weights, devices[0]);
+    if (!tipmask || S < 2 || L < ndev) return fail(PHYLO_B200_EINVAL, "create_multi: need tip masks and at least one pattern per device");
+    std::vector<phylo_b200_ctx*> ctx;
+    auto bail = [&](int rc) {
+        const std::string keep = g_err;
+        for (auto* c : ctx) delete c;
+        g_err = keep;
+        return rc;
+    };
+    for (int i = 0; i < ndev; ++i) {
+        const int lo = (int)((long long)L * i / ndev), hi = (int)((long long)L * (i + 1) / ndev), Li = hi - lo;
+        std::vector<uint8_t> tm((size_t)S * Li);
+        for (int s = 0; s < S; ++s) std::memcpy(tm.data() + (size_t)s * Li, tipmask + (size_t)s * L + lo, (size_t)Li);
+        phylo_b200_ctx* c = nullptr;
+        if (int rc = create_common(&c, S, Li, C, model, flags, peel, tm.data(), nullptr, weights ? weights + lo : nullptr,
+                                   devices[i]))
+            return bail(rc);
+        ctx.push_back(c);
+    }
+    phylo_b200_ctx* h = ctx[0];
+    const char* nop = std::getenv("PHYLO_B200_NO_P2P");
+    const bool allow_p2p = !(nop && nop[0] && nop[0] != '0');
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming);
+    for (int i = 1; i < ndev && e == cudaSuccess; ++i) {
+        phylo_b200_ctx* p = ctx[i];
+        bool direct = p->device == h->device;
+        if (!direct && allow_p2p) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, h->device, p->device) == cudaSuccess && can) {
+                cudaSetDevice(h->device);
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(p->device, 0);
+                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) direct = true;
+                (void)cudaGetLastError();
+            }
+        }
+        cudaEvent_t ev = nullptr;
+        e = cudaSetDevice(p->device);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        p->is_peer = true;
+        h->peers.push_back(p);
+        h->peer_ev.push_back(ev);
+        h->peer_direct.push_back(direct ? 1 : 0);
+    }
+    if (e != cudaSuccess) {
+        for (int i = (int)h->peers.size() + 1; i < ndev; ++i) delete ctx[i];  // not yet owned by h
+        delete h;
+        return fail(PHYLO_B200_ECUDA, std::string("create_multi: ") + cudaGetErrorString(e));
+    }
+    cudaSetDevice(h->device);
+    h->use_graphs = false;
+    *out = h;
+    return 0;
+}
+
 void phylo_b200_destroy(phylo_b200_handle h) {
     if (h && h == g_default) g_default = nullptr;
     delete h;
@@ -486,6 +567,7 @@ int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int patt
         return fail(PHYLO_B200_EINVAL, "pattern_blocks must be 0, 1, 2 or 4");
     h->req_K = patterns_per_thread;
     h->req_PB = pattern_blocks;
+    for (auto* p : h->peers) { p->req_K = patterns_per_thread; p->req_PB = pattern_blocks; }
     return 0;
 }
 
@@ -493,6 +575,7 @@ int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     if (slots < 0) return fail(PHYLO_B200_EINVAL, "slots must be >= 0 (0 = automatic)");
     h->req_cap = slots;
+    for (auto* p : h->peers) p->req_cap = slots;
     return 0;
 }
 
@@ -500,6 +583,7 @@ int phylo_b200_set_precision(phylo_b200_handle h, int bits) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     if (bits != 32 && bits != 64) return fail(PHYLO_B200_EINVAL, "precision must be 64 or 32");
     h->prec = bits;
+    for (auto* p : h->peers) p->prec = bits;
     return 0;
 }
 
@@ -539,6 +623,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 9: return h->plan.depth_pre;
         case 10: return h->ntiles;
         case 11: return h->slots;
+        case 12: return 1 + (long long)h->peers.size();
     }
     return PHYLO_B200_EINVAL;
 }
@@ -550,6 +635,11 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
     if (!h || B < 1 || !blens) return fail(PHYLO_B200_EINVAL, "upload: bad arguments");
     if (h->nsubst > 0 && !subst) return fail(PHYLO_B200_EINVAL, "upload: subst is NULL");
     if (h->model != PHYLO_B200_JC69 && !freqs) return fail(PHYLO_B200_EINVAL, "upload: freqs is NULL");
+    for (auto* p : h->peers) {  // the shards on the other devices read the same packed block
+        CU_TRY(cudaSetDevice(p->device));
+        if (int rc = ensure_batch(p, B)) return rc;
+        CU_TRY(cudaStreamSynchronize(p->stream));
+    }
     CU_TRY(cudaSetDevice(h->device));
     if (int rc = ensure_batch(h, B)) return rc;
     // the pinned staging buffer may still feed a copy in flight
@@ -568,6 +658,12 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
 int phylo_b200_upload(phylo_b200_handle h, int B, const double* blens, const double* subst, const double* freqs,
                       const double* rs, const double* ps) {
     if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps)) return rc;
+    for (auto* p : h->peers) {
+        CU_TRY(cudaSetDevice(p->device));
+        CU_TRY(cudaMemcpyAsync(p->d_params.p, h->h_params.p, sizeof(double) * B * h->lay.stride, cudaMemcpyHostToDevice,
+                               p->stream));
+    }
+    CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, sizeof(double) * B * h->lay.stride, cudaMemcpyHostToDevice,
                            h->stream));
     return 0;
@@ -590,12 +686,61 @@ int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
 
 int run_enqueue(phylo_b200_ctx* h, int B, bool grad);
 
+// run_prepare on every shard of the handle
+int run_prepare_all(phylo_b200_ctx* h, int B, bool grad) {
+    for (auto* p : h->peers) {
+        CU_TRY(cudaSetDevice(p->device));
+        if (int rc = run_prepare(p, B, grad)) return rc;
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    return run_prepare(h, B, grad);
+}
+
+// Multi-device handle: fork from this context's stream, run every shard on its own device and stream, join,
+// and add the peers' result rows to d_out on this device.  with_copies: H2D of the packed parameters (from
+// this context's pinned block) before, D2H of the summed rows after.
+int multi_enqueue(phylo_b200_ctx* h, int B, bool grad, bool with_copies) {
+    const size_t in_bytes = sizeof(double) * B * h->lay.stride, count = (size_t)B * h->nout;
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaEventRecord(h->fork_ev, h->stream));
+    for (size_t i = 0; i < h->peers.size(); ++i) {
+        phylo_b200_ctx* p = h->peers[i];
+        CU_TRY(cudaSetDevice(p->device));
+        CU_TRY(cudaStreamWaitEvent(p->stream, h->fork_ev, 0));  // also orders the peer's memsets after the last sum
+        if (with_copies) CU_TRY(cudaMemcpyAsync(p->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, p->stream));
+        if (int rc = run_enqueue(p, B, grad)) return rc;
+        CU_TRY(cudaEventRecord(h->peer_ev[i], p->stream));
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    if (with_copies) CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = run_enqueue(h, B, grad)) return rc;
+    PeerRows rows{};
+    rows.n = (int)h->peers.size();
+    for (size_t i = 0; i < h->peers.size(); ++i) {
+        phylo_b200_ctx* p = h->peers[i];
+        CU_TRY(cudaStreamWaitEvent(h->stream, h->peer_ev[i], 0));
+        if (h->peer_direct[i]) {
+            rows.src[i] = p->d_out.p;
+        } else {
+            double* dst = h->d_stage.p + i * count;
+            CU_TRY(cudaMemcpyPeerAsync(dst, h->device, p->d_out.p, p->device, sizeof(double) * count, h->stream));
+            rows.src[i] = dst;
+        }
+    }
+    launch_peer_sum(h->d_out.p, rows, count, h->stream);
+    CU_TRY(cudaGetLastError());
+    h->last_launches += 1;
+    if (with_copies)
+        CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
 }  // namespace
 
 int phylo_b200_run(phylo_b200_handle h, int B, int want_grad) {
     if (!h || B < 1) return fail(PHYLO_B200_EINVAL, "run: bad arguments");
-    CU_TRY(cudaSetDevice(h->device));
-    if (int rc = run_prepare(h, B, want_grad != 0)) return rc;
+    if (int rc = run_prepare_all(h, B, want_grad != 0)) return rc;
+    if (!h->peers.empty()) return multi_enqueue(h, B, want_grad != 0, false);
     return run_enqueue(h, B, want_grad != 0);
 }
 
@@ -666,6 +811,7 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
 int eval_enqueue(phylo_b200_ctx* h, int B, bool grad) {
+    if (!h->peers.empty()) return multi_enqueue(h, B, grad, true);  // one stream per device: plain launches
     const size_t in_bytes = sizeof(double) * B * h->lay.stride, out_bytes = sizeof(double) * B * h->nout;
     const bool graphable = h->use_graphs && !h->timing && h->stream != nullptr;
     if (!graphable) {
@@ -736,7 +882,7 @@ int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double* blens, const
                           double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
     if (!h || !logp) return fail(PHYLO_B200_EINVAL, "eval: NULL handle or logp");
     if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps)) return rc;
-    if (int rc = run_prepare(h, B, want_grad != 0)) return rc;
+    if (int rc = run_prepare_all(h, B, want_grad != 0)) return rc;
     if (int rc = eval_enqueue(h, B, want_grad != 0)) return rc;
     CU_TRY(cudaStreamSynchronize(h->stream));
     bool finite = true;

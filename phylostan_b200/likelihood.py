@@ -62,6 +62,8 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_create_tipdata.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, _dp, _dp, i]
     if hasattr(L, "phylo_b200_create_device"):  # absent from older A/B builds (tools/ab_sweep.py)
         L.phylo_b200_create_device.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, vp, vp, i]
+    if hasattr(L, "phylo_b200_create_multi"):
+        L.phylo_b200_create_multi.argtypes = [ctypes.POINTER(vp), i, i, i, i, i, ip, bp, _dp, ip, i]
     L.phylo_b200_destroy.argtypes = [vp]
     L.phylo_b200_destroy.restype = None
     for name in ("bcount", "nsubst", "ncat", "nout", "sync"):
@@ -140,9 +142,12 @@ class TreeLikelihood:
     """
 
     def __init__(self, peel, tipmask=None, weights=None, *, tipdata=None, model="GTR", categories: int = 1,
-                 rooted: bool = True, normalize: bool = True, device: int = 0, device_tips=None):
+                 rooted: bool = True, normalize: bool = True, device: int = 0, device_tips=None,
+                 devices: Optional[Sequence[int]] = None):
         """``device_tips`` = (tipmask_ptr, L, weights_ptr or None): the alignment is already resident on
-        ``device`` as uint8 [S, L] masks / float64 [L] weights (e.g. torch tensors' ``data_ptr()``)."""
+        ``device`` as uint8 [S, L] masks / float64 [L] weights (e.g. torch tensors' ``data_ptr()``).
+        ``devices`` = several CUDA ordinals: ONE handle whose site patterns are sharded over those GPUs
+        (``phylo_b200_create_multi``); every call below then runs all shards and returns their sum."""
         L_ = lib()
         self._h = None
         self.model = MODELS[model] if isinstance(model, str) else int(model)
@@ -173,7 +178,22 @@ class TreeLikelihood:
                 raise ValueError("weights must be [L]")
             rc = L_.phylo_b200_create_tipdata(ctypes.byref(h), self.S, self.L, self.C, self.model, flags,
                                               peel.ctypes.data_as(ip), _ptr(td), _ptr(w), self.device)
+        elif devices is not None and len(devices) > 1:
+            tm = np.ascontiguousarray(tipmask, dtype=np.uint8)
+            if tm.ndim != 2 or tm.shape[0] != self.S:
+                raise ValueError("tipmask must be [S, L]")
+            self.L = tm.shape[1]
+            if w is not None and w.shape != (self.L,):
+                raise ValueError("weights must be [L]")
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            self.device = int(dv[0])
+            rc = L_.phylo_b200_create_multi(ctypes.byref(h), self.S, self.L, self.C, self.model, flags,
+                                            peel.ctypes.data_as(ip),
+                                            tm.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _ptr(w),
+                                            dv.ctypes.data_as(ip), len(dv))
         else:
+            if devices is not None and len(devices) == 1:
+                self.device = int(devices[0])
             tm = np.ascontiguousarray(tipmask, dtype=np.uint8)
             if tm.ndim != 2 or tm.shape[0] != self.S:
                 raise ValueError("tipmask must be [S, L]")
@@ -310,7 +330,7 @@ class TreeLikelihood:
 
     def info(self) -> dict:
         names = ["stack_depth", "patterns_per_thread", "threads_per_cta", "grid", "smem_bytes", "padded_patterns",
-                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots"]
+                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots", "shards"]
         return {n: int(lib().phylo_b200_info(self._h, k)) for k, n in enumerate(names)}
 
     def unpack(self, out: np.ndarray) -> ValueGrad:

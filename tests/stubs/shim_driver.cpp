@@ -6,6 +6,7 @@
 #include <cmath>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <vector>
@@ -62,7 +63,18 @@ int main(int argc, char** argv) {
     std::fclose(f);
     if (!ok) return 5;
     phylo_b200_handle h = 0;
-    if (phylo_b200_create(&h, S, L, C, model, flags, peel.data(), tips.data(), w.data(), 0)) {
+    // PHYLO_SHIM_DEVICES="0,1,...": one handle over several GPUs (phylo_b200_create_multi); the Stan-facing
+    // calls below are unchanged
+    std::vector<int> devs;
+    if (const char* dv = std::getenv("PHYLO_SHIM_DEVICES"))
+        for (const char* q = dv; *q;) {
+            devs.push_back(std::atoi(q));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+    if (devs.size() > 1 ? phylo_b200_create_multi(&h, S, L, C, model, flags, peel.data(), tips.data(), w.data(), devs.data(),
+                                                   (int)devs.size())
+                        : phylo_b200_create(&h, S, L, C, model, flags, peel.data(), tips.data(), w.data(), 0)) {
         std::fprintf(stderr, "create: %s\n", phylo_b200_last_error());
         return 6;
     }

@@ -724,3 +724,60 @@ def test_gpu_fp32_mode_deep_tree_rescaling():
         got = lik.value_grad(bl, synth.RATES0, synth.FREQS0, rs, ps)
     assert abs(got.log_P - want.logp) <= 5e-6 * abs(want.logp)
     assert np.max(np.abs(got.grad_blens - want.grad_blens)) <= 1e-3 * max(1.0, np.max(np.abs(want.grad_blens)))
+
+
+def _device_lists():
+    """Shard layouts the box can run: several shards on GPU 0 always, real device lists when there are more GPUs."""
+    import torch
+    n = torch.cuda.device_count()
+    lists = [[0, 0], [0, 0, 0]]
+    if n >= 2:
+        lists += [list(range(n)), [1, 0]]
+    return lists
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,model,rooted,C", [("DS1", O.GTR, False, 4), ("fluA", O.HKY, True, 4), ("HCV", O.JC69, True, 1)])
+@pytest.mark.parametrize("p2p", [True, False])
+def test_gpu_multi_device_handle_matches_oracle(datasets, monkeypatch, name, model, rooted, C, p2p):
+    """phylo_b200_create_multi: ONE handle whose pattern shards sit on several devices (or several shards on one);
+    the single-call entry points return the sum over shards -- against the oracle on the whole alignment, with
+    the peers' rows read over peer memory (p2p) or staged by cudaMemcpyPeer (PHYLO_B200_NO_P2P=1)."""
+    if not p2p:
+        monkeypatch.setenv("PHYLO_B200_NO_P2P", "1")
+    d = datasets[name]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(77)
+    B = 5
+    draws = [random_params(model, S, rooted, C, rng) for _ in range(B)]
+    wants = [O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, *p, rooted=rooted) for p in draws]
+    stack = lambda k: (np.stack([p[k] for p in draws]) if draws[0][k] is not None and np.size(draws[0][k]) else None)
+    for devs in _device_lists():
+        with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model=model, categories=C, rooted=rooted,
+                               devices=devs) as lik:
+            assert lik.info()["shards"] == len(devs)
+            got1 = lik.value_grad(*draws[0])                               # phylo_b200_eval
+            assert_parity(got1, wants[0], jc=model == O.JC69)
+            assert abs(lik.loglik(*draws[1]) - wants[1].logp) <= RTOL_LOGP * abs(wants[1].logp)   # value only
+            vg = lik.value_grad(stack(0), stack(1), stack(2), stack(3), stack(4))               # phylo_b200_eval_batch
+            lik.upload(stack(0), stack(1), stack(2), stack(3), stack(4))                       # split form
+            for _ in range(3):                                            # back-to-back runs: the fork/join ordering
+                lik.run(B, True)
+            rows = lik.download(B)
+            for b in range(B):
+                one = lk.ValueGrad(float(vg.log_P[b]), vg.grad_blens[b], vg.grad_subst[b], vg.grad_freqs[b], vg.grad_rs[b],
+                                   vg.grad_ps[b])
+                assert_parity(one, wants[b], jc=model == O.JC69)
+                u = lik.unpack(rows[b:b + 1])
+                assert_parity(lk.ValueGrad(float(u.log_P[0]), u.grad_blens[0], u.grad_subst[0], u.grad_freqs[0], u.grad_rs[0],
+                                           u.grad_ps[0]), wants[b], jc=model == O.JC69)
+
+
+@pytest.mark.gpu
+def test_gpu_multi_device_handle_errors(datasets):
+    d = datasets["DS1"]
+    with pytest.raises(lk.PhyloB200Error):     # more shards than patterns
+        lk.TreeLikelihood(d["peel"], d["tipmask"][:, :2], d["weights"][:2], model="GTR", categories=4, rooted=False,
+                          devices=[0, 0, 0])
+    with pytest.raises(lk.PhyloB200Error):     # a device that does not exist
+        lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=False, devices=[0, 99])

@@ -117,8 +117,11 @@ def test_shim_compiles_as_cxx14_and_fails_loudly_without_handle(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,model,rooted,C", [("fluA", 1, True, 4), ("DS1", 2, False, 4), ("HCV", 0, True, 1)])
-def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, model, rooted, C):
+@pytest.mark.parametrize("name,model,rooted,C,devices", [("fluA", 1, True, 4, ""), ("DS1", 2, False, 4, ""), ("HCV", 0, True, 1, ""),
+                                                         ("DS1", 2, False, 4, "multi"), ("fluA", 1, True, 4, "multi")])
+def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, model, rooted, C, devices):
+    """devices == "multi": the same Stan-facing calls over ONE multi-device handle (phylo_b200_create_multi): every
+    visible GPU, or three pattern shards on GPU 0 when the box has one."""
     from oracle import oracle as O
     from phylostan_b200 import encode as E
     d = datasets[name]
@@ -154,7 +157,12 @@ def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, mo
                 f.write(np.ascontiguousarray(a, dtype=np.float64).tobytes())
         args.append(str(hpath))
     exe = _build_driver(tmp_path)
-    r = subprocess.run([exe] + args, capture_output=True, text=True)
+    env = dict(os.environ)
+    if devices == "multi":
+        import torch
+        n = torch.cuda.device_count()
+        env["PHYLO_SHIM_DEVICES"] = ",".join(str(i) for i in range(n)) if n > 1 else "0,0,0"
+    r = subprocess.run([exe] + args, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     got = json.loads(r.stdout.strip().splitlines()[-1])
     if rooted:
