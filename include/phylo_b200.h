@@ -170,6 +170,37 @@ PHYLO_B200_API int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const i
                                                     double *g_freqs, double *g_rs, double *g_ps);
 
 /*
+ * The same front ends for B draws with the heights -> blens step and its reverse sweep ON THE DEVICE
+ * (generate_script.py:660-679 / :682-708 as a kernel in front of the P-matrix
+ * kernel, the d/dheights and d/drates gather as a kernel behind the contraction; one H2D of
+ * [heights | rates], one D2H of the results, no host loop over branches).  autocorr selects the :682-708 form.
+ * heights [B][S-1], rates [B][nrates], outputs with leading dimension B; the map and `lowers` are uploaded once
+ * per distinct map.  A draw whose heights give a negative or non-finite branch length fails the call with
+ * PHYLO_B200_EDOMAIN (as phylo_b200_eval_batch does for such blens).
+ */
+PHYLO_B200_API int phylo_b200_eval_heights_batch(phylo_b200_handle h, int autocorr, const int32_t *map, int B,
+                                                 const double *heights, const double *lowers, const double *rates,
+                                                 int nrates, const double *subst, const double *freqs,
+                                                 const double *rs, const double *ps, int want_grad, double *logp,
+                                                 double *g_heights, double *g_rates, double *g_subst,
+                                                 double *g_freqs, double *g_rs, double *g_ps);
+
+/*
+ * ... and with the ratio parametrisation of the heights on the device as well (generate_script.py:711-735
+ * `transform`, :738-752 its log-Jacobian): props [B][S-2] (pre-order of the internal non-root nodes) and
+ * root_height [B] in; logp [B] (likelihood only), logjac [B], heights [B][S-1] (optional) out.  The reverse
+ * sweep returns d(logp + logjac)/dprops [B][S-2] and /droot_height [B]; hbar_extra [B][S-1] (optional) is an
+ * additional adjoint of the heights -- a tree prior's gradient -- pushed through the same sweep.
+ */
+PHYLO_B200_API int phylo_b200_eval_ratios_batch(phylo_b200_handle h, int autocorr, const int32_t *map, int B,
+                                                const double *props, const double *root_height, const double *lowers,
+                                                const double *rates, int nrates, const double *subst,
+                                                const double *freqs, const double *rs, const double *ps,
+                                                const double *hbar_extra, int want_grad, double *logp, double *logjac,
+                                                double *heights, double *g_props, double *g_root, double *g_rates,
+                                                double *g_subst, double *g_freqs, double *g_rs, double *g_ps);
+
+/*
  * Host-only helpers (no GPU) for drivers that keep the ratio parametrisation of the node heights outside
  * Stan: heights = transform(props, root_height, map, lowers) of phylostan/generate_script.py:711-735
  * with its log-Jacobian (:738-752), for B draws, and the reverse sweep through it.  props [B][S-2] are

@@ -508,6 +508,49 @@ class ClockModel(_ModelBase):
             gth -= np.bincount(rows * G + g_at.ravel(), weights=coal.ravel().astype(float), minlength=B * G).reshape(B, G)
         return logp, gt[:, S:nn], gth
 
+    def _device_front_end(self) -> bool:
+        """The handle runs heights -> blens and the reverse sweeps on the device (PHYLO_B200_HOST_FRONT_END=1: keep them here)."""
+        import os
+        return hasattr(self.lik, "value_grad_ratios_batch") and os.environ.get("PHYLO_B200_HOST_FRONT_END", "0") in ("", "0")
+
+    def _likelihood_ratios(self, sub, rs_, ps_, hbar_extra, want_grad):
+        """One ``phylo_b200_eval_ratios_batch`` call: (logL, site-model gradients, d/dprops, d/droot height, d/drate(s)),
+        the last three with the tree prior's ``hbar_extra`` and the log-Jacobian included.  A rejected batch is retried
+        draw by draw; a rejected draw is -inf with a zero gradient (as ``_likelihood``)."""
+        from .likelihood import ValueGrad
+        n = sub["props"].shape[0]
+        rates = sub["rate"][:, None] if self.clock == "strict" else sub["substrates"]
+        subst = self._subst_arg(sub)
+
+        def call(sl):
+            cut = lambda a: None if a is None else a[sl]
+            return self.lik.value_grad_ratios_batch(self.map32, sub["props"][sl], sub["height"][sl], rates[sl], self.lowers_or_none,
+                                                    cut(subst), cut(sub.get("freqs")), rs_[sl], ps_[sl],
+                                                    hbar_extra=cut(hbar_extra), want_grad=want_grad)
+        try:
+            parts = [call(slice(None))]
+        except Exception as e:
+            if type(e).__name__ != "PhyloDomainError":
+                raise
+            parts = []
+            for i in range(n):
+                try:
+                    parts.append(call(slice(i, i + 1)))
+                except Exception as e1:
+                    if type(e1).__name__ != "PhyloDomainError":
+                        raise
+                    z = lambda k: np.zeros((1, k))
+                    parts.append({"logp": np.full(1, -np.inf), "g_props": z(self.S - 2), "g_root": np.zeros(1),
+                                  "g_rates": z(rates.shape[1]),
+                                  "rest": ValueGrad(np.full(1, -np.inf), None, z(max(self.lik.nsubst, 0)), z(4), z(self.C), z(self.C))})
+        cat = lambda f: np.concatenate([f(p) for p in parts])
+        ll = cat(lambda p: p["logp"])
+        if not want_grad:
+            return ll, None, None, None, None
+        vg = ValueGrad(ll, None, cat(lambda p: p["rest"].grad_subst), cat(lambda p: p["rest"].grad_freqs),
+                       cat(lambda p: p["rest"].grad_rs), cat(lambda p: p["rest"].grad_ps))
+        return ll, vg, cat(lambda p: p["g_props"]), cat(lambda p: p["g_root"]), cat(lambda p: p["g_rates"])
+
     def log_prob_grad(self, Z: np.ndarray, want_grad: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
         Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
         B = Z.shape[0]
@@ -534,10 +577,16 @@ class ClockModel(_ModelBase):
         n = span.shape[0]
         h = sub["heights"]
         rate_b = sub["rate"][:, None] if strict else sub["substrates"][:, self.node]     # per pre-order row
-        blens = np.empty((n, self.bcount))
-        blens[:, self.node] = rate_b * span                                          # generate_script.py:660-679
-        args = (blens, self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
-        ll, vg = self._likelihood(args, want_grad)
+        # heights -> blens, the likelihood and the reverse sweeps down to d/dprops run in ONE library call on the
+        # device when the handle offers it (phylo_b200_eval_ratios_batch); the tree prior is evaluated first so
+        # that its adjoint of the heights rides through the same sweep.  Otherwise (pattern shards over
+        # torch.distributed, the CPU tests' stand-in likelihoods) the chain rule is done here.
+        device_front = self._device_front_end()
+        if not device_front:
+            blens = np.empty((n, self.bcount))
+            blens[:, self.node] = rate_b * span                                      # generate_script.py:660-679
+            args = (blens, self._subst_arg(sub), sub.get("freqs"), rs_, ps_)
+            ll, vg = self._likelihood(args, want_grad)
         prior = self._prior_common(sub)
         if constant:
             theta = sub["theta"]
@@ -565,33 +614,41 @@ class ClockModel(_ModelBase):
             resid = ls - mu[:, None]
             prior += (-ls - resid ** 2 / (2.0 * sd[:, None] ** 2)).sum(axis=1) - self.bcount * np.log(sd)
             prior += -1000.0 * mean + (0.5396 - 1.0) * np.log(sd) - 2.6184 * sd
+        if device_front:
+            ll, vg, gp, g_root, g_lik_rates = self._likelihood_ratios(sub, rs_, ps_, g_coal_h if want_grad else None, want_grad)
         lp[idx] = ll + prior + sub["logjac_heights"] + sub["logj"]
         if not want_grad:
             return lp, None
         g = np.zeros((n, self.dim))
-        gb = np.reshape(vg.grad_blens, (n, self.bcount))[:, self.node]               # per pre-order row
-        w = rate_b * gb
-        hbar = g_coal_h + (w @ self.scatter_blens if isinstance(self.scatter_blens, np.ndarray)
-                           else (self.scatter_blens @ w.T).T)
-        # reverse sweep of the ratio transform and of its log-Jacobian (library host code)
-        from .likelihood import ratios_reverse
-        gp, g_root = ratios_reverse(self.map32, self.lowers_or_none, sub["props"], h, hbar)
+        if device_front:
+            gb_span = g_lik_rates                                                    # d logL / d rate(s): [n, 1] or node order
+        else:
+            gb = np.reshape(vg.grad_blens, (n, self.bcount))[:, self.node]           # per pre-order row
+            w = rate_b * gb
+            hbar = g_coal_h + (w @ self.scatter_blens if isinstance(self.scatter_blens, np.ndarray)
+                               else (self.scatter_blens @ w.T).T)
+            # reverse sweep of the ratio transform and of its log-Jacobian (library host code)
+            from .likelihood import ratios_reverse
+            gp, g_root = ratios_reverse(self.map32, self.lowers_or_none, sub["props"], h, hbar)
+            if strict:
+                gb_span = (gb * span).sum(axis=1)[:, None]
+            else:
+                gb_span = np.zeros((n, self.bcount))
+                gb_span[:, self.node] = gb * span                                    # likelihood, node order
         p = sub["props"]
         g[:, self.slices["props"]] = gp * p * (1.0 - p) + (1.0 - 2.0 * p)
         g[:, self.slices["height"]] = (g_root * (sub["height"] - self.lower_root) + 1.0)[:, None]
         if strict:
-            g_rate = (gb * span).sum(axis=1) - 1000.0
+            g_rate = gb_span[:, 0] - 1000.0
             g[:, self.slices["rate"]] = (g_rate * sub["rate"] + 1.0)[:, None]
         elif self.clock == "uced":
-            gs = np.zeros((n, self.bcount))
-            gs[:, self.node] = gb * span
+            gs = gb_span.copy()
             gs += -1.0 / mean[:, None]
             g[:, self.slices["substrates"]] = gs * s_ + 1.0
             g_mean = -self.bcount / mean + s_.sum(axis=1) / mean ** 2 - 1000.0
             g[:, self.slices["uced_mean"]] = (g_mean * mean + 1.0)[:, None]
         else:
-            gs = np.zeros((n, self.bcount))
-            gs[:, self.node] = gb * span                                             # likelihood, node order
+            gs = gb_span.copy()
             gs += -1.0 / s_ - resid / (sd[:, None] ** 2 * s_)
             g[:, self.slices["substrates"]] = gs * s_ + 1.0
             r1 = resid.sum(axis=1) / sd ** 2                                         # d prior / d mu

@@ -1325,6 +1325,161 @@ __global__ void __launch_bounds__(256) weights_pad_kernel(const double* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// K6: clock-tree front end -- heights / ratios + rates -> branch lengths, and the chain rule back
+// ------------------------------------------------------------------------------------------
+
+// rate multiplier of the branch in pre-order row j and the (up to two) rate slots it reads
+// (generate_script.py:660-679: strict / per-branch; :682-708: mean of the rates at the two ends, the root's
+// rate being substrates[map[2,1]] and the branch above map[2,1] using its own rate alone)
+__device__ __forceinline__ void clock_slots(const ClockArgs& a, int j, int node, int par, int& s0, int& s1) {
+    if (!a.autocorr) { s0 = a.nrates == 1 ? 0 : node - 1; s1 = -1; return; }
+    s0 = node - 1;
+    s1 = j == 1 ? -1 : (par == a.nn ? a.map[2] - 1 : par - 1);
+}
+
+// One CTA per draw.  The ratio transform is a recursion down the tree (a node's height needs its parent's):
+// thread 0 walks the pre-order rows; everything else is one thread per branch.
+__global__ void __launch_bounds__(128) clock_forward_kernel(const ClockArgs a) {
+    const int b = blockIdx.x, S = a.S, nn = a.nn;
+    const double* in = a.in + (size_t)b * a.in_ld;
+    double* h = a.hwork + (size_t)b * 2 * (S - 1);
+    double* ho = a.hout + (size_t)b * a.hout_ld;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    if (a.ratios) {
+        if (threadIdx.x == 0) {  // generate_script.py:711-735 and its log-Jacobian :738-752
+            const double* p = in;
+            h[a.map[0] - S - 1] = in[S - 2];  // root height follows the S-2 proportions
+            double lj = 0.0;
+            int k = 0;
+            for (int j = 1; j < nn; ++j) {
+                const int node = a.map[2 * j], par = a.map[2 * j + 1];
+                if (node <= S) continue;
+                const double lo = a.lowers ? a.lowers[node - 1] : 0.0, span = h[par - S - 1] - lo;
+                h[node - S - 1] = lo + span * p[k++];
+                lj += log(span);
+            }
+            ho[(S - 1) + a.nrates + (S - 2) + 1] = lj;
+        }
+    } else {
+        for (int k = threadIdx.x; k < S - 1; k += blockDim.x) h[k] = in[k];
+    }
+    __syncthreads();
+    const double* rates = in + (S - 1);
+    double* t = a.params + (size_t)b * a.stride + a.off_t;
+    for (int j = 1 + threadIdx.x; j < nn; j += blockDim.x) {
+        const int node = a.map[2 * j], par = a.map[2 * j + 1];
+        int s0, s1;
+        clock_slots(a, j, node, par, s0, s1);
+        const double r = s1 < 0 ? rates[s0] : 0.5 * (rates[s0] + rates[s1]);
+        const double lo = node > S ? h[node - S - 1] : (a.lowers ? a.lowers[node - 1] : 0.0);
+        const double bl = r * (h[par - S - 1] - lo);
+        t[node - 1] = bl;
+        if (!(bl >= 0.0) || !isfinite(bl)) bad = 1;  // what pack_draw rejects on the host path
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ho[a.hout_ld - 1] = bad ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(128) clock_reverse_kernel(const ClockArgs a) {
+    const int b = blockIdx.x, S = a.S, nn = a.nn;
+    const double* in = a.in + (size_t)b * a.in_ld;
+    const double* rates = in + (S - 1);
+    const double* h = a.hwork + (size_t)b * 2 * (S - 1);
+    double* hb = a.hwork + (size_t)b * 2 * (S - 1) + (S - 1);
+    double* ho = a.hout + (size_t)b * a.hout_ld;
+    const double* gbl = a.out + (size_t)b * a.nout + 1;  // d/dblens[node - 1]
+    double* g_rates = ho + (S - 1);
+    // r g and span g of the branch in pre-order row j
+    auto branch = [&](int j, double& rg, double& sg, int& s0, int& s1) {
+        const int node = a.map[2 * j], par = a.map[2 * j + 1];
+        clock_slots(a, j, node, par, s0, s1);
+        const double r = s1 < 0 ? rates[s0] : 0.5 * (rates[s0] + rates[s1]);
+        const double lo = node > S ? h[node - S - 1] : (a.lowers ? a.lowers[node - 1] : 0.0);
+        const double g = gbl[node - 1];
+        rg = r * g;
+        sg = (h[par - S - 1] - lo) * g;
+    };
+    // d/dheights: an internal node gathers + r g from the branches of its two children and - r g from its own
+    for (int k = threadIdx.x; k < S - 1; k += blockDim.x) {
+        double rg, sg, acc = 0.0;
+        int s0, s1;
+        branch(a.kids[2 * k], rg, sg, s0, s1); acc += rg;
+        branch(a.kids[2 * k + 1], rg, sg, s0, s1); acc += rg;
+        const int own = a.row_of[S + k];
+        if (own > 0) { branch(own, rg, sg, s0, s1); acc -= rg; }
+        ho[k] = acc;
+        hb[k] = acc + (a.has_extra ? in[(S - 1) + a.nrates + k] : 0.0);
+    }
+    // d/drates
+    if (a.nrates == 1) {  // strict clock: sum over branches (fixed tree order -> reproducible)
+        __shared__ double part[128];
+        double acc = 0.0;
+        for (int j = 1 + threadIdx.x; j < nn; j += blockDim.x) {
+            double rg, sg;
+            int s0, s1;
+            branch(j, rg, sg, s0, s1);
+            acc += sg;
+        }
+        part[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = 64; o > 0; o >>= 1) {
+            if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) g_rates[0] = part[0];
+    } else if (!a.autocorr) {
+        for (int j = 1 + threadIdx.x; j < nn; j += blockDim.x) {
+            double rg, sg;
+            int s0, s1;
+            branch(j, rg, sg, s0, s1);
+            g_rates[s0] = sg;
+        }
+    } else {  // slot m-1 gathers its own branch and half of each child's; the root's stand-in gathers the root's children
+        const int first = a.map[2];
+        for (int m = 1 + threadIdx.x; m < nn; m += blockDim.x) {  // node m, slot m - 1
+            double rg, sg, acc = 0.0;
+            int s0, s1;
+            const int own = a.row_of[m - 1];
+            branch(own, rg, sg, s0, s1);
+            acc += s1 < 0 ? sg : 0.5 * sg;
+            if (m > S) {
+                for (int c = 0; c < 2; ++c) {
+                    const int jr = a.kids[2 * (m - S - 1) + c];
+                    branch(jr, rg, sg, s0, s1);
+                    if (s1 == m - 1) acc += 0.5 * sg;
+                }
+            }
+            if (m == first) {
+                for (int c = 0; c < 2; ++c) {
+                    const int jr = a.kids[2 * (nn - S - 1) + c];
+                    branch(jr, rg, sg, s0, s1);
+                    if (s1 == m - 1) acc += 0.5 * sg;
+                }
+            }
+            g_rates[m - 1] = acc;
+        }
+    }
+    if (!a.ratios) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // reverse sweep of the ratio transform and of its log-Jacobian: children before parents
+        const double* p = in;
+        double* gp = ho + (S - 1) + a.nrates;
+        int k = S - 2;
+        for (int j = nn - 1; j >= 1; --j) {
+            const int node = a.map[2 * j], par = a.map[2 * j + 1];
+            if (node <= S) continue;
+            --k;
+            const double lo = a.lowers ? a.lowers[node - 1] : 0.0, span = h[par - S - 1] - lo;
+            const double nb = hb[node - S - 1];
+            gp[k] = nb * span;
+            hb[par - S - 1] += nb * p[k] + 1.0 / span;
+        }
+        gp[S - 2] = hb[a.map[0] - S - 1];  // d/droot_height
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K5: multi-device handles -- add the other shards' result rows (peer memory) to this device's
 // ------------------------------------------------------------------------------------------
 
@@ -1460,6 +1615,9 @@ void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream) {
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
     tips_index_kernel<<<grid, 256, 0, stream>>>(d_tips, total);
 }
+
+void launch_clock_forward(const ClockArgs& a, cudaStream_t stream) { clock_forward_kernel<<<a.B, 128, 0, stream>>>(a); }
+void launch_clock_reverse(const ClockArgs& a, cudaStream_t stream) { clock_reverse_kernel<<<a.B, 128, 0, stream>>>(a); }
 
 void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStream_t stream) {
     const int grid = (int)std::min<size_t>((count + 255) / 256, 148);

@@ -140,6 +140,26 @@ struct PeerRows {
 };
 void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStream_t stream);
 
+// Clock-tree front end on the device (phylo_b200_eval_heights_batch / _ratios_batch): node heights (or their
+// ratio parametrisation) and clock rates of B draws -> branch lengths written straight into the packed
+// parameter blocks (clock_forward), and the chain rule back from d/dblens (clock_reverse).
+// generate_script.py:660-679 (heights_to_blens), :682-708 (autocorrelated), :711-752 (transform + log-Jacobian).
+struct ClockArgs {
+    const int32_t* map;       // [nn][2] (node, parent), pre-order, 1-based; row 0 = root
+    const int32_t* kids;      // [S-1][2] pre-order rows of the two children of internal node S+1+k
+    const int32_t* row_of;    // [nn] pre-order row of node k+1
+    const double* lowers;     // [nn] or NULL
+    const double* in;         // [B][in_ld]: heights S-1 (or props S-2, root 1) | rates nrates | hbar_extra S-1
+    double* params;           // [B][stride] packed parameter blocks (off_t receives the branch lengths)
+    const double* out;        // [B][nout] result rows of the likelihood (d/dblens at 1 + node - 1)
+    double* hwork;            // [B][2(S-1)] heights and their adjoint
+    double* hout;             // [B][hout_ld]: g_heights S-1 | g_rates nrates | g_props S-2 | g_root | logjac | status
+    int S, nn, nrates, autocorr, ratios, has_extra, B;
+    int in_ld, hout_ld, off_t, stride, nout;
+};
+void launch_clock_forward(const ClockArgs& a, cudaStream_t stream);
+void launch_clock_reverse(const ClockArgs& a, cudaStream_t stream);
+
 // jc: the scalar-statistic kernel needs no reduction rows
 size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false);
 size_t sweep_stack_bytes(int D, int K, int nthreads, int prec);  // first region of the above

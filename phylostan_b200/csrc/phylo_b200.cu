@@ -124,6 +124,15 @@ struct phylo_b200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false, ev_has_contract = false;
 
+    // clock-tree front end on the device (eval_heights_batch / eval_ratios_batch): the pre-order map and what is
+    // derived from it are uploaded once per map, the per-draw inputs every call
+    std::vector<int32_t> c_map;
+    std::vector<double> c_lowers;
+    bool c_has_lowers = false, c_valid = false;
+    DevBuf<int32_t> d_cmap, d_ckids, d_crow;
+    DevBuf<double> d_clowers, d_cin, d_hwork, d_hout;
+    PinnedBuf<double> h_cin, h_hout;
+
     // multi-device handle (phylo_b200_create_multi): this context is pattern shard 0, `peers` are the shards on
     // the other devices.  Every evaluation forks from this context's stream (fork_ev), runs all shards on their
     // own streams and joins on peer_ev[i]; the peers' result rows are then added to d_out here -- read in place
@@ -143,6 +152,8 @@ struct phylo_b200_ctx {
         cudaSetDevice(device);
         if (fork_ev) cudaEventDestroy(fork_ev);
         d_stage.release();
+        d_cmap.release(); d_ckids.release(); d_crow.release(); d_clowers.release(); d_cin.release();
+        d_hwork.release(); d_hout.release(); h_cin.release(); h_hout.release();
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
@@ -686,6 +697,30 @@ int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
 
 int run_enqueue(phylo_b200_ctx* h, int B, bool grad);
 
+// a clock-tree front-end call in flight: what the kernels of one shard need besides the context
+struct ClockJob {
+    int autocorr, ratios, has_extra, nrates, in_ld, hout_ld;
+};
+
+ClockArgs clock_args(const phylo_b200_ctx* c, const ClockJob& j, int B) {
+    ClockArgs a{};
+    a.map = c->d_cmap.p; a.kids = c->d_ckids.p; a.row_of = c->d_crow.p;
+    a.lowers = c->c_has_lowers ? c->d_clowers.p : nullptr;
+    a.in = c->d_cin.p; a.params = c->d_params.p; a.out = c->d_out.p; a.hwork = c->d_hwork.p; a.hout = c->d_hout.p;
+    a.S = c->S; a.nn = c->nn; a.nrates = j.nrates; a.autocorr = j.autocorr; a.ratios = j.ratios; a.has_extra = j.has_extra;
+    a.B = B; a.in_ld = j.in_ld; a.hout_ld = j.hout_ld; a.off_t = c->lay.off_t; a.stride = c->lay.stride; a.nout = c->nout;
+    return a;
+}
+
+// H2D of the front end's per-draw inputs (staged in `src`'s pinned block) and the heights -> blens kernel, on
+// c's stream; the packed parameter block must already be on its way (same stream)
+int clock_forward_enqueue(phylo_b200_ctx* c, const phylo_b200_ctx* src, const ClockJob& j, int B) {
+    CU_TRY(cudaMemcpyAsync(c->d_cin.p, src->h_cin.p, sizeof(double) * B * j.in_ld, cudaMemcpyHostToDevice, c->stream));
+    launch_clock_forward(clock_args(c, j, B), c->stream);
+    CU_TRY(cudaGetLastError());
+    return 0;
+}
+
 // run_prepare on every shard of the handle
 int run_prepare_all(phylo_b200_ctx* h, int B, bool grad) {
     for (auto* p : h->peers) {
@@ -699,7 +734,7 @@ int run_prepare_all(phylo_b200_ctx* h, int B, bool grad) {
 // Multi-device handle: fork from this context's stream, run every shard on its own device and stream, join,
 // and add the peers' result rows to d_out on this device.  with_copies: H2D of the packed parameters (from
 // this context's pinned block) before, D2H of the summed rows after.
-int multi_enqueue(phylo_b200_ctx* h, int B, bool grad, bool with_copies) {
+int multi_enqueue(phylo_b200_ctx* h, int B, bool grad, bool with_copies, const ClockJob* job = nullptr) {
     const size_t in_bytes = sizeof(double) * B * h->lay.stride, count = (size_t)B * h->nout;
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaEventRecord(h->fork_ev, h->stream));
@@ -708,11 +743,13 @@ int multi_enqueue(phylo_b200_ctx* h, int B, bool grad, bool with_copies) {
         CU_TRY(cudaSetDevice(p->device));
         CU_TRY(cudaStreamWaitEvent(p->stream, h->fork_ev, 0));  // also orders the peer's memsets after the last sum
         if (with_copies) CU_TRY(cudaMemcpyAsync(p->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, p->stream));
+        if (job) { if (int rc = clock_forward_enqueue(p, h, *job, B)) return rc; }
         if (int rc = run_enqueue(p, B, grad)) return rc;
         CU_TRY(cudaEventRecord(h->peer_ev[i], p->stream));
     }
     CU_TRY(cudaSetDevice(h->device));
     if (with_copies) CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (job) { if (int rc = clock_forward_enqueue(h, h, *job, B)) return rc; }
     if (int rc = run_enqueue(h, B, grad)) return rc;
     PeerRows rows{};
     rows.n = (int)h->peers.size();
@@ -908,6 +945,28 @@ int phylo_b200_eval(phylo_b200_handle h, const double* blens, const double* subs
                                  g_rs, g_ps);
 }
 
+// The pre-order map of phylostan/utils.py:84-90: row 0 = (root, 0); every other node exactly once, after its
+// parent, under an internal parent with exactly two children.  One check for every front-end entry.
+static int validate_map(const char* who, int S, const int32_t* map) {
+    const int nn = 2 * S - 1;
+    if (map[0] != nn) return fail(PHYLO_B200_EINVAL, std::string(who) + ": map row 0 must hold the root (node 2S-1)");
+    std::vector<int> row(nn + 1, -1), nkids(nn + 1, 0);
+    row[nn] = 0;
+    for (int j = 1; j < nn; ++j) {
+        const int node = map[2 * j], par = map[2 * j + 1];
+        if (node < 1 || node >= nn || par <= S || par > nn)
+            return fail(PHYLO_B200_EINVAL, std::string(who) + ": malformed pre-order map row " + std::to_string(j));
+        if (row[node] >= 0)
+            return fail(PHYLO_B200_EINVAL, std::string(who) + ": node " + std::to_string(node) + " appears twice in the map");
+        if (row[par] < 0)
+            return fail(PHYLO_B200_EINVAL, std::string(who) + ": map row " + std::to_string(j) + " precedes its parent's row");
+        if (++nkids[par] > 2)
+            return fail(PHYLO_B200_EINVAL, std::string(who) + ": node " + std::to_string(par) + " has more than two children");
+        row[node] = j;
+    }
+    return 0;  // nn - 1 distinct nodes in nn - 1 rows: every non-root node appears exactly once
+}
+
 // heights -> branch lengths on the host (O(S)), likelihood on the device, chain rule back on the host.
 // autocorr == 0: generate_script.py:660-679 (strict / uncorrelated clocks);
 // autocorr == 1: generate_script.py:682-708 (branch rate = mean of the rates at its two ends).
@@ -923,11 +982,7 @@ static int eval_heights_impl(phylo_b200_handle h, int autocorr, const int32_t* m
     if (autocorr ? nrates != h->bcount : (nrates != 1 && nrates != h->bcount))
         return fail(PHYLO_B200_EINVAL, std::string(who) + (autocorr ? ": nrates must be 2S-2" : ": nrates must be 1 or 2S-2"));
     std::vector<double> blens(h->bcount, 0.0), gb(h->bcount, 0.0);
-    for (int j = 1; j < nn; ++j) {
-        const int node = map[2 * j], par = map[2 * j + 1];
-        if (node < 1 || node >= nn || par <= S || par > nn)
-            return fail(PHYLO_B200_EINVAL, std::string(who) + ": malformed pre-order map row " + std::to_string(j));
-    }
+    if (int rc = validate_map(who, S, map)) return rc;
     // rate multiplier of the branch above `node`, and the (up to two) rate slots it reads
     const int first = map[2] - 1;  // map[2,1] of the Stan program: the first child of the root
     auto slots = [&](int j, int& s0, int& s1) {
@@ -988,6 +1043,156 @@ int phylo_b200_eval_heights_autocorr(phylo_b200_handle h, const int32_t* map, co
                              g_heights, g_rates, g_subst, g_freqs, g_rs, g_ps);
 }
 
+// Batched front end with the heights -> blens step and its chain rule ON THE DEVICE: B draws, one H2D of
+// [heights | rates (| hbar_extra)], clock_forward -> the three likelihood kernels -> clock_reverse, one D2H.
+// ratios != 0: `heights` holds [B][S-1] = S-2 proportions then the root height; the ratio transform, its
+// log-Jacobian and their reverse sweep run on the device too.
+static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, int ratios, const int32_t* map, int B,
+                            const double* heights, const double* lowers, const double* rates, int nrates,
+                            const double* subst, const double* freqs, const double* rs, const double* ps,
+                            const double* hbar_extra, int want_grad, double* logp, double* logjac, double* heights_out,
+                            double* g_heights, double* g_props, double* g_root, double* g_rates, double* g_subst,
+                            double* g_freqs, double* g_rs, double* g_ps) {
+    if (!h || !map || !heights || !rates || !logp || B < 1) return fail(PHYLO_B200_EINVAL, std::string(who) + ": bad arguments");
+    if (!h->rooted) return fail(PHYLO_B200_EINVAL, std::string(who) + " needs a rooted (clock) handle");
+    const int S = h->S, nn = h->nn;
+    if (autocorr ? nrates != h->bcount : (nrates != 1 && nrates != h->bcount))
+        return fail(PHYLO_B200_EINVAL, std::string(who) + (autocorr ? ": nrates must be 2S-2" : ": nrates must be 1 or 2S-2"));
+    // static part: (re)upload when the map or the sampling dates change
+    const bool same = h->c_valid && h->c_map.size() == (size_t)2 * nn && std::equal(map, map + 2 * nn, h->c_map.begin()) &&
+                      h->c_has_lowers == (lowers != nullptr) &&
+                      (!lowers || std::equal(lowers, lowers + nn, h->c_lowers.begin()));
+    if (!same) {
+        if (int rc = validate_map(who, S, map)) return rc;
+        h->c_valid = false;
+        std::vector<int32_t> row(nn, 0), kids(2 * (size_t)(S - 1), 0), nk(S - 1, 0);
+        for (int j = 1; j < nn; ++j) {
+            row[map[2 * j] - 1] = j;
+            const int k = map[2 * j + 1] - S - 1;
+            kids[2 * k + nk[k]++] = j;
+        }
+        for (int k = 0; k < S - 1; ++k)
+            if (nk[k] != 2) return fail(PHYLO_B200_EINVAL, std::string(who) + ": internal node without two children in the map");
+        std::vector<phylo_b200_ctx*> all{h};
+        all.insert(all.end(), h->peers.begin(), h->peers.end());
+        for (auto* c : all) {
+            CU_TRY(cudaSetDevice(c->device));
+            CU_TRY(cudaStreamSynchronize(c->stream));
+            CU_TRY(c->d_cmap.ensure(2 * (size_t)nn)); CU_TRY(c->d_ckids.ensure(kids.size())); CU_TRY(c->d_crow.ensure(nn));
+            CU_TRY(cudaMemcpy(c->d_cmap.p, map, sizeof(int32_t) * 2 * nn, cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(c->d_ckids.p, kids.data(), sizeof(int32_t) * kids.size(), cudaMemcpyHostToDevice));
+            CU_TRY(cudaMemcpy(c->d_crow.p, row.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+            c->c_has_lowers = lowers != nullptr;
+            if (lowers) {
+                CU_TRY(c->d_clowers.ensure(nn));
+                CU_TRY(cudaMemcpy(c->d_clowers.p, lowers, sizeof(double) * nn, cudaMemcpyHostToDevice));
+            }
+        }
+        h->c_map.assign(map, map + 2 * nn);
+        if (lowers) h->c_lowers.assign(lowers, lowers + nn); else h->c_lowers.clear();
+        h->c_valid = true;
+    }
+    ClockJob job{};
+    job.autocorr = autocorr; job.ratios = ratios; job.has_extra = hbar_extra && want_grad ? 1 : 0; job.nrates = nrates;
+    job.in_ld = (S - 1) + nrates + (job.has_extra ? S - 1 : 0);
+    job.hout_ld = (S - 1) + nrates + (S - 2) + 3;
+    // parameter blocks (branch lengths are filled in on the device) and the front end's inputs
+    static thread_local std::vector<double> zeros;
+    zeros.assign((size_t)B * h->bcount, 0.0);
+    if (int rc = pack_batch(h, B, zeros.data(), subst, freqs, rs, ps)) return rc;
+    {
+        std::vector<phylo_b200_ctx*> all{h};
+        all.insert(all.end(), h->peers.begin(), h->peers.end());
+        for (auto* c : all) {
+            CU_TRY(cudaSetDevice(c->device));
+            CU_TRY(c->d_cin.ensure((size_t)B * job.in_ld));
+            CU_TRY(c->d_hwork.ensure((size_t)B * 2 * (S - 1)));
+            CU_TRY(c->d_hout.ensure((size_t)B * job.hout_ld));
+        }
+        CU_TRY(cudaSetDevice(h->device));
+        CU_TRY(h->h_cin.ensure((size_t)B * job.in_ld));
+        CU_TRY(h->h_hout.ensure((size_t)B * job.hout_ld));
+    }
+    for (int b = 0; b < B; ++b) {
+        double* dst = h->h_cin.p + (size_t)b * job.in_ld;
+        std::memcpy(dst, heights + (size_t)b * (S - 1), sizeof(double) * (S - 1));
+        std::memcpy(dst + (S - 1), rates + (size_t)b * nrates, sizeof(double) * nrates);
+        if (job.has_extra) std::memcpy(dst + (S - 1) + nrates, hbar_extra + (size_t)b * (S - 1), sizeof(double) * (S - 1));
+    }
+    const bool grad = want_grad != 0;
+    if (int rc = run_prepare_all(h, B, grad)) return rc;
+    const size_t in_bytes = sizeof(double) * B * h->lay.stride, out_bytes = sizeof(double) * B * h->nout;
+    if (!h->peers.empty()) {
+        if (int rc = multi_enqueue(h, B, grad, true, &job)) return rc;
+    } else {
+        CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = clock_forward_enqueue(h, h, job, B)) return rc;
+        if (int rc = run_enqueue(h, B, grad)) return rc;
+        CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (grad) {
+        launch_clock_reverse(clock_args(h, job, B), h->stream);
+        CU_TRY(cudaGetLastError());
+        h->last_launches += 1;
+    }
+    h->last_launches += 1;
+    CU_TRY(cudaMemcpyAsync(h->h_hout.p, h->d_hout.p, sizeof(double) * B * job.hout_ld, cudaMemcpyDeviceToHost, h->stream));
+    if (heights_out)  // [heights | adjoint] rows of the work buffer: only the first half is wanted
+        CU_TRY(cudaMemcpy2DAsync(heights_out, sizeof(double) * (S - 1), h->d_hwork.p, sizeof(double) * 2 * (S - 1),
+                                 sizeof(double) * (S - 1), B, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    bool finite = true;
+    for (int d = 0; d < B; ++d) {
+        const double* o = h->h_out.p + (size_t)d * h->nout;
+        const double* ho = h->h_hout.p + (size_t)d * job.hout_ld;
+        if (ho[job.hout_ld - 1] != 0.0)
+            return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": a branch length is negative or not finite");
+        logp[d] = o[0];
+        finite = finite && std::isfinite(o[0]);
+        if (logjac) logjac[d] = ratios ? ho[job.hout_ld - 2] : 0.0;
+        if (!grad) continue;
+        if (g_heights) std::memcpy(g_heights + (size_t)d * (S - 1), ho, sizeof(double) * (S - 1));
+        if (g_rates) std::memcpy(g_rates + (size_t)d * nrates, ho + (S - 1), sizeof(double) * nrates);
+        if (ratios && g_props && S > 2) std::memcpy(g_props + (size_t)d * (S - 2), ho + (S - 1) + nrates, sizeof(double) * (S - 2));
+        if (ratios && g_root) g_root[d] = ho[(S - 1) + nrates + (S - 2)];
+        if (g_subst && h->nsubst) std::memcpy(g_subst + (size_t)d * h->nsubst, o + h->off_subst, sizeof(double) * h->nsubst);
+        if (g_freqs) std::memcpy(g_freqs + (size_t)d * 4, o + h->off_freqs, sizeof(double) * 4);
+        if (g_rs) std::memcpy(g_rs + (size_t)d * h->C, o + h->off_rs, sizeof(double) * h->C);
+        if (g_ps) std::memcpy(g_ps + (size_t)d * h->C, o + h->off_ps, sizeof(double) * h->C);
+    }
+    if (!finite) return fail(PHYLO_B200_EDOMAIN, "log-likelihood is not finite (impossible pattern or underflow)");
+    return 0;
+}
+
+int phylo_b200_eval_heights_batch(phylo_b200_handle h, int autocorr, const int32_t* map, int B, const double* heights,
+                                  const double* lowers, const double* rates, int nrates, const double* subst,
+                                  const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
+                                  double* g_heights, double* g_rates, double* g_subst, double* g_freqs, double* g_rs,
+                                  double* g_ps) {
+    return clock_batch_impl(h, "eval_heights_batch", autocorr != 0, 0, map, B, heights, lowers, rates, nrates, subst, freqs,
+                            rs, ps, nullptr, want_grad, logp, nullptr, nullptr, g_heights, nullptr, nullptr, g_rates,
+                            g_subst, g_freqs, g_rs, g_ps);
+}
+
+int phylo_b200_eval_ratios_batch(phylo_b200_handle h, int autocorr, const int32_t* map, int B, const double* props,
+                                 const double* root_height, const double* lowers, const double* rates, int nrates,
+                                 const double* subst, const double* freqs, const double* rs, const double* ps,
+                                 const double* hbar_extra, int want_grad, double* logp, double* logjac, double* heights,
+                                 double* g_props, double* g_root, double* g_rates, double* g_subst, double* g_freqs,
+                                 double* g_rs, double* g_ps) {
+    if (!h || !props || !root_height || B < 1) return fail(PHYLO_B200_EINVAL, "eval_ratios_batch: bad arguments");
+    const int S = h->S;
+    static thread_local std::vector<double> pr;  // [B][S-1] = proportions then the root height
+    pr.resize((size_t)B * (S - 1));
+    for (int b = 0; b < B; ++b) {
+        if (S > 2) std::memcpy(pr.data() + (size_t)b * (S - 1), props + (size_t)b * (S - 2), sizeof(double) * (S - 2));
+        pr[(size_t)b * (S - 1) + (S - 2)] = root_height[b];
+    }
+    return clock_batch_impl(h, "eval_ratios_batch", autocorr != 0, 1, map, B, pr.data(), lowers, rates, nrates, subst, freqs,
+                            rs, ps, hbar_extra, want_grad, logp, logjac, heights, nullptr, g_props, g_root, g_rates,
+                            g_subst, g_freqs, g_rs, g_ps);
+}
+
 // Host-only: the ratio transform of the node heights (generate_script.py:711-735) and its log-Jacobian
 // (:738-752) for B draws, and the reverse sweep through it.  O(B S); no GPU.
 // props [B][S-2] are consumed in pre-order of the internal non-root nodes, as the Stan loop does.
@@ -995,12 +1200,7 @@ int phylo_b200_ratios_forward(int S, const int32_t* map, const double* lowers, i
                               const double* root_height, double* heights, double* logjac) {
     if (S < 2 || !map || B < 1 || !props || !root_height || !heights) return fail(PHYLO_B200_EINVAL, "ratios_forward: bad arguments");
     const int nn = 2 * S - 1;
-    for (int j = 1; j < nn; ++j) {
-        const int node = map[2 * j], par = map[2 * j + 1];
-        if (node < 1 || node >= nn || par <= S || par > nn)
-            return fail(PHYLO_B200_EINVAL, "ratios_forward: malformed pre-order map row " + std::to_string(j));
-    }
-    if (map[0] <= S || map[0] > nn) return fail(PHYLO_B200_EINVAL, "ratios_forward: map row 0 must hold the root");
+    if (int rc = validate_map("ratios_forward", S, map)) return rc;
     for (int b = 0; b < B; ++b) {
         double* h = heights + (size_t)b * (S - 1);
         const double* p = props + (size_t)b * (S - 2);
@@ -1026,6 +1226,7 @@ int phylo_b200_ratios_reverse(int S, const int32_t* map, const double* lowers, i
     if (S < 2 || !map || B < 1 || !props || !heights || !hbar || !g_props || !g_root)
         return fail(PHYLO_B200_EINVAL, "ratios_reverse: bad arguments");
     const int nn = 2 * S - 1;
+    if (int rc = validate_map("ratios_reverse", S, map)) return rc;
     std::vector<int> slot(nn, -1);
     int k = 0;
     for (int j = 1; j < nn; ++j)

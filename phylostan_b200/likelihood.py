@@ -73,6 +73,11 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_eval_heights.argtypes = [vp, ip, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp,
                                           _dp, _dp]
     L.phylo_b200_eval_heights_autocorr.argtypes = L.phylo_b200_eval_heights.argtypes
+    if hasattr(L, "phylo_b200_eval_heights_batch"):
+        L.phylo_b200_eval_heights_batch.argtypes = [vp, i, ip, i, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp,
+                                                    _dp, _dp, _dp, _dp]
+        L.phylo_b200_eval_ratios_batch.argtypes = [vp, i, ip, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp, i, _dp,
+                                                   _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_upload.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_run.argtypes = [vp, i, i]
     L.phylo_b200_device_out.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i)]
@@ -281,6 +286,62 @@ class TreeLikelihood:
                   _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps), 1, _ptr(logp), _ptr(gh), _ptr(gr), _ptr(gs), _ptr(gf),
                   _ptr(grs), _ptr(gps)))
         return float(logp[0]), gh, gr, ValueGrad(float(logp[0]), None, gs[:self.nsubst], gf, grs, gps)
+
+    def _clock_inputs(self, B, rates, lowers, subst, freqs, rs, ps):
+        rt = _arr(np.reshape(rates, (B, -1)))
+        lo = None if lowers is None else _arr(lowers, (2 * self.S - 1,))
+        subst = None if self.nsubst == 0 else _arr(np.reshape(subst, (B, -1)), (B, self.nsubst))
+        freqs = None if freqs is None else _arr(np.reshape(freqs, (B, -1)), (B, 4))
+        rs = None if rs is None else _arr(np.reshape(rs, (B, -1)), (B, self.C))
+        ps = None if ps is None else _arr(np.reshape(ps, (B, -1)), (B, self.C))
+        return rt, lo, subst, freqs, rs, ps
+
+    def value_grad_heights_batch(self, map_, heights, rates, lowers=None, subst=None, freqs=None, rs=None, ps=None,
+                                 autocorrelated=False, want_grad=True):
+        """B draws of the clock-tree front end with heights -> blens and its chain rule on the device
+        (``phylo_b200_eval_heights_batch``).  heights [B, S-1]; rates [B] / [B, 1] (strict) or [B, 2S-2].
+        Returns (logp [B], d/dheights [B, S-1], d/drates [B, nrates], ValueGrad of the site-model parameters)."""
+        m = np.ascontiguousarray(map_, dtype=np.int32)
+        hts = _arr(np.atleast_2d(heights))
+        B = hts.shape[0]
+        if hts.shape != (B, self.S - 1):
+            raise ValueError("heights must be [B, S-1]")
+        rt, lo, subst, freqs, rs, ps = self._clock_inputs(B, rates, lowers, subst, freqs, rs, ps)
+        nr = rt.shape[1]
+        logp, gh, gr = np.zeros(B), np.zeros((B, self.S - 1)), np.zeros((B, nr))
+        gs, gf = np.zeros((B, max(self.nsubst, 1))), np.zeros((B, 4))
+        grs, gps = np.zeros((B, self.C)), np.zeros((B, self.C))
+        _check(lib().phylo_b200_eval_heights_batch(
+            self._h, int(bool(autocorrelated)), m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B, _ptr(hts), _ptr(lo),
+            _ptr(rt), nr, _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps), int(bool(want_grad)), _ptr(logp), _ptr(gh), _ptr(gr),
+            _ptr(gs), _ptr(gf), _ptr(grs), _ptr(gps)))
+        return logp, gh, gr, ValueGrad(logp, None, gs[:, :self.nsubst], gf, grs, gps)
+
+    def value_grad_ratios_batch(self, map_, props, root_height, rates, lowers=None, subst=None, freqs=None, rs=None,
+                                ps=None, hbar_extra=None, autocorrelated=False, want_grad=True):
+        """The same with the ratio parametrisation of the heights (generate_script.py:711-752) on the device too
+        (``phylo_b200_eval_ratios_batch``): props [B, S-2], root_height [B]; ``hbar_extra`` [B, S-1] is an extra
+        adjoint of the heights (a tree prior's gradient) pushed through the reverse sweep.  Returns a dict:
+        logp, logjac, heights, g_props (of logp + logjac), g_root, g_rates, rest (ValueGrad)."""
+        m = np.ascontiguousarray(map_, dtype=np.int32)
+        pr = _arr(np.atleast_2d(props))
+        B = pr.shape[0]
+        if pr.shape != (B, self.S - 2):
+            raise ValueError("props must be [B, S-2]")
+        rh = _arr(np.reshape(root_height, (B,)))
+        rt, lo, subst, freqs, rs, ps = self._clock_inputs(B, rates, lowers, subst, freqs, rs, ps)
+        hx = None if hbar_extra is None else _arr(np.atleast_2d(hbar_extra), (B, self.S - 1))
+        nr = rt.shape[1]
+        logp, lj, hts = np.zeros(B), np.zeros(B), np.zeros((B, self.S - 1))
+        gp, groot, gr = np.zeros((B, max(self.S - 2, 1))), np.zeros(B), np.zeros((B, nr))
+        gs, gf = np.zeros((B, max(self.nsubst, 1))), np.zeros((B, 4))
+        grs, gps = np.zeros((B, self.C)), np.zeros((B, self.C))
+        _check(lib().phylo_b200_eval_ratios_batch(
+            self._h, int(bool(autocorrelated)), m.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B, _ptr(pr), _ptr(rh),
+            _ptr(lo), _ptr(rt), nr, _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps), _ptr(hx), int(bool(want_grad)), _ptr(logp),
+            _ptr(lj), _ptr(hts), _ptr(gp), _ptr(groot), _ptr(gr), _ptr(gs), _ptr(gf), _ptr(grs), _ptr(gps)))
+        return {"logp": logp, "logjac": lj, "heights": hts, "g_props": gp[:, :self.S - 2], "g_root": groot, "g_rates": gr,
+                "rest": ValueGrad(logp, None, gs[:, :self.nsubst], gf, grs, gps)}
 
     # ------------------------------------------------------------------ resident / split form
     def upload(self, blens, subst=None, freqs=None, rs=None, ps=None) -> int:

@@ -663,3 +663,25 @@ def test_uced_skyride_model_is_the_stan_program_and_its_gradient():
         e = np.zeros(m.dim); e[k] = 1e-6
         fd = (m.log_prob(Z + e) - m.log_prob(Z - e)) / 2e-6
         assert np.allclose(fd, G[:, k], rtol=1e-4, atol=1e-4), (k, fd, G[:, k])
+
+
+@pytest.mark.gpu
+def test_gpu_clock_model_device_front_end_equals_host_chain_rule(monkeypatch):
+    """ClockModel on a library handle runs heights -> blens, the likelihood and the reverse sweeps down to d/dprops in
+    one phylo_b200_eval_ratios_batch call; PHYLO_B200_HOST_FRONT_END=1 keeps the chain rule in numpy.  Same numbers,
+    and a draw whose proportions make the library reject it is -inf with a zero gradient on both paths."""
+    from phylostan_b200 import likelihood as lk
+    d, S, lowers, heights, ora, grid, m_cpu = _hcv_model()
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=True) as lik:
+        m = advi.ClockModel(lik, "GTR", d["map"], lowers, clock="ucln", coalescent="skygrid", grid=grid)
+        assert m._device_front_end()
+        rng = np.random.default_rng(12)
+        Z = np.stack([_ucln_point(m, heights, lowers, rng) for _ in range(5)])
+        lp_d, G_d = m.log_prob_grad(Z)
+        lv_d = m.log_prob(Z)
+        monkeypatch.setenv("PHYLO_B200_HOST_FRONT_END", "1")
+        assert not m._device_front_end()
+        lp_h, G_h = m.log_prob_grad(Z)
+    assert np.max(np.abs(lp_d - lp_h) / np.abs(lp_h)) <= 1e-12
+    assert np.max(np.abs(lv_d - lp_h) / np.abs(lp_h)) <= 1e-12
+    assert np.max(np.abs(G_d - G_h) / np.maximum(1.0, np.abs(G_h))) <= 1e-8

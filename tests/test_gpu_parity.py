@@ -781,3 +781,96 @@ def test_gpu_multi_device_handle_errors(datasets):
                           devices=[0, 0, 0])
     with pytest.raises(lk.PhyloB200Error):     # a device that does not exist
         lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, rooted=False, devices=[0, 99])
+
+
+def _tree_heights(d):
+    """Node heights and sampling dates consistent with the data set's own tree file."""
+    S = d["tipmask"].shape[0]
+    nn = 2 * S - 1
+    depth = {nn: 0.0}
+    for node, par in d["map"][1:]:
+        depth[int(node)] = depth[int(par)] + d["tree_blens"][int(node) - 1]
+    top = max(depth.values())
+    heights = np.array([top - depth[S + 1 + k] for k in range(S - 1)])
+    lowers = np.zeros(nn)
+    for k in range(1, S + 1):
+        lowers[k - 1] = top - depth[k]
+    for node, par in list(d["map"][1:])[::-1]:      # an internal node's lower bound: its oldest descendant tip (utils.py:92-104)
+        lowers[int(par) - 1] = max(lowers[int(par) - 1], lowers[int(node) - 1])
+    return heights, lowers
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clock", ["strict", "branch", "autocorr"])
+@pytest.mark.parametrize("devices", [None, [0, 0]])
+def test_gpu_heights_batch_on_device_matches_host_front_end(datasets, clock, devices):
+    """phylo_b200_eval_heights_batch (heights -> blens and the d/dheights, d/drates gather as device kernels, B draws
+    per call) against the single-draw host front end, which is pinned against the oracle and torch autograd above."""
+    d = datasets["fluA"]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(41)
+    _, lowers = _tree_heights(d)
+    B = 4
+    # valid time trees by construction: heights from random proportions (host ratio transform)
+    heights, _ = lk.ratios_forward(d["map"], lowers, rng.uniform(0.2, 0.9, (B, S - 2)), lowers.max() + rng.uniform(2.0, 20.0, B))
+    nr = 1 if clock == "strict" else 2 * S - 2
+    rates = rng.lognormal(np.log(0.005), 0.3, (B, nr))
+    subst = rng.dirichlet(np.ones(6), B)
+    fr = rng.dirichlet(np.ones(4) * 5, B)
+    rs = np.stack([E.weibull_rates(x, 4) for x in (0.4, 0.5, 0.8, 1.3)])
+    ps = rng.dirichlet(np.ones(4) * 4, B)
+    auto = clock == "autocorr"
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4, devices=devices) as lik:
+        logp, gh, gr, rest = lik.value_grad_heights_batch(d["map"], heights, rates, lowers, subst, fr, rs, ps, autocorrelated=auto)
+        lv, _, _, _ = lik.value_grad_heights_batch(d["map"], heights, rates, lowers, subst, fr, rs, ps, autocorrelated=auto,
+                                                   want_grad=False)
+        np.testing.assert_allclose(lv, logp, rtol=1e-13)
+        for b in range(B):
+            w_logp, w_h, w_r, w_rest = lik.value_grad_heights(d["map"], heights[b], rates[b], lowers, subst[b], fr[b], rs[b],
+                                                              ps[b], autocorrelated=auto)
+            assert abs(logp[b] - w_logp) <= RTOL_LOGP * abs(w_logp)
+            for g, w in ((gh[b], w_h), (gr[b], w_r), (rest.grad_subst[b], w_rest.grad_subst), (rest.grad_freqs[b], w_rest.grad_freqs),
+                         (rest.grad_rs[b], w_rest.grad_rs), (rest.grad_ps[b], w_rest.grad_ps)):
+                assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
+        bad = heights.copy()
+        bad[2, 5] = -1.0                      # below a descendant: negative branch length -> domain error, as eval_batch
+        with pytest.raises(lk.PhyloDomainError):
+            lik.value_grad_heights_batch(d["map"], bad, rates, lowers, subst, fr, rs, ps, autocorrelated=auto)
+        m2 = np.array(d["map"]).copy()
+        m2[3] = m2[2]                         # a node listed twice
+        with pytest.raises(lk.PhyloB200Error):
+            lik.value_grad_heights_batch(m2, heights, rates, lowers, subst, fr, rs, ps, autocorrelated=auto)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,strict", [("fluA", True), ("HCV", False)])
+def test_gpu_ratios_batch_on_device(datasets, name, strict):
+    """phylo_b200_eval_ratios_batch: ratio transform + log-Jacobian, heights -> blens, likelihood, and the whole
+    reverse sweep (with a tree prior's adjoint of the heights riding along) in one device pass, against the
+    composition host ratios_forward -> single-draw front end -> host ratios_reverse."""
+    d = datasets[name]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(43)
+    _, lowers = _tree_heights(d)
+    B = 3
+    props = rng.uniform(0.2, 0.9, (B, S - 2))
+    root = lowers.max() + rng.uniform(5.0, 30.0, B)
+    nr = 1 if strict else 2 * S - 2
+    rates = rng.lognormal(np.log(0.002), 0.3, (B, nr))
+    subst, fr = rng.dirichlet(np.ones(6), B), rng.dirichlet(np.ones(4) * 5, B)
+    rs = np.stack([E.weibull_rates(x, 4) for x in (0.4, 0.7, 1.2)])
+    ps = np.full((B, 4), 0.25)
+    extra = rng.normal(0, 1.0, (B, S - 1))
+    heights, logjac = lk.ratios_forward(d["map"], lowers, props, root)
+    with lk.TreeLikelihood(d["peel"], d["tipmask"], d["weights"], model="GTR", categories=4) as lik:
+        got = lik.value_grad_ratios_batch(d["map"], props, root, rates, lowers, subst, fr, rs, ps, hbar_extra=extra)
+        np.testing.assert_allclose(got["heights"], heights, rtol=1e-13, atol=1e-12)
+        np.testing.assert_allclose(got["logjac"], logjac, rtol=1e-13)
+        for b in range(B):
+            w_logp, w_h, w_r, w_rest = lik.value_grad_heights(d["map"], heights[b], rates[b], lowers, subst[b], fr[b], rs[b], ps[b])
+            assert abs(got["logp"][b] - w_logp) <= RTOL_LOGP * abs(w_logp)
+            hbar = (w_h + extra[b])[None, :].copy()
+            gp, groot = lk.ratios_reverse(d["map"], lowers, props[b:b + 1], heights[b:b + 1], hbar)
+            for g, w in ((got["g_props"][b], gp[0]), (got["g_root"][b:b + 1], groot), (got["g_rates"][b], w_r),
+                         (got["rest"].grad_subst[b], w_rest.grad_subst), (got["rest"].grad_rs[b], w_rest.grad_rs)):
+                assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
