@@ -526,7 +526,7 @@ class ClockModel(_ModelBase):
             cut = lambda a: None if a is None else a[sl]
             return self.lik.value_grad_ratios_batch(self.map32, sub["props"][sl], sub["height"][sl], rates[sl], self.lowers_or_none,
                                                     cut(subst), cut(sub.get("freqs")), rs_[sl], ps_[sl],
-                                                    hbar_extra=cut(hbar_extra), want_grad=want_grad)
+                                                    hbar_extra=cut(hbar_extra), want_grad=want_grad, return_heights=False)
         try:
             parts = [call(slice(None))]
         except Exception as e:

@@ -117,7 +117,7 @@ struct phylo_b200_ctx {
     // eval_batch replays a captured CUDA graph (H2D copy, memsets, the three kernels, D2H copy): for
     // fluA-sized problems the six stream calls cost more CPU time than the GPU needs to run them
     struct EvalGraph { cudaGraphExec_t exec = nullptr; std::vector<unsigned long long> sig; };
-    std::map<std::pair<int, int>, EvalGraph> graphs;  // (B, want_grad) -> executable graph + what it baked in
+    std::map<std::vector<int>, EvalGraph> graphs;  // (B, want_grad, front-end job) -> executable graph + what it baked in
     bool use_graphs = true;
     bool use_jc_scalar = true;  // JC69 gradient runs use the scalar-statistic sweep (PHYLO_B200_NO_JC_SCALAR=1: generic)
     bool timing = false;
@@ -131,7 +131,7 @@ struct phylo_b200_ctx {
     bool c_has_lowers = false, c_valid = false;
     DevBuf<int32_t> d_cmap, d_ckids, d_crow;
     DevBuf<double> d_clowers, d_cin, d_hwork, d_hout;
-    PinnedBuf<double> h_cin, h_hout;
+    PinnedBuf<double> h_cin, h_hout, h_hts;
 
     // multi-device handle (phylo_b200_create_multi): this context is pattern shard 0, `peers` are the shards on
     // the other devices.  Every evaluation forks from this context's stream (fork_ev), runs all shards on their
@@ -153,7 +153,7 @@ struct phylo_b200_ctx {
         if (fork_ev) cudaEventDestroy(fork_ev);
         d_stage.release();
         d_cmap.release(); d_ckids.release(); d_crow.release(); d_clowers.release(); d_cin.release();
-        d_hwork.release(); d_hout.release(); h_cin.release(); h_hout.release();
+        d_hwork.release(); d_hout.release(); h_cin.release(); h_hout.release(); h_hts.release();
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
@@ -699,7 +699,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad);
 
 // a clock-tree front-end call in flight: what the kernels of one shard need besides the context
 struct ClockJob {
-    int autocorr, ratios, has_extra, nrates, in_ld, hout_ld;
+    int autocorr, ratios, has_extra, nrates, in_ld, hout_ld, want_heights;
 };
 
 ClockArgs clock_args(const phylo_b200_ctx* c, const ClockJob& j, int B) {
@@ -847,18 +847,52 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
-int eval_enqueue(phylo_b200_ctx* h, int B, bool grad) {
-    if (!h->peers.empty()) return multi_enqueue(h, B, grad, true);  // one stream per device: plain launches
+// the part of a front-end call that follows the likelihood kernels: reverse sweep, D2H of its results
+int clock_tail_enqueue(phylo_b200_ctx* h, const ClockJob& job, int B, bool grad) {
+    if (grad) {
+        launch_clock_reverse(clock_args(h, job, B), h->stream);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaMemcpyAsync(h->h_hout.p, h->d_hout.p, sizeof(double) * B * job.hout_ld, cudaMemcpyDeviceToHost, h->stream));
+    if (job.want_heights)  // [heights | adjoint] rows of the work buffer: only the first half is wanted
+        CU_TRY(cudaMemcpy2DAsync(h->h_hts.p, sizeof(double) * (h->S - 1), h->d_hwork.p, sizeof(double) * 2 * (h->S - 1),
+                                 sizeof(double) * (h->S - 1), B, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+// everything between the packed host blocks and the host result blocks, on h's stream
+int eval_sequence(phylo_b200_ctx* h, int B, bool grad, const ClockJob* job) {
     const size_t in_bytes = sizeof(double) * B * h->lay.stride, out_bytes = sizeof(double) * B * h->nout;
+    CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (job) { if (int rc = clock_forward_enqueue(h, h, *job, B)) return rc; }
+    if (int rc = run_enqueue(h, B, grad)) return rc;
+    CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (job) { if (int rc = clock_tail_enqueue(h, *job, B, grad)) return rc; }
+    return 0;
+}
+
+int eval_enqueue(phylo_b200_ctx* h, int B, bool grad, const ClockJob* job = nullptr) {
+    if (!h->peers.empty()) {  // one stream per device: plain launches
+        if (int rc = multi_enqueue(h, B, grad, true, job)) return rc;
+        return job ? clock_tail_enqueue(h, *job, B, grad) : 0;
+    }
     const bool graphable = h->use_graphs && !h->timing && h->stream != nullptr;
+    const int nlaunch = (grad ? 3 : 2) + (job ? (grad ? 2 : 1) : 0);
     if (!graphable) {
-        CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
-        if (int rc = run_enqueue(h, B, grad)) return rc;
-        CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (int rc = eval_sequence(h, B, grad, job)) return rc;
+        h->last_launches = nlaunch;
         return 0;
     }
-    auto& g = h->graphs[{B, grad ? 1 : 0}];
-    const auto sig = graph_signature(h);
+    std::vector<int> key{B, grad ? 1 : 0};
+    if (job) key.insert(key.end(), {1, job->autocorr, job->ratios, job->has_extra, job->nrates, job->want_heights});
+    auto& g = h->graphs[key];
+    auto sig = graph_signature(h);
+    if (job) {
+        auto u = [](const void* p) { return (unsigned long long)(uintptr_t)p; };
+        sig.insert(sig.end(), {u(h->d_cin.p), u(h->d_hwork.p), u(h->d_hout.p), u(h->h_cin.p), u(h->h_hout.p), u(h->h_hts.p),
+                               u(h->d_cmap.p), u(h->d_ckids.p), u(h->d_crow.p), u(h->d_clowers.p),
+                               (unsigned long long)h->c_has_lowers});
+    }
     if (!g.exec || g.sig != sig) {
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
         if (h->graphs.size() > 16) {  // a caller cycling through many batch sizes: keep the cache small
@@ -871,27 +905,24 @@ int eval_enqueue(phylo_b200_ctx* h, int B, bool grad) {
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
             (void)cudaGetLastError();  // a stream that cannot be captured (e.g. the legacy default stream): plain launches
             h->use_graphs = false;
-            h->graphs.erase({B, grad ? 1 : 0});
-            return eval_enqueue(h, B, grad);
+            h->graphs.erase(key);
+            return eval_enqueue(h, B, grad, job);
         }
-        int rc = 0;
-        cudaError_t e = cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream);
-        if (e == cudaSuccess) rc = run_enqueue(h, B, grad);
-        if (e == cudaSuccess && rc == 0)
-            e = cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream);
-        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (e != cudaSuccess || e2 != cudaSuccess) {
+        const int rc = eval_sequence(h, B, grad, job);
+        const std::string why = g_err;
+        const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return fail(rc, why); }
+        if (e2 != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
-            return fail(PHYLO_B200_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+            return fail(PHYLO_B200_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e2));
         }
-        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        const cudaError_t e = cudaGraphInstantiate(&g.exec, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) { g.exec = nullptr; return fail(PHYLO_B200_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
         g.sig = sig;
     }
     CU_TRY(cudaGraphLaunch(g.exec, h->stream));
-    h->last_launches = grad ? 3 : 2;
+    h->last_launches = nlaunch;
     return 0;
 }
 
@@ -1096,6 +1127,7 @@ static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, 
     job.autocorr = autocorr; job.ratios = ratios; job.has_extra = hbar_extra && want_grad ? 1 : 0; job.nrates = nrates;
     job.in_ld = (S - 1) + nrates + (job.has_extra ? S - 1 : 0);
     job.hout_ld = (S - 1) + nrates + (S - 2) + 3;
+    job.want_heights = heights_out != nullptr;
     // parameter blocks (branch lengths are filled in on the device) and the front end's inputs
     static thread_local std::vector<double> zeros;
     zeros.assign((size_t)B * h->bcount, 0.0);
@@ -1112,6 +1144,7 @@ static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, 
         CU_TRY(cudaSetDevice(h->device));
         CU_TRY(h->h_cin.ensure((size_t)B * job.in_ld));
         CU_TRY(h->h_hout.ensure((size_t)B * job.hout_ld));
+        if (job.want_heights) CU_TRY(h->h_hts.ensure((size_t)B * (S - 1)));
     }
     for (int b = 0; b < B; ++b) {
         double* dst = h->h_cin.p + (size_t)b * job.in_ld;
@@ -1121,26 +1154,9 @@ static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, 
     }
     const bool grad = want_grad != 0;
     if (int rc = run_prepare_all(h, B, grad)) return rc;
-    const size_t in_bytes = sizeof(double) * B * h->lay.stride, out_bytes = sizeof(double) * B * h->nout;
-    if (!h->peers.empty()) {
-        if (int rc = multi_enqueue(h, B, grad, true, &job)) return rc;
-    } else {
-        CU_TRY(cudaMemcpyAsync(h->d_params.p, h->h_params.p, in_bytes, cudaMemcpyHostToDevice, h->stream));
-        if (int rc = clock_forward_enqueue(h, h, job, B)) return rc;
-        if (int rc = run_enqueue(h, B, grad)) return rc;
-        CU_TRY(cudaMemcpyAsync(h->h_out.p, h->d_out.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
-    }
-    if (grad) {
-        launch_clock_reverse(clock_args(h, job, B), h->stream);
-        CU_TRY(cudaGetLastError());
-        h->last_launches += 1;
-    }
-    h->last_launches += 1;
-    CU_TRY(cudaMemcpyAsync(h->h_hout.p, h->d_hout.p, sizeof(double) * B * job.hout_ld, cudaMemcpyDeviceToHost, h->stream));
-    if (heights_out)  // [heights | adjoint] rows of the work buffer: only the first half is wanted
-        CU_TRY(cudaMemcpy2DAsync(heights_out, sizeof(double) * (S - 1), h->d_hwork.p, sizeof(double) * 2 * (S - 1),
-                                 sizeof(double) * (S - 1), B, cudaMemcpyDeviceToHost, h->stream));
+    if (int rc = eval_enqueue(h, B, grad, &job)) return rc;
     CU_TRY(cudaStreamSynchronize(h->stream));
+    if (heights_out) std::memcpy(heights_out, h->h_hts.p, sizeof(double) * B * (S - 1));
     bool finite = true;
     for (int d = 0; d < B; ++d) {
         const double* o = h->h_out.p + (size_t)d * h->nout;

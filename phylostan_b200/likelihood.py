@@ -318,7 +318,7 @@ class TreeLikelihood:
         return logp, gh, gr, ValueGrad(logp, None, gs[:, :self.nsubst], gf, grs, gps)
 
     def value_grad_ratios_batch(self, map_, props, root_height, rates, lowers=None, subst=None, freqs=None, rs=None,
-                                ps=None, hbar_extra=None, autocorrelated=False, want_grad=True):
+                                ps=None, hbar_extra=None, autocorrelated=False, want_grad=True, return_heights=True):
         """The same with the ratio parametrisation of the heights (generate_script.py:711-752) on the device too
         (``phylo_b200_eval_ratios_batch``): props [B, S-2], root_height [B]; ``hbar_extra`` [B, S-1] is an extra
         adjoint of the heights (a tree prior's gradient) pushed through the reverse sweep.  Returns a dict:
@@ -332,7 +332,7 @@ class TreeLikelihood:
         rt, lo, subst, freqs, rs, ps = self._clock_inputs(B, rates, lowers, subst, freqs, rs, ps)
         hx = None if hbar_extra is None else _arr(np.atleast_2d(hbar_extra), (B, self.S - 1))
         nr = rt.shape[1]
-        logp, lj, hts = np.zeros(B), np.zeros(B), np.zeros((B, self.S - 1))
+        logp, lj, hts = np.zeros(B), np.zeros(B), (np.zeros((B, self.S - 1)) if return_heights else None)
         gp, groot, gr = np.zeros((B, max(self.S - 2, 1))), np.zeros(B), np.zeros((B, nr))
         gs, gf = np.zeros((B, max(self.nsubst, 1))), np.zeros((B, 4))
         grs, gps = np.zeros((B, self.C)), np.zeros((B, self.C))
