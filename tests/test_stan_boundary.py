@@ -198,3 +198,34 @@ def test_shim_value_and_gradient_through_stan_types(tmp_path, datasets, name, mo
         assert abs(got["pruning_loglik"] - want.logp) <= 1e-10 * abs(want.logp)
         assert tol(got["pruning_grad"], want.grad_blens)
         assert got["domain_error"] is True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devs", ["0", "0,0"])
+def test_run_side_publish_creates_the_default_handle(datasets, devs):
+    """phylostan_b200.run.publish -- what the patched `phylostan run` calls with its Stan data dict
+    (phylostan/phylostan.py:183-287): the handle the shim will find, on one GPU or sharded over several."""
+    import argparse
+    from oracle import oracle as O
+    from phylostan_b200 import encode as E, likelihood as lk, run
+    d = datasets["fluA"]
+    S, L = d["tipmask"].shape
+    tipdata = np.zeros((S, L, 4))
+    for s in range(4):
+        tipdata[:, :, s] = (d["tipmask"] >> s) & 1
+    data = {"peel": d["peel"], "tipdata": tipdata, "weights": d["weights"], "C": 4, "S": S, "L": L}
+    arg = argparse.Namespace(model="HKY", clock="strict", gpu_likelihood=True, gpu_devices=devs)
+    lik = run.publish(arg, data)
+    try:
+        assert lk.lib().phylo_b200_get_default() == lik._h.value
+        assert lik.info()["shards"] == len(devs.split(","))
+        rng = np.random.default_rng(3)
+        bl = rng.exponential(0.05, 2 * S - 2) + 1e-4
+        kappa, fr, rs, ps = np.array([5.0]), rng.dirichlet(np.ones(4) * 5), E.weibull_rates(0.5, 4), np.full(4, 0.25)
+        got = lik.value_grad(bl, kappa, fr, rs, ps)
+        want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.HKY, bl, kappa, fr, rs, ps)
+        assert abs(got.log_P - want.logp) <= 1e-10 * abs(want.logp)
+        assert np.max(np.abs(got.grad_blens - want.grad_blens) / np.maximum(1, np.abs(want.grad_blens))) <= 1e-8
+    finally:
+        lk.set_default(None)
+        lik.close()
