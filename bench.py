@@ -515,8 +515,14 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "sweep_traffic.json")
         if os.path.exists(tp):
+            # a constant of one ncu capture: only reported when THIS run launched the same kernel shape on the same
+            # problem shape (otherwise null -- a stale capture must not pass for a measurement)
             tj = json.load(open(tp))
-            traffic = tj.get("dram_bytes_per_evaluation")
+            cap = tj.get("capture", {})
+            same = (cap.get("taxa") == S_TAXA and cap.get("patterns") == L_PATTERNS and cap.get("categories") == N_CAT
+                    and cap.get("precision") == (32 if args.fp32 else 64)
+                    and all(cap.get(k) == info[k] for k in ("patterns_per_thread", "threads_per_cta", "stack_slots", "smem_bytes")))
+            traffic = tj.get("dram_bytes_per_evaluation") if same else None
             traffic = traffic * B if traffic else None   # one launch sweeps B draws
         if not args.fp32:
             parity["ok"] = all(v["ok"] for v in parity.values() if isinstance(v, dict))
@@ -545,7 +551,8 @@ def run_ours(args):
                          "survey_model_bytes_per_launch": alg,
                          "frac_vs_survey_model": alg / (sweep_ms * 1e-3) / 1e9 / peak,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the capture named in "
-                                           "profiles/sweep_traffic.json (a constant of that capture, not of this run)",
+                                           "profiles/sweep_traffic.json (a constant of that capture, not of this run; null when this run's "
+                                           "kernel shape differs from the captured one)",
                          "note": "algorithmic bytes = this design's own minimum DRAM traffic, 33 L C (2S-3) + 2SL + 8L per "
                                  "evaluation (one write + one read of every internal partial and its rescale byte, tip "
                                  "codes once per sweep), confirmed by ncu (traffic); frac_vs_survey_model uses SURVEY "

@@ -14,11 +14,11 @@
 #ifndef PHYLO_RSM
 #define PHYLO_RSM 0     // K > 1: 4x4 statistics summed over the warp through shared memory (0: shuffle exchange)
 #endif
-#ifndef PHYLO_BYTECP
-#define PHYLO_BYTECP 0  // byte operands through a cp.async shared-memory ring (1) or a two-step register look-ahead (0)
-#endif
 #ifndef PHYLO_PF
 #define PHYLO_PF 1      // pre-order: L2 prefetch of the scratch lines two steps ahead
+#endif
+#ifndef PHYLO_TIPRING
+#define PHYLO_TIPRING 0  // 1: 128-thread CTAs of simple-tip handles take their tip codes through the per-warp TipRing (A/B: +0.4 %, two more copies of the tip codes)
 #endif
 #ifndef PHYLO_PRETIP
 #define PHYLO_PRETIP 0  // pre-order: a simple tip child's message is a column of P (tip records column-major)
@@ -451,7 +451,8 @@ struct Ring {
     int slot;                    // ring slot (0..5) of the current record
     int lane;
 
-    __device__ __forceinline__ void issue() {
+    template <class F>
+    __device__ __forceinline__ void issue(F&& extra) {
         const unsigned dst = sbuf + wchunk * (kRecChunk * REC) + lane * 16;
         const unsigned char* s = next + lane * 16;
         constexpr int kTail = kRecChunk * REC - 512;  // bytes beyond the first 32 x 16 B (REC = 320) ...
@@ -461,29 +462,32 @@ struct Ring {
         } else if (remaining == 1 && lane < REC / 16) {
             cp_async16(dst, s);
         }
+        extra();            // the tip-code ring rides in the same commit group
         cp_async_commit();  // always commit: keeps the group count uniform
         next += kRecChunk * REC;
         remaining -= kRecChunk;
         wchunk = wchunk == kRecBufs - 1 ? 0 : wchunk + 1;
     }
     // afterwards records 0, 1 (and 2, 3 once step 0 ran) are in flight; call step(0) before reading
-    __device__ __forceinline__ void start(const unsigned char* stream, int n) {
+    template <class F>
+    __device__ __forceinline__ void start(const unsigned char* stream, int n, F&& extra) {
         cp_async_wait<0>();
         __syncwarp();
         next = stream;
         remaining = n;
         wchunk = 0;
         slot = 0;
-        issue();
-        issue();
+        issue(extra);
+        issue(extra);
     }
     // top of step i: afterwards the records of steps i, i+1, i+2 (even i: and i+3) are readable, and so
     // is every byte-operand block committed before this call
-    __device__ __forceinline__ void step(int i) {
+    template <class F>
+    __device__ __forceinline__ void step(int i, F&& extra) {
         if (i) slot = slot == kRecChunk * kRecBufs - 1 ? 0 : slot + 1;
         if ((i & 1) == 0) {
             __syncwarp();  // every lane is done with the chunk about to be overwritten
-            issue();
+            issue(extra);
             cp_async_wait<1>();
             __syncwarp();
         }
@@ -495,27 +499,46 @@ struct Ring {
     }
 };
 
-// Per-warp ring of BYTE operands (tip codes of both children, rescale exponents of the node): the
-// 32 K bytes a warp needs for one operand of one step are contiguous in global memory, so 2 K lanes
-// copy them with one 16-byte cp.async each, two to three steps before they are used, in the same
-// commit-group cadence as the record ring.  Nothing waits in a register (the register look-ahead this
-// replaces stalled every post-order step on its rotation: a tip-code line takes longer to arrive than
-// a step runs) and nothing passes through L1 (.cg), so the exponents written earlier by this kernel
-// are read coherently.  Step i uses slot i & 3: steps i, i+1 are being consumed while i+2, i+3 land.
+// Per-warp ring of TIP CODES in consumption order (TR kernels: 128-thread CTAs of simple-tip handles).  The handle
+// keeps, per sweep, a copy of the tip codes laid out [tile][slot][32 K]: slot s of a tile holds the codes of the
+// s-th tip child the sweep meets (child a before child b within a step).  A warp's codes therefore form ONE
+// contiguous stream per tile, and a chunk of four slots is a single cp.async per lane that rides in the record
+// ring's commit group -- no per-tip address arithmetic, no registers waiting on loads, and a look-ahead of 8-12
+// slots (the two-step register look-ahead this replaces was the kernel's largest single stall: a tip-code line
+// takes longer to arrive from HBM than two post-order steps run).  Twelve slots; a chunk is fetched at every
+// even step while at most eight slots are unread, which keeps at least four complete slots ahead of the two
+// steps that follow (a step consumes at most two).
 template <int K>
-struct ByteRing {
-    static constexpr int kBlk = 32 * K;     // bytes of one operand block
-    static constexpr int kSlot = 3 * kBlk;  // operands 0, 1: children's tip codes; 2: rescale exponents
-    static constexpr int kBytes = 4 * kSlot;
+struct TipRing {
+    static constexpr int kSlot = 32 * K;   // bytes: this warp's codes of one tip
+    static constexpr int kSlots = 12;
+    static constexpr int kBytes = kSlots * kSlot;
+    static constexpr int kLps = kSlot / 16;  // lanes (16 B each) per slot
     const unsigned char* buf;
     unsigned sbuf;
     int lane;
-    __device__ __forceinline__ void fetch(int step, int op, const uint8_t* src) const {
-        if (lane < 2 * K) cp_async16(sbuf + (step & 3) * kSlot + op * kBlk + lane * 16, src + lane * 16);
+    const uint8_t* src;  // next slot to fetch of this tile's stream
+    int left;            // slots of the stream not yet fetched
+    int unread;          // slots fetched and not yet consumed
+    int wpos, rpos;      // ring positions of the next chunk / the next read
+    __device__ __forceinline__ void start(const uint8_t* stream, int nslots) {
+        src = stream; left = nslots; unread = 0; wpos = 0; rpos = 0;
     }
-    // this lane's K bytes as one packed word: byte j = (w >> 8 j) & 0xff
-    __device__ __forceinline__ unsigned get(int step, int op) const {
-        const unsigned char* p = buf + (step & 3) * kSlot + op * kBlk + lane * K;
+    __device__ __forceinline__ void fetch() {
+        if (unread <= kSlots - 4 && left > 0) {
+            const int q = lane / kLps;  // slot of the chunk this lane copies into
+            if (lane < 4 * kLps && q < left) cp_async16(sbuf + (wpos + q) * kSlot + (lane % kLps) * 16, src + lane * 16);
+            src += 4 * kSlot;
+            left -= 4;
+            unread += 4;
+            wpos = wpos == kSlots - 4 ? 0 : wpos + 4;
+        }
+    }
+    // this lane's K codes of the next tip: byte j = (w >> 8 j) & 0xff
+    __device__ __forceinline__ unsigned get() {
+        const unsigned char* p = buf + rpos * kSlot + lane * K;
+        rpos = rpos == kSlots - 1 ? 0 : rpos + 1;
+        --unread;
         if (K == 4) return *reinterpret_cast<const unsigned*>(p);
         if (K == 2) return *reinterpret_cast<const unsigned short*>(p);
         return *p;
@@ -568,7 +591,9 @@ __device__ __forceinline__ void warp_reduce16_smem(const T (&v)[16], T* __restri
 // instead of the 4x4 statistic: with T = sum_x q_n(x) (P_a p_a)(x) (P_b p_b)(x),
 //   <A_b p_b^T, Q P_b> / mu = mean(p_b) sum(A_b) - T,   <A_a p_a^T, Q P_a> / mu = mean(p_a) sum(A_a) - T.
 // The scalar goes to entry 0 of the branch's G block; the contraction multiplies by mu.
-template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC>
+// TR: tip codes come through the per-warp TipRing from the handle's traversal-ordered copies (a.tips_post /
+// a.tips_pre) instead of per-step loads from the [S][Lpad] rows.
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC, bool TR>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -587,11 +612,13 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     Ring<R::kRec> ring;
     ring.buf = sm_p + warp * (R::kRec * kRecChunk * kRecBufs);
     sm_p += (NT / 32) * (R::kRec * kRecChunk * kRecBufs);
-    ByteRing<K> bytes;
-    bytes.buf = sm_p + warp * ByteRing<K>::kBytes;
-    bytes.sbuf = (unsigned)__cvta_generic_to_shared(bytes.buf);
-    bytes.lane = lane;
-    if (PHYLO_BYTECP) sm_p += (NT / 32) * ByteRing<K>::kBytes;
+    TipRing<K> tr;
+    tr.buf = sm_p + warp * TipRing<K>::kBytes;
+    tr.sbuf = (unsigned)__cvta_generic_to_shared(tr.buf);
+    tr.lane = lane;
+    tr.start(nullptr, 0);
+    if (TR) sm_p += (NT / 32) * TipRing<K>::kBytes;
+    auto tipfetch = [&]() { if (TR) tr.fetch(); };
     // K == 1 (small, latency-bound problems): the two 4x4 statistics of a step are summed over the warp
     // in one pass, [32 entries][33] per warp; K > 1: one child at a time, [16 entries][34] per warp
     T* const red = reinterpret_cast<T*>(sm_p) + warp * (K == 1 ? 32 * 33 : 16 * 34);
@@ -628,30 +655,15 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             etot[j] = 0;
             tos[j][0] = tos[j][1] = tos[j][2] = tos[j][3] = T(0);
         }
-        ring.start(a.spost + stream_off, nsteps);
-        ring.step(0);
-#if PHYLO_BYTECP
-        // tip codes of the children of steps 0..3 -> byte ring (two commit groups)
-        {
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (u < nsteps) {
-                    const PostRec* r = reinterpret_cast<const PostRec*>(ring.rec(u));
-                    if (r->flags & 1) bytes.fetch(u, 0, tipw + r->tip_a);
-                    if (r->flags & 2) bytes.fetch(u, 1, tipw + r->tip_b);
-                    if (u == 1) cp_async_commit();
-                }
-            if (nsteps < 2) cp_async_commit();
-            cp_async_commit();
-            cp_async_wait<1>();
-            __syncwarp();
-        }
-#else
+        const size_t wblock = (size_t)(pat0 - lane * K) / (32 * K);  // this warp's block of 32 K patterns
+        if (TR) tr.start(a.tips_post + wblock * a.S * TipRing<K>::kSlot, a.S);
+        ring.start(a.spost + stream_off, nsteps, tipfetch);
+        ring.step(0, tipfetch);
         // tip codes of the children of steps i (ca, cb), i+1 (ca1, cb1) and, inside the loop, i+2:
-        // K codes per lane packed in one word, loaded two steps ahead of their use
+        // K codes per lane packed in one word, loaded two steps ahead of their use (TR: from the tip ring)
         const uint8_t* tipp = tipw + lane * K;
         unsigned ca = 0u, cb = 0u, ca1 = 0u, cb1 = 0u;
-        {
+        if (!TR) {
             const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
             if (r0->flags & 1) ca = ldg_bytes<K>(tipp + r0->tip_a);
             if (r0->flags & 2) cb = ldg_bytes<K>(tipp + r0->tip_b);
@@ -661,7 +673,6 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 if (r1->flags & 2) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
             }
         }
-#endif
         V* srow = sct;  // scratch row of step i
         uint8_t* drow = dlt;
         // value-only kernels unroll by two (measured +6 % at K = 4, +13 % at K = 2; nothing in the gradient
@@ -669,37 +680,20 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         constexpr int kPostUnroll = GRAD ? 1 : 2;
 #pragma unroll kPostUnroll
         for (int i = 0; i < nsteps; ++i) {
-#if PHYLO_BYTECP
-            if (i) {
-                ring.step(i);
-                if ((i & 1) == 0) {  // records i+2, i+3 just became readable: their tip codes -> byte ring
-#pragma unroll
-                    for (int u = 2; u < 4; ++u)
-                        if (i + u < nsteps) {
-                            const PostRec* r = reinterpret_cast<const PostRec*>(ring.rec(u));
-                            if (r->flags & 1) bytes.fetch(i + u, 0, tipw + r->tip_a);
-                            if (r->flags & 2) bytes.fetch(i + u, 1, tipw + r->tip_b);
-                        }
-                    cp_async_commit();
-                }
-            }
-            const unsigned char* rec = ring.rec(0);
-            const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
-            const int fl = s1.w;
-            const unsigned ca = (fl & 1) ? bytes.get(i, 0) : 0u, cb = (fl & 2) ? bytes.get(i, 1) : 0u;
-#else
-            if (i) ring.step(i);
+            if (i) ring.step(i, tipfetch);
             const unsigned char* rec = ring.rec(0);
             const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
             const int fl = s1.w;
             unsigned ca2 = 0u, cb2 = 0u;
-            if (i + 2 < nsteps) {  // tip codes of step i+2 -> registers
+            if (TR) {
+                if (fl & 1) ca = tr.get();
+                if (fl & 2) cb = tr.get();
+            } else if (i + 2 < nsteps) {  // tip codes of step i+2 -> registers
                 const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(2));
                 const int nf = n->flags;
                 if (nf & 1) ca2 = ldg_bytes<K>(tipp + n->tip_a);
                 if (nf & 2) cb2 = ldg_bytes<K>(tipp + n->tip_b);
             }
-#endif
             T ma[K][4], mb[K][4];
             if (DEEP && (fl & 16)) {  // rare: child a was parked above the capped stack, in its scratch row
                 T M[16];
@@ -786,9 +780,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             if (GRAD && PHYLO_ABLATE != 3 && PHYLO_ABLATE != 6) stcs_bytes<K>(drow, kpack);
             srow += SS;
             drow += K * NT;
-#if !PHYLO_BYTECP
-            ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2;
-#endif
+            if (!TR) { ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2; }
         }
 
         // -------------------------------------------------------------- root: site likelihoods
@@ -796,7 +788,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         double pi[4];
 #pragma unroll
         for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
-        if (GRAD) ring.start(a.spre + stream_off, nsteps);  // overlaps the root exchange
+        if (GRAD) {  // overlaps the root exchange
+            if (TR) tr.start(a.tips_pre + wblock * a.S * TipRing<K>::kSlot, a.S);
+            ring.start(a.spre + stream_off, nsteps, tipfetch);
+        }
         double rdot[K];
         __syncthreads();  // every warp has emptied its stack: the exchange arrays may borrow it
 #pragma unroll
@@ -837,41 +832,22 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 
         // -------------------------------------------------------------- pre-order
         if (GRAD) {
-            ring.step(0);
-#if PHYLO_BYTECP
-            // byte operands of steps n: tip codes of the children (0, 1), rescale exponents of the node (2)
-            {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (u < nsteps) {
-                        const PreRec* r = reinterpret_cast<const PreRec*>(ring.rec(u));
-                        if (r->row_a < 0) bytes.fetch(u, 0, tipw + r->tip_a);
-                        if (r->row_b < 0) bytes.fetch(u, 1, tipw + r->tip_b);
-                        bytes.fetch(u, 2, dlw + r->dl_n);
-                        if (u == 1) cp_async_commit();
-                    }
-                if (nsteps < 2) cp_async_commit();
-                cp_async_commit();
-                cp_async_wait<1>();
-                __syncwarp();
-            }
-#else
+            ring.step(0, tipfetch);
             // packed byte operands of steps i (ca, cb, dcur = rescale exponents of the node) and i+1
             unsigned dcur, d1 = 0u;
             ca = cb = ca1 = cb1 = 0u;
             {
                 const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
-                if (r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
-                if (r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
+                if (!TR && r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
+                if (!TR && r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
                 dcur = ld_bytes<K>(dlt + r0->dl_n);
                 if (nsteps > 1) {
                     const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
-                    if (r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
-                    if (r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
+                    if (!TR && r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
+                    if (!TR && r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
                     d1 = ld_bytes<K>(dlt + r1->dl_n);
                 }
             }
-#endif
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
             // children's partials of the current step; loaded from scratch during the previous step's
             // tail (after their last use there), so no extra registers and a reduction's worth of cover
@@ -892,41 +868,21 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 }
             }
             for (int i = 0; i < nsteps; ++i) {
-#if PHYLO_BYTECP
-                if (i) {
-                    ring.step(i);
-                    if ((i & 1) == 0) {
-#pragma unroll
-                        for (int u = 2; u < 4; ++u)
-                            if (i + u < nsteps) {
-                                const PreRec* r = reinterpret_cast<const PreRec*>(ring.rec(u));
-                                if (r->row_a < 0) bytes.fetch(i + u, 0, tipw + r->tip_a);
-                                if (r->row_b < 0) bytes.fetch(i + u, 1, tipw + r->tip_b);
-                                bytes.fetch(i + u, 2, dlw + r->dl_n);
-                            }
-                        cp_async_commit();
-                    }
-                }
-#else
-                if (i) ring.step(i);
-#endif
+                if (i) ring.step(i, tipfetch);
                 const unsigned char* rec = ring.rec(0);
                 const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
                 const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
                 const int rowa = s1.x, rowb = s1.y;
-#if PHYLO_BYTECP
-                const unsigned ca = rowa < 0 ? bytes.get(i, 0) : 0u, cb = rowb < 0 ? bytes.get(i, 1) : 0u;
-                const unsigned dcur = bytes.get(i, 2);
-#else
                 unsigned ca2 = 0u, cb2 = 0u, d2 = 0u;
-#endif
+                if (TR) {
+                    if (rowa < 0) ca = tr.get();
+                    if (rowb < 0) cb = tr.get();
+                }
                 if (i + 2 < nsteps) {  // operands of step i+2: bytes -> registers, scratch lines -> L2
                     const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
                     const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
                     if (n1.x < 0) {
-#if !PHYLO_BYTECP
-                        ca2 = ldg_bytes<K>(tipp + n->tip_a);
-#endif
+                        if (!TR) ca2 = ldg_bytes<K>(tipp + n->tip_a);
                     } else if (PHYLO_PF) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
@@ -934,18 +890,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.x, j) + h * NT);
                     }
                     if (n1.y < 0) {
-#if !PHYLO_BYTECP
-                        cb2 = ldg_bytes<K>(tipp + n->tip_b);
-#endif
+                        if (!TR) cb2 = ldg_bytes<K>(tipp + n->tip_b);
                     } else if (PHYLO_PF) {
 #pragma unroll
                         for (int j = 0; j < K; ++j)
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
-#if !PHYLO_BYTECP
                     d2 = ld_bytes<K>(dlt + n1.z);
-#endif
                 }
                 // q(node) lives in the TOS registers for the whole step: either it is still there (the
                 // node was the previous step's first child) or it is popped from the shared-memory stack
@@ -1108,9 +1060,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
                     }
                 }
-#if !PHYLO_BYTECP
-                ca = ca1; cb = cb1; dcur = d1; ca1 = ca2; cb1 = cb2; d1 = d2;
-#endif
+                if (!TR) { ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2; }
+                dcur = d1; d1 = d2;
             }
         }
 
@@ -1314,6 +1265,22 @@ __global__ void __launch_bounds__(256) tips_index_kernel(uint8_t* __restrict__ t
     }
 }
 
+// [S][Lpad] code rows -> [ntiles][S][T] in consumption order: slot s of every tile holds the T codes of tip order[s]
+__global__ void __launch_bounds__(256) tips_reorder_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                            const int32_t* __restrict__ order, int S, int Lpad, int T,
+                                                            size_t total) {
+    // one thread per 4 bytes (T is a multiple of 32, Lpad of 512)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total / 4; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i * 4;
+        const int j = (int)(b % T);
+        const size_t ts = b / T;
+        const int s = (int)(ts % S);
+        const size_t tile = ts / S;
+        *reinterpret_cast<uint32_t*>(dst + b) =
+            *reinterpret_cast<const uint32_t*>(src + (size_t)order[s] * Lpad + tile * T + j);
+    }
+}
+
 // weights [L] (or NULL: ones) -> [Lpad] (padding = 0); flags[1] is raised on a non-finite weight
 __global__ void __launch_bounds__(256) weights_pad_kernel(const double* __restrict__ w, double* __restrict__ dst, int L,
                                                            int Lpad, int* __restrict__ flags) {
@@ -1507,10 +1474,11 @@ template <> struct Cfg<float, 4> { static constexpr int minb = 3; };
 
 typedef void (*SweepFn)(const SweepArgs);
 
+// 128-thread CTAs of simple-tip handles take their tip codes through the TipRing (PHYLO_TIPRING)
 template <typename T, int K, bool GRAD, bool TIPS, bool DEEP, bool JC = false>
 SweepFn pick_kernel(int nthreads) {
-    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP, JC>;
-    return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC>;
+    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP, JC, TIPS && PHYLO_TIPRING>;
+    return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC, false>;
 }
 
 // scalar-statistic gradient kernels (JC69, fp64, whole stack on chip)
@@ -1558,6 +1526,8 @@ SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, boo
 
 int sweep_max_threads(int) { return 512; }
 
+bool sweep_uses_tipring(bool tips, int nthreads) { return PHYLO_TIPRING && tips && nthreads == 128; }
+
 int record_bytes(int prec) { return prec == 32 ? kRecBytesF32 : kRecBytes; }
 
 size_t sweep_stack_bytes(int D, int K, int nthreads, int prec) {
@@ -1567,14 +1537,14 @@ size_t sweep_stack_bytes(int D, int K, int nthreads, int prec) {
 }
 
 // [stack | record rings | byte rings | reduction rows], all per warp except the stack
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc) {
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc, bool tips) {
     const size_t val = prec == 32 ? 4 : 8;
     const size_t warps = nthreads / 32;
     size_t red = 0;
     if (K == 1) red = warps * 32 * 33 * val;                       // both children in one pass
     else if (PHYLO_RSM && !jc) red = warps * 16 * 34 * val;        // one child at a time
     return sweep_stack_bytes(D, K, nthreads, prec) + warps * record_bytes(prec) * kRecChunk * kRecBufs +
-           (PHYLO_BYTECP ? warps * (4 * 3 * 32 * K) : 0) + red;
+           (sweep_uses_tipring(tips, nthreads) ? warps * (size_t)(12 * 32 * K) : 0) + red;
 }
 
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
@@ -1608,6 +1578,13 @@ void launch_tips_prepare(const uint8_t* d_src, uint8_t* d_dst, int S, int L, int
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
     tips_pad_kernel<<<grid, 256, 0, stream>>>(d_src, d_dst, L, Lpad, total, d_flags);
     weights_pad_kernel<<<(Lpad + 255) / 256, 256, 0, stream>>>(d_w, d_wdst, L, Lpad, d_flags);
+}
+
+void launch_tips_reorder(const uint8_t* d_tips, uint8_t* d_dst, const int32_t* d_order, int S, int Lpad, int T, int ntiles,
+                         cudaStream_t stream) {
+    const size_t total = (size_t)ntiles * S * T;
+    const int grid = (int)std::min<size_t>((total / 4 + 255) / 256, (size_t)148 * 32);
+    tips_reorder_kernel<<<grid, 256, 0, stream>>>(d_tips, d_dst, d_order, S, Lpad, T, total);
 }
 
 void launch_tips_index(uint8_t* d_tips, int S, int Lpad, cudaStream_t stream) {

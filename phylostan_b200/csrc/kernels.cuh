@@ -89,6 +89,8 @@ struct StreamArgs {
 
 struct SweepArgs {
     const uint8_t* tips;      // [S][Lpad] 4-bit state masks, or column indices 0..4 when every tip is simple
+    const uint8_t* tips_post; // TR kernels: the same codes as [tile][slot][32 K] in post-order / pre-order consumption
+    const uint8_t* tips_pre;  //   order (slot = s-th tip child met by the sweep, child a before child b)
     const double* weights;    // [Lpad]
     const double* params;     // [B][stride]
     const unsigned char* spost;
@@ -161,7 +163,11 @@ void launch_clock_forward(const ClockArgs& a, cudaStream_t stream);
 void launch_clock_reverse(const ClockArgs& a, cudaStream_t stream);
 
 // jc: the scalar-statistic kernel needs no reduction rows
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false);
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false, bool tips = false);
+bool sweep_uses_tipring(bool tips, int nthreads);  // 128-thread CTAs of simple-tip handles
+// [S][Lpad] code rows -> [ntiles][S][T] with slot s = tip d_order[s] (0-based), T = patterns per tile
+void launch_tips_reorder(const uint8_t* d_tips, uint8_t* d_dst, const int32_t* d_order, int S, int Lpad, int T, int ntiles,
+                         cudaStream_t stream);
 size_t sweep_stack_bytes(int D, int K, int nthreads, int prec);  // first region of the above
 int record_bytes(int prec);
 int sweep_max_threads(int K);  // largest CTA the K-variant is compiled for

@@ -93,6 +93,12 @@ struct phylo_b200_ctx {
 
     // static device data
     DevBuf<uint8_t> d_tips;
+    // TR kernels: the tip codes once more per sweep, [block of 32 K patterns][slot][32 K] in the order the sweep
+    // consumes them (built on the device the first time a tiling with this K runs)
+    DevBuf<uint8_t> d_tips_post, d_tips_pre;
+    DevBuf<int32_t> d_tip_order;  // [2][S]: tip (0-based) of every slot, post-order then pre-order
+    int tipring_K = 0;            // K the copies above were built for (0: none); the pre-order copy only for gradient runs
+    bool tipring_pre = false;
     DevBuf<double> d_weights;
     DevBuf<PostStep> d_post;
     DevBuf<PreStep> d_pre;
@@ -155,6 +161,7 @@ struct phylo_b200_ctx {
         d_cmap.release(); d_ckids.release(); d_crow.release(); d_clowers.release(); d_cin.release();
         d_hwork.release(); d_hout.release(); h_cin.release(); h_hout.release(); h_hts.release();
         d_tips.release(); d_weights.release(); d_post.release(); d_pre.release();
+        d_tips_post.release(); d_tips_pre.release(); d_tip_order.release();
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
@@ -185,7 +192,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     auto slots_for = [&](int k, int nt, int want, bool j) {
         for (int dd = Dmax; dd >= (j ? Dfull : Dmin); --dd) {
             int occ = 0;
-            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec, j);
+            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple);
             if (sm <= h->smem_optin &&
                 sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sm, &occ, j) == cudaSuccess &&
                 occ >= want)
@@ -214,7 +221,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
                 if (dd < 0) continue;
                 int occ = 0;
                 if (sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt,
-                                    sweep_smem_bytes(dd, k, nt, h->prec, j), &occ, j) != cudaSuccess || occ < 1)
+                                    sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple), &occ, j) != cudaSuccess || occ < 1)
                     continue;
                 const double items = (double)B * ((h->L + 32 * k - 1) / (32 * k));
                 const double w = items / ((double)occ * h->num_sms);
@@ -249,7 +256,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             return fail(PHYLO_B200_EINVAL,
                         "tree too deep for the shared-memory stack (depth " + std::to_string(Dfull) + ")");
     }
-    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun);
+    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun, h->tips_simple);
     const int tpat = PB * 32 * K;
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun;
     h->ntiles = (h->L + tpat - 1) / tpat;
@@ -687,6 +694,37 @@ namespace {
 int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
     if ((size_t)B * h->lay.stride > h->d_params.n) return fail(PHYLO_B200_EINVAL, "run: upload B draws first");
     if (int rc = resolve_tiling(h, B, grad)) return rc;
+    if (sweep_uses_tipring(h->tips_simple, h->NT) && (h->tipring_K != h->K || (grad && !h->tipring_pre))) {
+        const int S = h->S, T = 32 * h->K, nblocks = h->Lpad / T;
+        if (!h->d_tip_order.p) {  // slot -> tip, in the order each sweep meets its tip children (a before b)
+            std::vector<int32_t> order;
+            for (const PostStep& p : h->plan.post) {
+                if (p.a < S) order.push_back(p.a);
+                if (p.b < S) order.push_back(p.b);
+            }
+            for (const PreStep& p : h->plan.pre) {
+                if (p.a < S) order.push_back(p.a);
+                if (p.b < S) order.push_back(p.b);
+            }
+            if ((int)order.size() != 2 * S) return fail(PHYLO_B200_EINVAL, "internal: every tip must be a child exactly once");
+            CU_TRY(h->d_tip_order.ensure(order.size()));
+            CU_TRY(cudaMemcpy(h->d_tip_order.p, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        }
+        CU_TRY(cudaStreamSynchronize(h->stream));  // a sweep reading the old copies may still run
+        if (h->tipring_K != h->K) {
+            h->tipring_K = 0; h->tipring_pre = false;
+            CU_TRY(h->d_tips_post.ensure((size_t)S * h->Lpad));
+            launch_tips_reorder(h->d_tips.p, h->d_tips_post.p, h->d_tip_order.p, S, h->Lpad, T, nblocks, h->stream);
+            CU_TRY(cudaGetLastError());
+        }
+        if (grad && !h->tipring_pre) {
+            CU_TRY(h->d_tips_pre.ensure((size_t)S * h->Lpad));
+            launch_tips_reorder(h->d_tips.p, h->d_tips_pre.p, h->d_tip_order.p + S, S, h->Lpad, T, nblocks, h->stream);
+            CU_TRY(cudaGetLastError());
+            h->tipring_pre = true;
+        }
+        h->tipring_K = h->K;
+    }
     if (grad) {
         const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
         CU_TRY(h->d_scratch.ensure(rows * 2));  // 16-byte vectors; fp32 uses half of them
@@ -802,7 +840,8 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
 
     SweepArgs a{};
-    a.tips = h->d_tips.p; a.weights = h->d_weights.p; a.params = h->d_params.p;
+    a.tips = h->d_tips.p; a.tips_post = h->d_tips_post.p; a.tips_pre = h->d_tips_pre.p;
+    a.weights = h->d_weights.p; a.params = h->d_params.p;
     a.spost = h->d_spost.p; a.spre = h->d_spre.p;
     a.scratch = h->d_scratch.p; a.dscr = h->d_dscr.p; a.G = h->d_G.p; a.out = h->d_out.p;
     a.lay = h->lay;
@@ -843,7 +882,7 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
             u(h->d_dscr.p), u(h->h_params.p), u(h->h_out.p), u(h->stream), (unsigned long long)h->K,
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
             (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
-            (unsigned long long)h->jc_run};
+            (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p)};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
