@@ -18,7 +18,9 @@
 #define PHYLO_PF 1      // pre-order: L2 prefetch of the scratch lines two steps ahead
 #endif
 #ifndef PHYLO_TIPRING
-#define PHYLO_TIPRING 0  // 1: 128-thread CTAs of simple-tip handles take their tip codes through the per-warp TipRing (A/B: +0.4 %, two more copies of the tip codes)
+#define PHYLO_TIPRING 1  // value-only kernels (128-thread CTAs, simple-tip handles) take their tip codes through the per-warp
+                         // TipRing: +6 / +10 / +17 % at K = 4 / 2 / 1 (r2_ab_6.log); 2: gradient kernels too (+0.4 %, and a
+                         // second traversal-ordered copy of the alignment: not worth it)
 #endif
 #ifndef PHYLO_PRETIP
 #define PHYLO_PRETIP 0  // pre-order: a simple tip child's message is a column of P (tip records column-major)
@@ -1477,7 +1479,8 @@ typedef void (*SweepFn)(const SweepArgs);
 // 128-thread CTAs of simple-tip handles take their tip codes through the TipRing (PHYLO_TIPRING)
 template <typename T, int K, bool GRAD, bool TIPS, bool DEEP, bool JC = false>
 SweepFn pick_kernel(int nthreads) {
-    if (nthreads == 128) return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP, JC, TIPS && PHYLO_TIPRING>;
+    if (nthreads == 128)
+        return sweep_kernel<T, K, GRAD, TIPS, 128, Cfg<T, K>::minb, DEEP, JC, TIPS && (PHYLO_TIPRING == 2 || (PHYLO_TIPRING == 1 && !GRAD))>;
     return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC, false>;
 }
 
@@ -1526,7 +1529,9 @@ SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, boo
 
 int sweep_max_threads(int) { return 512; }
 
-bool sweep_uses_tipring(bool tips, int nthreads) { return PHYLO_TIPRING && tips && nthreads == 128; }
+bool sweep_uses_tipring(bool tips, int nthreads, bool grad) {
+    return tips && nthreads == 128 && (PHYLO_TIPRING == 2 || (PHYLO_TIPRING == 1 && !grad));
+}
 
 int record_bytes(int prec) { return prec == 32 ? kRecBytesF32 : kRecBytes; }
 
@@ -1537,14 +1542,14 @@ size_t sweep_stack_bytes(int D, int K, int nthreads, int prec) {
 }
 
 // [stack | record rings | byte rings | reduction rows], all per warp except the stack
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc, bool tips) {
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc, bool tips, bool grad) {
     const size_t val = prec == 32 ? 4 : 8;
     const size_t warps = nthreads / 32;
     size_t red = 0;
     if (K == 1) red = warps * 32 * 33 * val;                       // both children in one pass
     else if (PHYLO_RSM && !jc) red = warps * 16 * 34 * val;        // one child at a time
     return sweep_stack_bytes(D, K, nthreads, prec) + warps * record_bytes(prec) * kRecChunk * kRecBufs +
-           (sweep_uses_tipring(tips, nthreads) ? warps * (size_t)(12 * 32 * K) : 0) + red;
+           (sweep_uses_tipring(tips, nthreads, grad) ? warps * (size_t)(12 * 32 * K) : 0) + red;
 }
 
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {

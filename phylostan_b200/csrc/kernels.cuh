@@ -163,8 +163,8 @@ void launch_clock_forward(const ClockArgs& a, cudaStream_t stream);
 void launch_clock_reverse(const ClockArgs& a, cudaStream_t stream);
 
 // jc: the scalar-statistic kernel needs no reduction rows
-size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false, bool tips = false);
-bool sweep_uses_tipring(bool tips, int nthreads);  // 128-thread CTAs of simple-tip handles
+size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc = false, bool tips = false, bool grad = true);
+bool sweep_uses_tipring(bool tips, int nthreads, bool grad);  // value-only kernels, 128-thread CTAs, simple-tip handles
 // [S][Lpad] code rows -> [ntiles][S][T] with slot s = tip d_order[s] (0-based), T = patterns per tile
 void launch_tips_reorder(const uint8_t* d_tips, uint8_t* d_dst, const int32_t* d_order, int S, int Lpad, int T, int ntiles,
                          cudaStream_t stream);

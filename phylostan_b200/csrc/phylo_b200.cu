@@ -192,7 +192,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
     auto slots_for = [&](int k, int nt, int want, bool j) {
         for (int dd = Dmax; dd >= (j ? Dfull : Dmin); --dd) {
             int occ = 0;
-            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple);
+            const size_t sm = sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple, grad);
             if (sm <= h->smem_optin &&
                 sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt, sm, &occ, j) == cudaSuccess &&
                 occ >= want)
@@ -221,7 +221,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
                 if (dd < 0) continue;
                 int occ = 0;
                 if (sweep_occupancy(h->prec, h->tips_simple, k, grad, dd < Dfull, nt,
-                                    sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple), &occ, j) != cudaSuccess || occ < 1)
+                                    sweep_smem_bytes(dd, k, nt, h->prec, j, h->tips_simple, grad), &occ, j) != cudaSuccess || occ < 1)
                     continue;
                 const double items = (double)B * ((h->L + 32 * k - 1) / (32 * k));
                 const double w = items / ((double)occ * h->num_sms);
@@ -256,7 +256,7 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             return fail(PHYLO_B200_EINVAL,
                         "tree too deep for the shared-memory stack (depth " + std::to_string(Dfull) + ")");
     }
-    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun, h->tips_simple);
+    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun, h->tips_simple, grad);
     const int tpat = PB * 32 * K;
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun;
     h->ntiles = (h->L + tpat - 1) / tpat;
@@ -694,7 +694,7 @@ namespace {
 int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
     if ((size_t)B * h->lay.stride > h->d_params.n) return fail(PHYLO_B200_EINVAL, "run: upload B draws first");
     if (int rc = resolve_tiling(h, B, grad)) return rc;
-    if (sweep_uses_tipring(h->tips_simple, h->NT) && (h->tipring_K != h->K || (grad && !h->tipring_pre))) {
+    if (sweep_uses_tipring(h->tips_simple, h->NT, grad) && (h->tipring_K != h->K || (grad && !h->tipring_pre))) {
         const int S = h->S, T = 32 * h->K, nblocks = h->Lpad / T;
         if (!h->d_tip_order.p) {  // slot -> tip, in the order each sweep meets its tip children (a before b)
             std::vector<int32_t> order;
