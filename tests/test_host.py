@@ -284,3 +284,31 @@ def test_ratio_transform_helpers_match_the_stan_loops():
     bad[5, 1] = 1                                            # a tip as parent
     with pytest.raises(lk.PhyloB200Error):
         lk.ratios_forward(bad, lowers, props, root)
+
+
+def test_front_end_map_validation_is_shared_by_forward_and_reverse():
+    """One validation for every front-end entry (round-1 advice: ratios_reverse indexed with unchecked map rows, and a
+    duplicated or missing node went unnoticed): row 0 = root, every node once, after its parent, two children each."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "fluA.npz"))
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(8)
+    props, root = rng.uniform(0.1, 0.9, (2, S - 2)), np.array([30.0, 40.0])
+    h, _ = lk.ratios_forward(d["map"], None, props, root)
+    good = np.array(d["map"])
+
+    def broken(edit):
+        m = good.copy()
+        edit(m)
+        return m
+    cases = {
+        "root not in row 0": broken(lambda m: m.__setitem__((0, 0), int(m[1, 0]))),
+        "node twice": broken(lambda m: m.__setitem__(3, m[2].copy())),
+        "child before its parent": broken(lambda m: m.__setitem__(slice(1, None), m[:0:-1].copy())),
+        "out of range": broken(lambda m: m.__setitem__((4, 0), 2 * S + 5)),
+        "tip as parent": broken(lambda m: m.__setitem__((5, 1), 1)),
+    }
+    for name, m in cases.items():
+        with pytest.raises(lk.PhyloB200Error):
+            lk.ratios_forward(m, None, props, root)
+        with pytest.raises(lk.PhyloB200Error):
+            lk.ratios_reverse(m, None, props, h, np.ones((2, S - 1)))
