@@ -457,7 +457,7 @@ struct Ring {
     __device__ __forceinline__ void issue(F&& extra) {
         const unsigned dst = sbuf + wchunk * (kRecChunk * REC) + lane * 16;
         const unsigned char* s = next + lane * 16;
-        constexpr int kTail = kRecChunk * REC - 512;  // bytes beyond the first 32 x 16 B (REC = 320) ...
+        constexpr int kTail = kRecChunk * REC - 512;  // bytes of a two-record chunk beyond the first 32 x 16 B (fp64: 768 B per chunk)
         if (remaining >= 2) {
             if (kTail >= 0 || lane < (kRecChunk * REC) / 16) cp_async16(dst, s);
             if (kTail > 0 && lane < kTail / 16) cp_async16(dst + 512, s + 512);
