@@ -494,6 +494,36 @@ def run_ours(args):
         parity["e2e_vs_resident"] = {"what": "host-buffer API result vs device-resident result, draw 0",
                                      "logL_rel": e2e_vs_resident["logL_rel"],
                                      "grad_max_err": e2e_vs_resident["grad_max_err"], "ok": e2e_vs_resident["ok"]}
+    # ---- secondary numbers of the same handle, reported separately (not the headline): the value-only sweep and the
+    #      optional fp32-with-scaling mode with its error against the fp64 rows just timed
+    extras = None
+    if world == 1 and not args.fp32 and not args.no_extras:
+        def timed(grad, n=3):
+            lik.run(B, grad)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(n):
+                lik.run(B, grad)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        lik.upload(bl, rates, freqs, rs, ps)
+        ms_value = timed(False)
+        lik.set_precision(32)
+        ms32 = timed(True)
+        r32 = lik.download(B)
+        lik.set_precision(64)
+        g64, g32 = local_rows[:, 1:], r32[:, 1:]
+        extras = {
+            "value_only": {"ms_per_step": ms_value, "tree_evals_per_s": B / ms_value * 1e3,
+                           "value": B * L_PATTERNS * N_CAT / ms_value * 1e3, "unit": UNIT.replace("evals", "value-only evals")},
+            "fp32_with_scaling": {"ms_per_step": ms32, "tree_evals_per_s": B / ms32 * 1e3, "value": B * L_PATTERNS * N_CAT / ms32 * 1e3,
+                                  "unit": UNIT, "dtype": "f32 partials / f64 sums",
+                                  "error_vs_fp64": {
+                                      "logL_max_rel": float(np.max(np.abs(r32[:, 0] - local_rows[:, 0]) / np.abs(local_rows[:, 0]))),
+                                      "grad_max_abs_over_max_abs": float(np.max(np.abs(g32 - g64)) / np.max(np.abs(g64))),
+                                      "grad_median_rel": float(np.median(np.abs(g32 - g64) / np.maximum(1e-300, np.abs(g64))))},
+                                  "note": "optional mode, outside the 1e-10 / 1e-8 parity guarantee"}}
     lik.close()
     del out_t
 
@@ -560,6 +590,7 @@ def run_ours(args):
             "cpu_baseline": cpu, "clocks": clocks,
             "parity": parity,
             "config4": config4,
+            "extras": extras,
             "checksum_logL_draw0": float(res[0, 0]),
         }
         if ref64 is not None and world == 1:
@@ -598,6 +629,7 @@ def main():
     ap.add_argument("--kernel-times", action="store_true", help="read per-kernel events every step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the 1-thread cpu_baseline sample (the parity oracle run stays)")
     ap.add_argument("--no-config4", action="store_true", help="skip the 10k x 1M strong-scaling block")
+    ap.add_argument("--no-extras", action="store_true", help="skip the value-only / fp32-mode block (N = 1 only)")
     ap.add_argument("--fp32", action="store_true",
                     help="optional fp32-with-scaling mode (reported separately; NOT the headline, dtype f32)")
     args = ap.parse_args()
