@@ -75,3 +75,27 @@ def test_run_side_helpers_without_gpu():
     assert not run.enabled(p.parse_args([])) and run.devices(p.parse_args([])) == [0]
     with pytest.raises(ValueError):
         run.devices(p.parse_args(["--gpu-devices", "-1"]))
+
+
+def test_stan_model_hook_loads_the_library_first_and_passes_the_shim(tmp_path):
+    """run.stan_model = what the patched phylostan calls instead of pystan.StanModel(file=...): libphylo_b200 is loaded
+    RTLD_GLOBAL before the compile (so the model extension's phylo_b200_* symbols bind), and the compile gets
+    allow_undefined + the shim header + include directories that exist (the eigen/eigen.py:79-87 mechanism)."""
+    from phylostan_b200 import likelihood, run
+    seen = {}
+
+    class FakePystan:
+        @staticmethod
+        def StanModel(file=None, **kw):
+            seen["lib_loaded"] = likelihood._lib is not None
+            seen["file"], seen["kw"] = file, kw
+            return "model"
+    script = tmp_path / "m.stan"
+    script.write_text("model{}")
+    assert run.stan_model(str(script), FakePystan) == "model"
+    assert seen["lib_loaded"] and seen["file"] == str(script)
+    kw = seen["kw"]
+    assert kw["allow_undefined"] is True and kw["includes"] == ["phylo_b200_stan.hpp"]
+    assert all(os.path.isdir(d) for d in kw["include_dirs"])
+    assert any(os.path.exists(os.path.join(d, "phylo_b200_stan.hpp")) for d in kw["include_dirs"])
+    assert any(os.path.exists(os.path.join(d, "phylo_b200.h")) for d in kw["include_dirs"])
