@@ -3,14 +3,11 @@
 
 #include <algorithm>
 
-#ifndef PHYLO_ABLATE
-#define PHYLO_ABLATE 0  // profiling experiments only: 1 = skip the cross-lane G reduction, 2 = skip only its RED
-#endif
-// Build-time switches kept for A/B measurements (profiles/README.md, round 2); the defaults are the product.
-// Measured on the 1000 x 100k bench shape, 16 draws, K = 4 (r2_ab_*.log): the shared-memory reduction and the
-// cp.async byte ring remove ~130 / ~40 instructions per warp-step but lengthen the step's dependency chain and
-// cost shared memory (a stack slot, i.e. the DEEP variant): 134 vs 146 evaluations/s; the pre-order tip
-// shortcut removes 13 % of the FP64 work and is neutral to slower (register spills).
+// Build-time switches kept for A/B measurements (csrc/build_variant.sh, tools/ab_sweep.py; results in
+// profiles/README.md, round 2); the defaults are the product.  On the 1000 x 100k bench shape: the shared-memory
+// reduction removes ~130 instructions per warp-step but needs a stack slot's worth of shared memory at K = 4 (136.6 vs
+// 142.4 evaluations/s) and changes nothing at K = 2, where it fits (117.7 vs 119.9); without the L2 prefetch 137.5; the
+// pre-order tip shortcut removes 13 % of the FP64 work and is neutral to slower (register spills).
 #ifndef PHYLO_RSM
 #define PHYLO_RSM 0     // K > 1: 4x4 statistics summed over the warp through shared memory (0: shuffle exchange)
 #endif
@@ -166,15 +163,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 // entry i to dst[i].
 template <typename T>
 __device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* __restrict__ dst, int lane) {
-#if PHYLO_ABLATE == 1
-    {
-        T t = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) t += v[i];
-        if (t == T(1.2345e-30)) atomicAdd(dst, (double)t);
-        return;
-    }
-#endif
     T a8[8], a4[4], a2[2], a1;
     bool hi = lane & 16;
 #pragma unroll
@@ -200,10 +188,6 @@ __device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* _
         a1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
     a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-#if PHYLO_ABLATE == 2
-    if (a1 == T(1.2345e-30)) atomicAdd(dst, (double)a1);  // experiment: shuffle reduction without the RED
-    return;
-#endif
     if (!(lane & 1)) atomicAdd(dst + ((lane >> 1) & 15), (double)a1);
 }
 
@@ -212,10 +196,6 @@ __device__ __forceinline__ void warp_reduce16_atomic(const T (&v)[16], double* _
 // both and the two REDs.
 template <typename T>
 __device__ __forceinline__ void warp_reduce16_head(const T (&v)[16], T (&a4)[4], int lane) {
-#if PHYLO_ABLATE == 7
-    a4[0] = a4[1] = a4[2] = a4[3] = v[0];
-    return;
-#endif
     T a8[8];
     bool hi = lane & 16;
 #pragma unroll
@@ -233,10 +213,6 @@ __device__ __forceinline__ void warp_reduce16_head(const T (&v)[16], T (&a4)[4],
 template <typename T>
 __device__ __forceinline__ void warp_reduce4x2_tail_atomic(const T (&x4)[4], const T (&y4)[4], double* __restrict__ dx,
                                                            double* __restrict__ dy, int lane) {
-#if PHYLO_ABLATE == 7
-    if (x4[0] == T(1.2345e-30)) atomicAdd(dx, (double)y4[0]);
-    return;
-#endif
     T x2[2], y2[2], x1, y1;
     bool hi = lane & 4;
 #pragma unroll
@@ -271,9 +247,6 @@ __device__ __forceinline__ void cp_async_wait() {
 // K consecutive bytes (K = 1, 2, 4) of a lane as one packed word: byte j = (w >> 8 j) & 0xff
 template <int K>
 __device__ __forceinline__ unsigned ldg_bytes(const uint8_t* p) {
-#if PHYLO_ABLATE == 4
-    return (unsigned)(reinterpret_cast<uintptr_t>(p) & 0x03030303u);  // experiment: no tip-code traffic
-#endif
     if (K == 4) return __ldg(reinterpret_cast<const unsigned*>(p));
     if (K == 2) return __ldg(reinterpret_cast<const unsigned short*>(p));
     return __ldg(p);
@@ -777,9 +750,9 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             if (GRAD) {
 #pragma unroll
                 for (int j = 0; j < K; ++j)
-                    if (PHYLO_ABLATE != 3 && PHYLO_ABLATE != 6) st4cs(srow + j * (VP * NT), NT, tos[j]);
+                    st4cs(srow + j * (VP * NT), NT, tos[j]);
             }
-            if (GRAD && PHYLO_ABLATE != 3 && PHYLO_ABLATE != 6) stcs_bytes<K>(drow, kpack);
+            if (GRAD) stcs_bytes<K>(drow, kpack);
             srow += SS;
             drow += K * NT;
             if (!TR) { ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2; }
@@ -855,18 +828,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             // tail (after their last use there), so no extra registers and a reduction's worth of cover
             T pa[K][4], pbv[K][4];
             {
-                const int i_abl = 0;
-                (void)i_abl;
                 const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(0) + 16);  // row_a, row_b, ...
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
-                    if (PHYLO_ABLATE != 5 && PHYLO_ABLATE != 6) {
-                        if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
-                        if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
-                    } else if (i_abl == 0) {
-                        pa[j][0] = pa[j][1] = pa[j][2] = pa[j][3] = T(0.25);
-                        pbv[j][0] = pbv[j][1] = pbv[j][2] = pbv[j][3] = T(0.25);
-                    }
+                    if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                    if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                 }
             }
             for (int i = 0; i < nsteps; ++i) {
@@ -980,7 +946,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
                                 for (int y = 0; y < 4; ++y)
-                                    if (PHYLO_ABLATE != 7) G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
+                                    G[4 * x + y] = fma(Ab[j][x], pbv[j][y], G[4 * x + y]);
                         }
                     }
                     if (s2.x >= 0) {  // b is internal: q(b) = P_b^T A_b   (eigen.j2:151-153)
@@ -1013,7 +979,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             for (int x = 0; x < 4; ++x)
 #pragma unroll
                                 for (int y = 0; y < 4; ++y)
-                                    if (PHYLO_ABLATE != 7) G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
+                                    G[4 * x + y] = fma(Aa[j][x], pa[j][y], G[4 * x + y]);
                     }
                     if (s2.w & 1) {
                         T M[16];
@@ -1026,10 +992,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(1) + 16);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
-                            if (PHYLO_ABLATE != 5 && PHYLO_ABLATE != 6) {
-                                if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
-                                if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
-                            }
+                            if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                            if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                         }
                     }
                     if (JC) {  // two scalars per lane: lanes 0..15 finish child b's sum, lanes 16..31 child a's
