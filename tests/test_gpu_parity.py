@@ -874,3 +874,29 @@ def test_gpu_ratios_batch_on_device(datasets, name, strict):
             for g, w in ((got["g_props"][b], gp[0]), (got["g_root"][b:b + 1], groot), (got["g_rates"][b], w_r),
                          (got["rest"].grad_subst[b], w_rest.grad_subst), (got["rest"].grad_rs[b], w_rest.grad_rs)):
                 assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= TOL_GRAD
+
+
+def _ref_cpp_cases():
+    import json
+    from conftest import GOLDEN
+    return json.load(open(os.path.join(GOLDEN, "ref_eigen_cpp.json")))["cases"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _ref_cpp_cases(), ids=lambda c: c["name"])
+def test_gpu_matches_the_reference_cpp(case):
+    """The library against the numbers the reference's own C++ `vbsky_loglik` (eigen/eigen.j2) printed for the same tree,
+    alignment, Q and branch lengths (tests/golden/ref_eigen_cpp.json): log_P, and its gradient vector -- which is
+    times[i] * dlogP/dtimes[i] (eigen.j2:165), so the library's true derivative is multiplied by the branch length."""
+    peel, tm = np.array(case["peel"], dtype=np.int32), np.array(case["tipmask"], dtype=np.uint8)
+    L = tm.shape[1]
+    subst = np.array(case["subst"]) if case["subst"] else None
+    with lk.TreeLikelihood(peel, tm, np.ones(L), model=case["model"], categories=1, normalize=case["normalize"]) as lik:
+        for run in case["runs"]:
+            bl = np.array(run["blens"])
+            got = lik.value_grad(bl, subst, np.array(case["freqs"]), np.ones(1), np.ones(1))
+            assert abs(got.log_P - run["log_P"]) <= RTOL_LOGP * abs(run["log_P"])
+            want = np.array(run["grad_times_t"])
+            assert np.max(np.abs(got.grad_blens * bl - want) / np.maximum(1.0, np.abs(want))) <= TOL_GRAD
+            assert abs(lik.loglik(bl, subst, np.array(case["freqs"]), np.ones(1), np.ones(1)) - run["log_P"]) \
+                <= RTOL_LOGP * abs(run["log_P"])
