@@ -6,6 +6,10 @@
  *   post-order      eigen/eigen.j2:122-141  == generate_script.py:998-1005 / 1025-1034
  *   pre-order       eigen/eigen.j2:144-157  == pruner/tree.cpp:228-242
  *   L and gradient  eigen/eigen.j2:160-167, generate_script.py:1006-1010 / 1035-1040
+ * Parity pins (tests/test_oracle.py): the closed form of eigen/test_ll_3tax.py (tests/golden/ll_3tax.json); the
+ * reference's own C++ vbsky_loglik, eigen/eigen.j2 rendered, compiled and run by oracle/build_ref.py, for JC69 / HKY /
+ * GTR rate matrices -- log_P and the branch gradient (tests/golden/ref_eigen_cpp.json); the NumPy GTR class of
+ * scripts/phylo.py for P(t) (tests/golden/gtr_pt.json); SURVEY App. B anchors.
  * Extensions the reference only gets through Stan's autodiff (unpinned by reference tests):
  *   d/d(rates|kappa), d/dfreqs, d/drs, d/dps  -- done here through per-branch 4x4
  *   statistics contracted with dP/dtheta, where dP/dtheta comes from Van Loan's
