@@ -243,6 +243,14 @@ PHYLO_B200_API int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_t
  * depth, 11 = slots used by the last run).  Value-only runs always keep the whole stack on chip. */
 PHYLO_B200_API int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots);
 
+/* Tuning / testing: where fp64 gradient runs with 4 patterns per thread keep their stack of pending vectors.
+ * ctas_per_sm = 0: shared memory (two CTAs per SM); 2 or 3: tensor memory (tcgen05.ld / tcgen05.st as a per-thread
+ * scratchpad), the children's partials staged through a shared-memory operand ring, that many CTAs per SM.
+ * -1 = the library's default (also what the environment variable PHYLO_B200_SWEEP_TM=0|2|3 overrides at create
+ * time).  Runs the variant does not cover (value only, fp32, K != 4, JC69 scalar kernel) ignore it;
+ * phylo_b200_info 13 = what the last run used. */
+PHYLO_B200_API int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_per_sm);
+
 /* Arithmetic of the sweeps: 64 (default; the parity-tested product path) or 32, the optional
  * "fp32 with scaling" mode: partials, transition matrices and 4x4 statistics in float with
  * power-of-two rescaling in units of 2^24, log-likelihood and gradient sums in double.  Its error is
@@ -258,7 +266,8 @@ PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
 /* Introspection: what = 0 stack depth D, 1 patterns per thread, 2 threads per CTA, 3 grid size,
  * 4 dynamic shared memory bytes, 5 padded pattern count, 6 kernels launched by the last run,
  * 7 scratch bytes allocated on the device, 8 / 9 post- / pre-order stack depth, 10 pattern tiles,
- * 11 shared-memory stack slots of the last run, 12 pattern shards (devices) behind the handle. */
+ * 11 on-chip stack slots of the last run, 12 pattern shards (devices) behind the handle,
+ * 13 sweep variant of the last run (0 shared-memory stack, 2 / 3 tensor-memory stack with that many CTAs per SM). */
 PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 
 /*

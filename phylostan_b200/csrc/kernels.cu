@@ -372,9 +372,9 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.tip_a = (long long)na * a.Lpad;
             pr.tip_b = (long long)nb * a.Lpad;
             const bool a_hbm = s0.z >= a.slots;  // parked above the capped shared-memory stack
-            pr.off_a = s0.z < 0 ? 0 : a_hbm ? __ldg(a.node_row + na) * a.SS : s0.z * a.SS;
+            pr.off_a = s0.z < 0 ? 0 : a_hbm ? __ldg(a.node_row + na) * a.SS : s0.z * a.slot_stride;
             pr.off_b = 0;  // an internal second child is always the previous result (TOS)
-            pr.off_spill = spill >= 0 && spill < a.slots ? spill * a.SS : -1;
+            pr.off_spill = spill >= 0 && spill < a.slots ? spill * a.slot_stride : -1;
             pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
                        (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0);
             const int4* src = reinterpret_cast<const int4*>(&pr);
@@ -394,8 +394,8 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
             pr.dl_n = s1.z * a.KNT;
             const bool n_hbm = s0.w >= a.slots, b_hbm = s1.x >= a.slots;
-            pr.off_n = s0.w < 0 ? -1 : n_hbm ? s1.z * a.SS : s0.w * a.SS;   // s1.z = rown
-            pr.off_b = s1.x < 0 ? -1 : b_hbm ? rowb * a.SS : s1.x * a.SS;
+            pr.off_n = s0.w < 0 ? -1 : n_hbm ? s1.z * a.SS : s0.w * a.slot_stride;   // s1.z = rown
+            pr.off_b = s1.x < 0 ? -1 : b_hbm ? rowb * a.SS : s1.x * a.slot_stride;
             pr.g_a = na * a.lay.C * 16;
             pr.g_b = nb * a.lay.C * 16;
             pr.flags = (s1.y ? 1 : 0) | (n_hbm ? 2 : 0) | (b_hbm ? 4 : 0);
@@ -1056,6 +1056,500 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 }
 
 // ------------------------------------------------------------------------------------------
+// K2b: the gradient sweep with its stack in TENSOR MEMORY (fp64, K patterns per lane, 128-thread CTAs)
+// ------------------------------------------------------------------------------------------
+//
+// The sweep above is bound by the number of warps an SM can hold: 255 registers per thread and a 98 KB
+// shared-memory stack per CTA allow two CTAs = two warps per scheduler, which leaves the FP64 pipe idle whenever both
+// are between their FMA sections (profiles/README.md, round 2).  Blackwell's 256 KB of tensor memory per SM is
+// otherwise unused here and can be addressed without any MMA: tcgen05.st / tcgen05.ld .32x32b give every thread of
+// a warp its own TMEM lane, i.e. a private scratchpad of up to 512 words.  This variant keeps the stack of pending
+// 4-state vectors there (one slot = K x 4 doubles = 8 K columns; measured as fast as shared memory,
+// tools/micro/tmem_stack_bench.cu), which frees the shared memory for an OPERAND RING: the children's partials of
+// step i+1 are copied from the HBM scratch into shared memory with cp.async while step i runs (one 4 KB slot per
+// child and warp; a tip child's 0/1 vectors are decoded into the same kind of slot), so no partial waits in
+// registers across a step boundary and every pass of a step reads its operands with two LDS.128.  With the
+// operands out of the register file the step is written as short passes with ONE 4x4 accumulator live
+// (A_b -> G_b -> q(b) -> A_a -> G_a -> q(a)), which fits 168 registers: three CTAs per SM.
+// Stack positions beyond the TMEM slots are parked in the HBM scratch exactly as in the DEEP variant above.
+
+// ("memory" clobbers or not, pops issued early or where they are needed, "=d" outputs instead of the 32-bit halves:
+// all measured, profiles/r2_logs/r2_ab_13.log / r2_ab_14.log -- no difference beyond what the register allocator makes of them)
+__device__ __forceinline__ void tm_st4(uint32_t addr, const double (&x)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr),
+                 "r"(__double2loint(x[0])), "r"(__double2hiint(x[0])), "r"(__double2loint(x[1])), "r"(__double2hiint(x[1])),
+                 "r"(__double2loint(x[2])), "r"(__double2hiint(x[2])), "r"(__double2loint(x[3])), "r"(__double2hiint(x[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld4_raw(uint32_t addr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+// The destination registers are guarded by the scoreboard like those of any load (the wait compiles to a scoreboard
+// wait); the PTX model asks for tcgen05.wait::ld before they are read, and the values are passed through it so that
+// no use is scheduled above it.
+__device__ __forceinline__ void tm_wait_ld(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+template <int K>
+__device__ __forceinline__ void tm_push(uint32_t addr, const double (&x)[K][4]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) tm_st4(addr + 8 * j, x[j]);
+    tm_wait_st();
+}
+template <int K>
+__device__ __forceinline__ void tm_pop(uint32_t addr, double (&x)[K][4]) {
+    uint32_t r[K][8];
+#pragma unroll
+    for (int j = 0; j < K; ++j) tm_ld4_raw(addr + 8 * j, r[j]);
+#pragma unroll
+    for (int j = 0; j < K; ++j) tm_wait_ld(r[j]);  // the first one waits, the others only order the reads
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) x[j][s] = __hiloint2double((int)r[j][2 * s + 1], (int)r[j][2 * s]);
+}
+
+template <int MINB> struct TmCfg;
+template <> struct TmCfg<3> { static constexpr int colsA = 128, colsB = 32; };  // 3 x 160 of the SM's 512 columns
+template <> struct TmCfg<2> { static constexpr int colsA = 256, colsB = 0; };
+
+template <int K, bool TIPS, int MINB>
+__global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) {
+    typedef double T;
+    typedef Real<double> R;
+    typedef double2 V;
+    constexpr int NT = 128, VP = 2;
+    constexpr int kOps = kTmOpSlots;                 // operand slots per warp: both children of steps i and i+1
+    constexpr int kOpBytes = K * VP * 32 * 16;       // one child's K partials of a warp, [j][half][lane] x 16 B
+    constexpr int colsA = TmCfg<MINB>::colsA, colsB = TmCfg<MINB>::colsB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t tm_base[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.C, nsteps = a.nsteps;
+    const int c = warp % C, pb = warp / C;
+    // shared memory: [operand rings | record rings]; the root's category exchange borrows the operand rings, which
+    // are empty between the two sweeps
+    unsigned char* const ops = smem_raw + warp * (kOps * kOpBytes) + lane * 16;   // this lane's column of the warp's slots
+    const unsigned ops_s = (unsigned)__cvta_generic_to_shared(ops);
+    double* ex_l = reinterpret_cast<double*>(smem_raw);                        // [K][NT]
+    int* ex_e = reinterpret_cast<int*>(ex_l + K * NT);                         // [K][NT]
+    Ring<R::kRec> ring;
+    ring.buf = smem_raw + (NT / 32) * (kOps * kOpBytes) + warp * (R::kRec * kRecChunk * kRecBufs);
+    ring.sbuf = (unsigned)__cvta_generic_to_shared(ring.buf);
+    ring.lane = lane;
+    ring.next = nullptr;
+    ring.remaining = 0;
+    ring.wchunk = 0;
+    ring.slot = 0;
+    auto noop = []() {};
+
+    // tensor memory: one warp allocates, everybody reads the base addresses
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tm_base[0])), "r"(colsA));
+        if (colsB)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&tm_base[1])), "r"(colsB));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const uint32_t tm_lane = (uint32_t)(32 * (warp & 3)) << 16;
+    const uint32_t tmA = tm_base[0] + tm_lane, tmB = (colsB ? tm_base[1] : 0u) + tm_lane - colsA;
+    // column offset of a stack slot (8 K per slot, from the record) -> TMEM address of this warp's lanes
+#define TM(off) ((colsB && (off) >= colsA) ? tmB + (uint32_t)(off) : tmA + (uint32_t)(off))
+
+    const int tpat = (NT / (32 * C)) * 32 * K;
+    V* const sct = reinterpret_cast<V*>(a.scratch) + (size_t)blockIdx.x * a.scratch_stride + tid;
+    uint8_t* const dlt = a.dscr + (size_t)blockIdx.x * a.dscr_stride + tid * K;  // K exponents per lane, packed
+#define SC(off, j) (sct + (off) + (j) * (VP * NT))
+    // operand slot s of this warp: entry j of this lane
+#define OP(s, j) (reinterpret_cast<const V*>(ops + (s) * kOpBytes) + (j) * (VP * 32))
+
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+        const int d = item / a.ntiles, tile = item - d * a.ntiles;
+        const double* prm = a.params + (size_t)d * a.lay.stride;
+        const int pat0 = tile * tpat + pb * 32 * K + lane * K;  // this lane's K consecutive patterns: pat0 + j
+        const uint8_t* tipp = a.tips + pat0;
+        const size_t stream_off = ((size_t)d * C + c) * nsteps * R::kRec;
+
+        // -------------------------------------------------------------- post-order
+        int etot[K];
+        T tos[K][4];  // most recent partial (top of stack), kept in registers
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            etot[j] = 0;
+            tos[j][0] = tos[j][1] = tos[j][2] = tos[j][3] = T(0);
+        }
+        ring.start(a.spost + stream_off, nsteps, noop);
+        ring.step(0, noop);
+        unsigned ca = 0u, cb = 0u, ca1 = 0u, cb1 = 0u;
+        {
+            const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
+            if (r0->flags & 1) ca = ldg_bytes<K>(tipp + r0->tip_a);
+            if (r0->flags & 2) cb = ldg_bytes<K>(tipp + r0->tip_b);
+            if (nsteps > 1) {
+                const PostRec* r1 = reinterpret_cast<const PostRec*>(ring.rec(1));
+                if (r1->flags & 1) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
+                if (r1->flags & 2) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
+            }
+        }
+        V* srow = sct;  // scratch row of step i
+        uint8_t* drow = dlt;
+        for (int i = 0; i < nsteps; ++i) {
+            if (i) ring.step(i, noop);
+            const unsigned char* rec = ring.rec(0);
+            const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
+            const int fl = s1.w;
+            unsigned ca2 = 0u, cb2 = 0u;
+            if (i + 2 < nsteps) {  // tip codes of step i+2 -> registers
+                const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(2));
+                const int nf = n->flags;
+                if (nf & 1) ca2 = ldg_bytes<K>(tipp + n->tip_a);
+                if (nf & 2) cb2 = ldg_bytes<K>(tipp + n->tip_b);
+            }
+            T ma[K][4], mb[K][4];
+            // child a: tip, the TOS, a TMEM slot or (rare) its scratch row
+            if (TIPS && (fl & 1)) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, BYTE_OF(ca, j), ma[j]);
+            } else {
+                T pa[K][4];
+                if (fl & 16) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) ld4cs(SC(s1.x, j), NT, pa[j]);
+                } else if (fl & 1) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) tip_vec<false>(BYTE_OF(ca, j), pa[j]);
+                } else if (fl & 4) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) pa[j][s] = tos[j][s];
+                } else {
+                    tm_pop<K>(TM(s1.x), pa);
+                }
+                T M[16];
+                lds_mat(rec + 64, M);
+#pragma unroll
+                for (int j = 0; j < K; ++j) matvec(M, pa[j], ma[j]);
+            }
+            if (TIPS && (fl & 2)) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), mb[j]);
+            } else {
+                T M[16];
+                lds_mat(rec + 64 + R::kMat, M);
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    T p[4];
+                    if (!TIPS && (fl & 2)) {
+                        tip_vec<false>(BYTE_OF(cb, j), p);
+                    } else {  // an internal second child is always the previous step's result
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) p[s] = tos[j][s];
+                    }
+                    matvec(M, p, mb[j]);
+                }
+            }
+            if (s1.z >= 0) tm_push<K>(TM(s1.z), tos);  // the previous result still waits for its sibling
+            unsigned kpack = 0u;
+            bool tiny = false;
+            const T kTiny = R::tiny();
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s) tos[j][s] = ma[j][s] * mb[j][s];
+                tiny |= tos[j][0] < kTiny && tos[j][1] < kTiny && tos[j][2] < kTiny && tos[j][3] < kTiny;
+            }
+            if (tiny) {  // rare: per-(pattern,category) rescaling by exact powers of two
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    T (&p)[4] = tos[j];
+                    if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {
+                        const T mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+                        if (mx > T(0)) {
+                            const int kexp = min((-R::exponent(mx)) / R::kUnit, R::kMaxK);
+                            const T f = R::pow2(kexp);
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) p[s] *= f;
+                            etot[j] += kexp;
+                            kpack |= (unsigned)kexp << (8 * j);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) st4cs(srow + j * (VP * NT), NT, tos[j]);
+            stcs_bytes<K>(drow, kpack);
+            srow += K * VP * NT;
+            drow += K * NT;
+            ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2;
+        }
+
+        // -------------------------------------------------------------- root: site likelihoods
+        const double ps_c = prm[a.lay.off_ps + c];
+        double pi[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) pi[s] = prm[a.lay.off_pi + s];
+        ring.start(a.spre + stream_off, nsteps, noop);  // overlaps the root exchange
+        double rdot[K];
+        __syncthreads();  // every warp is done with its operand ring (previous item): the exchange may borrow it
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            rdot[j] = pi[0] * tos[j][0] + pi[1] * tos[j][1] + pi[2] * tos[j][2] + pi[3] * tos[j][3];  // generate_script.py:1007
+            ex_l[j * NT + tid] = ps_c * rdot[j];
+            ex_e[j * NT + tid] = etot[j];
+        }
+        __syncthreads();
+        double acc_logl = 0.0, acc_dps = 0.0, acc_dpi[4] = {0.0, 0.0, 0.0, 0.0};
+        constexpr int kMaxDe = 960 / R::kUnit;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int base = j * NT + pb * C * 32 + lane;
+            int emin = ex_e[base];
+            for (int cc = 1; cc < C; ++cc) emin = min(emin, ex_e[base + cc * 32]);
+            double sum = 0.0;
+            for (int cc = 0; cc < C; ++cc) {
+                const int de = ex_e[base + cc * 32] - emin;
+                sum += de > kMaxDe ? 0.0 : ex_l[base + cc * 32] * pow2_neg(R::kUnit * de);
+            }
+            const double w = a.weights[pat0 + j];
+            if (c == 0) acc_logl += w * (log(sum) - (double)emin * (R::kUnit * 0.6931471805599453));
+            const int de = etot[j] - emin;
+            const double fac = de > kMaxDe ? 0.0 : w * pow2_neg(R::kUnit * de) / sum;
+            acc_dps += fac * rdot[j];
+            const double f = fac * ps_c;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                acc_dpi[s] += f * tos[j][s];
+                tos[j][s] = pi[s] * f;  // q(root): weight, 1/L and the category share folded in
+            }
+        }
+        __syncthreads();  // the exchange has been read: the region is the operand ring again
+
+        // -------------------------------------------------------------- pre-order
+        {
+            // operand slots: child a of step i -> slot (2 i) & 3, child b -> slot (2 i + 1) & 3.  An internal child's
+            // partial is copied from its scratch row one step ahead (cp.async, in the record ring's commit
+            // group); a tip child's 0/1 vectors are written into its slot at the top of its own step.
+            auto fetch = [&](const unsigned char* r, int st2) {   // st2 = (2 * step) & 3
+                const int4 r1 = *reinterpret_cast<const int4*>(r + 16);  // row_a, row_b, ...
+                if (r1.x >= 0) {
+                    const V* src = SC(r1.x, 0);
+                    const unsigned dst = ops_s + st2 * kOpBytes;
+#pragma unroll
+                    for (int q = 0; q < K * VP; ++q) cp_async16(dst + q * 512, src + q * NT);
+                }
+                if (r1.y >= 0) {
+                    const V* src = SC(r1.y, 0);
+                    const unsigned dst = ops_s + (st2 + 1) * kOpBytes;
+#pragma unroll
+                    for (int q = 0; q < K * VP; ++q) cp_async16(dst + q * 512, src + q * NT);
+                }
+            };
+            cp_async_wait<0>();   // records 0..3 of the pre-order stream
+            __syncwarp();
+            fetch(ring.rec(0), 0);
+            cp_async_commit();
+            // packed byte operands of steps i (ca, cb, dcur = rescale exponents of the node) and i+1
+            unsigned dcur, d1 = 0u;
+            ca = cb = ca1 = cb1 = 0u;
+            {
+                const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
+                if (r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
+                if (r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
+                dcur = ld_bytes<K>(dlt + r0->dl_n);
+                if (nsteps > 1) {
+                    const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
+                    if (r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
+                    if (r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
+                    d1 = ld_bytes<K>(dlt + r1->dl_n);
+                }
+            }
+            double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
+            for (int i = 0; i < nsteps; ++i) {
+                if (i) ring.slot = ring.slot == kRecChunk * kRecBufs - 1 ? 0 : ring.slot + 1;
+                cp_async_wait<0>();  // this step's operands and the records up to i + 2 (even i: i + 3)
+                __syncwarp();        // every lane is done with the record chunk about to be overwritten
+                const int sa = (2 * i) & 3, sb = sa + 1, sn = (sa + 2) & 3;
+                const unsigned char* rec = ring.rec(0);
+                const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // row_a, row_b, dl_n, off_n
+                const int4 s2 = *reinterpret_cast<const int4*>(rec + 32);  // off_b, g_a, g_b, flags
+                const bool npop = s1.w >= 0 && !(s2.w & 2);  // q(node) waits in tensor memory
+                if ((i & 1) == 0) {
+                    ring.issue([&]() { if (i + 1 < nsteps) fetch(ring.rec(1), sn); });
+                } else {
+                    if (i + 1 < nsteps) fetch(ring.rec(1), sn);
+                    cp_async_commit();
+                }
+                const int rowa = s1.x, rowb = s1.y;
+                unsigned ca2 = 0u, cb2 = 0u, d2 = 0u;
+                if (i + 2 < nsteps) {  // byte operands of step i+2 -> registers
+                    const PreRec* n = reinterpret_cast<const PreRec*>(ring.rec(2));
+                    const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
+                    if (n1.x < 0) ca2 = ldg_bytes<K>(tipp + n->tip_a);
+                    if (n1.y < 0) cb2 = ldg_bytes<K>(tipp + n->tip_b);
+                    d2 = ld_bytes<K>(dlt + n1.z);
+                }
+                // tip children: decode into their operand slots
+                if (rowa < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        tip_vec<TIPS>(BYTE_OF(ca, j), p);
+                        st4(const_cast<V*>(OP(sa, j)), 32, p);
+                    }
+                }
+                if (rowb < 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        tip_vec<TIPS>(BYTE_OF(cb, j), p);
+                        st4(const_cast<V*>(OP(sb, j)), 32, p);
+                    }
+                }
+                // q(node): still in the TOS registers, popped from tensor memory, or (rare) parked in p(node)'s scratch row
+                T (&qn)[K][4] = tos;
+                if (s2.w & 2) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) ld4cs(SC(s1.w, j), NT, qn[j]);
+                } else if (npop) {
+                    tm_pop<K>(TM(s1.w), qn);
+                }
+                if (dcur) {  // rare: this node was rescaled in the post-order for some pattern of this lane
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        if (BYTE_OF(dcur, j)) {
+                            const T f = R::pow2((int)BYTE_OF(dcur, j));
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) qn[j][s] *= f;
+                        }
+                }
+                // A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
+                T Ab[K][4];
+                {
+                    T M[16];
+                    lds_mat(rec + 64, M);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4], m[4];
+                        ld4(OP(sa, j), 32, p);
+                        matvec(M, p, m);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
+                    }
+                }
+                // G_b = sum_j A_b p_b^T
+                T gb4[4];
+                {
+                    T G[16];
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) G[x] = T(0);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        ld4(OP(sb, j), 32, p);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Ab[j][x], p[y], G[4 * x + y]);
+                    }
+                    warp_reduce16_head(G, gb4, lane);
+                }
+                // q(b) = P_b^T A_b (eigen.j2:151-153) waits in tensor memory; A_a = q_n o (P_b p_b) takes q_n's registers
+                {
+                    T M[16];
+                    lds_mat(rec + 64 + R::kMat, M);
+                    if (s2.x >= 0) {
+                        T q[K][4];
+#pragma unroll
+                        for (int j = 0; j < K; ++j) matTvec(M, Ab[j], q[j]);
+                        if (s2.w & 4) {  // rare: parked over p(b)'s scratch row (already copied into the operand ring)
+#pragma unroll
+                            for (int j = 0; j < K; ++j) st4cs(SC(s2.x, j), NT, q[j]);
+                        } else {
+                            tm_push<K>(TM(s2.x), q);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4], m[4];
+                        ld4(OP(sb, j), 32, p);
+                        matvec(M, p, m);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) qn[j][s] *= m[s];  // now A_a
+                    }
+                }
+                T (&Aa)[K][4] = tos;
+                {
+                    T G[16], ga4[4];
+#pragma unroll
+                    for (int x = 0; x < 16; ++x) G[x] = T(0);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        ld4(OP(sa, j), 32, p);
+#pragma unroll
+                        for (int x = 0; x < 4; ++x)
+#pragma unroll
+                            for (int y = 0; y < 4; ++y) G[4 * x + y] = fma(Aa[j][x], p[y], G[4 * x + y]);
+                    }
+                    warp_reduce16_head(G, ga4, lane);
+                    warp_reduce4x2_tail_atomic(gb4, ga4, Gd + s2.z, Gd + s2.y, lane);
+                }
+                if (s2.w & 1) {  // a is internal and is processed next: q(a) = P_a^T A_a becomes the TOS
+                    T M[16];
+                    lds_mat(rec + 64, M);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T q[4];
+                        matTvec(M, Aa[j], q);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) tos[j][s] = q[s];
+                    }
+                }
+                ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2;
+                dcur = d1; d1 = d2;
+            }
+        }
+
+        // -------------------------------------------------------------- per-item scalars
+        double* od = a.out + (size_t)d * a.nout;
+        if (c == 0) {
+            acc_logl = warp_sum(acc_logl);
+            if (lane == 0) atomicAdd(od, acc_logl);
+        }
+        acc_dps = warp_sum(acc_dps);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) acc_dpi[s] = warp_sum(acc_dpi[s]);
+        if (lane == 0) {
+            atomicAdd(od + a.off_out_ps + c, acc_dps);
+            if (a.lay.ntheta > 0) {  // JC69 fixes the frequencies: no derivative to report
+#pragma unroll
+                for (int s = 0; s < 4; ++s) atomicAdd(od + a.off_out_freqs + s, acc_dpi[s]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm_base[0]), "r"(colsA));
+        if (colsB) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm_base[1]), "r"(colsB));
+    }
+#undef TM
+#undef SC
+#undef OP
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: contraction of the branch statistics
 // ------------------------------------------------------------------------------------------
 
@@ -1479,7 +1973,9 @@ SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, boo
 #ifdef PHYLO_FAST_BUILD  // compile-time experiments only: the fp64 K = 4 / 2 gradient kernels of simple-tip handles
     if (prec != 64 || !tips || !grad || jc || nthreads != 128) return nullptr;
     if (K == 4) return deep ? pick_kernel<double, 4, true, true, true>(128) : pick_kernel<double, 4, true, true, false>(128);
+#if PHYLO_FAST_BUILD < 2
     if (K == 2) return deep ? pick_kernel<double, 2, true, true, true>(128) : pick_kernel<double, 2, true, true, false>(128);
+#endif
     return nullptr;
 #else
     if (jc && prec == 64 && grad && !deep) return tips ? pick_kernel_jc<true>(K, nthreads) : pick_kernel_jc<false>(K, nthreads);
@@ -1568,6 +2064,52 @@ void launch_clock_reverse(const ClockArgs& a, cudaStream_t stream) { clock_rever
 void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStream_t stream) {
     const int grid = (int)std::min<size_t>((count + 255) / 256, 148);
     peer_sum_kernel<<<grid, 256, 0, stream>>>(out, peers, count);
+}
+
+typedef void (*SweepTmFn)(const SweepArgs);
+static SweepTmFn pick_tm(bool tips, int K, int ctas) {
+    if (K != 4) return nullptr;
+#ifdef PHYLO_FAST_BUILD  // compile-time experiments only
+    if (ctas == 3 && tips) return sweep_tm_kernel<4, true, 3>;
+    return nullptr;
+#else
+    if (ctas == 3) return tips ? sweep_tm_kernel<4, true, 3> : sweep_tm_kernel<4, false, 3>;
+    if (ctas == 2) return tips ? sweep_tm_kernel<4, true, 2> : sweep_tm_kernel<4, false, 2>;
+    return nullptr;
+#endif
+}
+
+bool sweep_tm_available(int prec, int K, int nthreads, bool grad, bool jc) {
+    return prec == 64 && K == 4 && nthreads == 128 && grad && !jc;
+}
+
+int sweep_tm_slots(int K, int ctas) { return (ctas == 3 ? 160 : 256) / (8 * K); }
+
+size_t sweep_tm_smem_bytes(int K) {
+    return (size_t)4 * (kTmOpSlots * (size_t)K * 2 * 32 * 16 + kRecBytes * kRecChunk * kRecBufs);
+}
+
+cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* n) {
+    SweepTmFn kern = pick_tm(tips, K, ctas);
+    if (!kern) return cudaErrorInvalidValue;
+    const size_t smem = sweep_tm_smem_bytes(K);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // the occupancy calculator does not know how many TMEM columns the kernel allocates and answers 1; what bounds
+    // the residency is registers (launch bounds) and shared memory, both sized for `ctas`
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, 128, smem);
+    if (e == cudaSuccess && *n >= 1) *n = ctas;
+    return e;
+}
+
+cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream) {
+    SweepTmFn kern = pick_tm(tips, K, ctas);
+    if (!kern) return cudaErrorInvalidValue;
+    const size_t smem = sweep_tm_smem_bytes(K);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, 128, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream) {

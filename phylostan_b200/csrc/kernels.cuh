@@ -34,6 +34,7 @@ constexpr int kRecBytes = 384;   // fp64 record: [desc 64 B | P_a slot 160 B | P
 constexpr int kRecBytesF32 = 224;  // fp32 mode: [desc 64 B | P_a slot 80 B | P_b slot 80 B]
 constexpr int kRecChunk = 2;     // records per cp.async group
 constexpr int kRecBufs = 3;      // ring depth in chunks
+constexpr int kTmOpSlots = 4;    // TMEM-stack sweep: operand slots per warp (both children of steps i and i+1)
 
 // offsets (in doubles) inside one draw's parameter block
 struct ParamLayout {
@@ -85,6 +86,8 @@ struct StreamArgs {
     // of p(node), which nobody reads any more by then.
     const int* node_row;      // [2S-1] node id -> its own post-order step (= scratch row), -1 for tips
     int slots;
+    int slot_stride;          // offset unit of an ON-CHIP stack slot: SS (shared-memory stack, in 16-byte vectors) or
+                              // 8 K (tensor-memory stack, in 32-bit columns)
 };
 
 struct SweepArgs {
@@ -126,6 +129,13 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool gr
                          size_t smem, cudaStream_t stream, bool jc = false);
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
                             int* blocks_per_sm, bool jc = false);
+// Gradient sweep with the stack in tensor memory (fp64, K = 4, 128-thread CTAs): `ctas` = 2 or 3 resident CTAs per
+// SM, sweep_tm_slots stack slots on chip (positions beyond them are parked in the scratch like the `deep` variant)
+bool sweep_tm_available(int prec, int K, int nthreads, bool grad, bool jc);
+int sweep_tm_slots(int K, int ctas);
+size_t sweep_tm_smem_bytes(int K);
+cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream);
+cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* blocks_per_sm);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
 // device-resident tip masks [S][L] / weights [L] (NULL: ones) -> padded rows; d_flags[2]: {some cell is not
 // simple, some weight is not finite}

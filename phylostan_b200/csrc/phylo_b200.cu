@@ -80,6 +80,8 @@ struct PinnedBuf {
 
 }  // namespace
 
+constexpr int kDefaultSweepTm = 0;  // fp64 K = 4 gradient runs: 0 shared-memory stack, 2 / 3 tensor-memory stack
+
 struct phylo_b200_ctx {
     int S = 0, L = 0, C = 0, model = 0, flags = 0, device = 0;
     int nn = 0, bcount = 0, nsubst = 0, nout = 0, Lpad = 0;
@@ -116,6 +118,8 @@ struct phylo_b200_ctx {
     int K = 1, PB = 1, NT = 0, grid = 0, ntiles = 0;
     int slots = 0;  // shared-memory stack slots of the last run (< plan.depth(): the rest is parked in HBM)
     bool jc_run = false;  // the last resolved launch is the JC69 scalar-statistic kernel
+    int req_tm = kDefaultSweepTm;  // tensor-memory-stack sweep for fp64 K = 4 gradient runs: 0 off, 2 / 3 = resident CTAs per SM
+    int tm = 0;           // what the last resolved launch uses (0: shared-memory stack)
     size_t smem = 0;
     int last_launches = 0;
 
@@ -256,12 +260,21 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             return fail(PHYLO_B200_EINVAL,
                         "tree too deep for the shared-memory stack (depth " + std::to_string(Dfull) + ")");
     }
-    const size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun, h->tips_simple, grad);
+    size_t smem = sweep_smem_bytes(D, K, NT, h->prec, jrun, h->tips_simple, grad);
     const int tpat = PB * 32 * K;
-    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun;
     h->ntiles = (h->L + tpat - 1) / tpat;
     int occ = 0;
-    CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun));
+    // the stack in tensor memory: three (or two) CTAs per SM, positions beyond its slots parked like above
+    int tm = 0;
+    if (h->req_tm && sweep_tm_available(h->prec, K, NT, grad, jrun) && h->req_cap == 0) {
+        const int dt = std::min(Dfull, sweep_tm_slots(K, h->req_tm));
+        if (Dfull - dt <= kMaxParked && sweep_tm_smem_bytes(K) <= h->smem_optin &&
+            sweep_tm_prepare(h->tips_simple, K, h->req_tm, &occ) == cudaSuccess && occ >= 1) {
+            tm = h->req_tm; D = dt; smem = sweep_tm_smem_bytes(K);
+        }
+    }
+    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun; h->tm = tm;
+    if (!tm) CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -428,6 +441,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     h->stream = h->own_stream;
     if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
     if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
+    if (const char* tm = std::getenv("PHYLO_B200_SWEEP_TM")) h->req_tm = tm[0] == '3' ? 3 : tm[0] == '2' ? 2 : 0;
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
             delete h;
@@ -589,6 +603,15 @@ int phylo_b200_set_tiling(phylo_b200_handle h, int patterns_per_thread, int patt
     return 0;
 }
 
+int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_per_sm) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    if (ctas_per_sm != -1 && ctas_per_sm != 0 && ctas_per_sm != 2 && ctas_per_sm != 3)
+        return fail(PHYLO_B200_EINVAL, "sweep variant must be -1 (default), 0, 2 or 3");
+    h->req_tm = ctas_per_sm < 0 ? kDefaultSweepTm : ctas_per_sm;
+    for (auto* p : h->peers) p->req_tm = h->req_tm;
+    return 0;
+}
+
 int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     if (slots < 0) return fail(PHYLO_B200_EINVAL, "slots must be >= 0 (0 = automatic)");
@@ -642,6 +665,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 10: return h->ntiles;
         case 11: return h->slots;
         case 12: return 1 + (long long)h->peers.size();
+        case 13: return h->tm;
     }
     return PHYLO_B200_EINVAL;
 }
@@ -835,6 +859,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     sa.S = h->S; sa.tips_simple = h->tips_simple;
     sa.node_row = h->d_node_row.p;
     sa.slots = grad ? h->slots : h->plan.depth();
+    sa.slot_stride = grad && h->tm ? 8 * h->K : sa.SS;
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
@@ -853,7 +878,8 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
     const bool deep = grad && h->slots < h->plan.depth();
     const bool jc = grad && h->jc_run;
-    CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc));
+    if (grad && h->tm) CU_TRY(launch_sweep_tm(a, h->tips_simple, h->K, h->tm, h->grid, st));
+    else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {
@@ -882,7 +908,7 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
             u(h->d_dscr.p), u(h->h_params.p), u(h->h_out.p), u(h->stream), (unsigned long long)h->K,
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
             (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
-            (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p)};
+            (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p), (unsigned long long)h->tm};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible

@@ -86,6 +86,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_set_tiling.argtypes = [vp, i, i]
     L.phylo_b200_set_precision.argtypes = [vp, i]
     L.phylo_b200_set_stack_slots.argtypes = [vp, i]
+    L.phylo_b200_set_sweep_variant.argtypes = [vp, i]
     L.phylo_b200_set_timing.argtypes = [vp, i]
     L.phylo_b200_get_timing.argtypes = [vp, _dp]
     L.phylo_b200_info.argtypes = [vp, i]
@@ -372,6 +373,11 @@ class TreeLikelihood:
     def set_tiling(self, patterns_per_thread: int = 0, pattern_blocks: int = 0) -> None:
         _check(lib().phylo_b200_set_tiling(self._h, patterns_per_thread, pattern_blocks))
 
+    def set_sweep_variant(self, ctas_per_sm: int = -1) -> None:
+        """Stack of fp64 K = 4 gradient runs: 0 shared memory, 2 / 3 tensor memory with that many CTAs per SM,
+        -1 the library's default (``info()['sweep_variant']`` tells what the last run used)."""
+        _check(lib().phylo_b200_set_sweep_variant(self._h, int(ctas_per_sm)))
+
     def set_stack_slots(self, slots: int = 0) -> None:
         """Shared-memory stack slots for gradient runs (0 = automatic); fewer than ``info()['stack_depth']``
         parks the top stack positions in the per-CTA HBM scratch."""
@@ -391,7 +397,8 @@ class TreeLikelihood:
 
     def info(self) -> dict:
         names = ["stack_depth", "patterns_per_thread", "threads_per_cta", "grid", "smem_bytes", "padded_patterns",
-                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots", "shards"]
+                 "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots", "shards",
+                 "sweep_variant"]
         return {n: int(lib().phylo_b200_info(self._h, k)) for k, n in enumerate(names)}
 
     def unpack(self, out: np.ndarray) -> ValueGrad:

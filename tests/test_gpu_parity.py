@@ -639,6 +639,67 @@ def test_gpu_capped_stack_parks_entries_in_hbm(prec):
                 assert np.max(np.abs(lp - got.log_P) / np.abs(lp)) < (1e-12 if prec == 64 else 1e-5)
 
 
+@pytest.mark.parametrize("ctas", [3, 2])
+def test_gpu_tensor_memory_stack_sweep_matches_oracle(ctas, datasets):
+    """The gradient sweep with its stack in tensor memory (phylo_b200_set_sweep_variant: tcgen05.ld / tcgen05.st as a
+    per-thread scratchpad, children's partials staged through a shared-memory operand ring, 3 or 2 CTAs per SM)
+    against the oracle: simple tips and general masks, a stack that fits the TMEM slots and one that does not
+    (positions beyond them parked in the HBM scratch), batches, an unrooted tree, and the runs it does not cover."""
+    # 600 taxa: stack depth 5 -- all of it in tensor memory; general masks take the non-simple-tip instantiation
+    for S, L, seed, masks in ((150, 700, 77, False), (40, 130, 5, True), (600, 1500, 9, False)):
+        prob = synth.make_problem(S, L, 4, seed=seed)
+        tipmask = prob.tipmask.copy()
+        if masks:
+            rng = np.random.default_rng(3)
+            sel = rng.random(tipmask.shape) < 0.1
+            tipmask[sel] = np.array([3, 5, 6, 9, 10, 12, 7], dtype=np.uint8)[rng.integers(0, 7, size=int(sel.sum()))]
+        bl, rates, freqs, rs, ps = synth.make_draws(prob, 3)
+        want = [O.loglik_grad(prob.peel, tipmask, prob.weights, O.GTR, bl[i], rates[i], freqs[i], rs[i], ps[i])
+                for i in range(3)]
+        with make(prob.peel, tipmask, prob.weights, O.GTR, 4) as lik:
+            lik.set_tiling(4, 1)
+            lik.set_sweep_variant(ctas)
+            got = lik.value_grad(bl, rates, freqs, rs, ps)
+            info = lik.info()
+            assert info["sweep_variant"] == ctas and info["stack_slots"] == info["stack_depth"]
+            for i in range(3):
+                assert_parity(lk.ValueGrad(got.log_P[i], got.grad_blens[i], got.grad_subst[i], got.grad_freqs[i],
+                                           got.grad_rs[i], got.grad_ps[i]), want[i])
+            # runs the variant does not cover fall back to the shared-memory stack: value only, K = 2, fp32
+            lp = lik.loglik(bl, rates, freqs, rs, ps)
+            assert lik.info()["sweep_variant"] == 0
+            assert np.max(np.abs(lp - got.log_P) / np.abs(lp)) < 1e-12
+            lik.set_tiling(2, 1)
+            assert_parity(lik.value_grad(bl[0], rates[0], freqs[0], rs[0], ps[0]), want[0])
+            assert lik.info()["sweep_variant"] == 0
+    # a caterpillar-free deep stack: 3 CTAs per SM have five TMEM slots, so a depth-6 tree parks its top position
+    prob = synth.make_problem(1000, 640, 4)
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 2)
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        lik.set_tiling(4, 1)
+        lik.set_sweep_variant(ctas)
+        got = lik.value_grad(bl, rates, freqs, rs, ps)
+        info = lik.info()
+        assert info["sweep_variant"] == ctas
+        if ctas == 3 and info["stack_depth"] > 5:
+            assert info["stack_slots"] == 5
+        for i in range(2):
+            want = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[i], rates[i], freqs[i], rs[i], ps[i])
+            assert_parity(lk.ValueGrad(got.log_P[i], got.grad_blens[i], got.grad_subst[i], got.grad_freqs[i],
+                                       got.grad_rs[i], got.grad_ps[i]), want)
+    # unrooted tree with real ambiguity codes, HKY
+    d = datasets["DS1"]
+    rng = np.random.default_rng(11)
+    dr = random_params(O.HKY, 27, False, 4, rng)
+    with make(d["peel"], d["tipmask"], d["weights"], O.HKY, 4, rooted=False) as lik:
+        lik.set_tiling(4, 1)
+        lik.set_sweep_variant(ctas)
+        assert_parity(lik.value_grad(*dr), O.loglik_grad(d["peel"], d["tipmask"], d["weights"], O.HKY, *dr, rooted=False))
+        assert lik.info()["sweep_variant"] == ctas
+        with pytest.raises(Exception):
+            lik.set_sweep_variant(5)
+
+
 def test_gpu_deep_tree_gets_the_widest_tile():
     """3000 taxa: stack depth 7 does not fit the K = 4 tile twice per SM; the capped stack does."""
     prob = synth.make_problem(3000, 2048, 4)

@@ -2,7 +2,8 @@
 """A/B timing of sweep-kernel builds on the BASELINE config-3 shape (GPU box only).
 
     python tools/ab_sweep.py [B] [L] [S]            # parent: one child process per library
-    PHYLO_AB_LIBS="r1,nopf,..."                      # names under phylostan_b200/csrc/variants/, "" = the in-tree build
+    PHYLO_AB_LIBS="r1,nopf,..."                      # names under phylostan_b200/csrc/variants/, "" = the in-tree build;
+                                                     # "name@3" runs it with PHYLO_B200_SWEEP_TM=3 (tensor-memory stack)
     PHYLO_AB_CASES="4:0,4:5,2:0"                     # K:slots pairs (slots 0 = automatic)
 
 Every child prints the sweep time of each case (CUDA events of the library, best of 3 after 2 warm-ups) and
@@ -63,6 +64,9 @@ def main():
     ref = None
     for name in libs:
         env = dict(os.environ, PHYLO_AB_CHILD="1")
+        name, _, tm = name.partition("@")   # "lib@3": run that library with PHYLO_B200_SWEEP_TM=3
+        if tm:
+            env["PHYLO_B200_SWEEP_TM"] = tm
         if name:
             env["PHYLO_B200_LIB"] = os.path.join(ROOT, "phylostan_b200", "csrc", "variants", f"libphylo_b200_{name}.so")
         p = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, capture_output=True, text=True)
@@ -71,7 +75,7 @@ def main():
             print(f"[{name or 'in-tree'}] FAILED rc={p.returncode}\n{p.stdout[-2000:]}\n{p.stderr[-3000:]}", flush=True)
             continue
         for r in json.loads(line[0][9:]):
-            tag = f"[{name or 'in-tree':10s}] grad={int(r['grad'])} K={r['K']} slots={r.get('slots', '-')}/{r.get('depth', '-')}"
+            tag = f"[{(name or 'in-tree') + ('@' + tm if tm else ''):10s}] grad={int(r['grad'])} K={r['K']} slots={r.get('slots', '-')}/{r.get('depth', '-')}"
             if "error" in r:
                 print(f"{tag} ERROR {r['error']}", flush=True)
                 continue

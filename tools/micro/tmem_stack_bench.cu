@@ -43,6 +43,7 @@ __device__ __forceinline__ uint32_t word(int tid, int ver, int k) { return (uint
 
 struct Out {
     unsigned long long errors, t_start, t_end, cyc_tm_st, cyc_tm_ld, cyc_sm_st, cyc_sm_ld, cyc_tm_rt, cyc_sm_rt;
+    unsigned long long cyc_tm_sparse, cyc_sm_sparse;
     unsigned smid, baseA, baseB;
 };
 
@@ -172,6 +173,46 @@ __global__ void __launch_bounds__(128, CTAS_PER_SM) bench(Out* out, int iters) {
     }
     long long c6 = clock64();
 
+    // (4) the sweep kernel's access pattern: one entry load every few thousand cycles, FP64 work in between
+    double f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = 1.0 + 1e-9 * (tid + k);
+    unsigned long long sparse_tm = 0, sparse_sm = 0;
+    for (int it = 0; it < 128; ++it) {
+#pragma unroll 1
+        for (int r = 0; r < 24; ++r)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fma(f[k], 1.0000001, 1e-12);
+        long long a0 = clock64();
+        uint32_t v[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tm_ld8(slot_addr(it % kSlots) + 8 * j, v[j]);
+        tm_wait_ld();
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x += v[j][k];
+        acc[1] += x;
+        long long a1 = clock64();
+        sparse_tm += (acc[1] == 0xdeadbeefu) ? 0 : (a1 - a0);
+#pragma unroll 1
+        for (int r = 0; r < 24; ++r)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) f[k] = fma(f[k], 1.0000001, 1e-12);
+        long long b0 = clock64();
+        uint4 w[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[q] = sm[((it & 3) * 8 + q) * 128 + tid];
+        uint32_t y = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y += w[q].x + w[q].y + w[q].z + w[q].w;
+        acc[2] += y;
+        long long b1 = clock64();
+        sparse_sm += (acc[2] == 0xdeadbeefu) ? 0 : (b1 - b0);
+    }
+    if (f[0] + f[7] + f[15] == 12345.0) acc[3] += 1;
+
     // every CTA of the grid must hold its columns at the same time: spin until all have arrived
     __shared__ unsigned long long serr[4];
     for (int o = 16; o > 0; o >>= 1) errors += __shfl_xor_sync(0xffffffffu, errors, o);
@@ -185,6 +226,7 @@ __global__ void __launch_bounds__(128, CTAS_PER_SM) bench(Out* out, int iters) {
         o.t_start = t0; o.t_end = t1;
         o.cyc_tm_st = c1 - c0; o.cyc_tm_ld = c2 - c1; o.cyc_tm_rt = c3 - c2;
         o.cyc_sm_st = c4 - c3; o.cyc_sm_ld = c5 - c4; o.cyc_sm_rt = c6 - c5;
+        o.cyc_tm_sparse = sparse_tm; o.cyc_sm_sparse = sparse_sm;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(o.smid));
         o.baseA = baseA; o.baseB = baseB;
         out[blockIdx.x] = o;
@@ -212,13 +254,14 @@ int main() {
     std::vector<Out> h(grid);
     cudaMemcpy(h.data(), d, sizeof(Out) * grid, cudaMemcpyDeviceToHost);
     unsigned long long errors = 0, smax = 0, emin = ~0ull;
-    double st = 0, ld = 0, rt = 0, sst = 0, sld = 0, srt = 0;
+    double st = 0, ld = 0, rt = 0, sst = 0, sld = 0, srt = 0, sp_tm = 0, sp_sm = 0;
     std::vector<int> per_sm(sms, 0);
     for (auto& o : h) {
         errors += o.errors;
         smax = o.t_start > smax ? o.t_start : smax;
         emin = o.t_end < emin ? o.t_end : emin;
         st += o.cyc_tm_st; ld += o.cyc_tm_ld; rt += o.cyc_tm_rt; sst += o.cyc_sm_st; sld += o.cyc_sm_ld; srt += o.cyc_sm_rt;
+        sp_tm += o.cyc_tm_sparse; sp_sm += o.cyc_sm_sparse;
         per_sm[o.smid % sms]++;
     }
     int maxper = 0;
@@ -232,5 +275,7 @@ int main() {
     printf("cycles per 32-word entry and thread (all %d warps of the SM busy with the same loop):\n", 4 * CTAS_PER_SM);
     printf("  TMEM  store+wait %.1f   load+wait %.1f   store->load round trip %.1f\n", st / n, ld / n, rt / n);
     printf("  smem  store      %.1f   load      %.1f   store->load round trip %.1f\n", sst / n, sld / n, srt / n);
+    printf("one entry load + use between blocks of 384 DFMA per thread (the sweep's access pattern), cycles: TMEM %.1f   smem %.1f\n",
+           sp_tm / (128.0 * grid), sp_sm / (128.0 * grid));
     return errors ? 2 : 0;
 }
