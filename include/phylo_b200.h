@@ -136,6 +136,16 @@ PHYLO_B200_API int phylo_b200_eval_batch(phylo_b200_handle h, int B, const doubl
                           double *logp, double *g_blens, double *g_subst, double *g_freqs,
                           double *g_rs, double *g_ps);
 
+/* The same, but a draw that phylo_b200_eval would reject does not fail the batch: status[d] = 0 (evaluated),
+ * 1 (parameters out of domain: negative or non-finite branch length, rates, frequencies ... -- not evaluated) or
+ * 2 (log-likelihood not finite: impossible pattern or underflow).  For status[d] != 0, logp[d] = -inf and the
+ * draw's gradient rows are zero, which is what Stan does with a rejected draw (std::domain_error in
+ * eigen/prune_stan.hpp's caller).  Returns 0 whenever the call itself ran, whatever the draws' states. */
+PHYLO_B200_API int phylo_b200_eval_batch_status(phylo_b200_handle h, int B, const double *blens, const double *subst,
+                          const double *freqs, const double *rs, const double *ps, int want_grad,
+                          double *logp, double *g_blens, double *g_subst, double *g_freqs,
+                          double *g_rs, double *g_ps, int32_t *status);
+
 /*
  * Node-height front end for clock trees (replaces the generated Stan loop `heights_to_blens`,
  * phylostan/generate_script.py:660-679, and its reverse sweep on Stan's tape):

@@ -195,10 +195,14 @@ class _ModelBase:
             g[:, self.slices["freqs"]] = simplex_adjoint(gf, sub["_freqs"])
 
     def _likelihood(self, args, want_grad):
-        """One batched library call; if the library rejects the batch (a draw with a non-finite likelihood --
-        its ``std::domain_error`` case), the draws are evaluated one by one and the offending ones get -inf
-        and a zero gradient, which is what Stan does with a rejected draw."""
+        """One batched library call.  Rejected draws (parameters out of domain, a non-finite likelihood -- the
+        ``std::domain_error`` case of the Stan shim) get -inf and a zero gradient, which is what Stan does with a
+        rejected draw: ``phylo_b200_eval_batch_status`` marks them inside the one call; a back end without it (the
+        CPU stand-ins of the tests, ``ShardedLikelihood``) is retried draw by draw."""
         from .likelihood import ValueGrad
+        if hasattr(self.lik, "value_grad_masked"):  # the library marks rejected draws itself (eval_batch_status)
+            vg, _ = self.lik.value_grad_masked(*args, want_grad=want_grad)
+            return np.atleast_1d(vg.log_P), (vg if want_grad else None)
         try:
             if want_grad:
                 vg = self.lik.value_grad(*args)

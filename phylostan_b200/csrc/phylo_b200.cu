@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <new>
 #include <string>
@@ -672,8 +673,10 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
 
 namespace {
 // validate, size the per-batch buffers and pack the draws into the pinned staging buffer (no copy yet)
+// status != NULL: a draw that fails validation is marked 1 and gets the parameter block of the first valid draw
+// (so the kernels have something harmless to chew on); *nvalid = number of valid draws
 int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subst, const double* freqs,
-               const double* rs, const double* ps) {
+               const double* rs, const double* ps, int32_t* status = nullptr, int* nvalid = nullptr) {
     if (!h || B < 1 || !blens) return fail(PHYLO_B200_EINVAL, "upload: bad arguments");
     if (h->nsubst > 0 && !subst) return fail(PHYLO_B200_EINVAL, "upload: subst is NULL");
     if (h->model != PHYLO_B200_JC69 && !freqs) return fail(PHYLO_B200_EINVAL, "upload: freqs is NULL");
@@ -687,12 +690,21 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
     // the pinned staging buffer may still feed a copy in flight
     CU_TRY(cudaStreamSynchronize(h->stream));
     std::string why;
+    int first_ok = -1, ok = 0;
     for (int d = 0; d < B; ++d) {
-        if (!pack_draw(h, blens + (size_t)d * h->bcount, subst ? subst + (size_t)d * h->nsubst : nullptr,
-                       freqs ? freqs + (size_t)d * 4 : nullptr, rs ? rs + (size_t)d * h->C : nullptr,
-                       ps ? ps + (size_t)d * h->C : nullptr, h->h_params.p + (size_t)d * h->lay.stride, why))
-            return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": " + why);
+        const bool good = pack_draw(h, blens + (size_t)d * h->bcount, subst ? subst + (size_t)d * h->nsubst : nullptr,
+                                    freqs ? freqs + (size_t)d * 4 : nullptr, rs ? rs + (size_t)d * h->C : nullptr,
+                                    ps ? ps + (size_t)d * h->C : nullptr, h->h_params.p + (size_t)d * h->lay.stride, why);
+        if (!good && !status) return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": " + why);
+        if (status) status[d] = good ? 0 : 1;
+        if (good) { ++ok; if (first_ok < 0) first_ok = d; }
     }
+    if (status && first_ok >= 0)
+        for (int d = 0; d < B; ++d)
+            if (status[d])
+                std::memcpy(h->h_params.p + (size_t)d * h->lay.stride, h->h_params.p + (size_t)first_ok * h->lay.stride,
+                            sizeof(double) * h->lay.stride);
+    if (nvalid) *nvalid = ok;
     return 0;
 }
 }  // namespace
@@ -1010,28 +1022,55 @@ int phylo_b200_download(phylo_b200_handle h, int B, double* out) {
     return 0;
 }
 
-int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double* blens, const double* subst,
-                          const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
-                          double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+static int eval_batch_impl(phylo_b200_handle h, int B, const double* blens, const double* subst, const double* freqs,
+                           const double* rs, const double* ps, int want_grad, double* logp, double* g_blens,
+                           double* g_subst, double* g_freqs, double* g_rs, double* g_ps, int32_t* status) {
     if (!h || !logp) return fail(PHYLO_B200_EINVAL, "eval: NULL handle or logp");
-    if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps)) return rc;
-    if (int rc = run_prepare_all(h, B, want_grad != 0)) return rc;
-    if (int rc = eval_enqueue(h, B, want_grad != 0)) return rc;
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    int nvalid = B;
+    if (int rc = pack_batch(h, B, blens, subst, freqs, rs, ps, status, &nvalid)) return rc;
+    if (nvalid > 0) {  // (status calls only) nothing to run when every draw was rejected
+        if (int rc = run_prepare_all(h, B, want_grad != 0)) return rc;
+        if (int rc = eval_enqueue(h, B, want_grad != 0)) return rc;
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
     bool finite = true;
     for (int d = 0; d < B; ++d) {
         const double* o = h->h_out.p + (size_t)d * h->nout;
-        logp[d] = o[0];
-        finite = finite && std::isfinite(o[0]);
+        const bool ran = nvalid > 0 && !(status && status[d]);
+        const bool good = ran && std::isfinite(o[0]);
+        finite = finite && (good || !ran);
+        if (status && ran && !good) status[d] = 2;
+        const bool blank = status && !good;  // a rejected draw: -inf and a zero gradient
+        logp[d] = blank ? -std::numeric_limits<double>::infinity() : o[0];
         if (!want_grad) continue;
-        if (g_blens) std::memcpy(g_blens + (size_t)d * h->bcount, o + 1, sizeof(double) * h->bcount);
-        if (g_subst && h->nsubst) std::memcpy(g_subst + (size_t)d * h->nsubst, o + h->off_subst, sizeof(double) * h->nsubst);
-        if (g_freqs) std::memcpy(g_freqs + (size_t)d * 4, o + h->off_freqs, sizeof(double) * 4);
-        if (g_rs) std::memcpy(g_rs + (size_t)d * h->C, o + h->off_rs, sizeof(double) * h->C);
-        if (g_ps) std::memcpy(g_ps + (size_t)d * h->C, o + h->off_ps, sizeof(double) * h->C);
+        auto put = [&](double* dst, size_t n, const double* src) {
+            if (blank) std::memset(dst, 0, sizeof(double) * n);
+            else std::memcpy(dst, src, sizeof(double) * n);
+        };
+        if (g_blens) put(g_blens + (size_t)d * h->bcount, h->bcount, o + 1);
+        if (g_subst && h->nsubst) put(g_subst + (size_t)d * h->nsubst, h->nsubst, o + h->off_subst);
+        if (g_freqs) put(g_freqs + (size_t)d * 4, 4, o + h->off_freqs);
+        if (g_rs) put(g_rs + (size_t)d * h->C, h->C, o + h->off_rs);
+        if (g_ps) put(g_ps + (size_t)d * h->C, h->C, o + h->off_ps);
     }
-    if (!finite) return fail(PHYLO_B200_EDOMAIN, "log-likelihood is not finite (impossible pattern or underflow)");
+    if (!status && !finite) return fail(PHYLO_B200_EDOMAIN, "log-likelihood is not finite (impossible pattern or underflow)");
     return 0;
+}
+
+int phylo_b200_eval_batch(phylo_b200_handle h, int B, const double* blens, const double* subst,
+                          const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
+                          double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps) {
+    return eval_batch_impl(h, B, blens, subst, freqs, rs, ps, want_grad, logp, g_blens, g_subst, g_freqs, g_rs, g_ps,
+                           nullptr);
+}
+
+int phylo_b200_eval_batch_status(phylo_b200_handle h, int B, const double* blens, const double* subst,
+                                 const double* freqs, const double* rs, const double* ps, int want_grad, double* logp,
+                                 double* g_blens, double* g_subst, double* g_freqs, double* g_rs, double* g_ps,
+                                 int32_t* status) {
+    if (!status) return fail(PHYLO_B200_EINVAL, "eval_batch_status: status is NULL");
+    return eval_batch_impl(h, B, blens, subst, freqs, rs, ps, want_grad, logp, g_blens, g_subst, g_freqs, g_rs, g_ps,
+                           status);
 }
 
 int phylo_b200_eval(phylo_b200_handle h, const double* blens, const double* subst, const double* freqs,

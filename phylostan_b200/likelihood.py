@@ -78,6 +78,7 @@ def lib() -> ctypes.CDLL:
                                                     _dp, _dp, _dp, _dp]
         L.phylo_b200_eval_ratios_batch.argtypes = [vp, i, ip, i, _dp, _dp, _dp, _dp, i, _dp, _dp, _dp, _dp, _dp, i, _dp,
                                                    _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+    L.phylo_b200_eval_batch_status.argtypes = L.phylo_b200_eval_batch.argtypes + [ip]
     L.phylo_b200_upload.argtypes = [vp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_run.argtypes = [vp, i, i]
     L.phylo_b200_device_out.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i)]
@@ -257,6 +258,20 @@ class TreeLikelihood:
         if single:
             return ValueGrad(float(logp[0]), gb[0], gs[0], gf[0], gr[0], gp[0])
         return ValueGrad(logp, gb, gs, gf, gr, gp)
+
+    def value_grad_masked(self, blens, subst=None, freqs=None, rs=None, ps=None, want_grad=True):
+        """A batch in which rejected draws do not fail the call (``phylo_b200_eval_batch_status``): returns
+        (ValueGrad, status [B]) with status 0 = evaluated, 1 = parameters out of domain, 2 = log-likelihood not
+        finite; rejected draws carry ``-inf`` and a zero gradient -- what Stan does with a rejected draw."""
+        _, B, blens, subst, freqs, rs, ps = self._inputs(blens, subst, freqs, rs, ps)
+        logp, status = np.zeros(B), np.zeros(B, dtype=np.int32)
+        gb, gs = np.zeros((B, self.bcount)), np.zeros((B, max(self.nsubst, 1)))
+        gf, gr, gp = np.zeros((B, 4)), np.zeros((B, self.C)), np.zeros((B, self.C))
+        g = (_ptr(gb), _ptr(gs), _ptr(gf), _ptr(gr), _ptr(gp)) if want_grad else (None,) * 5
+        _check(lib().phylo_b200_eval_batch_status(self._h, B, _ptr(blens), _ptr(subst), _ptr(freqs), _ptr(rs), _ptr(ps),
+                                                  int(bool(want_grad)), _ptr(logp), *g,
+                                                  status.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return ValueGrad(logp, gb, gs[:, :self.nsubst], gf, gr, gp), status
 
     def loglik(self, blens, subst=None, freqs=None, rs=None, ps=None):
         """Value only (post-order sweep only; ADVI's ELBO draws use this)."""

@@ -554,6 +554,39 @@ def test_gpu_zero_likelihood_is_not_finite(datasets):
         assert np.isfinite(ok)
 
 
+def test_gpu_batch_status_marks_rejected_draws(datasets):
+    """phylo_b200_eval_batch_status: a draw the single-draw call would reject (negative branch length; all branch
+    lengths zero, i.e. likelihood 0) gets status 1 / 2, -inf and a zero gradient; the other draws of the batch equal
+    their single-draw results.  phylo_b200_eval_batch on the same batch fails as a whole."""
+    d = datasets["DS1"]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(4)
+    draws = [random_params(O.GTR, S, False, 4, rng) for _ in range(5)]
+    stack = [np.stack([dr[i] for dr in draws]) for i in range(5)]
+    stack[0][1, 3] = -0.01        # out of domain
+    stack[0][3, :] = 0.0          # impossible: sites with two different observed states
+    with make(d["peel"], d["tipmask"], d["weights"], O.GTR, 4, rooted=False) as lik:
+        with pytest.raises(lk.PhyloDomainError):
+            lik.value_grad(*stack)
+        vg, status = lik.value_grad_masked(*stack)
+        assert status.tolist() == [0, 1, 0, 2, 0]
+        for i in (1, 3):
+            assert vg.log_P[i] == -np.inf
+            for g in (vg.grad_blens, vg.grad_subst, vg.grad_freqs, vg.grad_rs, vg.grad_ps):
+                assert not g[i].any()
+        for i in (0, 2, 4):
+            one = lik.value_grad(*draws[i])
+            assert abs(vg.log_P[i] - one.log_P) <= 1e-12 * abs(one.log_P)
+            np.testing.assert_allclose(vg.grad_blens[i], one.grad_blens, rtol=1e-10, atol=1e-9)
+            np.testing.assert_allclose(vg.grad_subst[i], one.grad_subst, rtol=1e-10, atol=1e-9)
+        lp, status = lik.value_grad_masked(*stack, want_grad=False)
+        assert status.tolist() == [0, 1, 0, 2, 0] and np.isfinite(lp.log_P[[0, 2, 4]]).all()
+        bad = [a.copy() for a in stack]
+        bad[0][:] = -1.0          # every draw rejected: nothing runs
+        vg, status = lik.value_grad_masked(*bad)
+        assert status.tolist() == [1] * 5 and np.all(vg.log_P == -np.inf) and not vg.grad_blens.any()
+
+
 def test_gpu_heights_front_end_autocorrelated(datasets):
     """heights_to_blens_autocorr (generate_script.py:682-708): the Stan loops restated literally in torch
     fp64, their reverse sweep by autograd, the likelihood part from the oracle."""
