@@ -52,7 +52,9 @@ def algorithmic_bytes(S, L, C):
 
 def design_bytes(S, L, C):
     """Minimum DRAM traffic of the depth-first sweep actually implemented: one write and one read of
-    every internal partial (32 B) and of its rescale byte, tip codes once per sweep, weights once."""
+    every internal partial (32 B) and of its rescale byte, tip codes once per sweep, weights once.  (The message-
+    statistic sweep stores the S-2 messages of the non-root internal nodes instead of S-1 partials: one row of 2S-3
+    less, 0.05 % at S = 1000 -- the same formula is kept.)"""
     return (32.0 + 1.0) * L * C * (2 * S - 3) + 2.0 * S * L + 8.0 * L
 
 
@@ -551,7 +553,8 @@ def run_ours(args):
             cap = tj.get("capture", {})
             same = (cap.get("taxa") == S_TAXA and cap.get("patterns") == L_PATTERNS and cap.get("categories") == N_CAT
                     and cap.get("precision") == (32 if args.fp32 else 64)
-                    and all(cap.get(k) == info[k] for k in ("patterns_per_thread", "threads_per_cta", "stack_slots", "smem_bytes")))
+                    and all(cap.get(k) == info[k] for k in ("patterns_per_thread", "threads_per_cta", "stack_slots", "smem_bytes",
+                                                            "message_statistic", "sweep_variant")))
             traffic = tj.get("dram_bytes_per_evaluation") if same else None
             traffic = traffic * B if traffic else None   # one launch sweeps B draws
         if not args.fp32:
@@ -566,7 +569,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": cfg,
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta", "grid",
-                                            "smem_bytes", "tiles")},
+                                            "smem_bytes", "tiles", "message_statistic", "sweep_variant")},
             "tree_evals_per_s": value / (Lg * N_CAT),
             "node_updates_per_s": value * (S_TAXA - 1),
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
@@ -576,7 +579,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(B * lik.nout * 8)},
             "gpu_launches": int(args.steps * info["kernel_launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "sweep_kernel<double,4,GRAD,TIPS,128>", "launch_ms": sweep_ms,
+                         "traffic": traffic,
+                         "kernel": "sweep_kernel<double,4,GRAD,TIPS,128" + (",MSG>" if info["message_statistic"] else ">"),
+                         "launch_ms": sweep_ms,
                          "algorithmic_bytes_per_launch": des, "peak_source": peak_src,
                          "survey_model_bytes_per_launch": alg,
                          "frac_vs_survey_model": alg / (sweep_ms * 1e-3) / 1e9 / peak,

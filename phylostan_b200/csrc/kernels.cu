@@ -377,8 +377,11 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.off_spill = spill >= 0 && spill < a.slots ? spill * a.slot_stride : -1;
             pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
                        (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0);
+            pr.row_a = na >= a.S ? __ldg(a.node_row + na) * a.SS : -1;
+            pr.row_b = nb >= a.S ? __ldg(a.node_row + nb) * a.SS : -1;
+            pr.pad0 = pr.pad1 = 0;
             const int4* src = reinterpret_cast<const int4*>(&pr);
-            rd[0] = src[0]; rd[1] = src[1]; rd[2] = make_int4(0, 0, 0, 0); rd[3] = make_int4(0, 0, 0, 0);
+            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
         }
     } else {
         const int4* s = reinterpret_cast<const int4*>(a.pre + i);
@@ -406,7 +409,7 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
     double m[16];
     const int node = child ? nb : na;
     pmatrix(prm, a.lay, node, c, a.bcount, a.jc_closed, m);
-    if (a.tips_simple && (which == 0 || PHYLO_PRETIP) && node < a.S) store_tipmat(rec + 64 + Real<T>::kMat * child, m, T());
+    if (a.tips_simple && (which == 0 || PHYLO_PRETIP || a.msg) && node < a.S) store_tipmat(rec + 64 + Real<T>::kMat * child, m, T());
     else store_mat(rec + 64 + Real<T>::kMat * child, m, T());
 }
 
@@ -568,7 +571,16 @@ __device__ __forceinline__ void warp_reduce16_smem(const T (&v)[16], T* __restri
 // The scalar goes to entry 0 of the branch's G block; the contraction multiplies by mu.
 // TR: tip codes come through the per-warp TipRing from the handle's traversal-ordered copies (a.tips_post /
 // a.tips_pre) instead of per-step loads from the [S][Lpad] rows.
-template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC, bool TR>
+// MSG (gradient runs of simple-tip handles, whole stack on chip): the MESSAGE statistic.  The post-order stores, at
+// the parent's step, the messages mu_c = P_c p_c of its internal children instead of the parent's own partial (the
+// same number of rows), so the pre-order never multiplies a partial by P again: A_b = q_n o mu_a, A_a = q_n o mu_b,
+// a tip child's message is a column of P, and the statistic is G~_b = sum A_b mu_b^T = G_b P_b^T (72 instead of 104
+// FP64 instructions per pattern and step with two internal children, 40 instead of 72 for a cherry).  The
+// contraction undoes the factor analytically: <G_b, Q P_b> = <G~_b, Q> (Q and P_b commute), and
+// <G_b, dP_b/dtheta> = <m1^T G~_b m2^T o Phi, X_theta> with Phi_ij = (e^{(l_i - l_j) tau} - 1) / (l_i - l_j), which
+// amplifies rounding by e^{|l_i - l_j| tau}: the host only chooses MSG while that stays below e^12 for every
+// branch and category of the batch.
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC, bool TR, bool MSG = false>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -721,6 +733,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                 for (int j = 0; j < K; ++j) st4(ST(s1.z, j), NT, tos[j]);
             }
+            if (GRAD && MSG) {  // the children's messages go to the children's rows; tips have none
+                const int2 rw = *reinterpret_cast<const int2*>(rec + 32);  // row_a, row_b
+                if (rw.x >= 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) st4cs(SC(rw.x, j), NT, ma[j]);
+                }
+                if (rw.y >= 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) st4cs(SC(rw.y, j), NT, mb[j]);
+                }
+            }
             unsigned kpack = 0u;
             bool tiny = false;
             const T kTiny = R::tiny();
@@ -747,7 +770,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                 }
             }
-            if (GRAD) {
+            if (GRAD && !MSG) {
 #pragma unroll
                 for (int j = 0; j < K; ++j)
                     st4cs(srow + j * (VP * NT), NT, tos[j]);
@@ -890,15 +913,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148).  One (warp-uniform)
                 // branch per operand kind; a simple tip's message is a column of P (PRETIP streams).
                 T Aa[K][4], Ab[K][4];
-                if (rowa < 0) {
+                if (rowa < 0) {  // MSG: pa / pbv hold MESSAGES, a tip's is a column of P
 #pragma unroll
-                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
+                    for (int j = 0; j < K; ++j) {
+                        if (MSG) tip_msg<V>(rec + 64, BYTE_OF(ca, j), pa[j]);
+                        else tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
+                    }
                 }
                 if (rowb < 0) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
+                    for (int j = 0; j < K; ++j) {
+                        if (MSG) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), pbv[j]);
+                        else tip_vec<TIPS>(BYTE_OF(cb, j), pbv[j]);
+                    }
                 }
-                if (PHYLO_PRETIP && TIPS && rowa < 0) {
+                if (MSG) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * pa[j][s];
+                } else if (PHYLO_PRETIP && TIPS && rowa < 0) {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T m[4];
@@ -925,11 +959,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     for (int x = 0; x < 16; ++x) G[x] = T(0);
                     const bool btip = PHYLO_PRETIP && TIPS && rowb < 0;  // tip: the message is a column of P_b
                     T M[16];
-                    if (!btip) lds_mat(rec + 64 + R::kMat, M);
+                    if (MSG ? s2.x >= 0 : !btip) lds_mat(rec + 64 + R::kMat, M);  // MSG: only q(b) needs P_b
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T m[4];
-                        if (btip) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), m);
+                        if (MSG) {
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) m[s] = pbv[j][s];
+                        } else if (btip) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), m);
                         else matvec(M, pbv[j], m);
 #pragma unroll
                         for (int s = 0; s < 4; ++s) Aa[j][s] = qn[j][s] * m[s];
@@ -1612,6 +1649,9 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
         const double* Q = prm + a.lay.off_Q;
         if (a.jc_scalar) {  // the sweep already contracted with (J/4 - P): entry 0 holds <G, Q P> / mu, mu = -4/3 Q_00
             g = G[0] * (-Q[0] * (4.0 / 3.0));
+        } else if (a.msg) {  // G holds G~ = G P^T, and <G, Q P> = tr(P^-1 G~^T Q P) = <G~, Q> because Q and P commute
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g = fma(G[i], Q[i], g);
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1647,6 +1687,17 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
             // expm1 only ever sees a non-positive argument (long branches: 0 * inf otherwise).  F is
             // symmetric: six expm1 for the off-diagonal pairs, F_ii = tau e^{l_i tau}.
             double F[16];
+            if (a.msg) {
+                // message statistic: <G, dP> = <G~, dP P^-1> and dP P^-1 = m1 (X o Phi) m2 with
+                // Phi_ij = F_ij e^{-l_j tau} = (e^{(l_i - l_j) tau} - 1) / (l_i - l_j), Phi_ii = tau (not symmetric)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double x = (lam[i] - lam[j]) * tau;
+                        F[4 * i + j] = i == j ? tau : tau * (fabs(x) < 1e-8 ? 1.0 + 0.5 * x : expm1(x) / x);
+                    }
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 F[5 * i] = tau * ex[i];
@@ -1655,6 +1706,7 @@ __global__ void __launch_bounds__(128) contract_kernel(const ContractArgs a) {
                     const double x = fabs(lam[i] - lam[j]) * tau;
                     F[4 * i + j] = F[4 * j + i] = tau * fmax(ex[i], ex[j]) * (x < 1e-8 ? 1.0 - 0.5 * x : -expm1(-x) / x);
                 }
+            }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1942,6 +1994,18 @@ SweepFn pick_kernel(int nthreads) {
     return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC, false>;
 }
 
+// message-statistic gradient kernels (fp64, simple tips, 128-thread CTAs, whole stack on chip)
+SweepFn pick_kernel_msg(int K) {
+    switch (K) {
+#if !defined(PHYLO_FAST_BUILD) || PHYLO_FAST_BUILD < 2
+        case 1: return sweep_kernel<double, 1, true, true, 128, Cfg<double, 1>::minb, false, false, PHYLO_TIPRING == 2, true>;
+        case 2: return sweep_kernel<double, 2, true, true, 128, Cfg<double, 2>::minb, false, false, PHYLO_TIPRING == 2, true>;
+#endif
+        case 4: return sweep_kernel<double, 4, true, true, 128, Cfg<double, 4>::minb, false, false, PHYLO_TIPRING == 2, true>;
+    }
+    return nullptr;
+}
+
 // scalar-statistic gradient kernels (JC69, fp64, whole stack on chip)
 template <bool TIPS>
 SweepFn pick_kernel_jc(int K, int nthreads) {
@@ -1969,7 +2033,8 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
     return nullptr;
 }
 
-SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false) {
+SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false) {
+    if (msg) return prec == 64 && tips && grad && !deep && !jc && nthreads == 128 ? pick_kernel_msg(K) : nullptr;
 #ifdef PHYLO_FAST_BUILD  // compile-time experiments only: the fp64 K = 4 / 2 gradient kernels of simple-tip handles
     if (prec != 64 || !tips || !grad || jc || nthreads != 128) return nullptr;
     if (K == 4) return deep ? pick_kernel<double, 4, true, true, true>(128) : pick_kernel<double, 4, true, true, false>(128);
@@ -2018,9 +2083,13 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
     else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
+bool sweep_msg_available(int prec, bool tips, bool grad, bool deep, int nthreads, bool jc) {
+    return prec == 64 && tips && grad && !deep && !jc && nthreads == 128;
+}
+
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream, bool jc) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc);
+                         size_t smem, cudaStream_t stream, bool jc, bool msg) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -2029,8 +2098,8 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool gr
 }
 
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n,
-                            bool jc) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc);
+                            bool jc, bool msg) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

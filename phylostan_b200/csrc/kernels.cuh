@@ -58,6 +58,8 @@ struct alignas(16) PostRec {
     int32_t off_a, off_b;     // shared-memory stack offset of the child's partial (when it sits in a slot)
     int32_t off_spill;        // stack offset that receives the previous TOS first, or -1
     int32_t flags;            // 1: a is a tip, 2: b is a tip, 4: a is the TOS, 8: b is the TOS
+    int32_t row_a, row_b;     // scratch offsets of the children's own rows, -1 for tips (message-statistic sweep:
+    int32_t pad0, pad1;       //   the MESSAGE P_c p_c of an internal child is stored there, at its parent's step)
 };
 struct alignas(16) PreRec {
     long long tip_a, tip_b;   // byte offset of the child's tip-code row
@@ -68,7 +70,7 @@ struct alignas(16) PreRec {
     int32_t g_a, g_b;         // offsets (doubles) of the children's 4x4 statistics blocks
     int32_t flags;            // 1: a is internal -> q(a) becomes the TOS
 };
-static_assert(sizeof(PostRec) == 32 && sizeof(PreRec) == 48, "record descriptors must fit the 64-byte header");
+static_assert(sizeof(PostRec) == 48 && sizeof(PreRec) == 48, "record descriptors must fit the 64-byte header");
 
 struct StreamArgs {
     const double* params;     // [B][stride]
@@ -86,6 +88,7 @@ struct StreamArgs {
     // of p(node), which nobody reads any more by then.
     const int* node_row;      // [2S-1] node id -> its own post-order step (= scratch row), -1 for tips
     int slots;
+    int msg;                  // message-statistic sweep: tip children of the PRE-order stream get the column-major layout too
     int slot_stride;          // offset unit of an ON-CHIP stack slot: SS (shared-memory stack, in 16-byte vectors) or
                               // 8 K (tensor-memory stack, in 32-bit columns)
 };
@@ -118,6 +121,7 @@ struct ContractArgs {
     ParamLayout lay;
     int bcount, C, nn, nout, nsubst, nsteps, S, tips_simple;
     int jc_scalar;            // entry 0 of a G block holds <G, Q P> / mu (JC69 scalar-statistic sweep)
+    int msg;                  // the G blocks hold the message statistic G~ = sum A mu^T = G P^T
     int off_out_subst, off_out_freqs, off_out_rs;
 };
 
@@ -125,10 +129,13 @@ struct ContractArgs {
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
 // deep: the stream parks stack entries in the HBM scratch (gradient runs only)
 // jc: scalar-statistic gradient kernel of JC69 handles (fp64, gradient, not deep; ContractArgs::jc_scalar must agree)
+// msg: message-statistic gradient kernel (fp64, simple tips, 128-thread CTAs, whole stack on chip; StreamArgs::msg and
+// ContractArgs::msg must agree) -- see sweep_msg_available
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream, bool jc = false);
+                         size_t smem, cudaStream_t stream, bool jc = false, bool msg = false);
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
-                            int* blocks_per_sm, bool jc = false);
+                            int* blocks_per_sm, bool jc = false, bool msg = false);
+bool sweep_msg_available(int prec, bool tips, bool grad, bool deep, int nthreads, bool jc);
 // Gradient sweep with the stack in tensor memory (fp64, K = 4, 128-thread CTAs): `ctas` = 2 or 3 resident CTAs per
 // SM, sweep_tm_slots stack slots on chip (positions beyond them are parked in the scratch like the `deep` variant)
 bool sweep_tm_available(int prec, int K, int nthreads, bool grad, bool jc);

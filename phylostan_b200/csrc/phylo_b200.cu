@@ -81,6 +81,7 @@ struct PinnedBuf {
 
 }  // namespace
 
+constexpr double kMsgTauMax = 12.0;  // e^12 * 2^-53 = 1.8e-11 relative: two decades inside the 1e-8 gradient tolerance
 constexpr int kDefaultSweepTm = 0;  // fp64 K = 4 gradient runs: 0 shared-memory stack, 2 / 3 tensor-memory stack
 
 struct phylo_b200_ctx {
@@ -121,6 +122,15 @@ struct phylo_b200_ctx {
     bool jc_run = false;  // the last resolved launch is the JC69 scalar-statistic kernel
     int req_tm = kDefaultSweepTm;  // tensor-memory-stack sweep for fp64 K = 4 gradient runs: 0 off, 2 / 3 = resident CTAs per SM
     int tm = 0;           // what the last resolved launch uses (0: shared-memory stack)
+    // Message-statistic gradient sweep (kernels.cu, MSG): chosen per run when the handle allows it (fp64, simple tips,
+    // 128-thread CTAs, whole stack on chip) AND the packed batch does: its contraction amplifies rounding by
+    // e^{|l_i - l_j| t_b r_c}, so tau_bound = max over the batch of (max_b t_b)(max_c r_c)(l_max - l_min) must stay
+    // below kMsgTauMax.  PHYLO_B200_MSG=0 turns it off.
+    bool use_msg = true;
+    double tau_unit = 0.0;    // max over the batch of (max_c r_c)(l_max - l_min): tau_bound per unit of branch length
+    double tau_bound = 0.0;   // of the batch packed last (front ends that compute branch lengths on the device set
+                              // it from their own inputs)
+    bool msg_run = false;     // the last resolved launch uses the message statistic
     size_t smem = 0;
     int last_launches = 0;
 
@@ -274,8 +284,10 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             tm = h->req_tm; D = dt; smem = sweep_tm_smem_bytes(K);
         }
     }
-    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun; h->tm = tm;
-    if (!tm) CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun));
+    const bool msg = !tm && h->use_msg && sweep_msg_available(h->prec, h->tips_simple, grad, D < Dfull, NT, jrun) &&
+                     h->tau_bound < kMsgTauMax;
+    h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun; h->tm = tm; h->msg_run = msg;
+    if (!tm) CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun, msg));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
     const long long items = (long long)B * h->ntiles;
     h->grid = (int)std::min<long long>(items, (long long)occ * h->num_sms);
@@ -442,6 +454,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     h->stream = h->own_stream;
     if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
     if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
+    if (const char* ms = std::getenv("PHYLO_B200_MSG")) h->use_msg = !(ms[0] == '0');
     if (const char* tm = std::getenv("PHYLO_B200_SWEEP_TM")) h->req_tm = tm[0] == '3' ? 3 : tm[0] == '2' ? 2 : 0;
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
@@ -667,6 +680,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 11: return h->slots;
         case 12: return 1 + (long long)h->peers.size();
         case 13: return h->tm;
+        case 14: return h->msg_run ? 1 : 0;
     }
     return PHYLO_B200_EINVAL;
 }
@@ -691,6 +705,8 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
     CU_TRY(cudaStreamSynchronize(h->stream));
     std::string why;
     int first_ok = -1, ok = 0;
+    h->tau_bound = 0.0;
+    h->tau_unit = 0.0;
     for (int d = 0; d < B; ++d) {
         const bool good = pack_draw(h, blens + (size_t)d * h->bcount, subst ? subst + (size_t)d * h->nsubst : nullptr,
                                     freqs ? freqs + (size_t)d * 4 : nullptr, rs ? rs + (size_t)d * h->C : nullptr,
@@ -698,7 +714,17 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
         if (!good && !status) return fail(PHYLO_B200_EDOMAIN, "draw " + std::to_string(d) + ": " + why);
         if (status) status[d] = good ? 0 : 1;
         if (good) { ++ok; if (first_ok < 0) first_ok = d; }
+        if (good) {
+            const double* pd = h->h_params.p + (size_t)d * h->lay.stride;
+            double tmax = 0.0, rmax = 0.0, lmin = 0.0, lmax = 0.0;
+            for (int b = 0; b < h->bcount; ++b) tmax = std::max(tmax, pd[h->lay.off_t + b]);
+            for (int c = 0; c < h->C; ++c) rmax = std::max(rmax, pd[h->lay.off_rs + c]);
+            for (int k = 0; k < 4; ++k) { lmin = std::min(lmin, pd[h->lay.off_lam + k]); lmax = std::max(lmax, pd[h->lay.off_lam + k]); }
+            h->tau_unit = std::max(h->tau_unit, rmax * (lmax - lmin));
+            h->tau_bound = std::max(h->tau_bound, tmax * rmax * (lmax - lmin));
+        }
     }
+    for (auto* p : h->peers) { p->tau_bound = h->tau_bound; p->tau_unit = h->tau_unit; }
     if (status && first_ok >= 0)
         for (int d = 0; d < B; ++d)
             if (status[d])
@@ -872,6 +898,8 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     sa.node_row = h->d_node_row.p;
     sa.slots = grad ? h->slots : h->plan.depth();
     sa.slot_stride = grad && h->tm ? 8 * h->K : sa.SS;
+    const bool msg = grad && h->msg_run;
+    sa.msg = msg ? 1 : 0;
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
@@ -891,13 +919,13 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     const bool deep = grad && h->slots < h->plan.depth();
     const bool jc = grad && h->jc_run;
     if (grad && h->tm) CU_TRY(launch_sweep_tm(a, h->tips_simple, h->K, h->tm, h->grid, st));
-    else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc));
+    else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc, msg));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
     if (grad) {
         ContractArgs ca{};
         ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
-        ca.S = h->S; ca.tips_simple = h->tips_simple; ca.jc_scalar = jc ? 1 : 0;
+        ca.S = h->S; ca.tips_simple = h->tips_simple; ca.jc_scalar = jc ? 1 : 0; ca.msg = msg ? 1 : 0;
         ca.bcount = h->bcount; ca.C = h->C; ca.nn = h->nn; ca.nout = h->nout; ca.nsubst = h->nsubst;
         ca.off_out_subst = h->off_subst; ca.off_out_freqs = h->off_freqs; ca.off_out_rs = h->off_rs;
         launch_contract(ca, h->prec, B, st);
@@ -920,7 +948,8 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
             u(h->d_dscr.p), u(h->h_params.p), u(h->h_out.p), u(h->stream), (unsigned long long)h->K,
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
             (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
-            (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p), (unsigned long long)h->tm};
+            (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p), (unsigned long long)h->tm,
+            (unsigned long long)h->msg_run};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
@@ -1255,6 +1284,14 @@ static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, 
         std::memcpy(dst, heights + (size_t)b * (S - 1), sizeof(double) * (S - 1));
         std::memcpy(dst + (S - 1), rates + (size_t)b * nrates, sizeof(double) * nrates);
         if (job.has_extra) std::memcpy(dst + (S - 1) + nrates, hbar_extra + (size_t)b * (S - 1), sizeof(double) * (S - 1));
+    }
+    {   // branch lengths are computed on the device: bound them by (largest rate) x (largest height) of the batch
+        double hmax = 0.0, rmax = 0.0;
+        for (size_t i = 0; i < (size_t)B * (S - 1); ++i) hmax = std::max(hmax, std::fabs(heights[i]));
+        for (size_t i = 0; i < (size_t)B * nrates; ++i) rmax = std::max(rmax, std::fabs(rates[i]));
+        const double tb = hmax * rmax * h->tau_unit;
+        h->tau_bound = std::isfinite(tb) ? tb : 1e300;
+        for (auto* p : h->peers) p->tau_bound = h->tau_bound;
     }
     const bool grad = want_grad != 0;
     if (int rc = run_prepare_all(h, B, grad)) return rc;

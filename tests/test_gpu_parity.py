@@ -554,6 +554,50 @@ def test_gpu_zero_likelihood_is_not_finite(datasets):
         assert np.isfinite(ok)
 
 
+@pytest.mark.parametrize("name,model,rooted", [("fluA", O.GTR, True), ("DS1", O.HKY, False), ("HCV", O.GTR, True)])
+def test_gpu_message_statistic_sweep(datasets, monkeypatch, name, model, rooted):
+    """The message-statistic gradient sweep (G~ = sum A mu^T = G P^T, contraction <G~, Q> and
+    <m1^T G~ m2^T o Phi, X>) against the oracle and against the plain statistic (PHYLO_B200_MSG=0) for every tiling;
+    its contraction amplifies rounding by e^{(l_i - l_j) tau}, so the library only chooses it while
+    (largest branch) x (largest site rate) x (eigenvalue spread) < 12 -- checked on both sides of that bound, where
+    the gradient must still be inside the north-star tolerance."""
+    d = datasets[name]
+    S = d["tipmask"].shape[0]
+    rng = np.random.default_rng(21)
+    bl, subst, fr, rs, ps = random_params(model, S, rooted, 4, rng)
+    spread = np.ptp(lk.derive(MODEL_NAME[model], subst, fr)["lam"]) * rs.max()
+    want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, bl, subst, fr, rs, ps, rooted=rooted)
+    rows = {}
+    for env in ("1", "0"):
+        monkeypatch.setenv("PHYLO_B200_MSG", env)
+        with make(d["peel"], d["tipmask"], d["weights"], model, 4, rooted=rooted) as lik:
+            for K in (1, 2, 4):
+                lik.set_tiling(K, 1)
+                got = lik.value_grad(bl, subst, fr, rs, ps)
+                assert lik.info()["message_statistic"] == int(env)
+                assert_parity(got, want)
+                rows[(env, K)] = got.grad
+            if env == "0":
+                continue
+            # a batch is decided as a whole: one long branch in one draw sends all of it to the plain statistic
+            lik.set_tiling(0, 0)
+            for scale, msg in ((11.5, 1), (12.5, 0)):
+                b2 = bl.copy()
+                b2[rng.integers(b2.size)] = scale / spread
+                w2 = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, b2, subst, fr, rs, ps, rooted=rooted)
+                assert_parity(lik.value_grad(b2, subst, fr, rs, ps), w2)
+                assert lik.info()["message_statistic"] == msg
+                stack = [np.stack([x, y]) for x, y in zip((bl, subst, fr, rs, ps), (b2, subst, fr, rs, ps))]
+                vg = lik.value_grad(*stack)
+                assert lik.info()["message_statistic"] == msg
+                assert_parity(lk.ValueGrad(vg.log_P[1], vg.grad_blens[1], vg.grad_subst[1], vg.grad_freqs[1], vg.grad_rs[1],
+                                           vg.grad_ps[1]), w2)
+            # value-only runs have no statistic at all
+            lik.loglik(bl, subst, fr, rs, ps)
+    for K in (1, 2, 4):
+        np.testing.assert_allclose(rows[("1", K)], rows[("0", K)], rtol=1e-9, atol=1e-9)
+
+
 def test_gpu_batch_status_marks_rejected_draws(datasets):
     """phylo_b200_eval_batch_status: a draw the single-draw call would reject (negative branch length; all branch
     lengths zero, i.e. likelihood 0) gets status 1 / 2, -inf and a zero gradient; the other draws of the batch equal

@@ -65,7 +65,9 @@ def main():
     for name in libs:
         env = dict(os.environ, PHYLO_AB_CHILD="1")
         name, _, tm = name.partition("@")   # "lib@3": run that library with PHYLO_B200_SWEEP_TM=3
-        if tm:
+        if tm.startswith("m"):               # "lib@m0": the same with PHYLO_B200_MSG=0 (no message statistic)
+            env["PHYLO_B200_MSG"] = tm[1:]
+        elif tm:
             env["PHYLO_B200_SWEEP_TM"] = tm
         if name:
             env["PHYLO_B200_LIB"] = os.path.join(ROOT, "phylostan_b200", "csrc", "variants", f"libphylo_b200_{name}.so")
