@@ -361,10 +361,10 @@ def run_config4(args, world, rank, local, stream):
             "draws_per_step": B, "steps": steps, "ms_per_step": ms_step, "tree_evals_per_s": evals,
             "value": evals * C4_PATTERNS * N_CAT, "unit": UNIT,
             "sweep_ms": sweep_ms, "allreduce_ms": ar_ms, "allreduce_bytes": int(B * lik.nout * 8),
-            "kernel": "sweep_kernel<double,K,GRAD,TIPS,128,DEEP>" if info["stack_slots"] < info["stack_depth"]
-                      else "sweep_kernel<double,K,GRAD,TIPS,128>",
+            "kernel": ("sweep_kernel<double,K,GRAD,TIPS,128,DEEP" if info["stack_slots"] < info["stack_depth"]
+                       else "sweep_kernel<double,K,GRAD,TIPS,128") + (",MSG>" if info["message_statistic"] else ">"),
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta",
-                                            "grid", "smem_bytes", "tiles", "scratch_bytes")},
+                                            "grid", "smem_bytes", "tiles", "scratch_bytes", "message_statistic")},
             "design_bytes_per_launch": des, "dram_frac_of_measured_peak": des / (sweep_ms * 1e-3) / 1e9 / peak,
             "survey_Bvg_frac_all_gpus": algorithmic_bytes(C4_TAXA, C4_PATTERNS, N_CAT) * evals / (world * peak * 1e9),
             "setup_s": {"simulate_on_gpu": t_gen, "create_device": t_create},

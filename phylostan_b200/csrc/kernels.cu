@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.off_b = 0;  // an internal second child is always the previous result (TOS)
             pr.off_spill = spill >= 0 && spill < a.slots ? spill * a.slot_stride : -1;
             pr.flags = (s0.z == kSrcTip ? 1 : 0) | (s0.w == kSrcTip ? 2 : 0) | (s0.z == kSrcTos ? 4 : 0) |
-                       (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0);
+                       (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0) | (spill >= a.slots ? 32 : 0);
             pr.row_a = na >= a.S ? __ldg(a.node_row + na) * a.SS : -1;
             pr.row_b = nb >= a.S ? __ldg(a.node_row + nb) * a.SS : -1;
             pr.pad0 = pr.pad1 = 0;
@@ -571,7 +571,7 @@ __device__ __forceinline__ void warp_reduce16_smem(const T (&v)[16], T* __restri
 // The scalar goes to entry 0 of the branch's G block; the contraction multiplies by mu.
 // TR: tip codes come through the per-warp TipRing from the handle's traversal-ordered copies (a.tips_post /
 // a.tips_pre) instead of per-step loads from the [S][Lpad] rows.
-// MSG (gradient runs of simple-tip handles, whole stack on chip): the MESSAGE statistic.  The post-order stores, at
+// MSG (gradient runs of simple-tip handles): the MESSAGE statistic.  The post-order stores, at
 // the parent's step, the messages mu_c = P_c p_c of its internal children instead of the parent's own partial (the
 // same number of rows), so the pre-order never multiplies a partial by P again: A_b = q_n o mu_a, A_a = q_n o mu_b,
 // a tip child's message is a column of P, and the statistic is G~_b = sum A_b mu_b^T = G_b P_b^T (72 instead of 104
@@ -732,6 +732,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             if (s1.z >= 0) {  // the previous result still waits for its sibling: park it in shared memory
 #pragma unroll
                 for (int j = 0; j < K; ++j) st4(ST(s1.z, j), NT, tos[j]);
+            }
+            if (DEEP && MSG && (fl & 32)) {  // rare: it is parked above the capped stack -- in its own scratch row, which the
+                                             // message-statistic sweep has not written (its parent stores the message there later)
+#pragma unroll
+                for (int j = 0; j < K; ++j) st4cs(srow - SS + j * (VP * NT), NT, tos[j]);
             }
             if (GRAD && MSG) {  // the children's messages go to the children's rows; tips have none
                 const int2 rw = *reinterpret_cast<const int2*>(rec + 32);  // row_a, row_b
@@ -1994,14 +1999,15 @@ SweepFn pick_kernel(int nthreads) {
     return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC, false>;
 }
 
-// message-statistic gradient kernels (fp64, simple tips, 128-thread CTAs, whole stack on chip)
+// message-statistic gradient kernels (fp64, simple tips, 128-thread CTAs)
+template <bool DEEP>
 SweepFn pick_kernel_msg(int K) {
     switch (K) {
 #if !defined(PHYLO_FAST_BUILD) || PHYLO_FAST_BUILD < 2
-        case 1: return sweep_kernel<double, 1, true, true, 128, Cfg<double, 1>::minb, false, false, PHYLO_TIPRING == 2, true>;
-        case 2: return sweep_kernel<double, 2, true, true, 128, Cfg<double, 2>::minb, false, false, PHYLO_TIPRING == 2, true>;
+        case 1: return sweep_kernel<double, 1, true, true, 128, Cfg<double, 1>::minb, DEEP, false, PHYLO_TIPRING == 2, true>;
+        case 2: return sweep_kernel<double, 2, true, true, 128, Cfg<double, 2>::minb, DEEP, false, PHYLO_TIPRING == 2, true>;
 #endif
-        case 4: return sweep_kernel<double, 4, true, true, 128, Cfg<double, 4>::minb, false, false, PHYLO_TIPRING == 2, true>;
+        case 4: return sweep_kernel<double, 4, true, true, 128, Cfg<double, 4>::minb, DEEP, false, PHYLO_TIPRING == 2, true>;
     }
     return nullptr;
 }
@@ -2034,7 +2040,9 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
 }
 
 SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false) {
-    if (msg) return prec == 64 && tips && grad && !deep && !jc && nthreads == 128 ? pick_kernel_msg(K) : nullptr;
+    if (msg)
+        return prec == 64 && tips && grad && !jc && nthreads == 128 ? (deep ? pick_kernel_msg<true>(K) : pick_kernel_msg<false>(K))
+                                                                    : nullptr;
 #ifdef PHYLO_FAST_BUILD  // compile-time experiments only: the fp64 K = 4 / 2 gradient kernels of simple-tip handles
     if (prec != 64 || !tips || !grad || jc || nthreads != 128) return nullptr;
     if (K == 4) return deep ? pick_kernel<double, 4, true, true, true>(128) : pick_kernel<double, 4, true, true, false>(128);
@@ -2083,8 +2091,8 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
     else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }
 
-bool sweep_msg_available(int prec, bool tips, bool grad, bool deep, int nthreads, bool jc) {
-    return prec == 64 && tips && grad && !deep && !jc && nthreads == 128;
+bool sweep_msg_available(int prec, bool tips, bool grad, bool, int nthreads, bool jc) {
+    return prec == 64 && tips && grad && !jc && nthreads == 128;
 }
 
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,

@@ -57,7 +57,8 @@ struct alignas(16) PostRec {
     long long tip_a, tip_b;   // byte offset of the child's tip-code row (node * Lpad)
     int32_t off_a, off_b;     // shared-memory stack offset of the child's partial (when it sits in a slot)
     int32_t off_spill;        // stack offset that receives the previous TOS first, or -1
-    int32_t flags;            // 1: a is a tip, 2: b is a tip, 4: a is the TOS, 8: b is the TOS
+    int32_t flags;            // 1: a is a tip, 2: b is a tip, 4: a is the TOS, 8: b is the TOS, 16: a is parked in its scratch
+                              //   row, 32: the previous TOS is parked above the capped stack
     int32_t row_a, row_b;     // scratch offsets of the children's own rows, -1 for tips (message-statistic sweep:
     int32_t pad0, pad1;       //   the MESSAGE P_c p_c of an internal child is stored there, at its parent's step)
 };
@@ -129,7 +130,7 @@ struct ContractArgs {
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
 // deep: the stream parks stack entries in the HBM scratch (gradient runs only)
 // jc: scalar-statistic gradient kernel of JC69 handles (fp64, gradient, not deep; ContractArgs::jc_scalar must agree)
-// msg: message-statistic gradient kernel (fp64, simple tips, 128-thread CTAs, whole stack on chip; StreamArgs::msg and
+// msg: message-statistic gradient kernel (fp64, simple tips, 128-thread CTAs; StreamArgs::msg and
 // ContractArgs::msg must agree) -- see sweep_msg_available
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
                          size_t smem, cudaStream_t stream, bool jc = false, bool msg = false);

@@ -123,7 +123,7 @@ struct phylo_b200_ctx {
     int req_tm = kDefaultSweepTm;  // tensor-memory-stack sweep for fp64 K = 4 gradient runs: 0 off, 2 / 3 = resident CTAs per SM
     int tm = 0;           // what the last resolved launch uses (0: shared-memory stack)
     // Message-statistic gradient sweep (kernels.cu, MSG): chosen per run when the handle allows it (fp64, simple tips,
-    // 128-thread CTAs, whole stack on chip) AND the packed batch does: its contraction amplifies rounding by
+    // 128-thread CTAs) AND the packed batch does: its contraction amplifies rounding by
     // e^{|l_i - l_j| t_b r_c}, so tau_bound = max over the batch of (max_b t_b)(max_c r_c)(l_max - l_min) must stay
     // below kMsgTauMax.  PHYLO_B200_MSG=0 turns it off.
     bool use_msg = true;
