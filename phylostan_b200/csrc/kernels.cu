@@ -455,8 +455,8 @@ struct Ring {
         remaining = n;
         wchunk = 0;
         slot = 0;
-        issue(extra);
-        issue(extra);
+#pragma unroll
+        for (int q = 0; q < kRecBufs - 1; ++q) issue(extra);
     }
     // top of step i: afterwards the records of steps i, i+1, i+2 (even i: and i+3) are readable, and so
     // is every byte-operand block committed before this call
@@ -466,7 +466,7 @@ struct Ring {
         if ((i & 1) == 0) {
             __syncwarp();  // every lane is done with the chunk about to be overwritten
             issue(extra);
-            cp_async_wait<1>();
+            cp_async_wait<kRecBufs - 2>();
             __syncwarp();
         }
     }

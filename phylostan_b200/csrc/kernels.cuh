@@ -33,7 +33,10 @@ namespace phylo {
 constexpr int kRecBytes = 384;   // fp64 record: [desc 64 B | P_a slot 160 B | P_b slot 160 B]
 constexpr int kRecBytesF32 = 224;  // fp32 mode: [desc 64 B | P_a slot 80 B | P_b slot 80 B]
 constexpr int kRecChunk = 2;     // records per cp.async group
-constexpr int kRecBufs = 3;      // ring depth in chunks
+#ifndef PHYLO_RECBUFS
+#define PHYLO_RECBUFS 3
+#endif
+constexpr int kRecBufs = PHYLO_RECBUFS;  // ring depth in chunks (kRecBufs - 1 chunks are in flight ahead of the one being read)
 constexpr int kTmOpSlots = 4;    // TMEM-stack sweep: operand slots per warp (both children of steps i and i+1)
 
 // offsets (in doubles) inside one draw's parameter block
