@@ -239,6 +239,41 @@ def test_derive_x_theta_matches_finite_differences():
             np.testing.assert_allclose(d["m1"] @ d["X"][k] @ d["m2"], dQ, atol=2e-9)
 
 
+def test_message_statistic_contraction_identities():
+    """The algebra behind the message-statistic sweep, on the library's own eigen-system:
+    with G~ = G P^T,  <G, Q P> = <G~, Q>  and  <G, dP/dtheta> = <m1^T G~ m2^T o Phi, X_theta>,
+    Phi_ij = (e^{(l_i - l_j) tau} - 1) / (l_i - l_j), Phi_ii = tau -- and the rounding amplification e^{(l_i - l_j) tau}
+    that makes the library fall back to the plain statistic on long branches."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(8)
+    for model, subst in (("HKY", np.array([4.2])), ("GTR", rng.dirichlet(np.ones(6)) * 6)):
+        fr = rng.dirichlet(np.ones(4) * 4)
+        d = lk.derive(model, subst, fr)
+        Q, lam, m1, m2 = d["Q"], d["lam"], d["m1"], d["m2"]
+        theta = np.concatenate([subst, fr])
+        for tau in (1e-6, 0.03, 0.7, 4.0):
+            P = expm(Q * tau)
+            G = rng.normal(size=(4, 4))
+            Gt = G @ P.T
+            assert np.sum(G * (Q @ P)) == pytest.approx(np.sum(Gt * Q), rel=1e-11, abs=1e-13)
+            x = (lam[:, None] - lam[None, :]) * tau
+            with np.errstate(invalid="ignore", divide="ignore"):
+                Phi = tau * np.where(np.abs(x) < 1e-8, 1.0 + 0.5 * x, np.expm1(x) / x)
+            Ht = m1.T @ Gt @ m2.T
+            for k in range(theta.size):
+                h = 1e-6
+                tp, tm = theta.copy(), theta.copy()
+                tp[k] += h; tm[k] -= h
+                n = subst.size
+                dP = (expm(lk.derive(model, tp[:n], tp[n:])["Q"] * tau) - expm(lk.derive(model, tm[:n], tm[n:])["Q"] * tau)) / (2 * h)
+                want = np.sum(G * dP)
+                got = np.sum(Ht * Phi * d["X"][k])
+                assert got == pytest.approx(want, rel=2e-7, abs=2e-8)
+        # where it stops being usable: e^{spread * tau} of rounding amplification
+        tau = 40.0 / np.ptp(lam)
+        assert np.exp(np.ptp(lam) * tau) * 2.0 ** -53 > 1e-2
+
+
 def test_derive_rejects_out_of_domain():
     with pytest.raises(lk.PhyloDomainError):
         lk.derive("HKY", [float("nan")], [0.25] * 4)
