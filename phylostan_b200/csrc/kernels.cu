@@ -1160,7 +1160,10 @@ template <int MINB> struct TmCfg;
 template <> struct TmCfg<3> { static constexpr int colsA = 128, colsB = 32; };  // 3 x 160 of the SM's 512 columns
 template <> struct TmCfg<2> { static constexpr int colsA = 256, colsB = 0; };
 
-template <int K, bool TIPS, int MINB>
+// MSG: the message statistic (see sweep_kernel), simple-tip handles only: the post-order stores the children's
+// messages, a tip child's operand slot receives its column of P, and the two passes over the operands become
+// A_b / G~_b and A_a / G~_a without any product with P.
+template <int K, bool TIPS, int MINB, bool MSG = false>
 __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) {
     typedef double T;
     typedef Real<double> R;
@@ -1301,6 +1304,21 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                 }
             }
             if (s1.z >= 0) tm_push<K>(TM(s1.z), tos);  // the previous result still waits for its sibling
+            if (MSG) {
+                if (fl & 32) {  // rare: it is parked beyond the TMEM slots, in its own scratch row (not written otherwise)
+#pragma unroll
+                    for (int j = 0; j < K; ++j) st4cs(srow - K * VP * NT + j * (VP * NT), NT, tos[j]);
+                }
+                const int2 rw = *reinterpret_cast<const int2*>(rec + 32);  // row_a, row_b: the children's messages go there
+                if (rw.x >= 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) st4cs(SC(rw.x, j), NT, ma[j]);
+                }
+                if (rw.y >= 0) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) st4cs(SC(rw.y, j), NT, mb[j]);
+                }
+            }
             unsigned kpack = 0u;
             bool tiny = false;
             const T kTiny = R::tiny();
@@ -1327,8 +1345,10 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                     }
                 }
             }
+            if (!MSG) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) st4cs(srow + j * (VP * NT), NT, tos[j]);
+                for (int j = 0; j < K; ++j) st4cs(srow + j * (VP * NT), NT, tos[j]);
+            }
             stcs_bytes<K>(drow, kpack);
             srow += K * VP * NT;
             drow += K * NT;
@@ -1445,7 +1465,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T p[4];
-                        tip_vec<TIPS>(BYTE_OF(ca, j), p);
+                        if (MSG) tip_msg<V>(rec + 64, BYTE_OF(ca, j), p);  // the message: a column of P_a
+                        else tip_vec<TIPS>(BYTE_OF(ca, j), p);
                         st4(const_cast<V*>(OP(sa, j)), 32, p);
                     }
                 }
@@ -1453,7 +1474,8 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T p[4];
-                        tip_vec<TIPS>(BYTE_OF(cb, j), p);
+                        if (MSG) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), p);
+                        else tip_vec<TIPS>(BYTE_OF(cb, j), p);
                         st4(const_cast<V*>(OP(sb, j)), 32, p);
                     }
                 }
@@ -1476,7 +1498,15 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                 }
                 // A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148)
                 T Ab[K][4];
-                {
+                if (MSG) {  // the operand slots hold messages: A_b = q_n o mu_a
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T m[4];
+                        ld4(OP(sa, j), 32, m);
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) Ab[j][s] = qn[j][s] * m[s];
+                    }
+                } else {
                     T M[16];
                     lds_mat(rec + 64, M);
 #pragma unroll
@@ -1508,7 +1538,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                 // q(b) = P_b^T A_b (eigen.j2:151-153) waits in tensor memory; A_a = q_n o (P_b p_b) takes q_n's registers
                 {
                     T M[16];
-                    lds_mat(rec + 64 + R::kMat, M);
+                    if (!MSG || s2.x >= 0) lds_mat(rec + 64 + R::kMat, M);  // MSG: only q(b) needs P_b
                     if (s2.x >= 0) {
                         T q[K][4];
 #pragma unroll
@@ -1523,8 +1553,11 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         T p[4], m[4];
-                        ld4(OP(sb, j), 32, p);
-                        matvec(M, p, m);
+                        if (MSG) ld4(OP(sb, j), 32, m);
+                        else {
+                            ld4(OP(sb, j), 32, p);
+                            matvec(M, p, m);
+                        }
 #pragma unroll
                         for (int s = 0; s < 4; ++s) qn[j][s] *= m[s];  // now A_a
                     }
@@ -2144,12 +2177,13 @@ void launch_peer_sum(double* out, const PeerRows& peers, size_t count, cudaStrea
 }
 
 typedef void (*SweepTmFn)(const SweepArgs);
-static SweepTmFn pick_tm(bool tips, int K, int ctas) {
-    if (K != 4) return nullptr;
+static SweepTmFn pick_tm(bool tips, int K, int ctas, bool msg) {
+    if (K != 4 || (msg && !tips)) return nullptr;
 #ifdef PHYLO_FAST_BUILD  // compile-time experiments only
-    if (ctas == 3 && tips) return sweep_tm_kernel<4, true, 3>;
+    if (ctas == 3 && tips) return msg ? sweep_tm_kernel<4, true, 3, true> : sweep_tm_kernel<4, true, 3>;
     return nullptr;
 #else
+    if (msg) return ctas == 3 ? sweep_tm_kernel<4, true, 3, true> : ctas == 2 ? sweep_tm_kernel<4, true, 2, true> : nullptr;
     if (ctas == 3) return tips ? sweep_tm_kernel<4, true, 3> : sweep_tm_kernel<4, false, 3>;
     if (ctas == 2) return tips ? sweep_tm_kernel<4, true, 2> : sweep_tm_kernel<4, false, 2>;
     return nullptr;
@@ -2166,8 +2200,8 @@ size_t sweep_tm_smem_bytes(int K) {
     return (size_t)4 * (kTmOpSlots * (size_t)K * 2 * 32 * 16 + kRecBytes * kRecChunk * kRecBufs);
 }
 
-cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* n) {
-    SweepTmFn kern = pick_tm(tips, K, ctas);
+cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* n, bool msg) {
+    SweepTmFn kern = pick_tm(tips, K, ctas, msg);
     if (!kern) return cudaErrorInvalidValue;
     const size_t smem = sweep_tm_smem_bytes(K);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2179,8 +2213,8 @@ cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* n) {
     return e;
 }
 
-cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream) {
-    SweepTmFn kern = pick_tm(tips, K, ctas);
+cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream, bool msg) {
+    SweepTmFn kern = pick_tm(tips, K, ctas, msg);
     if (!kern) return cudaErrorInvalidValue;
     const size_t smem = sweep_tm_smem_bytes(K);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -145,8 +145,8 @@ bool sweep_msg_available(int prec, bool tips, bool grad, bool deep, int nthreads
 bool sweep_tm_available(int prec, int K, int nthreads, bool grad, bool jc);
 int sweep_tm_slots(int K, int ctas);
 size_t sweep_tm_smem_bytes(int K);
-cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream);
-cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* blocks_per_sm);
+cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int grid, cudaStream_t stream, bool msg = false);
+cudaError_t sweep_tm_prepare(bool tips, int K, int ctas, int* blocks_per_sm, bool msg = false);
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream);
 // device-resident tip masks [S][L] / weights [L] (NULL: ones) -> padded rows; d_flags[2]: {some cell is not
 // simple, some weight is not finite}

@@ -124,10 +124,11 @@ struct phylo_b200_ctx {
     int tm = 0;           // what the last resolved launch uses (0: shared-memory stack)
     // Message-statistic gradient sweep (kernels.cu, MSG): chosen per run when the handle allows it (fp64, simple tips,
     // 128-thread CTAs) AND the packed batch does: its contraction amplifies rounding by
-    // e^{|l_i - l_j| t_b r_c}, so tau_bound = max over the batch of (max_b t_b)(max_c r_c)(l_max - l_min) must stay
-    // below kMsgTauMax.  PHYLO_B200_MSG=0 turns it off.
+    // e^{|l_i - l_j| t_b r_c} (times the conditioning of the eigenvector matrices), so tau_bound = max over the batch
+    // of (max_b t_b)(max_c r_c)(l_max - l_min) + log(|m1|_F |m2|_F / 4) must stay below kMsgTauMax.  PHYLO_B200_MSG=0 turns it off.
     bool use_msg = true;
     double tau_unit = 0.0;    // max over the batch of (max_c r_c)(l_max - l_min): tau_bound per unit of branch length
+    double tau_cond = 0.0;    // max over the batch of log(|m1|_F |m2|_F / 4): the eigenvector matrices' share of the bound
     double tau_bound = 0.0;   // of the batch packed last (front ends that compute branch lengths on the device set
                               // it from their own inputs)
     bool msg_run = false;     // the last resolved launch uses the message statistic
@@ -284,8 +285,9 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             tm = h->req_tm; D = dt; smem = sweep_tm_smem_bytes(K);
         }
     }
-    const bool msg = !tm && h->use_msg && sweep_msg_available(h->prec, h->tips_simple, grad, D < Dfull, NT, jrun) &&
+    const bool msg = h->use_msg && sweep_msg_available(h->prec, h->tips_simple, grad, D < Dfull, NT, jrun) &&
                      h->tau_bound < kMsgTauMax;
+    if (tm && msg) CU_TRY(sweep_tm_prepare(h->tips_simple, K, tm, &occ, true));
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun; h->tm = tm; h->msg_run = msg;
     if (!tm) CU_TRY(sweep_occupancy(h->prec, h->tips_simple, K, grad, D < Dfull, NT, smem, &occ, jrun, msg));
     if (occ < 1) return fail(PHYLO_B200_ECUDA, "sweep kernel does not fit on an SM");
@@ -707,6 +709,7 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
     int first_ok = -1, ok = 0;
     h->tau_bound = 0.0;
     h->tau_unit = 0.0;
+    h->tau_cond = 0.0;
     for (int d = 0; d < B; ++d) {
         const bool good = pack_draw(h, blens + (size_t)d * h->bcount, subst ? subst + (size_t)d * h->nsubst : nullptr,
                                     freqs ? freqs + (size_t)d * 4 : nullptr, rs ? rs + (size_t)d * h->C : nullptr,
@@ -720,11 +723,17 @@ int pack_batch(phylo_b200_ctx* h, int B, const double* blens, const double* subs
             for (int b = 0; b < h->bcount; ++b) tmax = std::max(tmax, pd[h->lay.off_t + b]);
             for (int c = 0; c < h->C; ++c) rmax = std::max(rmax, pd[h->lay.off_rs + c]);
             for (int k = 0; k < 4; ++k) { lmin = std::min(lmin, pd[h->lay.off_lam + k]); lmax = std::max(lmax, pd[h->lay.off_lam + k]); }
+            // the eigenvector matrices' conditioning multiplies the same rounding error (skewed frequencies): it is
+            // counted in the exponent, log(|m1|_F |m2|_F / 4) being 0 for equal frequencies
+            double n1 = 0.0, n2 = 0.0;
+            for (int k = 0; k < 16; ++k) { n1 += pd[h->lay.off_m1 + k] * pd[h->lay.off_m1 + k]; n2 += pd[h->lay.off_m2 + k] * pd[h->lay.off_m2 + k]; }
+            const double cnd = std::max(0.0, 0.5 * std::log(n1 * n2) - std::log(4.0));
             h->tau_unit = std::max(h->tau_unit, rmax * (lmax - lmin));
-            h->tau_bound = std::max(h->tau_bound, tmax * rmax * (lmax - lmin));
+            h->tau_cond = std::max(h->tau_cond, cnd);
+            h->tau_bound = std::max(h->tau_bound, tmax * rmax * (lmax - lmin) + cnd);
         }
     }
-    for (auto* p : h->peers) { p->tau_bound = h->tau_bound; p->tau_unit = h->tau_unit; }
+    for (auto* p : h->peers) { p->tau_bound = h->tau_bound; p->tau_unit = h->tau_unit; p->tau_cond = h->tau_cond; }
     if (status && first_ok >= 0)
         for (int d = 0; d < B; ++d)
             if (status[d])
@@ -918,7 +927,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
     const bool deep = grad && h->slots < h->plan.depth();
     const bool jc = grad && h->jc_run;
-    if (grad && h->tm) CU_TRY(launch_sweep_tm(a, h->tips_simple, h->K, h->tm, h->grid, st));
+    if (grad && h->tm) CU_TRY(launch_sweep_tm(a, h->tips_simple, h->K, h->tm, h->grid, st, msg));
     else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc, msg));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
     h->last_launches = 2;
@@ -1289,7 +1298,7 @@ static int clock_batch_impl(phylo_b200_handle h, const char* who, int autocorr, 
         double hmax = 0.0, rmax = 0.0;
         for (size_t i = 0; i < (size_t)B * (S - 1); ++i) hmax = std::max(hmax, std::fabs(heights[i]));
         for (size_t i = 0; i < (size_t)B * nrates; ++i) rmax = std::max(rmax, std::fabs(rates[i]));
-        const double tb = hmax * rmax * h->tau_unit;
+        const double tb = hmax * rmax * h->tau_unit + h->tau_cond;
         h->tau_bound = std::isfinite(tb) ? tb : 1e300;
         for (auto* p : h->peers) p->tau_bound = h->tau_bound;
     }
