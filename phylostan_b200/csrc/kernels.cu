@@ -19,6 +19,13 @@
                          // TipRing: +6 / +10 / +17 % at K = 4 / 2 / 1 (r2_ab_6.log); 2: gradient kernels too (+0.4 %, and a
                          // second traversal-ordered copy of the alignment: not worth it)
 #endif
+#ifndef PHYLO_TMRED
+#define PHYLO_TMRED 1  // K > 1 fp64 gradient kernels of 128-thread CTAs: the two 4x4 statistics of a step are summed over the
+                       // warp through TENSOR MEMORY used as a transpose unit (tmr_* below) instead of the select / shuffle exchange
+#endif
+#ifndef PHYLO_POSTSPLIT
+#define PHYLO_POSTSPLIT 0  // post-order, child a: one matrix-vector loop per operand kind instead of copies into a common array
+#endif
 #ifndef PHYLO_PRETIP
 #define PHYLO_PRETIP 0  // pre-order: a simple tip child's message is a column of P (tip records column-major)
 #endif
@@ -269,6 +276,70 @@ __device__ __forceinline__ void stcs_bytes(uint8_t* p, unsigned w) {
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp sum of 32 per-lane doubles through tensor memory (no MMA): TMEM as a transpose unit
+// ------------------------------------------------------------------------------------------
+//
+// Every lane writes its 32 values (64 words) into its own TMEM lane with tcgen05.st.32x32b; tcgen05.ld.16x256b then
+// hands thread t, for g = 0..7, entry 4 g + (t & 3) of lanes t/4 and t/4 + 8 (second load, lane base 16: t/4 + 16 and
+// t/4 + 24) -- measured layout, tools/micro/tmem_transpose_probe.cu.  Four lanes are summed in registers, the other
+// eight (threads with the same t & 3) by three recursive-halving exchange levels, after which every thread owns ONE of
+// the 32 sums: entry 4 (4 b4 + 2 b3 + b2) + (t & 3), with b4 b3 b2 the bits 4, 3, 2 of t.  ~90 instructions instead of
+// the ~300 of two 16-value select / shuffle exchanges.
+__device__ __forceinline__ void tmr_store16(uint32_t addr, const double (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr + 8 * q),
+                     "r"(__double2loint(v[4 * q])), "r"(__double2hiint(v[4 * q])), "r"(__double2loint(v[4 * q + 1])),
+                     "r"(__double2hiint(v[4 * q + 1])), "r"(__double2loint(v[4 * q + 2])), "r"(__double2hiint(v[4 * q + 2])),
+                     "r"(__double2loint(v[4 * q + 3])), "r"(__double2hiint(v[4 * q + 3])));
+}
+// s[g] += entry 4 g + (t & 3) of the two lanes the load at `addr` (lane base 0 or 16) hands this thread
+__device__ __forceinline__ void tmr_load_add(uint32_t addr, double (&s)[8], bool first) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(addr));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const double lo = __hiloint2double((int)r[4 * g + 1], (int)r[4 * g]);
+        const double hi = __hiloint2double((int)r[4 * g + 3], (int)r[4 * g + 2]);
+        s[g] = first ? lo + hi : s[g] + (lo + hi);
+    }
+}
+// `tm` = this warp's TMEM address (its lane quadrant, 64 columns): columns 0..31 hold child b's 16 values of every lane,
+// 32..63 child a's (tmr_store16); adds the 32 warp sums to db[0..15] / da[0..15]
+__device__ __forceinline__ void tmr_finish(uint32_t tm, double* __restrict__ db, double* __restrict__ da, int lane) {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n");
+    double s[8];
+    tmr_load_add(tm, s, true);
+    tmr_load_add(tm + (16u << 16), s, false);
+    double a4[4], a2[2];
+    bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = hi ? s[i] : s[i + 4], keep = hi ? s[i + 4] : s[i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = hi ? a4[i] : a4[i + 2], keep = hi ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    hi = lane & 4;
+    const double send = hi ? a2[0] : a2[1], keep = hi ? a2[1] : a2[0];
+    const double tot = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    const int e = ((lane >> 2) & 7) * 4 + (lane & 3);  // bits 4 3 2 of the lane pick g, bits 1 0 the entry within it
+    atomicAdd(e < 16 ? db + e : da + (e - 16), tot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -617,6 +688,21 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
     ring.slot = 0;
     const int tpat = (NT / (32 * C)) * 32 * K;
     const int SS = K * VP * NT;  // vectors per stack slot / scratch row
+    // the statistics' warp sums go through tensor memory: 64 columns, every warp its own lane quadrant
+    constexpr bool kTmRed = PHYLO_TMRED && GRAD && !JC && K > 1 && NTC == 128 && sizeof(T) == 8;
+    __shared__ uint32_t tmr_base;
+    uint32_t tmr = 0u;
+    if (kTmRed) {
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(&tmr_base)), "r"(64));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n");
+        tmr = tmr_base + ((uint32_t)(32 * (warp & 3)) << 16);
+    }
 
     V* const stt = st + tid;
     V* const sct = reinterpret_cast<V*>(a.scratch) + (size_t)blockIdx.x * a.scratch_stride + tid;
@@ -697,6 +783,26 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             } else {
                 T M[16];
                 lds_mat(rec + 64, M);
+#if PHYLO_POSTSPLIT
+                if (fl & 4) {  // one loop per operand kind: no copies of the TOS into a common operand array
+#pragma unroll
+                    for (int j = 0; j < K; ++j) matvec(M, tos[j], ma[j]);
+                } else if (!TIPS && (fl & 1)) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        tip_vec<false>(BYTE_OF(ca, j), p);
+                        matvec(M, p, ma[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        T p[4];
+                        ld4(ST(s1.x, j), NT, p);
+                        matvec(M, p, ma[j]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     T p[4];
@@ -710,6 +816,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     }
                     matvec(M, p, ma[j]);
                 }
+#endif
             }
             if (TIPS && (fl & 2)) {
 #pragma unroll
@@ -1004,6 +1111,8 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     } else if (K == 1) {
 #pragma unroll
                         for (int x = 0; x < 16; ++x) red[x * 33 + lane] = G[x];
+                    } else if (kTmRed) {
+                        tmr_store16(tmr, reinterpret_cast<const double (&)[16]>(G));
                     } else if (PHYLO_RSM) {
                         warp_reduce16_smem(G, red, Gd + s2.z, lane);
                     } else {
@@ -1060,6 +1169,9 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         }
                         atomicAdd(Gd + (lane < 16 ? s2.z + lane : s2.y + lane - 16), (double)((s0 + s1_) + (s2s + s3)));
                         __syncwarp();  // the rows are rewritten by the next step
+                    } else if (kTmRed) {
+                        tmr_store16(tmr + 32, reinterpret_cast<const double (&)[16]>(G));
+                        tmr_finish(tmr, Gd + s2.z, Gd + s2.y, lane);
                     } else if (PHYLO_RSM) {
                         warp_reduce16_smem(G, red, Gd + s2.y, lane);
                     } else {
@@ -1093,6 +1205,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         }
     }
     cp_async_wait<0>();
+    if (kTmRed) {
+        asm volatile("tcgen05.fence::before_thread_sync;\n");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmr_base), "r"(64));
+    }
 #undef ST
 #undef SC
 }
@@ -2138,12 +2255,35 @@ cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool gr
     return cudaGetLastError();
 }
 
+// Resident CTAs per SM from registers and shared memory alone.  The occupancy calculator answers 1 for every kernel
+// that allocates tensor memory (it cannot know how many of the 512 columns the kernel asks for); the kernels here take
+// 64 (the statistics' warp sums) or 160 / 256 (the TMEM stack), and the hardware co-schedules them accordingly.
+static cudaError_t occupancy_by_hand(const void* kern, int nthreads, size_t smem, int* n) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    int dev = 0, regs_sm = 0, smem_sm = 0, thr_sm = 0, reserved = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&thr_sm, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+    const int warps = (nthreads + 31) / 32;
+    const int regs_warp = ((fa.numRegs * 32 + 255) / 256) * 256;  // allocated per warp in units of 256
+    const int by_regs = regs_sm / std::max(1, regs_warp * warps);
+    const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + reserved));
+    *n = std::max(0, std::min(std::min(by_regs, by_smem), thr_sm / nthreads));
+    return cudaSuccess;
+}
+
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n,
                             bool jc, bool msg) {
     SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (PHYLO_TMRED && grad && !jc && K > 1 && nthreads == 128 && prec == 64)  // the kernels that allocate tensor memory
+        return occupancy_by_hand(reinterpret_cast<const void*>(kern), nthreads, smem, n);
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, kern, nthreads, smem);
 }
 
