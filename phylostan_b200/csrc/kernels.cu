@@ -23,8 +23,16 @@
 #define PHYLO_TMRED 1  // K > 1 fp64 gradient kernels of 128-thread CTAs: the two 4x4 statistics of a step are summed over the
                        // warp through TENSOR MEMORY used as a transpose unit (tmr_* below) instead of the select / shuffle exchange
 #endif
+#ifndef PHYLO_TMRED_DPACK
+#define PHYLO_TMRED_DPACK 1   // tmr_store16: doubles unpacked inside the asm statement instead of by __double2loint / hiint
+                              // (+1.1 %: no spills, fewer moves); 2: the loads pack theirs inside the statement too
+#endif
+#ifndef PHYLO_MSGTIP_EARLY
+#define PHYLO_MSGTIP_EARLY 0  // message-statistic pre-order: a tip child's message (a column of P) is fetched where an internal
+                              // child's row is, at the end of the previous step, so both define the operand registers at one place
+#endif
 #ifndef PHYLO_POSTSPLIT
-#define PHYLO_POSTSPLIT 0  // post-order, child a: one matrix-vector loop per operand kind instead of copies into a common array
+#define PHYLO_POSTSPLIT 1  // post-order, child a: one matrix-vector loop per operand kind instead of copies into a common array
 #endif
 #ifndef PHYLO_PRETIP
 #define PHYLO_PRETIP 0  // pre-order: a simple tip child's message is a column of P (tip records column-major)
@@ -289,15 +297,41 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // the 32 sums: entry 4 (4 b4 + 2 b3 + b2) + (t & 3), with b4 b3 b2 the bits 4, 3, 2 of t.  ~90 instructions instead of
 // the ~300 of two 16-value select / shuffle exchanges.
 __device__ __forceinline__ void tmr_store16(uint32_t addr, const double (&v)[16]) {
+#if PHYLO_TMRED_DPACK
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        asm volatile(
+            "{\n .reg .b32 t<8>;\n mov.b64 {t0, t1}, %1;\n mov.b64 {t2, t3}, %2;\n mov.b64 {t4, t5}, %3;\n mov.b64 {t6, t7}, %4;\n"
+            " tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0, t1, t2, t3, t4, t5, t6, t7};\n}\n" ::"r"(addr + 8 * q),
+            "d"(v[4 * q]), "d"(v[4 * q + 1]), "d"(v[4 * q + 2]), "d"(v[4 * q + 3]));
+#else
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr + 8 * q),
                      "r"(__double2loint(v[4 * q])), "r"(__double2hiint(v[4 * q])), "r"(__double2loint(v[4 * q + 1])),
                      "r"(__double2hiint(v[4 * q + 1])), "r"(__double2loint(v[4 * q + 2])), "r"(__double2hiint(v[4 * q + 2])),
                      "r"(__double2loint(v[4 * q + 3])), "r"(__double2hiint(v[4 * q + 3])));
+#endif
 }
 // s[g] += entry 4 g + (t & 3) of the two lanes the load at `addr` (lane base 0 or 16) hands this thread
 __device__ __forceinline__ void tmr_load_add(uint32_t addr, double (&s)[8], bool first) {
+#if PHYLO_TMRED_DPACK > 1
+    double d[16];
+    asm volatile(
+        "{\n .reg .b32 t<32>;\n"
+        " tcgen05.ld.sync.aligned.16x256b.x8.b32 {t0, t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12, t13, t14, t15, t16, t17, t18, t19, "
+        "t20, t21, t22, t23, t24, t25, t26, t27, t28, t29, t30, t31}, [%16];\n"
+        " tcgen05.wait::ld.sync.aligned;\n"
+        " mov.b64 %0, {t0, t1};\n mov.b64 %1, {t2, t3};\n mov.b64 %2, {t4, t5};\n mov.b64 %3, {t6, t7};\n"
+        " mov.b64 %4, {t8, t9};\n mov.b64 %5, {t10, t11};\n mov.b64 %6, {t12, t13};\n mov.b64 %7, {t14, t15};\n"
+        " mov.b64 %8, {t16, t17};\n mov.b64 %9, {t18, t19};\n mov.b64 %10, {t20, t21};\n mov.b64 %11, {t22, t23};\n"
+        " mov.b64 %12, {t24, t25};\n mov.b64 %13, {t26, t27};\n mov.b64 %14, {t28, t29};\n mov.b64 %15, {t30, t31};\n}\n"
+        : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3]), "=d"(d[4]), "=d"(d[5]), "=d"(d[6]), "=d"(d[7]), "=d"(d[8]), "=d"(d[9]),
+          "=d"(d[10]), "=d"(d[11]), "=d"(d[12]), "=d"(d[13]), "=d"(d[14]), "=d"(d[15])
+        : "r"(addr));
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s[g] = first ? d[2 * g] + d[2 * g + 1] : s[g] + (d[2 * g] + d[2 * g + 1]);
+#else
     uint32_t r[32];
     asm volatile(
         "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
@@ -314,6 +348,7 @@ __device__ __forceinline__ void tmr_load_add(uint32_t addr, double (&s)[8], bool
         const double hi = __hiloint2double((int)r[4 * g + 3], (int)r[4 * g + 2]);
         s[g] = first ? lo + hi : s[g] + (lo + hi);
     }
+#endif
 }
 // `tm` = this warp's TMEM address (its lane quadrant, 64 columns): columns 0..31 hold child b's 16 values of every lane,
 // 32..63 child a's (tmr_store16); adds the 32 warp sums to db[0..15] / da[0..15]
@@ -962,12 +997,16 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             // children's partials of the current step; loaded from scratch during the previous step's
             // tail (after their last use there), so no extra registers and a reduction's worth of cover
             T pa[K][4], pbv[K][4];
+            constexpr bool kTipEarly = PHYLO_MSGTIP_EARLY && MSG && !TR;
             {
-                const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(0) + 16);  // row_a, row_b, ...
+                const unsigned char* r0 = ring.rec(0);
+                const int4 r1 = *reinterpret_cast<const int4*>(r0 + 16);  // row_a, row_b, ...
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                    else if (kTipEarly) tip_msg<V>(r0 + 64, BYTE_OF(ca, j), pa[j]);
                     if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                    else if (kTipEarly) tip_msg<V>(r0 + 64 + R::kMat, BYTE_OF(cb, j), pbv[j]);
                 }
             }
             for (int i = 0; i < nsteps; ++i) {
@@ -1025,14 +1064,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148).  One (warp-uniform)
                 // branch per operand kind; a simple tip's message is a column of P (PRETIP streams).
                 T Aa[K][4], Ab[K][4];
-                if (rowa < 0) {  // MSG: pa / pbv hold MESSAGES, a tip's is a column of P
+                if (!kTipEarly && rowa < 0) {  // MSG: pa / pbv hold MESSAGES, a tip's is a column of P
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (MSG) tip_msg<V>(rec + 64, BYTE_OF(ca, j), pa[j]);
                         else tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
                     }
                 }
-                if (rowb < 0) {
+                if (!kTipEarly && rowb < 0) {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (MSG) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), pbv[j]);
@@ -1140,11 +1179,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         for (int j = 0; j < K; ++j) matTvec(M, Aa[j], tos[j]);
                     }
                     if (i + 1 < nsteps) {  // pa / pbv are dead: fetch the next step's operands now
-                        const int4 r1 = *reinterpret_cast<const int4*>(ring.rec(1) + 16);
+                        const unsigned char* nrec = ring.rec(1);
+                        const int4 r1 = *reinterpret_cast<const int4*>(nrec + 16);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
                             if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                            else if (kTipEarly) tip_msg<V>(nrec + 64, BYTE_OF(ca1, j), pa[j]);
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                            else if (kTipEarly) tip_msg<V>(nrec + 64 + R::kMat, BYTE_OF(cb1, j), pbv[j]);
                         }
                     }
                     if (JC) {  // two scalars per lane: lanes 0..15 finish child b's sum, lanes 16..31 child a's
