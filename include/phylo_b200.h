@@ -261,6 +261,14 @@ PHYLO_B200_API int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots);
  * phylo_b200_info 13 = what the last run used. */
 PHYLO_B200_API int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_per_sm);
 
+/* Tuning: cherry tables (off by default).  In message-statistic runs with 4 patterns per thread, the message of a
+ * cherry -- an internal node whose two children are tips -- is looked up in a 25-entry table per (draw, category,
+ * cherry) built from the 5 x 5 code pairs of its tips, instead of being stored by the post-order sweep and read back
+ * by the pre-order sweep: a third less scratch traffic on coalescent trees (the site-repeat idea of the reference's
+ * pruner/tree.cpp:140-174 in the form that fits this design).  PHYLO_B200_CHERRY=1 in the environment at create time
+ * does the same; phylo_b200_info 15 = whether the last run used them. */
+PHYLO_B200_API int phylo_b200_set_cherry_tables(phylo_b200_handle h, int enabled);
+
 /* Arithmetic of the sweeps: 64 (default; the parity-tested product path) or 32, the optional
  * "fp32 with scaling" mode: partials, transition matrices and 4x4 statistics in float with
  * power-of-two rescaling in units of 2^24, log-likelihood and gradient sums in double.  Its error is
@@ -281,7 +289,9 @@ PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
  * 14 whether the last gradient run used the message statistic (fp64, simple tips, 128-thread CTAs and
  * (largest branch length) x (largest site rate) x (spread of Q's eigenvalues) + log(|m1|_F |m2|_F / 4) < 12 for every
  * draw of the batch;
- * PHYLO_B200_MSG=0 in the environment at create time turns it off). */
+ * PHYLO_B200_MSG=0 in the environment at create time turns it off),
+ * 15 whether that run took the messages of cherries (internal nodes with two tip children) from per-(draw, category)
+ * 25-entry tables instead of storing and re-reading them (phylo_b200_set_cherry_tables). */
 PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 
 /*

@@ -23,6 +23,10 @@
 #define PHYLO_TMRED 1  // K > 1 fp64 gradient kernels of 128-thread CTAs: the two 4x4 statistics of a step are summed over the
                        // warp through TENSOR MEMORY used as a transpose unit (tmr_* below) instead of the select / shuffle exchange
 #endif
+#ifndef PHYLO_ABL_CHERRY
+#define PHYLO_ABL_CHERRY 0  // TIMING ABLATION ONLY (wrong results): 1 = the messages of cherries are not stored, 2 = and the
+                            // pre-order reads one cached row instead of theirs -- what a cherry message table could save
+#endif
 #ifndef PHYLO_TMRED_DPACK
 #define PHYLO_TMRED_DPACK 1   // tmr_store16: doubles unpacked inside the asm statement instead of by __double2loint / hiint
                               // (+1.1 %: no spills, fewer moves); 2: the loads pack theirs inside the statement too
@@ -286,6 +290,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
 
+// message of a cherry for one pattern: entry `code` = 5 x + y of its 25 x 4 table (global memory, read-only path)
+__device__ __forceinline__ void cherry_msg(const double* __restrict__ tab, unsigned code, double (&m)[4]) {
+    const double2* t = reinterpret_cast<const double2*>(tab) + 2 * code;
+    const double2 u = __ldg(t), v = __ldg(t + 1);
+    m[0] = u.x; m[1] = u.y; m[2] = v.x; m[3] = v.y;
+}
+__device__ __forceinline__ void cherry_msg(const double*, unsigned, float (&)[4]) {}  // fp32 kernels never use the tables
+
 // ------------------------------------------------------------------------------------------
 // Warp sum of 32 per-lane doubles through tensor memory (no MMA): TMEM as a transpose unit
 // ------------------------------------------------------------------------------------------
@@ -485,6 +497,14 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
                        (s0.w == kSrcTos ? 8 : 0) | (a_hbm ? 16 : 0) | (spill >= a.slots ? 32 : 0);
             pr.row_a = na >= a.S ? __ldg(a.node_row + na) * a.SS : -1;
             pr.row_b = nb >= a.S ? __ldg(a.node_row + nb) * a.SS : -1;
+            if (PHYLO_ABL_CHERRY) {
+                if (na >= a.S) { const PostStep& q = a.post[__ldg(a.node_row + na)]; if (q.a < a.S && q.b < a.S) pr.row_a = -1; }
+                if (nb >= a.S) { const PostStep& q = a.post[__ldg(a.node_row + nb)]; if (q.a < a.S && q.b < a.S) pr.row_b = -1; }
+            }
+            if (a.node_cherry) {  // a cherry's message comes from its table: nothing to store
+                if (__ldg(a.node_cherry + na) >= 0) pr.row_a = -1;
+                if (__ldg(a.node_cherry + nb) >= 0) pr.row_b = -1;
+            }
             pr.pad0 = pr.pad1 = 0;
             const int4* src = reinterpret_cast<const int4*>(&pr);
             rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
@@ -501,6 +521,10 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.tip_b = (long long)nb * a.Lpad;
             pr.row_a = s1.w >= 0 ? s1.w * a.SS : -1;
             pr.row_b = rowb >= 0 ? rowb * a.SS : -1;
+            if (PHYLO_ABL_CHERRY == 2) {
+                if (s1.w >= 0) { const PostStep& q = a.post[s1.w]; if (q.a < a.S && q.b < a.S) pr.row_a = 0; }
+                if (rowb >= 0) { const PostStep& q = a.post[rowb]; if (q.a < a.S && q.b < a.S) pr.row_b = 0; }
+            }
             pr.dl_n = s1.z * a.KNT;
             const bool n_hbm = s0.w >= a.slots, b_hbm = s1.x >= a.slots;
             pr.off_n = s0.w < 0 ? -1 : n_hbm ? s1.z * a.SS : s0.w * a.slot_stride;   // s1.z = rown
@@ -508,8 +532,15 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.g_a = na * a.lay.C * 16;
             pr.g_b = nb * a.lay.C * 16;
             pr.flags = (s1.y ? 1 : 0) | (n_hbm ? 2 : 0) | (b_hbm ? 4 : 0);
+            pr.ctab_a = pr.ctab_b = 0;
+            if (a.node_cherry) {
+                const int ka = __ldg(a.node_cherry + na), kb = __ldg(a.node_cherry + nb);
+                const double* tab = a.ctab + ((size_t)d * a.lay.C + c) * a.ncherry * 100;
+                if (ka >= 0) { pr.row_a = -1; pr.tip_a = a.ctips_off + (long long)ka * a.Lpad; pr.ctab_a = (long long)(tab + ka * 100); }
+                if (kb >= 0) { pr.row_b = -1; pr.tip_b = a.ctips_off + (long long)kb * a.Lpad; pr.ctab_b = (long long)(tab + kb * 100); }
+            }
             const int4* src = reinterpret_cast<const int4*>(&pr);
-            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
+            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = src[3];
         }
     }
     double m[16];
@@ -686,7 +717,9 @@ __device__ __forceinline__ void warp_reduce16_smem(const T (&v)[16], T* __restri
 // <G_b, dP_b/dtheta> = <m1^T G~_b m2^T o Phi, X_theta> with Phi_ij = (e^{(l_i - l_j) tau} - 1) / (l_i - l_j), which
 // amplifies rounding by e^{|l_i - l_j| tau}: the host only chooses MSG while that stays below e^12 for every
 // branch and category of the batch.
-template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC, bool TR, bool MSG = false>
+// CH (with MSG): cherry tables -- see K3b below.
+template <typename T, int K, bool GRAD, bool TIPS, int NTC, int MINB, bool DEEP, bool JC, bool TR, bool MSG = false,
+          bool CH = false>
 __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const SweepArgs a) {
     typedef Real<T> R;
     typedef typename R::vec V;
@@ -998,14 +1031,20 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             // tail (after their last use there), so no extra registers and a reduction's worth of cover
             T pa[K][4], pbv[K][4];
             constexpr bool kTipEarly = PHYLO_MSGTIP_EARLY && MSG && !TR;
+            // cherry tables (the stream marks such children: row = -1, tip_* = combined-code row, ctab_* >= 0): their
+            // message is gathered where an internal child's row is loaded, one step ahead
+            constexpr bool kCherry = CH && MSG && !TR && sizeof(T) == 8;
             {
                 const unsigned char* r0 = ring.rec(0);
                 const int4 r1 = *reinterpret_cast<const int4*>(r0 + 16);  // row_a, row_b, ...
+                const longlong2 ct = kCherry ? *reinterpret_cast<const longlong2*>(r0 + 48) : make_longlong2(0, 0);
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                    else if (kCherry && ct.x) cherry_msg(reinterpret_cast<const double*>(ct.x), BYTE_OF(ca, j), pa[j]);
                     else if (kTipEarly) tip_msg<V>(r0 + 64, BYTE_OF(ca, j), pa[j]);
                     if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                    else if (kCherry && ct.y) cherry_msg(reinterpret_cast<const double*>(ct.y), BYTE_OF(cb, j), pbv[j]);
                     else if (kTipEarly) tip_msg<V>(r0 + 64 + R::kMat, BYTE_OF(cb, j), pbv[j]);
                 }
             }
@@ -1064,14 +1103,15 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 // A_a = q_n o (P_b p_b), A_b = q_n o (P_a p_a)   (eq (7), eigen.j2:148).  One (warp-uniform)
                 // branch per operand kind; a simple tip's message is a column of P (PRETIP streams).
                 T Aa[K][4], Ab[K][4];
-                if (!kTipEarly && rowa < 0) {  // MSG: pa / pbv hold MESSAGES, a tip's is a column of P
+                const longlong2 ct0 = kCherry ? *reinterpret_cast<const longlong2*>(rec + 48) : make_longlong2(0, 0);
+                if (!kTipEarly && rowa < 0 && !ct0.x) {  // MSG: pa / pbv hold MESSAGES, a tip's is a column of P
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (MSG) tip_msg<V>(rec + 64, BYTE_OF(ca, j), pa[j]);
                         else tip_vec<TIPS>(BYTE_OF(ca, j), pa[j]);
                     }
                 }
-                if (!kTipEarly && rowb < 0) {
+                if (!kTipEarly && rowb < 0 && !ct0.y) {
 #pragma unroll
                     for (int j = 0; j < K; ++j) {
                         if (MSG) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), pbv[j]);
@@ -1181,11 +1221,14 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     if (i + 1 < nsteps) {  // pa / pbv are dead: fetch the next step's operands now
                         const unsigned char* nrec = ring.rec(1);
                         const int4 r1 = *reinterpret_cast<const int4*>(nrec + 16);
+                        const longlong2 ct = kCherry ? *reinterpret_cast<const longlong2*>(nrec + 48) : make_longlong2(0, 0);
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
                             if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
+                            else if (kCherry && ct.x) cherry_msg(reinterpret_cast<const double*>(ct.x), BYTE_OF(ca1, j), pa[j]);
                             else if (kTipEarly) tip_msg<V>(nrec + 64, BYTE_OF(ca1, j), pa[j]);
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                            else if (kCherry && ct.y) cherry_msg(reinterpret_cast<const double*>(ct.y), BYTE_OF(cb1, j), pbv[j]);
                             else if (kTipEarly) tip_msg<V>(nrec + 64 + R::kMat, BYTE_OF(cb1, j), pbv[j]);
                         }
                     }
@@ -1784,6 +1827,61 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------
+// K3b: cherry tables (message-statistic runs)
+// ------------------------------------------------------------------------------------------
+//
+// SURVEY 8f rank 3 in the form that fits this design (the reference's unfinished pruner/ re-uses a subtree's partial
+// when the tip states under it repeat, pruner/tree.cpp:140-174): a cherry's partial depends on the pattern only through
+// the states of its two tips, 5 x 5 code pairs, so its MESSAGE to its parent, P_n ((P_a)[:, x] o (P_b)[:, y]), is a
+// 25-entry table per (draw, category, cherry).  The post-order then stores nothing for a cherry and the pre-order
+// gathers its message from the table (L1 / L2) instead of reading a scratch row back: a third of the internal nodes of
+// a coalescent tree are cherries, so a third of the scratch traffic goes away (26.4 -> 17.8 GB per evaluation on
+// config 3).  The arithmetic is the sweep's own, rescaling rule included (it depends on the partial only).
+
+__global__ void __launch_bounds__(256) cherry_codes_kernel(const uint8_t* __restrict__ tips, uint8_t* __restrict__ ctips,
+                                                            const int32_t* __restrict__ cherries, int Lpad, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t k = i / (size_t)Lpad, l = i - k * (size_t)Lpad;
+        const int ta = cherries[3 * k + 1], tb = cherries[3 * k + 2];
+        ctips[i] = (uint8_t)(5 * tips[(size_t)ta * Lpad + l] + tips[(size_t)tb * Lpad + l]);
+    }
+}
+
+__global__ void __launch_bounds__(128) cherry_table_kernel(const CherryArgs a) {
+    typedef Real<double> R;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * a.C * a.ncherry) return;
+    const int k = idx % a.ncherry, c = (idx / a.ncherry) % a.C, d = idx / (a.ncherry * a.C);
+    const double* prm = a.params + (size_t)d * a.lay.stride;
+    const int n = a.cherries[3 * k], ta = a.cherries[3 * k + 1], tb = a.cherries[3 * k + 2];
+    double Pa[16], Pb[16], Pn[16];
+    pmatrix(prm, a.lay, ta, c, a.bcount, a.jc_closed, Pa);
+    pmatrix(prm, a.lay, tb, c, a.bcount, a.jc_closed, Pb);
+    pmatrix(prm, a.lay, n, c, a.bcount, a.jc_closed, Pn);
+    double* out = a.ctab + (size_t)idx * 100;
+    const double kTiny = R::tiny();
+    for (int x = 0; x < 5; ++x)
+        for (int y = 0; y < 5; ++y) {
+            double p[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) p[s] = (x < 4 ? Pa[4 * s + x] : 1.0) * (y < 4 ? Pb[4 * s + y] : 1.0);
+            if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {  // the sweep's rescaling rule
+                const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+                if (mx > 0.0) {
+                    const double f = R::pow2(min((-R::exponent(mx)) / R::kUnit, R::kMaxK));
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) p[s] *= f;
+                }
+            }
+            double m[4];
+            matvec(Pn, p, m);
+            double2* o2 = reinterpret_cast<double2*>(out + 4 * (5 * x + y));
+            o2[0] = make_double2(m[0], m[1]);
+            o2[1] = make_double2(m[2], m[3]);
+        }
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: contraction of the branch statistics
 // ------------------------------------------------------------------------------------------
 
@@ -2191,9 +2289,10 @@ SweepFn pick_kernel(int nthreads) {
     return sweep_kernel<T, K, GRAD, TIPS, 0, 1, DEEP, JC, false>;
 }
 
-// message-statistic gradient kernels (fp64, simple tips, 128-thread CTAs)
+// message-statistic gradient kernels (fp64, simple tips, 128-thread CTAs); ch: with cherry tables (K = 4 only)
 template <bool DEEP>
-SweepFn pick_kernel_msg(int K) {
+SweepFn pick_kernel_msg(int K, bool ch) {
+    if (ch) return K == 4 ? sweep_kernel<double, 4, true, true, 128, Cfg<double, 4>::minb, DEEP, false, false, true, true> : nullptr;
     switch (K) {
 #if !defined(PHYLO_FAST_BUILD) || PHYLO_FAST_BUILD < 2
         case 1: return sweep_kernel<double, 1, true, true, 128, Cfg<double, 1>::minb, DEEP, false, PHYLO_TIPRING == 2, true>;
@@ -2231,10 +2330,12 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
     return nullptr;
 }
 
-SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false) {
+SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false,
+             bool ch = false) {
     if (msg)
-        return prec == 64 && tips && grad && !jc && nthreads == 128 ? (deep ? pick_kernel_msg<true>(K) : pick_kernel_msg<false>(K))
-                                                                    : nullptr;
+        return prec == 64 && tips && grad && !jc && nthreads == 128
+                   ? (deep ? pick_kernel_msg<true>(K, ch) : pick_kernel_msg<false>(K, ch))
+                   : nullptr;
 #ifdef PHYLO_FAST_BUILD  // compile-time experiments only: the fp64 K = 4 / 2 gradient kernels of simple-tip handles
     if (prec != 64 || !tips || !grad || jc || nthreads != 128) return nullptr;
     if (K == 4) return deep ? pick_kernel<double, 4, true, true, true>(128) : pick_kernel<double, 4, true, true, false>(128);
@@ -2287,9 +2388,11 @@ bool sweep_msg_available(int prec, bool tips, bool grad, bool, int nthreads, boo
     return prec == 64 && tips && grad && !jc && nthreads == 128;
 }
 
+bool sweep_cherry_available(int K) { return K == 4 && PHYLO_TIPRING != 2; }
+
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream, bool jc, bool msg) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg);
+                         size_t smem, cudaStream_t stream, bool jc, bool msg, bool ch) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg, ch);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -2319,8 +2422,8 @@ static cudaError_t occupancy_by_hand(const void* kern, int nthreads, size_t smem
 }
 
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem, int* n,
-                            bool jc, bool msg) {
-    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg);
+                            bool jc, bool msg, bool ch) {
+    SweepFn kern = pick(prec, tips, K, grad, deep, nthreads, jc, msg, ch);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -2403,6 +2506,18 @@ cudaError_t launch_sweep_tm(const SweepArgs& a, bool tips, int K, int ctas, int 
     if (e != cudaSuccess) return e;
     kern<<<grid, 128, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+void launch_cherry_tables(const CherryArgs& a, cudaStream_t stream) {
+    const int total = a.B * a.C * a.ncherry;
+    cherry_table_kernel<<<(total + 127) / 128, 128, 0, stream>>>(a);
+}
+
+void launch_cherry_codes(const uint8_t* d_tips, uint8_t* d_ctips, const int32_t* d_cherries, int ncherry, int Lpad,
+                         cudaStream_t stream) {
+    const size_t total = (size_t)ncherry * Lpad;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+    cherry_codes_kernel<<<grid, 256, 0, stream>>>(d_tips, d_ctips, d_cherries, Lpad, total);
 }
 
 void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream) {

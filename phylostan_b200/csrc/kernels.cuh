@@ -73,8 +73,10 @@ struct alignas(16) PreRec {
     int32_t off_b;            // stack offset receiving q(b), or -1 (b is a tip)
     int32_t g_a, g_b;         // offsets (doubles) of the children's 4x4 statistics blocks
     int32_t flags;            // 1: a is internal -> q(a) becomes the TOS
+    long long ctab_a, ctab_b; // cherry-table runs: device address of the child's 25 x 4 message table for this record's (draw,
+                              //   category), or 0; such a child has row = -1 and tip_* = its combined-code row
 };
-static_assert(sizeof(PostRec) == 48 && sizeof(PreRec) == 48, "record descriptors must fit the 64-byte header");
+static_assert(sizeof(PostRec) == 48 && sizeof(PreRec) == 64, "record descriptors must fit the 64-byte header");
 
 struct StreamArgs {
     const double* params;     // [B][stride]
@@ -93,6 +95,13 @@ struct StreamArgs {
     const int* node_row;      // [2S-1] node id -> its own post-order step (= scratch row), -1 for tips
     int slots;
     int msg;                  // message-statistic sweep: tip children of the PRE-order stream get the column-major layout too
+    // cherry tables (message-statistic runs): the message of a cherry (both children tips) depends on the pattern only
+    // through the 5 x 5 code pairs of its tips, so it is looked up in a per-(draw, category, cherry) table instead of
+    // being stored by the post-order and re-read by the pre-order
+    const int32_t* node_cherry;  // [2S-1] node -> cherry index or -1 (NULL: no cherry tables in this run)
+    long long ctips_off;         // byte offset of the combined-code rows [ncherry][Lpad] from the tip-code rows
+    const double* ctab;          // [B][C][ncherry][25][4]
+    int ncherry;
     int slot_stride;          // offset unit of an ON-CHIP stack slot: SS (shared-memory stack, in 16-byte vectors) or
                               // 8 K (tensor-memory stack, in 32-bit columns)
 };
@@ -116,6 +125,19 @@ struct SweepArgs {
     int off_out_freqs, off_out_ps;
 };
 
+// cherry tables: one thread per (draw, category, cherry)
+struct CherryArgs {
+    const double* params;
+    const int32_t* cherries;  // [ncherry][3]: node, first tip, second tip (0-based), in the post-order step's child order
+    double* ctab;
+    ParamLayout lay;
+    int B, C, ncherry, bcount, jc_closed;
+};
+void launch_cherry_tables(const CherryArgs& a, cudaStream_t stream);
+// combined codes 5 x + y of the two tips of every cherry, [ncherry][Lpad] (tip codes must be column indices 0..4)
+void launch_cherry_codes(const uint8_t* d_tips, uint8_t* d_ctips, const int32_t* d_cherries, int ncherry, int Lpad,
+                         cudaStream_t stream);
+
 struct ContractArgs {
     const unsigned char* spost;
     const int32_t* node_pos;  // [nn] 2 * post step + child slot of every non-root node
@@ -135,10 +157,12 @@ void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream);
 // jc: scalar-statistic gradient kernel of JC69 handles (fp64, gradient, not deep; ContractArgs::jc_scalar must agree)
 // msg: message-statistic gradient kernel (fp64, simple tips, 128-thread CTAs; StreamArgs::msg and
 // ContractArgs::msg must agree) -- see sweep_msg_available
+// ch (with msg): the instantiation that takes the messages of cherries from tables (sweep_cherry_available)
 cudaError_t launch_sweep(const SweepArgs& a, int prec, bool tips, int K, bool grad, bool deep, int grid, int nthreads,
-                         size_t smem, cudaStream_t stream, bool jc = false, bool msg = false);
+                         size_t smem, cudaStream_t stream, bool jc = false, bool msg = false, bool ch = false);
 cudaError_t sweep_occupancy(int prec, bool tips, int K, bool grad, bool deep, int nthreads, size_t smem,
-                            int* blocks_per_sm, bool jc = false, bool msg = false);
+                            int* blocks_per_sm, bool jc = false, bool msg = false, bool ch = false);
+bool sweep_cherry_available(int K);
 bool sweep_msg_available(int prec, bool tips, bool grad, bool deep, int nthreads, bool jc);
 // Gradient sweep with the stack in tensor memory (fp64, K = 4, 128-thread CTAs): `ctas` = 2 or 3 resident CTAs per
 // SM, sweep_tm_slots stack slots on chip (positions beyond them are parked in the scratch like the `deep` variant)

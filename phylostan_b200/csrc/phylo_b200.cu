@@ -132,6 +132,15 @@ struct phylo_b200_ctx {
     double tau_bound = 0.0;   // of the batch packed last (front ends that compute branch lengths on the device set
                               // it from their own inputs)
     bool msg_run = false;     // the last resolved launch uses the message statistic
+    // Cherry tables (message-statistic runs; kernels.cu K3b): a cherry's message to its parent comes from a 25-entry
+    // table per (draw, category, cherry) instead of a scratch row.  Opt-in: phylo_b200_set_cherry_tables /
+    // PHYLO_B200_CHERRY=1 (measured +1.3 % on config 3 for a third less scratch traffic: profiles/README.md).
+    bool use_cherry = false, cherry_run = false;
+    int ncherry = 0;
+    DevBuf<int32_t> d_node_cherry, d_cherries;   // [nn] node -> cherry index or -1; [ncherry][3] node, tip, tip
+    DevBuf<uint8_t> d_ctips;                     // [ncherry][Lpad] combined codes 5 x + y (built at the first such run)
+    bool ctips_built = false;
+    DevBuf<double> d_ctab;                       // [B][C][ncherry][25][4]
     size_t smem = 0;
     int last_launches = 0;
 
@@ -181,6 +190,7 @@ struct phylo_b200_ctx {
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
+        d_node_cherry.release(); d_cherries.release(); d_ctips.release(); d_ctab.release();
         h_params.release(); h_out.release();
         for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -446,7 +456,18 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     }
     std::vector<int32_t> node_row((size_t)h->nn, -1);  // internal node -> its own post-order step = scratch row
     for (size_t i = 0; i < h->plan.post.size(); ++i) node_row[h->plan.post[i].node] = (int32_t)i;
+    std::vector<int32_t> node_cherry((size_t)h->nn, -1), cherries;
+    for (const PostStep& p : h->plan.post)
+        if (p.a < S && p.b < S) {
+            node_cherry[p.node] = (int32_t)(cherries.size() / 3);
+            cherries.insert(cherries.end(), {p.node, p.a, p.b});
+        }
+    h->ncherry = (int)(cherries.size() / 3);
     cudaError_t e = cudaSuccess;
+    if ((e = up(h->d_node_cherry, node_cherry)) != cudaSuccess || (e = up(h->d_cherries, cherries)) != cudaSuccess) {
+        delete h;
+        return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    }
     if ((e = up(h->d_node_pos, node_pos)) != cudaSuccess || (e = up(h->d_node_row, node_row)) != cudaSuccess ||
         (e = up(h->d_post, h->plan.post)) != cudaSuccess || (e = up(h->d_pre, h->plan.pre)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -457,6 +478,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
     if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
     if (const char* ms = std::getenv("PHYLO_B200_MSG")) h->use_msg = !(ms[0] == '0');
+    if (const char* ch = std::getenv("PHYLO_B200_CHERRY")) h->use_cherry = ch[0] == '1';
     if (const char* tm = std::getenv("PHYLO_B200_SWEEP_TM")) h->req_tm = tm[0] == '3' ? 3 : tm[0] == '2' ? 2 : 0;
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
@@ -628,6 +650,13 @@ int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_per_sm) {
     return 0;
 }
 
+int phylo_b200_set_cherry_tables(phylo_b200_handle h, int enabled) {
+    if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
+    h->use_cherry = enabled != 0;
+    for (auto* p : h->peers) p->use_cherry = h->use_cherry;
+    return 0;
+}
+
 int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots) {
     if (!h) return fail(PHYLO_B200_EINVAL, "NULL handle");
     if (slots < 0) return fail(PHYLO_B200_EINVAL, "slots must be >= 0 (0 = automatic)");
@@ -683,6 +712,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 12: return 1 + (long long)h->peers.size();
         case 13: return h->tm;
         case 14: return h->msg_run ? 1 : 0;
+        case 15: return h->cherry_run ? 1 : 0;
     }
     return PHYLO_B200_EINVAL;
 }
@@ -795,6 +825,17 @@ int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
             h->tipring_pre = true;
         }
         h->tipring_K = h->K;
+    }
+    h->cherry_run = grad && h->msg_run && !h->tm && h->use_cherry && h->ncherry > 0 && h->tips_simple &&
+                    sweep_cherry_available(h->K);
+    if (h->cherry_run) {
+        if (!h->ctips_built) {
+            CU_TRY(h->d_ctips.ensure((size_t)h->ncherry * h->Lpad));
+            launch_cherry_codes(h->d_tips.p, h->d_ctips.p, h->d_cherries.p, h->ncherry, h->Lpad, h->stream);
+            CU_TRY(cudaGetLastError());
+            h->ctips_built = true;
+        }
+        CU_TRY(h->d_ctab.ensure((size_t)B * h->C * h->ncherry * 100));
     }
     if (grad) {
         const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
@@ -909,8 +950,19 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     sa.slot_stride = grad && h->tm ? 8 * h->K : sa.SS;
     const bool msg = grad && h->msg_run;
     sa.msg = msg ? 1 : 0;
+    const bool cherry = msg && h->cherry_run;
+    sa.node_cherry = cherry ? h->d_node_cherry.p : nullptr;
+    sa.ctips_off = cherry ? (long long)(h->d_ctips.p - h->d_tips.p) : 0;
+    sa.ctab = cherry ? h->d_ctab.p : nullptr; sa.ncherry = h->ncherry;
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
+    if (cherry) {
+        CherryArgs ch{};
+        ch.params = h->d_params.p; ch.cherries = h->d_cherries.p; ch.ctab = h->d_ctab.p; ch.lay = h->lay;
+        ch.B = B; ch.C = h->C; ch.ncherry = h->ncherry; ch.bcount = h->bcount; ch.jc_closed = h->jc_closed;
+        launch_cherry_tables(ch, st);
+        CU_TRY(cudaGetLastError());
+    }
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[1], st));
 
     SweepArgs a{};
@@ -928,9 +980,9 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     const bool deep = grad && h->slots < h->plan.depth();
     const bool jc = grad && h->jc_run;
     if (grad && h->tm) CU_TRY(launch_sweep_tm(a, h->tips_simple, h->K, h->tm, h->grid, st, msg));
-    else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc, msg));
+    else CU_TRY(launch_sweep(a, h->prec, h->tips_simple, h->K, grad, deep, h->grid, h->NT, h->smem, st, jc, msg, cherry));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[2], st));
-    h->last_launches = 2;
+    h->last_launches = cherry ? 3 : 2;
     if (grad) {
         ContractArgs ca{};
         ca.spost = h->d_spost.p; ca.node_pos = h->d_node_pos.p; ca.nsteps = h->S - 1; ca.params = h->d_params.p; ca.G = h->d_G.p; ca.out = h->d_out.p; ca.lay = h->lay;
@@ -940,7 +992,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
         launch_contract(ca, h->prec, B, st);
         CU_TRY(cudaGetLastError());
         if (h->timing) CU_TRY(cudaEventRecord(h->ev[3], st));
-        h->last_launches = 3;
+        h->last_launches = cherry ? 4 : 3;
     }
     if (h->timing) {
         CU_TRY(cudaEventRecord(h->ev[4], st));
@@ -958,7 +1010,7 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
             (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
             (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p), (unsigned long long)h->tm,
-            (unsigned long long)h->msg_run};
+            (unsigned long long)h->msg_run, (unsigned long long)h->cherry_run, u(h->d_ctab.p), u(h->d_ctips.p)};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible
@@ -992,7 +1044,7 @@ int eval_enqueue(phylo_b200_ctx* h, int B, bool grad, const ClockJob* job = null
         return job ? clock_tail_enqueue(h, *job, B, grad) : 0;
     }
     const bool graphable = h->use_graphs && !h->timing && h->stream != nullptr;
-    const int nlaunch = (grad ? 3 : 2) + (job ? (grad ? 2 : 1) : 0);
+    const int nlaunch = (grad ? 3 : 2) + (grad && h->cherry_run ? 1 : 0) + (job ? (grad ? 2 : 1) : 0);
     if (!graphable) {
         if (int rc = eval_sequence(h, B, grad, job)) return rc;
         h->last_launches = nlaunch;

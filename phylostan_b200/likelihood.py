@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_set_precision.argtypes = [vp, i]
     L.phylo_b200_set_stack_slots.argtypes = [vp, i]
     L.phylo_b200_set_sweep_variant.argtypes = [vp, i]
+    L.phylo_b200_set_cherry_tables.argtypes = [vp, i]
     L.phylo_b200_set_timing.argtypes = [vp, i]
     L.phylo_b200_get_timing.argtypes = [vp, _dp]
     L.phylo_b200_info.argtypes = [vp, i]
@@ -393,6 +394,11 @@ class TreeLikelihood:
         -1 the library's default (``info()['sweep_variant']`` tells what the last run used)."""
         _check(lib().phylo_b200_set_sweep_variant(self._h, int(ctas_per_sm)))
 
+    def set_cherry_tables(self, enabled: bool = True) -> None:
+        """Message-statistic runs take the messages of cherries from 25-entry tables instead of storing and re-reading
+        them (``info()['cherry_tables']`` tells whether the last run did)."""
+        _check(lib().phylo_b200_set_cherry_tables(self._h, int(bool(enabled))))
+
     def set_stack_slots(self, slots: int = 0) -> None:
         """Shared-memory stack slots for gradient runs (0 = automatic); fewer than ``info()['stack_depth']``
         parks the top stack positions in the per-CTA HBM scratch."""
@@ -413,7 +419,7 @@ class TreeLikelihood:
     def info(self) -> dict:
         names = ["stack_depth", "patterns_per_thread", "threads_per_cta", "grid", "smem_bytes", "padded_patterns",
                  "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots", "shards",
-                 "sweep_variant", "message_statistic"]
+                 "sweep_variant", "message_statistic", "cherry_tables"]
         return {n: int(lib().phylo_b200_info(self._h, k)) for k, n in enumerate(names)}
 
     def unpack(self, out: np.ndarray) -> ValueGrad:

@@ -162,7 +162,7 @@ def test_gpu_tilings_and_batch_agree(datasets):
             lik.set_tiling(K, PB)
             vg = lik.value_grad(*stack)
             info = lik.info()
-            assert info["kernel_launches"] == 3
+            assert info["kernel_launches"] == 3 + info["cherry_tables"]
             flat = np.concatenate([vg.log_P[:, None], vg.grad_blens, vg.grad_subst, vg.grad_freqs, vg.grad_rs,
                                    vg.grad_ps], axis=1)
             if base is None:
@@ -598,6 +598,56 @@ def test_gpu_message_statistic_sweep(datasets, monkeypatch, name, model, rooted)
             lik.loglik(bl, subst, fr, rs, ps)
     for K in (1, 2, 4):
         np.testing.assert_allclose(rows[("1", K)], rows[("0", K)], rtol=1e-9, atol=1e-9)
+
+
+def test_gpu_cherry_tables(datasets):
+    """Cherry tables (phylo_b200_set_cherry_tables): in message-statistic runs the message of a cherry comes from a
+    25-entry table per (draw, category, cherry) -- the 5 x 5 code pairs of its two tips, all-ones cells included --
+    instead of a scratch row.  Against the oracle on the reference's data sets (rooted, unrooted, a batch), on a
+    capped stack, and switched off again by everything that does not support them."""
+    rng = np.random.default_rng(31)
+    for name, model, rooted in (("fluA", O.GTR, True), ("DS1", O.HKY, False), ("HCV", O.GTR, True)):
+        d = datasets[name]
+        S = d["tipmask"].shape[0]
+        draws = [random_params(model, S, rooted, 4, rng) for _ in range(3)]
+        stack = [np.stack([dr[i] for dr in draws]) for i in range(5)]
+        with make(d["peel"], d["tipmask"], d["weights"], model, 4, rooted=rooted) as lik:
+            lik.set_tiling(4, 1)
+            lik.set_cherry_tables(True)
+            vg = lik.value_grad(*stack)
+            info = lik.info()
+            assert info["cherry_tables"] == 1 and info["message_statistic"] == 1 and info["kernel_launches"] == 4
+            for i, dr in enumerate(draws):
+                want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, *dr, rooted=rooted)
+                assert_parity(lk.ValueGrad(vg.log_P[i], vg.grad_blens[i], vg.grad_subst[i], vg.grad_freqs[i], vg.grad_rs[i],
+                                           vg.grad_ps[i]), want)
+            # not with K = 2, not on a long branch (no message statistic), not in value-only runs
+            lik.set_tiling(2, 1)
+            assert_parity(lik.value_grad(*draws[0]), O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, *draws[0], rooted=rooted))
+            assert lik.info()["cherry_tables"] == 0
+            lik.set_tiling(4, 1)
+            long = [x.copy() for x in draws[0]]
+            long[0][2] = 40.0
+            assert_parity(lik.value_grad(*long), O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, *long, rooted=rooted))
+            assert lik.info()["cherry_tables"] == 0 and lik.info()["message_statistic"] == 0
+            lik.set_cherry_tables(False)
+            lik.value_grad(*draws[0])
+            assert lik.info()["cherry_tables"] == 0
+    # a capped stack (the DEEP instantiation) and a tree with many cherries
+    prob = synth.make_problem(150, 700, 4, seed=77)
+    bl, rates, freqs, rs, ps = synth.make_draws(prob, 2)
+    with make(prob.peel, prob.tipmask, prob.weights, O.GTR, 4) as lik:
+        lik.set_cherry_tables(True)
+        depth = lik.info()["stack_depth"]
+        for slots in (0, depth - 1, 1):
+            lik.set_tiling(4, 1)
+            lik.set_stack_slots(slots)
+            got = lik.value_grad(bl, rates, freqs, rs, ps)
+            assert lik.info()["cherry_tables"] == 1
+            for i in range(2):
+                want = O.loglik_grad(prob.peel, prob.tipmask, prob.weights, O.GTR, bl[i], rates[i], freqs[i], rs[i], ps[i])
+                assert_parity(lk.ValueGrad(got.log_P[i], got.grad_blens[i], got.grad_subst[i], got.grad_freqs[i],
+                                           got.grad_rs[i], got.grad_ps[i]), want)
 
 
 def test_gpu_batch_status_marks_rejected_draws(datasets):

@@ -67,6 +67,8 @@ def main():
         name, _, tm = name.partition("@")   # "lib@3": run that library with PHYLO_B200_SWEEP_TM=3
         if tm.startswith("m"):               # "lib@m0": the same with PHYLO_B200_MSG=0 (no message statistic)
             env["PHYLO_B200_MSG"] = tm[1:]
+        elif tm.startswith("c"):             # "lib@c0": PHYLO_B200_CHERRY=0 (no cherry tables)
+            env["PHYLO_B200_CHERRY"] = tm[1:]
         elif tm:
             env["PHYLO_B200_SWEEP_TM"] = tm
         if name:

@@ -52,7 +52,7 @@ def parity():
                 e = err(got, want)
                 good = e[0] <= 1e-10 and e[1] <= 1e-8 and info["sweep_variant"] == variant
                 ok &= good
-                print(f"[{name:13s}] variant {variant} (ran {info['sweep_variant']}, msg {info['message_statistic']}, slots {info['stack_slots']}/{info['stack_depth']}, "
+                print(f"[{name:13s}] variant {variant} (ran {info['sweep_variant']}, msg {info['message_statistic']} cherry {info['cherry_tables']}, slots {info['stack_slots']}/{info['stack_depth']}, "
                       f"grid {info['grid']}, smem {info['smem_bytes']}): logL rel {e[0]:.1e} grad {e[1]:.1e} {'ok' if good else 'FAIL'}",
                       flush=True)
     return ok
@@ -81,7 +81,7 @@ def timing(B, L, S):
             if base is None:
                 base = out
             e = err(out, base)
-            print(f"[timing {S}x{L}x{B}] variant {variant} (ran {info['sweep_variant']}, msg {info['message_statistic']}, slots {info['stack_slots']}/{info['stack_depth']}, "
+            print(f"[timing {S}x{L}x{B}] variant {variant} (ran {info['sweep_variant']}, msg {info['message_statistic']} cherry {info['cherry_tables']}, slots {info['stack_slots']}/{info['stack_depth']}, "
                   f"grid {info['grid']}): sweep {min(ms):.2f} ms -> {B / min(ms) * 1e3:.1f} evals/s; vs first: logL rel {e[0]:.1e} "
                   f"grad {e[1]:.1e}", flush=True)
 
