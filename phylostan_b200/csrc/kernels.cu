@@ -1299,6 +1299,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #undef SC
 }
 
+// Parallel build (csrc/build.sh): this file is compiled several times with -DPHYLO_PART=p, each part instantiating
+// its share of sweep_kernel (1: fp64 simple tips, 2: fp64 masks, 3: fp32, 4: JC69 scalar / message statistic / cherry
+// tables) and part 0 everything else (the kernels below, the launchers).  Without PHYLO_PART: one translation unit.
+#if !defined(PHYLO_PART) || PHYLO_PART == 0
 // ------------------------------------------------------------------------------------------
 // K2b: the gradient sweep with its stack in TENSOR MEMORY (fp64, K patterns per lane, 128-thread CTAs)
 // ------------------------------------------------------------------------------------------
@@ -2265,6 +2269,8 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(double* __restrict__ out,
     }
 }
 
+#endif  // part 0
+
 // ------------------------------------------------------------------------------------------
 // launch plumbing
 // ------------------------------------------------------------------------------------------
@@ -2330,6 +2336,7 @@ SweepFn pick_kernel_k(int K, bool grad, bool deep, int nthreads) {
     return nullptr;
 }
 
+#ifndef PHYLO_PART
 SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false,
              bool ch = false) {
     if (msg)
@@ -2351,6 +2358,46 @@ SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, boo
 #endif
 }
 
+#endif
+
+}  // namespace
+
+#ifdef PHYLO_PART
+// the parts' share of the instantiations, one external function each (kernel stubs are ordinary host functions: a
+// pointer obtained in one translation unit launches, and is queried, from another)
+typedef void (*SweepFnX)(const SweepArgs);
+SweepFnX pick_part_f64_tips(int K, bool grad, bool deep, int nthreads);
+SweepFnX pick_part_f64_masks(int K, bool grad, bool deep, int nthreads);
+SweepFnX pick_part_f32(bool tips, int K, bool grad, bool deep, int nthreads);
+SweepFnX pick_part_special(bool tips, int K, bool deep, int nthreads, bool jc, bool msg, bool ch);
+#if PHYLO_PART == 1
+SweepFnX pick_part_f64_tips(int K, bool grad, bool deep, int nthreads) { return pick_kernel_k<double, true>(K, grad, deep, nthreads); }
+#elif PHYLO_PART == 2
+SweepFnX pick_part_f64_masks(int K, bool grad, bool deep, int nthreads) { return pick_kernel_k<double, false>(K, grad, deep, nthreads); }
+#elif PHYLO_PART == 3
+SweepFnX pick_part_f32(bool tips, int K, bool grad, bool deep, int nthreads) {
+    return tips ? pick_kernel_k<float, true>(K, grad, deep, nthreads) : pick_kernel_k<float, false>(K, grad, deep, nthreads);
+}
+#elif PHYLO_PART == 4
+SweepFnX pick_part_special(bool tips, int K, bool deep, int nthreads, bool jc, bool msg, bool ch) {
+    if (msg) return deep ? pick_kernel_msg<true>(K, ch) : pick_kernel_msg<false>(K, ch);
+    if (jc) return tips ? pick_kernel_jc<true>(K, nthreads) : pick_kernel_jc<false>(K, nthreads);
+    return nullptr;
+}
+#endif
+#endif
+
+#if !defined(PHYLO_PART) || PHYLO_PART == 0
+namespace {
+#ifdef PHYLO_PART
+SweepFn pick(int prec, bool tips, int K, bool grad, bool deep, int nthreads, bool jc = false, bool msg = false,
+             bool ch = false) {
+    if (msg) return prec == 64 && tips && grad && !jc && nthreads == 128 ? pick_part_special(tips, K, deep, nthreads, false, true, ch) : nullptr;
+    if (jc && prec == 64 && grad && !deep) return pick_part_special(tips, K, deep, nthreads, true, false, false);
+    if (prec == 32) return pick_part_f32(tips, K, grad, deep, nthreads);
+    return tips ? pick_part_f64_tips(K, grad, deep, nthreads) : pick_part_f64_masks(K, grad, deep, nthreads);
+}
+#endif
 }  // namespace
 
 int sweep_max_threads(int) { return 512; }
@@ -2525,5 +2572,7 @@ void launch_contract(const ContractArgs& a, int prec, int B, cudaStream_t stream
     if (prec == 32) contract_kernel<float><<<grid, 128, 0, stream>>>(a);
     else contract_kernel<double><<<grid, 128, 0, stream>>>(a);
 }
+
+#endif  // part 0
 
 }  // namespace phylo
