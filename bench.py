@@ -364,7 +364,8 @@ def run_config4(args, world, rank, local, stream):
             "kernel": ("sweep_kernel<double,K,GRAD,TIPS,128,DEEP" if info["stack_slots"] < info["stack_depth"]
                        else "sweep_kernel<double,K,GRAD,TIPS,128") + (",MSG>" if info["message_statistic"] else ">"),
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta",
-                                            "grid", "smem_bytes", "tiles", "scratch_bytes", "message_statistic")},
+                                            "grid", "smem_bytes", "tiles", "scratch_bytes", "message_statistic",
+                                            "cherry_tables")},
             "design_bytes_per_launch": des, "dram_frac_of_measured_peak": des / (sweep_ms * 1e-3) / 1e9 / peak,
             "survey_Bvg_frac_all_gpus": algorithmic_bytes(C4_TAXA, C4_PATTERNS, N_CAT) * evals / (world * peak * 1e9),
             "setup_s": {"simulate_on_gpu": t_gen, "create_device": t_create},
@@ -511,25 +512,25 @@ def run_ours(args):
             return e0.elapsed_time(e1) / n
         lik.upload(bl, rates, freqs, rs, ps)
         ms_value = timed(False)
-        # opt-in cherry tables: the same value + gradient step with the messages of cherries looked up instead of stored
-        # and re-read (a third less scratch traffic); checked against the rows of the timed run
-        lik.set_cherry_tables(True)
+        # the same value + gradient step WITHOUT the cherry tables (every internal node's message stored by the post-order
+        # and read back by the pre-order: a third more scratch traffic); checked against the rows of the timed run
+        lik.set_cherry_tables(False)
         ms_cherry = timed(True)
         rch = lik.download(B)
         cherry_used = lik.info()["cherry_tables"]
-        lik.set_cherry_tables(False)
+        lik.set_cherry_tables(True)
         lik.set_precision(32)
         ms32 = timed(True)
         r32 = lik.download(B)
         lik.set_precision(64)
         g64, g32 = local_rows[:, 1:], r32[:, 1:]
         extras = {
-            "cherry_tables": {"ms_per_step": ms_cherry, "tree_evals_per_s": B / ms_cherry * 1e3,
-                              "value": B * L_PATTERNS * N_CAT / ms_cherry * 1e3, "unit": UNIT, "used": int(cherry_used),
-                              "logL_max_rel_vs_default": float(np.max(np.abs(rch[:, 0] - local_rows[:, 0]) / np.abs(local_rows[:, 0]))),
-                              "grad_max_err_vs_default": float(np.max(np.abs(rch[:, 1:] - local_rows[:, 1:])
-                                                                      / np.maximum(1.0, np.abs(local_rows[:, 1:])))),
-                              "note": "phylo_b200_set_cherry_tables(1): whole step (tables + sweep + contraction), off by default"},
+            "without_cherry_tables": {"ms_per_step": ms_cherry, "tree_evals_per_s": B / ms_cherry * 1e3,
+                                      "value": B * L_PATTERNS * N_CAT / ms_cherry * 1e3, "unit": UNIT, "used": int(cherry_used),
+                                      "logL_max_rel_vs_default": float(np.max(np.abs(rch[:, 0] - local_rows[:, 0]) / np.abs(local_rows[:, 0]))),
+                                      "grad_max_err_vs_default": float(np.max(np.abs(rch[:, 1:] - local_rows[:, 1:])
+                                                                              / np.maximum(1.0, np.abs(local_rows[:, 1:])))),
+                                      "note": "phylo_b200_set_cherry_tables(0): whole step"},
             "value_only": {"ms_per_step": ms_value, "tree_evals_per_s": B / ms_value * 1e3,
                            "value": B * L_PATTERNS * N_CAT / ms_value * 1e3, "unit": UNIT.replace("evals", "value-only evals")},
             "fp32_with_scaling": {"ms_per_step": ms32, "tree_evals_per_s": B / ms32 * 1e3, "value": B * L_PATTERNS * N_CAT / ms32 * 1e3,
@@ -567,7 +568,7 @@ def run_ours(args):
             same = (cap.get("taxa") == S_TAXA and cap.get("patterns") == L_PATTERNS and cap.get("categories") == N_CAT
                     and cap.get("precision") == (32 if args.fp32 else 64)
                     and all(cap.get(k) == info[k] for k in ("patterns_per_thread", "threads_per_cta", "stack_slots", "smem_bytes",
-                                                            "message_statistic", "sweep_variant")))
+                                                            "message_statistic", "sweep_variant", "cherry_tables")))
             traffic = tj.get("dram_bytes_per_evaluation") if same else None
             traffic = traffic * B if traffic else None   # one launch sweeps B draws
         if not args.fp32:
@@ -582,7 +583,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": cfg,
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta", "grid",
-                                            "smem_bytes", "tiles", "message_statistic", "sweep_variant")},
+                                            "smem_bytes", "tiles", "message_statistic", "sweep_variant", "cherry_tables")},
             "tree_evals_per_s": value / (Lg * N_CAT),
             "node_updates_per_s": value * (S_TAXA - 1),
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
@@ -598,13 +599,17 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": des, "peak_source": peak_src,
                          "survey_model_bytes_per_launch": alg,
                          "frac_vs_survey_model": alg / (sweep_ms * 1e-3) / 1e9 / peak,
+                         "frac_of_measured_traffic": (traffic / (sweep_ms * 1e-3) / 1e9 / peak) if traffic else None,
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the capture named in "
                                            "profiles/sweep_traffic.json (a constant of that capture, not of this run; null when this run's "
                                            "kernel shape differs from the captured one)",
-                         "note": "algorithmic bytes = this design's own minimum DRAM traffic, 33 L C (2S-3) + 2SL + 8L per "
-                                 "evaluation (one write + one read of every internal partial and its rescale byte, tip "
-                                 "codes once per sweep), confirmed by ncu (traffic); frac_vs_survey_model uses SURVEY "
-                                 "8(d)'s level-synchronous B_vg, which this design does not move, and may exceed 1"},
+                         "note": "algorithmic bytes = the depth-first sweep's own DRAM traffic, 33 L C (2S-3) + 2SL + 8L per "
+                                 "evaluation (one write + one read of every internal partial / message and its rescale "
+                                 "byte, tip codes once per sweep) -- the basis of this number since round 1 (26.6 GB per "
+                                 "evaluation on config 3); with cherry tables the kernel moves a third less than that "
+                                 "(traffic, ncu; frac_of_measured_traffic is the DRAM fraction actually sustained); "
+                                 "frac_vs_survey_model uses SURVEY 8(d)'s level-synchronous B_vg, which this design does "
+                                 "not move, and may exceed 1"},
             "cpu_baseline": cpu, "clocks": clocks,
             "parity": parity,
             "config4": config4,

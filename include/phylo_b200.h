@@ -261,12 +261,12 @@ PHYLO_B200_API int phylo_b200_set_stack_slots(phylo_b200_handle h, int slots);
  * phylo_b200_info 13 = what the last run used. */
 PHYLO_B200_API int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_per_sm);
 
-/* Tuning: cherry tables (off by default).  In message-statistic runs with 4 patterns per thread, the message of a
+/* Tuning: cherry tables (on by default).  In message-statistic runs with 4 patterns per thread, the message of a
  * cherry -- an internal node whose two children are tips -- is looked up in a 25-entry table per (draw, category,
  * cherry) built from the 5 x 5 code pairs of its tips, instead of being stored by the post-order sweep and read back
  * by the pre-order sweep: a third less scratch traffic on coalescent trees (the site-repeat idea of the reference's
- * pruner/tree.cpp:140-174 in the form that fits this design).  PHYLO_B200_CHERRY=1 in the environment at create time
- * does the same; phylo_b200_info 15 = whether the last run used them. */
+ * pruner/tree.cpp:140-174 in the form that fits this design).  PHYLO_B200_CHERRY=0 in the environment at create time
+ * turns them off as well; phylo_b200_info 15 = whether the last run used them. */
 PHYLO_B200_API int phylo_b200_set_cherry_tables(phylo_b200_handle h, int enabled);
 
 /* Arithmetic of the sweeps: 64 (default; the parity-tested product path) or 32, the optional

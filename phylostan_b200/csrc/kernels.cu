@@ -23,6 +23,9 @@
 #define PHYLO_TMRED 1  // K > 1 fp64 gradient kernels of 128-thread CTAs: the two 4x4 statistics of a step are summed over the
                        // warp through TENSOR MEMORY used as a transpose unit (tmr_* below) instead of the select / shuffle exchange
 #endif
+#ifndef PHYLO_CHERRY_HOIST
+#define PHYLO_CHERRY_HOIST 1  // cherry-table kernels (2: every kernel): the operand preload branches once per child instead of once per pattern
+#endif
 #ifndef PHYLO_ABL_CHERRY
 #define PHYLO_ABL_CHERRY 0  // TIMING ABLATION ONLY (wrong results): 1 = the messages of cherries are not stored, 2 = and the
                             // pre-order reads one cached row instead of theirs -- what a cherry message table could save
@@ -1222,6 +1225,22 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                         const unsigned char* nrec = ring.rec(1);
                         const int4 r1 = *reinterpret_cast<const int4*>(nrec + 16);
                         const longlong2 ct = kCherry ? *reinterpret_cast<const longlong2*>(nrec + 48) : make_longlong2(0, 0);
+                        if ((kCherry && PHYLO_CHERRY_HOIST) || (PHYLO_CHERRY_HOIST > 1 && !kTipEarly)) {  // one warp-uniform branch per child, not one per pattern
+                            if (r1.x >= 0) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j) ld4cs(SC(r1.x, j), NT, pa[j]);
+                            } else if (ct.x) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j) cherry_msg(reinterpret_cast<const double*>(ct.x), BYTE_OF(ca1, j), pa[j]);
+                            }
+                            if (r1.y >= 0) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j) ld4cs(SC(r1.y, j), NT, pbv[j]);
+                            } else if (ct.y) {
+#pragma unroll
+                                for (int j = 0; j < K; ++j) cherry_msg(reinterpret_cast<const double*>(ct.y), BYTE_OF(cb1, j), pbv[j]);
+                            }
+                        } else {
 #pragma unroll
                         for (int j = 0; j < K; ++j) {
                             if (r1.x >= 0) ld4cs(SC(r1.x, j), NT, pa[j]);
@@ -1230,6 +1249,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                             if (r1.y >= 0) ld4cs(SC(r1.y, j), NT, pbv[j]);
                             else if (kCherry && ct.y) cherry_msg(reinterpret_cast<const double*>(ct.y), BYTE_OF(cb1, j), pbv[j]);
                             else if (kTipEarly) tip_msg<V>(nrec + 64 + R::kMat, BYTE_OF(cb1, j), pbv[j]);
+                        }
                         }
                     }
                     if (JC) {  // two scalars per lane: lanes 0..15 finish child b's sum, lanes 16..31 child a's

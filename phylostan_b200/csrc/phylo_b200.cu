@@ -133,9 +133,10 @@ struct phylo_b200_ctx {
                               // it from their own inputs)
     bool msg_run = false;     // the last resolved launch uses the message statistic
     // Cherry tables (message-statistic runs; kernels.cu K3b): a cherry's message to its parent comes from a 25-entry
-    // table per (draw, category, cherry) instead of a scratch row.  Opt-in: phylo_b200_set_cherry_tables /
-    // PHYLO_B200_CHERRY=1 (measured +1.3 % on config 3 for a third less scratch traffic: profiles/README.md).
-    bool use_cherry = false, cherry_run = false;
+    // table per (draw, category, cherry) instead of a scratch row: a third less scratch traffic, +4 % (short runs) to
+    // +6 % (sustained, power-capped) on config 3.  On by default; phylo_b200_set_cherry_tables(h, 0) / PHYLO_B200_CHERRY=0
+    // turn it off.
+    bool use_cherry = true, cherry_run = false;
     int ncherry = 0;
     DevBuf<int32_t> d_node_cherry, d_cherries;   // [nn] node -> cherry index or -1; [ncherry][3] node, tip, tip
     DevBuf<uint8_t> d_ctips;                     // [ncherry][Lpad] combined codes 5 x + y (built at the first such run)
@@ -478,7 +479,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     if (const char* ng = std::getenv("PHYLO_B200_NO_GRAPH")) h->use_graphs = !(ng[0] && ng[0] != '0');
     if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
     if (const char* ms = std::getenv("PHYLO_B200_MSG")) h->use_msg = !(ms[0] == '0');
-    if (const char* ch = std::getenv("PHYLO_B200_CHERRY")) h->use_cherry = ch[0] == '1';
+    if (const char* ch = std::getenv("PHYLO_B200_CHERRY")) h->use_cherry = !(ch[0] == '0');
     if (const char* tm = std::getenv("PHYLO_B200_SWEEP_TM")) h->req_tm = tm[0] == '3' ? 3 : tm[0] == '2' ? 2 : 0;
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {

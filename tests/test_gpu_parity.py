@@ -632,7 +632,7 @@ def test_gpu_cherry_tables(datasets):
             assert lik.info()["cherry_tables"] == 0 and lik.info()["message_statistic"] == 0
             lik.set_cherry_tables(False)
             lik.value_grad(*draws[0])
-            assert lik.info()["cherry_tables"] == 0
+            assert lik.info()["cherry_tables"] == 0 and lik.info()["kernel_launches"] == 3
     # a capped stack (the DEEP instantiation) and a tree with many cherries
     prob = synth.make_problem(150, 700, 4, seed=77)
     bl, rates, freqs, rs, ps = synth.make_draws(prob, 2)
