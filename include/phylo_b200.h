@@ -265,7 +265,8 @@ PHYLO_B200_API int phylo_b200_set_sweep_variant(phylo_b200_handle h, int ctas_pe
  * cherry -- an internal node whose two children are tips -- is looked up in a 25-entry table per (draw, category,
  * cherry) built from the 5 x 5 code pairs of its tips, instead of being stored by the post-order sweep and read back
  * by the pre-order sweep: a third less scratch traffic on coalescent trees (the site-repeat idea of the reference's
- * pruner/tree.cpp:140-174 in the form that fits this design).  PHYLO_B200_CHERRY=0 in the environment at create time
+ * pruner/tree.cpp:140-174 in the form that fits this design).  Pitchforks -- a cherry and a tip -- get 125-entry
+ * tables the same way (PHYLO_B200_TABLE_TIPS=2 in the environment at create time: cherries only).  PHYLO_B200_CHERRY=0 in the environment at create time
  * turns them off as well; phylo_b200_info 15 = whether the last run used them. */
 PHYLO_B200_API int phylo_b200_set_cherry_tables(phylo_b200_handle h, int enabled);
 

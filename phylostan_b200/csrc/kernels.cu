@@ -538,9 +538,9 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
             pr.ctab_a = pr.ctab_b = 0;
             if (a.node_cherry) {
                 const int ka = __ldg(a.node_cherry + na), kb = __ldg(a.node_cherry + nb);
-                const double* tab = a.ctab + ((size_t)d * a.lay.C + c) * a.ncherry * 100;
-                if (ka >= 0) { pr.row_a = -1; pr.tip_a = a.ctips_off + (long long)ka * a.Lpad; pr.ctab_a = (long long)(tab + ka * 100); }
-                if (kb >= 0) { pr.row_b = -1; pr.tip_b = a.ctips_off + (long long)kb * a.Lpad; pr.ctab_b = (long long)(tab + kb * 100); }
+                const double* tab = a.ctab + ((size_t)d * a.lay.C + c) * a.tab_entries * 4;
+                if (ka >= 0) { pr.row_a = -1; pr.tip_a = a.ctips_off + (long long)ka * a.Lpad; pr.ctab_a = (long long)(tab + 4 * __ldg(a.tab_off + ka)); }
+                if (kb >= 0) { pr.row_b = -1; pr.tip_b = a.ctips_off + (long long)kb * a.Lpad; pr.ctab_b = (long long)(tab + 4 * __ldg(a.tab_off + kb)); }
             }
             const int4* src = reinterpret_cast<const int4*>(&pr);
             rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = src[3];
@@ -1859,50 +1859,92 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
 // the states of its two tips, 5 x 5 code pairs, so its MESSAGE to its parent, P_n ((P_a)[:, x] o (P_b)[:, y]), is a
 // 25-entry table per (draw, category, cherry).  The post-order then stores nothing for a cherry and the pre-order
 // gathers its message from the table (L1 / L2) instead of reading a scratch row back: a third of the internal nodes of
-// a coalescent tree are cherries, so a third of the scratch traffic goes away (26.4 -> 17.8 GB per evaluation on
-// config 3).  The arithmetic is the sweep's own, rescaling rule included (it depends on the partial only).
+// a coalescent tree are cherries, so a third of the scratch traffic goes away (26.4 -> 17.6 GB per evaluation on
+// config 3).  The arithmetic is the sweep's own, rescaling rule included (it depends on the partial only).  The same
+// holds one level up: a pitchfork (a cherry and a tip, three tips below) has 125 code triples, 25 x + 5 y + z -- one
+// byte still -- and gets a 125-entry table (PHYLO_B200_TABLE_TIPS=2 restricts the tables to cherries).
 
 __global__ void __launch_bounds__(256) cherry_codes_kernel(const uint8_t* __restrict__ tips, uint8_t* __restrict__ ctips,
                                                             const int32_t* __restrict__ cherries, int Lpad, size_t total) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t k = i / (size_t)Lpad, l = i - k * (size_t)Lpad;
-        const int ta = cherries[3 * k + 1], tb = cherries[3 * k + 2];
-        ctips[i] = (uint8_t)(5 * tips[(size_t)ta * Lpad + l] + tips[(size_t)tb * Lpad + l]);
+        const int32_t* r = cherries + kTabRec * k;
+        int code = 5 * tips[(size_t)r[2] * Lpad + l] + tips[(size_t)r[3] * Lpad + l];
+        if (r[1] == 3) code = 5 * code + tips[(size_t)r[4] * Lpad + l];
+        ctips[i] = (uint8_t)code;
     }
 }
 
-__global__ void __launch_bounds__(128) cherry_table_kernel(const CherryArgs a) {
+// p <- p rescaled by the sweep's rule (all four entries below 2^-128: an exact power of 2^64)
+__device__ __forceinline__ void table_rescale(double (&p)[4]) {
     typedef Real<double> R;
+    const double kTiny = R::tiny();
+    if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {
+        const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
+        if (mx > 0.0) {
+            const double f = R::pow2(min((-R::exponent(mx)) / R::kUnit, R::kMaxK));
+#pragma unroll
+            for (int s = 0; s < 4; ++s) p[s] *= f;
+        }
+    }
+}
+// column x of P (x = 4: the all-ones column of an ambiguous cell), P row-major
+__device__ __forceinline__ void table_col(const double (&P)[16], int x, double (&m)[4]) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) m[s] = x < 4 ? P[4 * s + x] : 1.0;
+}
+
+__global__ void __launch_bounds__(128) cherry_table_kernel(const CherryArgs a) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.B * a.C * a.ncherry) return;
     const int k = idx % a.ncherry, c = (idx / a.ncherry) % a.C, d = idx / (a.ncherry * a.C);
     const double* prm = a.params + (size_t)d * a.lay.stride;
-    const int n = a.cherries[3 * k], ta = a.cherries[3 * k + 1], tb = a.cherries[3 * k + 2];
-    double Pa[16], Pb[16], Pn[16];
-    pmatrix(prm, a.lay, ta, c, a.bcount, a.jc_closed, Pa);
-    pmatrix(prm, a.lay, tb, c, a.bcount, a.jc_closed, Pb);
+    const int32_t* r = a.cherries + kTabRec * k;
+    const int n = r[0], ntips = r[1], shape = r[6];
+    double* out = a.ctab + (((size_t)d * a.C + c) * a.tab_entries + r[7]) * 4;
+    double P0[16], P1[16], P2[16], Pc[16], Pn[16];
+    pmatrix(prm, a.lay, r[2], c, a.bcount, a.jc_closed, P0);
+    pmatrix(prm, a.lay, r[3], c, a.bcount, a.jc_closed, P1);
     pmatrix(prm, a.lay, n, c, a.bcount, a.jc_closed, Pn);
-    double* out = a.ctab + (size_t)idx * 100;
-    const double kTiny = R::tiny();
+    if (ntips == 3) {
+        pmatrix(prm, a.lay, r[4], c, a.bcount, a.jc_closed, P2);
+        pmatrix(prm, a.lay, r[5], c, a.bcount, a.jc_closed, Pc);
+    }
+    const int nz = ntips == 3 ? 5 : 1;
     for (int x = 0; x < 5; ++x)
-        for (int y = 0; y < 5; ++y) {
-            double p[4];
+        for (int y = 0; y < 5; ++y)
+            for (int z = 0; z < nz; ++z) {
+                double u[4], v[4], p[4], m[4];
+                if (ntips == 2) {
+                    table_col(P0, x, u);
+                    table_col(P1, y, v);
+                } else if (shape == 0) {  // ((t0, t1), t2): the inner cherry's message, then the third tip's column
+                    double cu[4], cv[4], cp[4];
+                    table_col(P0, x, cu);
+                    table_col(P1, y, cv);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) p[s] = (x < 4 ? Pa[4 * s + x] : 1.0) * (y < 4 ? Pb[4 * s + y] : 1.0);
-            if (p[0] < kTiny && p[1] < kTiny && p[2] < kTiny && p[3] < kTiny) {  // the sweep's rescaling rule
-                const double mx = fmax(fmax(p[0], p[1]), fmax(p[2], p[3]));
-                if (mx > 0.0) {
-                    const double f = R::pow2(min((-R::exponent(mx)) / R::kUnit, R::kMaxK));
+                    for (int s = 0; s < 4; ++s) cp[s] = cu[s] * cv[s];
+                    table_rescale(cp);
+                    matvec(Pc, cp, u);
+                    table_col(P2, z, v);
+                } else {                  // (t0, (t1, t2))
+                    double cu[4], cv[4], cp[4];
+                    table_col(P1, y, cu);
+                    table_col(P2, z, cv);
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) p[s] *= f;
+                    for (int s = 0; s < 4; ++s) cp[s] = cu[s] * cv[s];
+                    table_rescale(cp);
+                    table_col(P0, x, u);
+                    matvec(Pc, cp, v);
                 }
+#pragma unroll
+                for (int s = 0; s < 4; ++s) p[s] = u[s] * v[s];
+                table_rescale(p);
+                matvec(Pn, p, m);
+                double2* o2 = reinterpret_cast<double2*>(out + 4 * ((5 * x + y) * nz + z));
+                o2[0] = make_double2(m[0], m[1]);
+                o2[1] = make_double2(m[2], m[3]);
             }
-            double m[4];
-            matvec(Pn, p, m);
-            double2* o2 = reinterpret_cast<double2*>(out + 4 * (5 * x + y));
-            o2[0] = make_double2(m[0], m[1]);
-            o2[1] = make_double2(m[2], m[3]);
-        }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -98,10 +98,12 @@ struct StreamArgs {
     // cherry tables (message-statistic runs): the message of a cherry (both children tips) depends on the pattern only
     // through the 5 x 5 code pairs of its tips, so it is looked up in a per-(draw, category, cherry) table instead of
     // being stored by the post-order and re-read by the pre-order
-    const int32_t* node_cherry;  // [2S-1] node -> cherry index or -1 (NULL: no cherry tables in this run)
-    long long ctips_off;         // byte offset of the combined-code rows [ncherry][Lpad] from the tip-code rows
-    const double* ctab;          // [B][C][ncherry][25][4]
-    int ncherry;
+    const int32_t* node_cherry;  // [2S-1] node -> table-node index or -1 (NULL: no tables in this run).  Table nodes are
+                                 // the internal nodes with two or three tips below them (cherries and pitchforks)
+    long long ctips_off;         // byte offset of the combined-code rows [ntab][Lpad] from the tip-code rows
+    const double* ctab;          // [B][C][tab_entries][4]: 25 (cherry) or 125 (pitchfork) messages per table node
+    const int32_t* tab_off;      // [ntab] first entry of every table node inside a (draw, category) block
+    int tab_entries;
     int slot_stride;          // offset unit of an ON-CHIP stack slot: SS (shared-memory stack, in 16-byte vectors) or
                               // 8 K (tensor-memory stack, in 32-bit columns)
 };
@@ -125,16 +127,19 @@ struct SweepArgs {
     int off_out_freqs, off_out_ps;
 };
 
-// cherry tables: one thread per (draw, category, cherry)
+// message tables: one thread per (draw, category, table node)
+constexpr int kTabRec = 8;    // ints per table node: node, ntips (2 | 3), t0, t1, t2 (-1), inner cherry node (-1),
+                              //   shape (pitchfork: 0 = ((t0, t1), t2), 1 = (t0, (t1, t2))), first table entry
 struct CherryArgs {
     const double* params;
-    const int32_t* cherries;  // [ncherry][3]: node, first tip, second tip (0-based), in the post-order step's child order
+    const int32_t* cherries;  // [ntab][kTabRec]; tips 0-based, in the post-order steps' child order (a before b)
     double* ctab;
     ParamLayout lay;
-    int B, C, ncherry, bcount, jc_closed;
+    int B, C, ncherry, tab_entries, bcount, jc_closed;
 };
 void launch_cherry_tables(const CherryArgs& a, cudaStream_t stream);
-// combined codes 5 x + y of the two tips of every cherry, [ncherry][Lpad] (tip codes must be column indices 0..4)
+// combined codes of the tips below every table node, 5 x + y or 25 x + 5 y + z, [ntab][Lpad] (tip codes must be column
+// indices 0..4)
 void launch_cherry_codes(const uint8_t* d_tips, uint8_t* d_ctips, const int32_t* d_cherries, int ncherry, int Lpad,
                          cudaStream_t stream);
 

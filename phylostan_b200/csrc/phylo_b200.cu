@@ -137,11 +137,12 @@ struct phylo_b200_ctx {
     // +6 % (sustained, power-capped) on config 3.  On by default; phylo_b200_set_cherry_tables(h, 0) / PHYLO_B200_CHERRY=0
     // turn it off.
     bool use_cherry = true, cherry_run = false;
-    int ncherry = 0;
-    DevBuf<int32_t> d_node_cherry, d_cherries;   // [nn] node -> cherry index or -1; [ncherry][3] node, tip, tip
-    DevBuf<uint8_t> d_ctips;                     // [ncherry][Lpad] combined codes 5 x + y (built at the first such run)
+    int ncherry = 0, tab_entries = 0;            // table nodes (cherries and pitchforks) and their entries per (draw, category)
+    DevBuf<int32_t> d_node_cherry, d_cherries;   // [nn] node -> table-node index or -1; [ncherry][kTabRec]
+    DevBuf<int32_t> d_tab_off;                   // [ncherry] first entry of every table node
+    DevBuf<uint8_t> d_ctips;                     // [ncherry][Lpad] combined codes 5 x + y / 25 x + 5 y + z (built at the first such run)
     bool ctips_built = false;
-    DevBuf<double> d_ctab;                       // [B][C][ncherry][25][4]
+    DevBuf<double> d_ctab;                       // [B][C][tab_entries][4]
     size_t smem = 0;
     int last_launches = 0;
 
@@ -191,7 +192,7 @@ struct phylo_b200_ctx {
         d_params.release(); d_G.release(); d_out.release();
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
-        d_node_cherry.release(); d_cherries.release(); d_ctips.release(); d_ctab.release();
+        d_node_cherry.release(); d_cherries.release(); d_tab_off.release(); d_ctips.release(); d_ctab.release();
         h_params.release(); h_out.release();
         for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -457,15 +458,33 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     }
     std::vector<int32_t> node_row((size_t)h->nn, -1);  // internal node -> its own post-order step = scratch row
     for (size_t i = 0; i < h->plan.post.size(); ++i) node_row[h->plan.post[i].node] = (int32_t)i;
-    std::vector<int32_t> node_cherry((size_t)h->nn, -1), cherries;
-    for (const PostStep& p : h->plan.post)
-        if (p.a < S && p.b < S) {
-            node_cherry[p.node] = (int32_t)(cherries.size() / 3);
-            cherries.insert(cherries.end(), {p.node, p.a, p.b});
+    // table nodes: internal nodes with two (cherry) or three (pitchfork: a cherry and a tip) tips below them
+    std::vector<int32_t> node_cherry((size_t)h->nn, -1), cherries, tab_off;
+    {
+        int max_tips = 3;
+        if (const char* tt = std::getenv("PHYLO_B200_TABLE_TIPS")) max_tips = tt[0] == '2' ? 2 : 3;
+        std::vector<std::vector<int32_t>> below((size_t)h->nn);  // tips below a node, a's before b's; empty = more than three
+        for (int k = 0; k < S; ++k) below[k] = {k};
+        int entries = 0;
+        for (const PostStep& p : h->plan.post) {
+            const auto &ta = below[p.a], &tb = below[p.b];
+            if (ta.empty() || tb.empty() || (int)(ta.size() + tb.size()) > max_tips) continue;
+            std::vector<int32_t> t = ta;
+            t.insert(t.end(), tb.begin(), tb.end());
+            below[p.node] = t;
+            const int nt = (int)t.size();
+            node_cherry[p.node] = (int32_t)tab_off.size();
+            tab_off.push_back(entries);
+            cherries.insert(cherries.end(), {p.node, nt, t[0], t[1], nt == 3 ? t[2] : -1,
+                                             nt == 3 ? (ta.size() == 2 ? p.a : p.b) : -1, nt == 3 && ta.size() == 1 ? 1 : 0, entries});
+            entries += nt == 3 ? 125 : 25;
         }
-    h->ncherry = (int)(cherries.size() / 3);
+        h->ncherry = (int)tab_off.size();
+        h->tab_entries = entries;
+    }
     cudaError_t e = cudaSuccess;
-    if ((e = up(h->d_node_cherry, node_cherry)) != cudaSuccess || (e = up(h->d_cherries, cherries)) != cudaSuccess) {
+    if ((e = up(h->d_node_cherry, node_cherry)) != cudaSuccess || (e = up(h->d_cherries, cherries)) != cudaSuccess ||
+        (e = up(h->d_tab_off, tab_off)) != cudaSuccess) {
         delete h;
         return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e));
     }
@@ -836,7 +855,7 @@ int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
             CU_TRY(cudaGetLastError());
             h->ctips_built = true;
         }
-        CU_TRY(h->d_ctab.ensure((size_t)B * h->C * h->ncherry * 100));
+        CU_TRY(h->d_ctab.ensure((size_t)B * h->C * h->tab_entries * 4));
     }
     if (grad) {
         const size_t rows = (size_t)h->grid * (h->S - 1) * h->K * h->NT;
@@ -954,13 +973,13 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     const bool cherry = msg && h->cherry_run;
     sa.node_cherry = cherry ? h->d_node_cherry.p : nullptr;
     sa.ctips_off = cherry ? (long long)(h->d_ctips.p - h->d_tips.p) : 0;
-    sa.ctab = cherry ? h->d_ctab.p : nullptr; sa.ncherry = h->ncherry;
+    sa.ctab = cherry ? h->d_ctab.p : nullptr; sa.tab_off = h->d_tab_off.p; sa.tab_entries = h->tab_entries;
     launch_stream(sa, h->prec, st);
     CU_TRY(cudaGetLastError());
     if (cherry) {
         CherryArgs ch{};
         ch.params = h->d_params.p; ch.cherries = h->d_cherries.p; ch.ctab = h->d_ctab.p; ch.lay = h->lay;
-        ch.B = B; ch.C = h->C; ch.ncherry = h->ncherry; ch.bcount = h->bcount; ch.jc_closed = h->jc_closed;
+        ch.B = B; ch.C = h->C; ch.ncherry = h->ncherry; ch.tab_entries = h->tab_entries; ch.bcount = h->bcount; ch.jc_closed = h->jc_closed;
         launch_cherry_tables(ch, st);
         CU_TRY(cudaGetLastError());
     }

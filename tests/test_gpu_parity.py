@@ -603,7 +603,7 @@ def test_gpu_message_statistic_sweep(datasets, monkeypatch, name, model, rooted)
 def test_gpu_cherry_tables(datasets):
     """Cherry tables (phylo_b200_set_cherry_tables): in message-statistic runs the message of a cherry comes from a
     25-entry table per (draw, category, cherry) -- the 5 x 5 code pairs of its two tips, all-ones cells included --
-    instead of a scratch row.  Against the oracle on the reference's data sets (rooted, unrooted, a batch), on a
+    instead of a scratch row, and that of a pitchfork (a cherry and a tip) from a 125-entry one.  Against the oracle on the reference's data sets (rooted, unrooted, a batch), on a
     capped stack, and switched off again by everything that does not support them."""
     rng = np.random.default_rng(31)
     for name, model, rooted in (("fluA", O.GTR, True), ("DS1", O.HKY, False), ("HCV", O.GTR, True)):
