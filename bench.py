@@ -568,7 +568,8 @@ def run_ours(args):
             same = (cap.get("taxa") == S_TAXA and cap.get("patterns") == L_PATTERNS and cap.get("categories") == N_CAT
                     and cap.get("precision") == (32 if args.fp32 else 64)
                     and all(cap.get(k) == info[k] for k in ("patterns_per_thread", "threads_per_cta", "stack_slots", "smem_bytes",
-                                                            "message_statistic", "sweep_variant", "cherry_tables")))
+                                                            "message_statistic", "sweep_variant", "cherry_tables",
+                                                            "post_order_tables")))
             traffic = tj.get("dram_bytes_per_evaluation") if same else None
             traffic = traffic * B if traffic else None   # one launch sweeps B draws
         if not args.fp32:
@@ -583,7 +584,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": cfg,
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta", "grid",
-                                            "smem_bytes", "tiles", "message_statistic", "sweep_variant", "cherry_tables")},
+                                            "smem_bytes", "tiles", "message_statistic", "sweep_variant", "cherry_tables",
+                                            "post_order_tables")},
             "tree_evals_per_s": value / (Lg * N_CAT),
             "node_updates_per_s": value * (S_TAXA - 1),
             "wall_ms_per_step": 1e3 * wall_s / args.steps,

@@ -292,6 +292,9 @@ __device__ __forceinline__ void stcs_bytes(uint8_t* p, unsigned w) {
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p));
+}
 
 // message of a cherry for one pattern: entry `code` = 5 x + y of its 25 x 4 table (global memory, read-only path)
 __device__ __forceinline__ void cherry_msg(const double* __restrict__ tab, unsigned code, double (&m)[4]) {
@@ -471,14 +474,14 @@ __device__ __forceinline__ void store_tipmat(unsigned char* dst, const double (&
 // does no index arithmetic beyond pointer + offset.  One thread per (sweep, draw, category, step, child).
 template <typename T>
 __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
-    const int per = a.lay.C * a.nsteps;
-    const int total = 4 * a.B * per;
+    const int nrec_post = a.B * a.lay.C * a.npost, nrec_pre = a.B * a.lay.C * a.nsteps;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+    if (idx >= 2 * (nrec_post + nrec_pre)) return;
     const int child = idx & 1, rr = idx >> 1;
-    const int which = rr / (a.B * per);  // 0 post-order stream, 1 pre-order stream
-    const int r = rr - which * a.B * per;
-    const int d = r / per, c = (r / a.nsteps) % a.lay.C, i = r % a.nsteps;
+    const int which = rr >= nrec_post;  // 0 post-order stream, 1 pre-order stream
+    const int r = which ? rr - nrec_post : rr;
+    const int ns = which ? a.nsteps : a.npost;
+    const int d = r / (a.lay.C * ns), c = (r / ns) % a.lay.C, i = r % ns;
     const double* prm = a.params + (size_t)d * a.lay.stride;
     unsigned char* rec = (which ? a.spre : a.spost) + (size_t)r * Real<T>::kRec;
     int na, nb;
@@ -509,8 +512,15 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
                 if (__ldg(a.node_cherry + nb) >= 0) pr.row_b = -1;
             }
             pr.pad0 = pr.pad1 = 0;
+            pr.ctab_a = pr.ctab_b = 0;
+            if (a.post_tables) {  // a leafified child: tip-like, its code row and its table
+                const int ka = __ldg(a.node_cherry + na), kb = __ldg(a.node_cherry + nb);
+                const double* tab = a.ctab + ((size_t)d * a.lay.C + c) * a.tab_entries * 4;
+                if (ka >= 0) { pr.tip_a = a.ctips_off + (long long)ka * a.Lpad; pr.ctab_a = (long long)(tab + 4 * __ldg(a.tab_off + ka)); }
+                if (kb >= 0) { pr.tip_b = a.ctips_off + (long long)kb * a.Lpad; pr.ctab_b = (long long)(tab + 4 * __ldg(a.tab_off + kb)); }
+            }
             const int4* src = reinterpret_cast<const int4*>(&pr);
-            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = make_int4(0, 0, 0, 0);
+            rd[0] = src[0]; rd[1] = src[1]; rd[2] = src[2]; rd[3] = src[3];
         }
     } else {
         const int4* s = reinterpret_cast<const int4*>(a.pre + i);
@@ -518,7 +528,8 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
         na = s0.y; nb = s0.z;
         if (child == 0) {
             const int4 s1 = __ldg(s + 1);  // dst_b a_internal rown rowa
-            const int rowb = __ldg(reinterpret_cast<const int*>(s + 2));
+            const int4 s2 = __ldg(s + 2);  // rowb parkn parkb -
+            const int rowb = s2.x;
             PreRec pr;
             pr.tip_a = (long long)na * a.Lpad;
             pr.tip_b = (long long)nb * a.Lpad;
@@ -528,10 +539,10 @@ __global__ void __launch_bounds__(128) stream_kernel(const StreamArgs a) {
                 if (s1.w >= 0) { const PostStep& q = a.post[s1.w]; if (q.a < a.S && q.b < a.S) pr.row_a = 0; }
                 if (rowb >= 0) { const PostStep& q = a.post[rowb]; if (q.a < a.S && q.b < a.S) pr.row_b = 0; }
             }
-            pr.dl_n = s1.z * a.KNT;
+            pr.dl_n = s1.z >= 0 ? s1.z * a.KNT : -1;   // s1.z = rown; -1: the post-order skipped this node, no exponents
             const bool n_hbm = s0.w >= a.slots, b_hbm = s1.x >= a.slots;
-            pr.off_n = s0.w < 0 ? -1 : n_hbm ? s1.z * a.SS : s0.w * a.slot_stride;   // s1.z = rown
-            pr.off_b = s1.x < 0 ? -1 : b_hbm ? rowb * a.SS : s1.x * a.slot_stride;
+            pr.off_n = s0.w < 0 ? -1 : n_hbm ? s2.y * a.SS : s0.w * a.slot_stride;   // parked: in the node's parking row
+            pr.off_b = s1.x < 0 ? -1 : b_hbm ? s2.z * a.SS : s1.x * a.slot_stride;
             pr.g_a = na * a.lay.C * 16;
             pr.g_b = nb * a.lay.C * 16;
             pr.flags = (s1.y ? 1 : 0) | (n_hbm ? 2 : 0) | (b_hbm ? 4 : 0);
@@ -790,6 +801,11 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         const int pat0 = tile * tpat + pb * 32 * K + lane * K;  // this lane's K consecutive patterns: pat0 + j
         const uint8_t* tipw = a.tips + (pat0 - lane * K);       // the warp's 32 K tip codes of a row start here
         const size_t stream_off = ((size_t)d * C + c) * nsteps * R::kRec;
+        const int npost = a.npost;  // fewer than nsteps when the table nodes are leaves of the post-order
+        const size_t stream_off_post = ((size_t)d * C + c) * npost * R::kRec;
+        // post-order message tables (kTab kernels): a leafified child is tip-like, its message comes from its table by
+        // the combined code of the tips below it, gathered one step ahead (ta / tb)
+        constexpr bool kTab = CH && MSG && !TR && sizeof(T) == 8;
 
         // -------------------------------------------------------------- post-order
         int etot[K];
@@ -801,7 +817,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         }
         const size_t wblock = (size_t)(pat0 - lane * K) / (32 * K);  // this warp's block of 32 K patterns
         if (TR) tr.start(a.tips_post + wblock * a.S * TipRing<K>::kSlot, a.S);
-        ring.start(a.spost + stream_off, nsteps, tipfetch);
+        ring.start(a.spost + stream_off_post, npost, tipfetch);
         ring.step(0, tipfetch);
         // tip codes of the children of steps i (ca, cb), i+1 (ca1, cb1) and, inside the loop, i+2:
         // K codes per lane packed in one word, loaded two steps ahead of their use (TR: from the tip ring)
@@ -811,10 +827,20 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             const PostRec* r0 = reinterpret_cast<const PostRec*>(ring.rec(0));
             if (r0->flags & 1) ca = ldg_bytes<K>(tipp + r0->tip_a);
             if (r0->flags & 2) cb = ldg_bytes<K>(tipp + r0->tip_b);
-            if (nsteps > 1) {
+            if (npost > 1) {
                 const PostRec* r1 = reinterpret_cast<const PostRec*>(ring.rec(1));
                 if (r1->flags & 1) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
                 if (r1->flags & 2) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
+            }
+        }
+        // kTab: the table entries a step will gather are prefetched into L1 one step ahead (the codes are known by then),
+        // so the gather itself costs what a tip's column lookup in shared memory costs and no register lives across steps
+        if (kTab) {
+            const longlong2 ct = *reinterpret_cast<const longlong2*>(ring.rec(0) + 48);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (ct.x) prefetch_l1(reinterpret_cast<const double*>(ct.x) + 4 * BYTE_OF(ca, j));
+                if (ct.y) prefetch_l1(reinterpret_cast<const double*>(ct.y) + 4 * BYTE_OF(cb, j));
             }
         }
         V* srow = sct;  // scratch row of step i
@@ -823,16 +849,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
         // kernels, whose code is larger)
         constexpr int kPostUnroll = GRAD ? 1 : 2;
 #pragma unroll kPostUnroll
-        for (int i = 0; i < nsteps; ++i) {
+        for (int i = 0; i < npost; ++i) {
             if (i) ring.step(i, tipfetch);
             const unsigned char* rec = ring.rec(0);
             const int4 s1 = *reinterpret_cast<const int4*>(rec + 16);  // off_a, off_b, off_spill, flags
             const int fl = s1.w;
+            const longlong2 ctp = kTab ? *reinterpret_cast<const longlong2*>(rec + 48) : make_longlong2(0, 0);
             unsigned ca2 = 0u, cb2 = 0u;
             if (TR) {
                 if (fl & 1) ca = tr.get();
                 if (fl & 2) cb = tr.get();
-            } else if (i + 2 < nsteps) {  // tip codes of step i+2 -> registers
+            } else if (i + 2 < npost) {  // tip codes of step i+2 -> registers
                 const PostRec* n = reinterpret_cast<const PostRec*>(ring.rec(2));
                 const int nf = n->flags;
                 if (nf & 1) ca2 = ldg_bytes<K>(tipp + n->tip_a);
@@ -848,6 +875,9 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                     ld4cs(SC(s1.x, j), NT, p);
                     matvec(M, p, ma[j]);
                 }
+            } else if (kTab && ctp.x) {     // leafified child: its message comes from its table (prefetched into L1)
+#pragma unroll
+                for (int j = 0; j < K; ++j) cherry_msg(reinterpret_cast<const double*>(ctp.x), BYTE_OF(ca, j), ma[j]);
             } else if (TIPS && (fl & 1)) {  // tip child: its message is a column of P_a
 #pragma unroll
                 for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64, BYTE_OF(ca, j), ma[j]);
@@ -889,7 +919,10 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 }
 #endif
             }
-            if (TIPS && (fl & 2)) {
+            if (kTab && ctp.y) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) cherry_msg(reinterpret_cast<const double*>(ctp.y), BYTE_OF(cb, j), mb[j]);
+            } else if (TIPS && (fl & 2)) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) tip_msg<V>(rec + 64 + R::kMat, BYTE_OF(cb, j), mb[j]);
             } else {
@@ -961,6 +994,17 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
             if (GRAD) stcs_bytes<K>(drow, kpack);
             srow += SS;
             drow += K * NT;
+            if (kTab && i + 1 < npost) {  // the next step's table entries -> L1 (its codes arrived a step ago)
+                const longlong2 ct = *reinterpret_cast<const longlong2*>(ring.rec(1) + 48);
+                if (ct.x) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) prefetch_l1(reinterpret_cast<const double*>(ct.x) + 4 * BYTE_OF(ca1, j));
+                }
+                if (ct.y) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) prefetch_l1(reinterpret_cast<const double*>(ct.y) + 4 * BYTE_OF(cb1, j));
+                }
+            }
             if (!TR) { ca = ca1; cb = cb1; ca1 = ca2; cb1 = cb2; }
         }
 
@@ -1021,12 +1065,12 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
                 const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
                 if (!TR && r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
                 if (!TR && r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
-                dcur = ld_bytes<K>(dlt + r0->dl_n);
+                dcur = r0->dl_n >= 0 ? ld_bytes<K>(dlt + r0->dl_n) : 0u;  // -1: the post-order skipped this node
                 if (nsteps > 1) {
                     const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
                     if (!TR && r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
                     if (!TR && r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
-                    d1 = ld_bytes<K>(dlt + r1->dl_n);
+                    d1 = r1->dl_n >= 0 ? ld_bytes<K>(dlt + r1->dl_n) : 0u;
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
@@ -1081,7 +1125,7 @@ __global__ void __launch_bounds__(NTC ? NTC : 512, MINB) sweep_kernel(const Swee
 #pragma unroll
                             for (int h = 0; h < VP; ++h) prefetch_l2(SC(n1.y, j) + h * NT);
                     }
-                    d2 = ld_bytes<K>(dlt + n1.z);
+                    d2 = n1.z >= 0 ? ld_bytes<K>(dlt + n1.z) : 0u;
                 }
                 // q(node) lives in the TOS registers for the whole step: either it is still there (the
                 // node was the previous step's first child) or it is popped from the shared-memory stack
@@ -1653,12 +1697,12 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                 const PreRec* r0 = reinterpret_cast<const PreRec*>(ring.rec(0));
                 if (r0->row_a < 0) ca = ldg_bytes<K>(tipp + r0->tip_a);
                 if (r0->row_b < 0) cb = ldg_bytes<K>(tipp + r0->tip_b);
-                dcur = ld_bytes<K>(dlt + r0->dl_n);
+                dcur = r0->dl_n >= 0 ? ld_bytes<K>(dlt + r0->dl_n) : 0u;
                 if (nsteps > 1) {
                     const PreRec* r1 = reinterpret_cast<const PreRec*>(ring.rec(1));
                     if (r1->row_a < 0) ca1 = ldg_bytes<K>(tipp + r1->tip_a);
                     if (r1->row_b < 0) cb1 = ldg_bytes<K>(tipp + r1->tip_b);
-                    d1 = ld_bytes<K>(dlt + r1->dl_n);
+                    d1 = r1->dl_n >= 0 ? ld_bytes<K>(dlt + r1->dl_n) : 0u;
                 }
             }
             double* Gd = a.G + ((size_t)d * a.nn * C + c) * 16;  // + node * C * 16
@@ -1684,7 +1728,7 @@ __global__ void __launch_bounds__(128, MINB) sweep_tm_kernel(const SweepArgs a) 
                     const int4 n1 = *reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(n) + 16);
                     if (n1.x < 0) ca2 = ldg_bytes<K>(tipp + n->tip_a);
                     if (n1.y < 0) cb2 = ldg_bytes<K>(tipp + n->tip_b);
-                    d2 = ld_bytes<K>(dlt + n1.z);
+                    d2 = n1.z >= 0 ? ld_bytes<K>(dlt + n1.z) : 0u;
                 }
                 // tip children: decode into their operand slots
                 if (rowa < 0) {
@@ -1924,7 +1968,7 @@ __global__ void __launch_bounds__(128) cherry_table_kernel(const CherryArgs a) {
                     table_col(P1, y, cv);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) cp[s] = cu[s] * cv[s];
-                    table_rescale(cp);
+                    if (!a.norescale) table_rescale(cp);
                     matvec(Pc, cp, u);
                     table_col(P2, z, v);
                 } else {                  // (t0, (t1, t2))
@@ -1933,13 +1977,13 @@ __global__ void __launch_bounds__(128) cherry_table_kernel(const CherryArgs a) {
                     table_col(P2, z, cv);
 #pragma unroll
                     for (int s = 0; s < 4; ++s) cp[s] = cu[s] * cv[s];
-                    table_rescale(cp);
+                    if (!a.norescale) table_rescale(cp);
                     table_col(P0, x, u);
                     matvec(Pc, cp, v);
                 }
 #pragma unroll
                 for (int s = 0; s < 4; ++s) p[s] = u[s] * v[s];
-                table_rescale(p);
+                if (!a.norescale) table_rescale(p);
                 matvec(Pn, p, m);
                 double2* o2 = reinterpret_cast<double2*>(out + 4 * ((5 * x + y) * nz + z));
                 o2[0] = make_double2(m[0], m[1]);
@@ -2488,7 +2532,7 @@ size_t sweep_smem_bytes(int D, int K, int nthreads, int prec, bool jc, bool tips
 }
 
 void launch_stream(const StreamArgs& a, int prec, cudaStream_t stream) {
-    const int total = 4 * a.B * a.lay.C * a.nsteps;
+    const int total = 2 * a.B * a.lay.C * (a.npost + a.nsteps);
     if (prec == 32) stream_kernel<float><<<(total + 127) / 128, 128, 0, stream>>>(a);
     else stream_kernel<double><<<(total + 127) / 128, 128, 0, stream>>>(a);
 }

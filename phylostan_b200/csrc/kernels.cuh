@@ -64,6 +64,8 @@ struct alignas(16) PostRec {
                               //   row, 32: the previous TOS is parked above the capped stack
     int32_t row_a, row_b;     // scratch offsets of the children's own rows, -1 for tips (message-statistic sweep:
     int32_t pad0, pad1;       //   the MESSAGE P_c p_c of an internal child is stored there, at its parent's step)
+    long long ctab_a, ctab_b; // post-order message tables: device address of a leafified child's table for this record's
+                              //   (draw, category), or 0; such a child is tip-like (flags 1 / 2) with tip_* = its code row
 };
 struct alignas(16) PreRec {
     long long tip_a, tip_b;   // byte offset of the child's tip-code row
@@ -76,7 +78,7 @@ struct alignas(16) PreRec {
     long long ctab_a, ctab_b; // cherry-table runs: device address of the child's 25 x 4 message table for this record's (draw,
                               //   category), or 0; such a child has row = -1 and tip_* = its combined-code row
 };
-static_assert(sizeof(PostRec) == 48 && sizeof(PreRec) == 64, "record descriptors must fit the 64-byte header");
+static_assert(sizeof(PostRec) == 64 && sizeof(PreRec) == 64, "record descriptors must fit the 64-byte header");
 
 struct StreamArgs {
     const double* params;     // [B][stride]
@@ -85,7 +87,9 @@ struct StreamArgs {
     unsigned char* spost;     // [B][C][S-1][kRecBytes]
     unsigned char* spre;      // [B][C][S-1][kRecBytes]
     ParamLayout lay;
-    int nsteps, bcount, jc_closed, B;
+    int nsteps, bcount, jc_closed, B;   // nsteps: pre-order steps (S - 1)
+    int npost;                // post-order steps: S - 1, or fewer when the plan leafifies the table nodes (post_tables)
+    int post_tables;          // the post-order takes the messages of table nodes from their tables too
     int Lpad, SS, KNT;        // tile geometry baked into the descriptors
     int S, tips_simple;       // tips_simple: tip children get the column-major 4x5 matrix layout
     // Capped shared-memory stack (gradient runs only): stack positions >= slots (the top of a deep
@@ -123,6 +127,7 @@ struct SweepArgs {
     ParamLayout lay;
     long long scratch_stride, dscr_stride;   // per CTA, in 16-byte vectors / bytes
     int S, nsteps, Lpad, ntiles, nitems, C, nn, nout, D;
+    int npost;                // post-order steps (<= nsteps, see StreamArgs)
     int stack_bytes;          // size of the stack region at the head of dynamic shared memory
     int off_out_freqs, off_out_ps;
 };
@@ -136,6 +141,7 @@ struct CherryArgs {
     double* ctab;
     ParamLayout lay;
     int B, C, ncherry, tab_entries, bcount, jc_closed;
+    int norescale;            // post-order tables: table nodes are never rescaled (neither sweep visits their partials)
 };
 void launch_cherry_tables(const CherryArgs& a, cudaStream_t stream);
 // combined codes of the tips below every table node, 5 x + y or 25 x + 5 y + z, [ntab][Lpad] (tip codes must be column

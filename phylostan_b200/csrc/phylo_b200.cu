@@ -82,6 +82,7 @@ struct PinnedBuf {
 }  // namespace
 
 constexpr double kMsgTauMax = 12.0;  // e^12 * 2^-53 = 1.8e-11 relative: two decades inside the 1e-8 gradient tolerance
+constexpr bool kDefaultPostTables = true;
 constexpr int kDefaultSweepTm = 0;  // fp64 K = 4 gradient runs: 0 shared-memory stack, 2 / 3 tensor-memory stack
 
 struct phylo_b200_ctx {
@@ -143,6 +144,14 @@ struct phylo_b200_ctx {
     DevBuf<uint8_t> d_ctips;                     // [ncherry][Lpad] combined codes 5 x + y / 25 x + 5 y + z (built at the first such run)
     bool ctips_built = false;
     DevBuf<double> d_ctab;                       // [B][C][tab_entries][4]
+    // Post-order message tables: a second plan whose post-order treats the table nodes as leaves (their message to the
+    // parent is the same table entry the pre-order gathers), so the post-order sweep runs half as many steps on a
+    // coalescent tree.  Table nodes are then never rescaled.  PHYLO_B200_POST_TABLES=0 turns it off.
+    Plan planB;
+    bool has_planB = false, use_post_tables = kDefaultPostTables, post_tables_run = false;
+    DevBuf<PostStep> d_postB;
+    DevBuf<PreStep> d_preB;
+    DevBuf<int32_t> d_node_rowB;
     size_t smem = 0;
     int last_launches = 0;
 
@@ -193,6 +202,7 @@ struct phylo_b200_ctx {
         d_spost.release(); d_spre.release(); d_node_pos.release(); d_node_row.release();
         d_scratch.release(); d_dscr.release();
         d_node_cherry.release(); d_cherries.release(); d_tab_off.release(); d_ctips.release(); d_ctab.release();
+        d_postB.release(); d_preB.release(); d_node_rowB.release();
         h_params.release(); h_out.release();
         for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -483,6 +493,18 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
         h->tab_entries = entries;
     }
     cudaError_t e = cudaSuccess;
+    if (h->ncherry > 0 && node_cherry[h->plan.root] < 0) {  // the second plan: table nodes are leaves of its post-order
+        std::vector<char> leaf((size_t)h->nn, 0);
+        for (int n = 0; n < h->nn; ++n) leaf[n] = node_cherry[n] >= 0;
+        std::string err2;
+        if (build_plan(S, peel, h->planB, err2, &leaf) && h->planB.depth() <= h->plan.depth()) {
+            std::vector<int32_t> rowB((size_t)h->nn, -1);
+            for (size_t i = 0; i < h->planB.post.size(); ++i) rowB[h->planB.post[i].node] = (int32_t)i;
+            h->has_planB = (e = up(h->d_postB, h->planB.post)) == cudaSuccess && (e = up(h->d_preB, h->planB.pre)) == cudaSuccess &&
+                           (e = up(h->d_node_rowB, rowB)) == cudaSuccess;
+            if (e != cudaSuccess) { delete h; return fail(PHYLO_B200_ECUDA, std::string("device setup: ") + cudaGetErrorString(e)); }
+        }
+    }
     if ((e = up(h->d_node_cherry, node_cherry)) != cudaSuccess || (e = up(h->d_cherries, cherries)) != cudaSuccess ||
         (e = up(h->d_tab_off, tab_off)) != cudaSuccess) {
         delete h;
@@ -499,6 +521,7 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     if (const char* nj = std::getenv("PHYLO_B200_NO_JC_SCALAR")) h->use_jc_scalar = !(nj[0] && nj[0] != '0');
     if (const char* ms = std::getenv("PHYLO_B200_MSG")) h->use_msg = !(ms[0] == '0');
     if (const char* ch = std::getenv("PHYLO_B200_CHERRY")) h->use_cherry = !(ch[0] == '0');
+    if (const char* pt = std::getenv("PHYLO_B200_POST_TABLES")) h->use_post_tables = !(pt[0] == '0');
     if (const char* tm = std::getenv("PHYLO_B200_SWEEP_TM")) h->req_tm = tm[0] == '3' ? 3 : tm[0] == '2' ? 2 : 0;
     for (auto& ev : h->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
@@ -733,6 +756,7 @@ long long phylo_b200_info(phylo_b200_handle h, int what) {
         case 13: return h->tm;
         case 14: return h->msg_run ? 1 : 0;
         case 15: return h->cherry_run ? 1 : 0;
+        case 16: return h->post_tables_run ? 1 : 0;
     }
     return PHYLO_B200_EINVAL;
 }
@@ -848,6 +872,7 @@ int run_prepare(phylo_b200_ctx* h, int B, bool grad) {
     }
     h->cherry_run = grad && h->msg_run && !h->tm && h->use_cherry && h->ncherry > 0 && h->tips_simple &&
                     sweep_cherry_available(h->K);
+    h->post_tables_run = h->cherry_run && h->use_post_tables && h->has_planB;
     if (h->cherry_run) {
         if (!h->ctips_built) {
             CU_TRY(h->d_ctips.ensure((size_t)h->ncherry * h->Lpad));
@@ -959,13 +984,15 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     if (grad) CU_TRY(cudaMemsetAsync(h->d_G.p, 0, sizeof(double) * B * h->nn * h->C * 16, st));
     if (h->timing) CU_TRY(cudaEventRecord(h->ev[0], st));
     StreamArgs sa{};
-    sa.params = h->d_params.p; sa.post = h->d_post.p; sa.pre = h->d_pre.p;
+    const bool ptab = grad && h->msg_run && h->cherry_run && h->post_tables_run;
+    sa.params = h->d_params.p; sa.post = ptab ? h->d_postB.p : h->d_post.p; sa.pre = ptab ? h->d_preB.p : h->d_pre.p;
+    sa.npost = ptab ? (int)h->planB.post.size() : h->S - 1; sa.post_tables = ptab ? 1 : 0;
     sa.spost = h->d_spost.p; sa.spre = h->d_spre.p; sa.lay = h->lay;
     sa.nsteps = h->S - 1; sa.bcount = h->bcount; sa.jc_closed = h->jc_closed; sa.B = B;
     const int VP = h->prec == 32 ? 1 : 2;  // 16-byte vectors per 4-state entry
     sa.Lpad = h->Lpad; sa.SS = h->K * VP * h->NT; sa.KNT = h->K * h->NT;
     sa.S = h->S; sa.tips_simple = h->tips_simple;
-    sa.node_row = h->d_node_row.p;
+    sa.node_row = ptab ? h->d_node_rowB.p : h->d_node_row.p;
     sa.slots = grad ? h->slots : h->plan.depth();
     sa.slot_stride = grad && h->tm ? 8 * h->K : sa.SS;
     const bool msg = grad && h->msg_run;
@@ -980,6 +1007,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
         CherryArgs ch{};
         ch.params = h->d_params.p; ch.cherries = h->d_cherries.p; ch.ctab = h->d_ctab.p; ch.lay = h->lay;
         ch.B = B; ch.C = h->C; ch.ncherry = h->ncherry; ch.tab_entries = h->tab_entries; ch.bcount = h->bcount; ch.jc_closed = h->jc_closed;
+        ch.norescale = ptab ? 1 : 0;
         launch_cherry_tables(ch, st);
         CU_TRY(cudaGetLastError());
     }
@@ -993,7 +1021,7 @@ int run_enqueue(phylo_b200_ctx* h, int B, bool grad) {
     a.lay = h->lay;
     a.scratch_stride = (long long)(h->S - 1) * h->K * VP * h->NT;
     a.dscr_stride = (long long)(h->S - 1) * h->K * h->NT;
-    a.S = h->S; a.nsteps = h->S - 1; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
+    a.S = h->S; a.nsteps = h->S - 1; a.npost = sa.npost; a.Lpad = h->Lpad; a.ntiles = h->ntiles; a.nitems = B * h->ntiles;
     a.C = h->C; a.nn = h->nn; a.nout = h->nout; a.D = h->slots;
     a.stack_bytes = (int)sweep_stack_bytes(h->slots, h->K, h->NT, h->prec);
     a.off_out_freqs = h->off_freqs; a.off_out_ps = h->off_ps;
@@ -1030,7 +1058,8 @@ std::vector<unsigned long long> graph_signature(const phylo_b200_ctx* h) {
             (unsigned long long)h->NT, (unsigned long long)h->grid, (unsigned long long)h->smem,
             (unsigned long long)h->slots, (unsigned long long)h->prec, (unsigned long long)h->ntiles,
             (unsigned long long)h->jc_run, u(h->d_tips_post.p), u(h->d_tips_pre.p), (unsigned long long)h->tm,
-            (unsigned long long)h->msg_run, (unsigned long long)h->cherry_run, u(h->d_ctab.p), u(h->d_ctips.p)};
+            (unsigned long long)h->msg_run, (unsigned long long)h->cherry_run, u(h->d_ctab.p), u(h->d_ctips.p),
+            (unsigned long long)h->post_tables_run};
 }
 
 // H2D of the packed parameters, the kernels, D2H of the result rows -- as one graph launch when possible

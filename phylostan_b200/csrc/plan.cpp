@@ -6,7 +6,7 @@
 
 namespace phylo {
 
-bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
+bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err, const std::vector<char>* leaf) {
     if (S < 2) { err = "need at least 2 tips"; return false; }
     if (!peel) { err = "peel is NULL"; return false; }
     const int nn = 2 * S - 1;
@@ -39,21 +39,30 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
     if (plan.root != nn - 1) { err = "root must be node 2S-1 (last peel row)"; return false; }
 
     // stack needs (children precede parents in peel, so one forward pass suffices)
+    // post-order view: a leafified node counts as a tip
+    auto inner = [&](int n) { return n >= S && !(leaf && (*leaf)[n]); };
     std::vector<int> need_post(nn, 0), need_pre(nn, 0);
     for (int i = 0; i < S - 1; ++i) {
         int p = peel[3 * i + 2] - 1, a = left[p], b = right[p];
         bool ia = a >= S, ib = b >= S;
         if (ia && ib) {
-            int hi = std::max(need_post[a], need_post[b]), lo = std::min(need_post[a], need_post[b]);
-            need_post[p] = std::max(hi, lo + 1);
             int hi2 = std::max(need_pre[a], need_pre[b]), lo2 = std::min(need_pre[a], need_pre[b]);
             need_pre[p] = std::max(lo2 + 1, hi2);
         } else if (ia || ib) {
             int c = ia ? a : b;
-            need_post[p] = std::max(1, need_post[c]);
             need_pre[p] = std::max(1, need_pre[c]);
         } else {
-            need_post[p] = need_pre[p] = 1;
+            need_pre[p] = 1;
+        }
+        ia = inner(a); ib = inner(b);
+        if (ia && ib) {
+            int hi = std::max(need_post[a], need_post[b]), lo = std::min(need_post[a], need_post[b]);
+            need_post[p] = std::max(hi, lo + 1);
+        } else if (ia || ib) {
+            int c = ia ? a : b;
+            need_post[p] = std::max(1, need_post[c]);
+        } else {
+            need_post[p] = 1;
         }
     }
 
@@ -64,7 +73,7 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
         std::vector<Frame> st;
         auto order = [&](int n, int& first, int& second) {
             int a = left[n], b = right[n];
-            bool ia = a >= S, ib = b >= S;
+            bool ia = inner(a), ib = inner(b);
             if (ia && ib) {
                 if (need_post[b] > need_post[a]) std::swap(a, b);
             } else if (ib) {
@@ -83,7 +92,7 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
             if (f.stage < 2) {
                 int c = f.stage == 0 ? f.first : f.second;
                 ++f.stage;
-                if (c >= S) {
+                if (inner(c)) {
                     Frame g{c, 0, 0, 0};
                     order(c, g.first, g.second);
                     st.push_back(g);
@@ -95,7 +104,7 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
             ps.b = f.second;
             ps.node = f.node;
             ps.spill = -1;
-            const bool ia = ps.a >= S, ib = ps.b >= S;
+            const bool ia = inner(ps.a), ib = inner(ps.b);
             if (ia && ib) {  // b was computed last (TOS); a waits on top of the shared-memory stack
                 ps.src_a = sp - 1;
                 ps.src_b = kSrcTos;
@@ -119,6 +128,12 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
         plan.depth_post = maxsp;
     }
 
+    // every internal node's parking row: its post-order row, or one behind them when the post-order skips it
+    std::vector<int> park_of(nn, -1);
+    {
+        int next = (int)plan.post.size();
+        for (int n = S; n < nn; ++n) park_of[n] = row_of[n] >= 0 ? row_of[n] : next++;
+    }
     // ---- pre-order: DFS from the root, smaller stack need first; q(first child) stays in TOS ----
     {
         std::vector<int> pending;  // nodes whose q sits in shared memory, slot = position
@@ -139,6 +154,8 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
             ps.rown = row_of[cur];
             ps.rowa = ia ? row_of[a] : -1;
             ps.rowb = ib ? row_of[b] : -1;
+            ps.parkn = park_of[cur];
+            ps.parkb = ib ? park_of[b] : -1;
             ps.dst_b = -1;
             if (ib) {
                 ps.dst_b = (int)pending.size();
@@ -159,7 +176,7 @@ bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err) {
         }
         plan.depth_pre = maxsp;
     }
-    if ((int)plan.post.size() != S - 1 || (int)plan.pre.size() != S - 1) {
+    if ((!leaf && (int)plan.post.size() != S - 1) || (int)plan.pre.size() != S - 1 || plan.post.empty()) {
         err = "peel does not describe a single binary tree";
         return false;
     }

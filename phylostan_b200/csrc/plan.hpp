@@ -34,9 +34,10 @@ struct alignas(16) PreStep {
     int32_t src_n;         // kSrcTos | shared-memory slot holding q(node)
     int32_t dst_b;         // shared-memory slot receiving q(b), or -1 (b is a tip)
     int32_t a_internal;    // 1 when q(a) must be produced (into TOS)
-    int32_t rown;          // scratch row of this node (rescale exponent written by the post-order)
-    int32_t rowa, rowb;    // scratch rows of the children's partials; -1 for tips
-    int32_t pad0, pad1, pad2;
+    int32_t rown;          // scratch row of this node (rescale exponent written by the post-order); -1: not visited by it
+    int32_t rowa, rowb;    // scratch rows of the children's partials; -1 for tips (and for leafified nodes, see build_plan)
+    int32_t parkn, parkb;  // a scratch row of this node / of b that may hold a parked q (every internal node has one)
+    int32_t pad2;
 };
 
 struct Plan {
@@ -49,6 +50,10 @@ struct Plan {
 
 // peel: [S-1][3] 1-based (child1, child2, parent) in post-order, root = 2S-1
 // (phylostan/utils.py:59-81).  Returns false and sets err on malformed input.
-bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err);
+// leaf (optional, [2S-1]): internal nodes the POST-order treats as leaves -- their message to the parent comes from a
+// table (phylo_b200.cu: message tables), so neither they nor anything below them gets a post-order step; a leafified
+// child has source kSrcTip.  The pre-order still visits every internal node; nodes without a post-order step have
+// rown = -1 and a parking row behind the post-order's rows.
+bool build_plan(int S, const int32_t* peel, Plan& plan, std::string& err, const std::vector<char>* leaf = nullptr);
 
 }  // namespace phylo

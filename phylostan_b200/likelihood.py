@@ -419,7 +419,7 @@ class TreeLikelihood:
     def info(self) -> dict:
         names = ["stack_depth", "patterns_per_thread", "threads_per_cta", "grid", "smem_bytes", "padded_patterns",
                  "kernel_launches", "scratch_bytes", "depth_post", "depth_pre", "tiles", "stack_slots", "shards",
-                 "sweep_variant", "message_statistic", "cherry_tables"]
+                 "sweep_variant", "message_statistic", "cherry_tables", "post_order_tables"]
         return {n: int(lib().phylo_b200_info(self._h, k)) for k, n in enumerate(names)}
 
     def unpack(self, out: np.ndarray) -> ValueGrad:

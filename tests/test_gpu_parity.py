@@ -617,6 +617,7 @@ def test_gpu_cherry_tables(datasets):
             vg = lik.value_grad(*stack)
             info = lik.info()
             assert info["cherry_tables"] == 1 and info["message_statistic"] == 1 and info["kernel_launches"] == 4
+            assert info["post_order_tables"] == 1   # the post-order skips the table nodes too
             for i, dr in enumerate(draws):
                 want = O.loglik_grad(d["peel"], d["tipmask"], d["weights"], model, *dr, rooted=rooted)
                 assert_parity(lk.ValueGrad(vg.log_P[i], vg.grad_blens[i], vg.grad_subst[i], vg.grad_freqs[i], vg.grad_rs[i],
