@@ -365,7 +365,7 @@ def run_config4(args, world, rank, local, stream):
                        else "sweep_kernel<double,K,GRAD,TIPS,128") + (",MSG>" if info["message_statistic"] else ">"),
             "tiling": {k: info[k] for k in ("stack_depth", "stack_slots", "patterns_per_thread", "threads_per_cta",
                                             "grid", "smem_bytes", "tiles", "scratch_bytes", "message_statistic",
-                                            "cherry_tables")},
+                                            "cherry_tables", "post_order_tables")},
             "design_bytes_per_launch": des, "dram_frac_of_measured_peak": des / (sweep_ms * 1e-3) / 1e9 / peak,
             "survey_Bvg_frac_all_gpus": algorithmic_bytes(C4_TAXA, C4_PATTERNS, N_CAT) * evals / (world * peak * 1e9),
             "setup_s": {"simulate_on_gpu": t_gen, "create_device": t_create},
