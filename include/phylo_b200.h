@@ -292,7 +292,8 @@ PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
  * draw of the batch;
  * PHYLO_B200_MSG=0 in the environment at create time turns it off),
  * 15 whether that run took the messages of cherries (internal nodes with two tip children) from per-(draw, category)
- * 25-entry tables instead of storing and re-reading them (phylo_b200_set_cherry_tables). */
+ * 25-entry tables instead of storing and re-reading them (phylo_b200_set_cherry_tables),
+ * 16 whether its post-order took them from the tables as well (second plan; PHYLO_B200_POST_TABLES=0 turns that off). */
 PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
 
 /*
@@ -301,12 +302,19 @@ PHYLO_B200_API long long phylo_b200_info(phylo_b200_handle h, int what);
  *           bookkeeping of eigen/eigen.j2:82-108).  The most recent vector stays in registers (TOS);
  *           operand sources are -1 tip, -2 TOS, >= 0 shared-memory slot.  post gets S-1 rows of 8 int32
  *           (a, b, src_a, src_b, spill_slot, node, 0, 0), pre gets S-1 rows of 12 int32
- *           (node, a, b, src_node, dst_b, a_internal, row_node, row_a, row_b, 0, 0, 0),
+ *           (node, a, b, src_node, dst_b, a_internal, row_node, row_a, row_b, park_node, park_b, 0),
  *           depth[2] = {post-order, pre-order} shared-memory stack depth (TOS excluded).
  *   derive  the per-draw model algebra of generate_script.py:799-825 / 855-881:
  *           out = [pi 4 | lambda 4 | m1 16 | m2 16 | Q 16 | X_theta ntheta*16]; returns ntheta.
  */
 PHYLO_B200_API int phylo_b200_plan(int S, const int32_t *peel, int32_t *post, int32_t *pre, int32_t *depth);
+/* plan_tables: the message-table nodes of the tree (internal nodes with two or, when max_tips = 3, three tips below
+ *           them; node_tab[2S-1] = table index or -1) and the second plan, whose post-order treats them as leaves:
+ *           post gets info[0] rows (a leafified child has source -1), pre gets S-1 rows in which a node the post-order
+ *           skips has row_node = -1 and fields 9 / 10 hold the parking rows of the node and of b;
+ *           info[4] = {post-order steps, table nodes, table entries per (draw, category), stack depth}. */
+PHYLO_B200_API int phylo_b200_plan_tables(int S, const int32_t *peel, int max_tips, int32_t *node_tab, int32_t *post,
+                                          int32_t *pre, int32_t *info);
 PHYLO_B200_API int phylo_b200_derive(int model, int flags, const double *subst, const double *freqs, double *out);
 
 /*

@@ -332,6 +332,34 @@ int ensure_batch(phylo_b200_ctx* h, int B) {
     return 0;
 }
 
+// Table nodes of a plan: the internal nodes with two (cherry) or three (pitchfork: a cherry and a tip) tips below them,
+// in post-order.  node_tab[n] = index or -1; rec = [ntab][kTabRec] (kernels.cuh); tab_off[k] = first table entry of
+// node k (25 or 125 each); returns the entries per (draw, category).
+int find_table_nodes(const Plan& plan, int S, int max_tips, std::vector<int32_t>& node_tab, std::vector<int32_t>& rec,
+                     std::vector<int32_t>& tab_off) {
+    const int nn = 2 * S - 1;
+    node_tab.assign((size_t)nn, -1);
+    rec.clear();
+    tab_off.clear();
+    std::vector<std::vector<int32_t>> below((size_t)nn);  // tips below a node, a's before b's; empty = more than max_tips
+    for (int k = 0; k < S; ++k) below[k] = {k};
+    int entries = 0;
+    for (const PostStep& p : plan.post) {
+        const auto &ta = below[p.a], &tb = below[p.b];
+        if (ta.empty() || tb.empty() || (int)(ta.size() + tb.size()) > max_tips) continue;
+        std::vector<int32_t> t = ta;
+        t.insert(t.end(), tb.begin(), tb.end());
+        below[p.node] = t;
+        const int nt = (int)t.size();
+        node_tab[p.node] = (int32_t)tab_off.size();
+        tab_off.push_back(entries);
+        rec.insert(rec.end(), {p.node, nt, t[0], t[1], nt == 3 ? t[2] : -1, nt == 3 ? (ta.size() == 2 ? p.a : p.b) : -1,
+                               nt == 3 && ta.size() == 1 ? 1 : 0, entries});
+        entries += nt == 3 ? 125 : 25;
+    }
+    return entries;
+}
+
 // on_device: tipmask / weights are DEVICE pointers on `device` (phylo_b200_create_device)
 int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int flags, const int32_t* peel,
                   const uint8_t* tipmask, const double* tipdata, const double* weights, int device,
@@ -469,28 +497,12 @@ int create_common(phylo_b200_handle* out, int S, int L, int C, int model, int fl
     std::vector<int32_t> node_row((size_t)h->nn, -1);  // internal node -> its own post-order step = scratch row
     for (size_t i = 0; i < h->plan.post.size(); ++i) node_row[h->plan.post[i].node] = (int32_t)i;
     // table nodes: internal nodes with two (cherry) or three (pitchfork: a cherry and a tip) tips below them
-    std::vector<int32_t> node_cherry((size_t)h->nn, -1), cherries, tab_off;
+    std::vector<int32_t> node_cherry, cherries, tab_off;
     {
         int max_tips = 3;
         if (const char* tt = std::getenv("PHYLO_B200_TABLE_TIPS")) max_tips = tt[0] == '2' ? 2 : 3;
-        std::vector<std::vector<int32_t>> below((size_t)h->nn);  // tips below a node, a's before b's; empty = more than three
-        for (int k = 0; k < S; ++k) below[k] = {k};
-        int entries = 0;
-        for (const PostStep& p : h->plan.post) {
-            const auto &ta = below[p.a], &tb = below[p.b];
-            if (ta.empty() || tb.empty() || (int)(ta.size() + tb.size()) > max_tips) continue;
-            std::vector<int32_t> t = ta;
-            t.insert(t.end(), tb.begin(), tb.end());
-            below[p.node] = t;
-            const int nt = (int)t.size();
-            node_cherry[p.node] = (int32_t)tab_off.size();
-            tab_off.push_back(entries);
-            cherries.insert(cherries.end(), {p.node, nt, t[0], t[1], nt == 3 ? t[2] : -1,
-                                             nt == 3 ? (ta.size() == 2 ? p.a : p.b) : -1, nt == 3 && ta.size() == 1 ? 1 : 0, entries});
-            entries += nt == 3 ? 125 : 25;
-        }
+        h->tab_entries = find_table_nodes(h->plan, S, max_tips, node_cherry, cherries, tab_off);
         h->ncherry = (int)tab_off.size();
-        h->tab_entries = entries;
     }
     cudaError_t e = cudaSuccess;
     if (h->ncherry > 0 && node_cherry[h->plan.root] < 0) {  // the second plan: table nodes are leaves of its post-order
@@ -1525,6 +1537,28 @@ int phylo_b200_plan(int S, const int32_t* peel, int32_t* post, int32_t* pre, int
     if (post) std::memcpy(post, plan.post.data(), plan.post.size() * sizeof(PostStep));
     if (pre) std::memcpy(pre, plan.pre.data(), plan.pre.size() * sizeof(PreStep));
     if (depth) { depth[0] = plan.depth_post; depth[1] = plan.depth_pre; }
+    return 0;
+}
+
+// Host-only hook (no GPU): the table nodes of a tree and the second plan, whose post-order treats them as leaves.
+// node_tab [2S-1]; post / pre as in phylo_b200_plan (post holds info[0] rows); info[4] = {post-order steps, table
+// nodes, table entries per (draw, category), stack depth}.  Returns PHYLO_B200_EINVAL when the tree has no such plan
+// (the root itself is a table node).
+int phylo_b200_plan_tables(int S, const int32_t* peel, int max_tips, int32_t* node_tab, int32_t* post, int32_t* pre,
+                           int32_t* info) {
+    Plan plan, planB;
+    std::string err;
+    if (!build_plan(S, peel, plan, err)) return fail(PHYLO_B200_EINVAL, err);
+    std::vector<int32_t> nt, rec, off;
+    const int entries = find_table_nodes(plan, S, max_tips == 2 ? 2 : 3, nt, rec, off);
+    if (off.empty() || nt[plan.root] >= 0) return fail(PHYLO_B200_EINVAL, "plan_tables: the root is a table node");
+    std::vector<char> leaf(nt.size(), 0);
+    for (size_t n = 0; n < nt.size(); ++n) leaf[n] = nt[n] >= 0;
+    if (!build_plan(S, peel, planB, err, &leaf)) return fail(PHYLO_B200_EINVAL, err);
+    if (node_tab) std::memcpy(node_tab, nt.data(), nt.size() * sizeof(int32_t));
+    if (post) std::memcpy(post, planB.post.data(), planB.post.size() * sizeof(PostStep));
+    if (pre) std::memcpy(pre, planB.pre.data(), planB.pre.size() * sizeof(PreStep));
+    if (info) { info[0] = (int32_t)planB.post.size(); info[1] = (int32_t)off.size(); info[2] = entries; info[3] = planB.depth(); }
     return 0;
 }
 

@@ -99,6 +99,7 @@ def lib() -> ctypes.CDLL:
     L.phylo_b200_ratios_forward.argtypes = [i, ip, _dp, i, _dp, _dp, _dp, _dp]
     L.phylo_b200_ratios_reverse.argtypes = [i, ip, _dp, i, _dp, _dp, _dp, _dp, _dp]
     L.phylo_b200_plan.argtypes = [i, ip, ip, ip, ip]
+    L.phylo_b200_plan_tables.argtypes = [i, ip, i, ip, ip, ip, ip]
     L.phylo_b200_derive.argtypes = [i, i, _dp, _dp, _dp]
     _lib = L
     return L
@@ -447,6 +448,21 @@ def plan(peel) -> dict:
     _check(lib().phylo_b200_plan(S, peel.ctypes.data_as(ip), post.ctypes.data_as(ip), pre.ctypes.data_as(ip),
                                  depth.ctypes.data_as(ip)))
     return {"post": post, "pre": pre, "depth_post": int(depth[0]), "depth_pre": int(depth[1])}
+
+
+def plan_tables(peel, max_tips: int = 3) -> dict:
+    """Message-table nodes of the tree and the second plan whose post-order treats them as leaves (no GPU needed)."""
+    peel = np.ascontiguousarray(peel, dtype=np.int32)
+    S = peel.shape[0] + 1
+    node_tab = np.zeros(2 * S - 1, dtype=np.int32)
+    post = np.zeros((S - 1, 8), dtype=np.int32)
+    pre = np.zeros((S - 1, 12), dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    _check(lib().phylo_b200_plan_tables(S, peel.ctypes.data_as(ip), int(max_tips), node_tab.ctypes.data_as(ip),
+                                        post.ctypes.data_as(ip), pre.ctypes.data_as(ip), info.ctypes.data_as(ip)))
+    return {"node_tab": node_tab, "post": post[:info[0]], "pre": pre, "post_steps": int(info[0]), "table_nodes": int(info[1]),
+            "table_entries": int(info[2]), "depth": int(info[3])}
 
 
 def ratios_forward(map_, lowers, props, root_height):

@@ -196,6 +196,56 @@ def test_plan_depth_bounds():
     assert p["depth_post"] == 5 and p["depth_pre"] == 5      # log2(64) live vectors, one of them in registers
 
 
+def test_plan_with_table_nodes_as_leaves(datasets):
+    """The second plan (message tables in the post-order): table nodes are the internal nodes with at most three tips
+    below them; the post-order has no step for them or for anything below them and sees them as tip-like children; the
+    pre-order still visits every internal node, knows which ones have no post-order row (no rescale exponents) and gives
+    every internal node a parking row of its own."""
+    rng = np.random.default_rng(3)
+    peels = [datasets[n]["peel"] for n in ("fluA", "DS1", "HCV")] + [synth.coalescent_peel(S, rng) for S in (8, 50, 333)]
+    for peel in peels:
+        S = peel.shape[0] + 1
+        full = lk.plan(peel)
+        for max_tips in (2, 3):
+            t = lk.plan_tables(peel, max_tips)
+            # tips below every node
+            ntips = np.ones(2 * S - 1, dtype=int)
+            for a, b, p in peel:
+                ntips[p - 1] = ntips[a - 1] + ntips[b - 1]
+            is_tab = t["node_tab"] >= 0
+            assert np.array_equal(is_tab, (np.arange(2 * S - 1) >= S) & (ntips <= max_tips))
+            assert t["table_nodes"] == int(is_tab.sum())
+            assert t["table_entries"] == 25 * int((is_tab & (ntips == 2)).sum()) + 125 * int((is_tab & (ntips == 3)).sum())
+            # post-order: one step per internal node that is not a table node, children before parents, leafified
+            # children tip-like
+            post = t["post"]
+            assert t["post_steps"] == post.shape[0] == S - 1 - t["table_nodes"]
+            done = set(range(S)) | set(np.nonzero(is_tab)[0].tolist())
+            for a, b, sa, sb, spill, node, _, _ in post:
+                assert a in done and b in done and not is_tab[node]
+                if is_tab[a] or a < S:
+                    assert sa == -1
+                if is_tab[b] or b < S:
+                    assert sb == -1
+                done.add(int(node))
+            assert int(post[-1][5]) == 2 * S - 2 and t["depth"] <= max(full["depth_post"], full["depth_pre"])
+            # pre-order: the same traversal as the full plan; rows only where the post-order has a step; parking rows
+            pre = t["pre"]
+            assert np.array_equal(pre[:, :6], full["pre"][:, :6])
+            row_of = {int(r[5]): i for i, r in enumerate(post)}
+            parks = set()
+            for node, a, b, src, dst_b, a_int, rown, rowa, rowb, parkn, parkb, _ in pre:
+                assert rown == row_of.get(int(node), -1)
+                assert rowa == row_of.get(int(a), -1) and rowb == row_of.get(int(b), -1)
+                assert 0 <= parkn < S - 1 and (parkn == rown or rown < 0)
+                parks.add(int(parkn))
+                if b >= S:
+                    assert 0 <= parkb < S - 1
+            assert len(parks) == S - 1   # one parking row per internal node
+    with pytest.raises(lk.PhyloB200Error):
+        lk.plan_tables(np.array([[1, 2, 4], [4, 3, 5]], dtype=np.int32))   # three taxa: the root is a pitchfork
+
+
 def test_plan_rejects_malformed_peel():
     with pytest.raises(lk.PhyloB200Error):
         lk.plan(np.array([[4, 3, 5], [1, 2, 4]], dtype=np.int32))      # parent before child
