@@ -22,6 +22,13 @@
 // step i+2 are prefetched into L2.  HBM traffic is one coalesced double2 write per internal-node
 // partial in the post-order (the CTA's scratch rows) and one read of it in the pre-order, plus
 // 1-byte tip codes; q never leaves the SM.
+//
+// Round 2, on top of that (kernels.cu has the details): the MESSAGE statistic (the rows hold P_c p_c, the pre-order
+// never multiplies by P again, the contraction undoes the factor analytically), the statistics' warp sums through
+// TENSOR MEMORY used as a transpose unit (tcgen05.st.32x32b in, tcgen05.ld.16x256b out), message TABLES for the
+// nodes with two or three tips below them (cherry_table_kernel; both sweeps look their messages up by a combined
+// tip code instead of computing, storing and re-reading them), and an opt-in variant that keeps the whole stack in
+// tensor memory (sweep_tm_kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
