@@ -67,5 +67,27 @@ def main():
               f"{100 * r['cherries']:.1f} % | {r['median_distinct']:.3f} |")
 
 
+def tables():
+    """What the library's structural message tables cover, from the tree alone (phylo_b200_plan_tables, CPU)."""
+    from phylostan_b200 import likelihood as lk, synth
+    rows = []
+    for name in ("fluA", "DS1", "HCV"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        rows.append((name, z["peel"]))
+    rows.append(("config-3 tree (1000 taxa)", synth.make_problem(1000, 64, 4, seed=synth.SEED_DATA).peel))
+    rows.append(("a 10 000-taxon coalescent tree (config-4 shape)", synth.coalescent_peel_fast(10000, np.random.default_rng(1))))
+    print("\n## Structural message tables (DESIGN.md section 7): nodes with at most three tips below them\n")
+    print("What the library's message tables cover, from the tree alone (`phylo_b200_plan_tables`, CPU):\n")
+    print("| tree | taxa | internal nodes | cherries | pitchforks | share of internal nodes | post-order steps left "
+          "| table entries per (draw, category) |")
+    print("|---|---|---|---|---|---|---|---|")
+    for name, peel in rows:
+        S = peel.shape[0] + 1
+        t2, t3 = lk.plan_tables(peel, 2), lk.plan_tables(peel, 3)
+        c, pf = t2["table_nodes"], t3["table_nodes"] - t2["table_nodes"]
+        print(f"| {name} | {S} | {S - 1} | {c} | {pf} | {100 * (c + pf) / (S - 1):.1f} % | {t3['post_steps']} | {t3['table_entries']} |")
+
+
 if __name__ == "__main__":
     main()
+    tables()
