@@ -287,7 +287,8 @@ PHYLO_B200_API int phylo_b200_get_timing(phylo_b200_handle h, double ms[4]);
  * 7 scratch bytes allocated on the device, 8 / 9 post- / pre-order stack depth, 10 pattern tiles,
  * 11 on-chip stack slots of the last run, 12 pattern shards (devices) behind the handle,
  * 13 sweep variant of the last run (0 shared-memory stack, 2 / 3 tensor-memory stack with that many CTAs per SM),
- * 14 whether the last gradient run used the message statistic (fp64, simple tips, 128-thread CTAs and
+ * 14 whether the last gradient run used the message statistic (fp64, simple tips, 128-thread CTAs, more than one
+ * pattern per thread and
  * (largest branch length) x (largest site rate) x (spread of Q's eigenvalues) + log(|m1|_F |m2|_F / 4) < 12 for every
  * draw of the batch;
  * PHYLO_B200_MSG=0 in the environment at create time turns it off),

@@ -307,7 +307,9 @@ int resolve_tiling(phylo_b200_ctx* h, int B, bool grad) {
             tm = h->req_tm; D = dt; smem = sweep_tm_smem_bytes(K);
         }
     }
-    const bool msg = h->use_msg && sweep_msg_available(h->prec, h->tips_simple, grad, D < Dfull, NT, jrun) &&
+    // (not at K = 1, the latency-bound shapes: there a tip's message lookup sits on the step's dependent chain and the
+    // plain statistic is 7 % faster -- fluA 144 against 154 us per gradient, profiles/r2_logs/r2_latency_final.log)
+    const bool msg = h->use_msg && K > 1 && sweep_msg_available(h->prec, h->tips_simple, grad, D < Dfull, NT, jrun) &&
                      h->tau_bound < kMsgTauMax;
     if (tm && msg) CU_TRY(sweep_tm_prepare(h->tips_simple, K, tm, &occ, true));
     h->K = K; h->PB = PB; h->NT = NT; h->smem = smem; h->slots = D; h->jc_run = jrun; h->tm = tm; h->msg_run = msg;
